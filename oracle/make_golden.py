@@ -24,9 +24,10 @@ OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 
 
 def digest(params, n_samples=16, seed=123):
     """per-tensor (sum, abs-sum, sampled elements) in float64."""
-    rs = np.random.RandomState(seed)
+    import zlib
     d = {}
     for n in sorted(params):
+        rs = np.random.RandomState((seed + zlib.crc32(n.encode())) % (2 ** 31))
         t = params[n].detach().double().reshape(-1).numpy()
         idx = rs.randint(0, t.size, size=min(n_samples, t.size))
         d[n] = np.concatenate([[t.sum(), np.abs(t).sum()], t[idx]])

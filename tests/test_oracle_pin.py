@@ -20,9 +20,10 @@ def _load(name):
 
 
 def _digest(params, n_samples=16, seed=123):
-    rs = np.random.RandomState(seed)
+    import zlib
     d = {}
     for n in sorted(params):
+        rs = np.random.RandomState((seed + zlib.crc32(n.encode())) % (2 ** 31))
         t = params[n].detach().double().reshape(-1).numpy()
         idx = rs.randint(0, t.size, size=min(n_samples, t.size))
         d[n] = np.concatenate([[t.sum(), np.abs(t).sum()], t[idx]])
