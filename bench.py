@@ -1,0 +1,332 @@
+#!/usr/bin/env python
+"""SGSAC updates/sec on B200 (BASELINE.json metric) -- one JSON line on stdout.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+
+N=1 workload = BASELINE.json configs[1]: SGSAC full update loop (critic + 2 attributions + mask-consistency,
+actor/alpha, target EMA, overlay aux update; all frequencies 2 so steps alternate odd/even), batch 128,
+9x84x84 uint8 frame stacks, synthetic replay (SURVEY.md 8d cfg 2).  N>1: the batch is sharded, 128 samples per
+rank (global batch 128*N = BASELINE config 4 at N=8), gradients all-reduced with NCCL; weak scaling.
+
+`value`   : updates/s with the replay ring resident in HBM (CUDA-event timed, max over ranks), times
+            global_batch/128 so it is the whole-job aggregate in batch-128 updates.
+`e2e`     : the same through the public API with HOST buffers: the replay frame ring lives in pinned host
+            memory and every step's sampled frames cross to the device inside the timed region, and the
+            step's loss vector is read back to the host every step.
+`roofline`: the dominant kernel family of the step, timed live with CUDA events around its launches.
+`cpu_baseline`: the oracle port of the reference update (oracle/sgsac_oracle.py) on the host cores.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+PER_GPU_BATCH = 128
+CAPACITY = 20000            # transitions; 20003 frames x 21 KB = 423 MB > 126 MB L2
+POOL_N = 2048               # overlay frames (43 MB)
+# algorithmic FLOPs per sample (minimal / de-duplicated schedule), FLOP = 2*MAC
+GFLOP_ODD, GFLOP_EVEN = 1.671, 3.712
+
+
+def env_int(k, d):
+    return int(os.environ.get(k, d))
+
+
+class NullLog:
+    def __init__(self):
+        self.last = {}
+
+    def log(self, k, v, step, n=1):
+        self.last[k] = v
+
+
+class ClockSampler(threading.Thread):
+    def __init__(self, gpu):
+        super().__init__(daemon=True)
+        self.gpu, self.rows, self.stop_flag = gpu, [], False
+
+    def run(self):
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.gpu)],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unsampled"]}
+        sm = sorted(float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": float(self.rows[0][1]) if self.rows[0][1].replace(".", "").isdigit() else None,
+                "reasons": reasons, "samples": len(self.rows)}
+
+
+def synthetic(capacity, A=2, seed=0):
+    rs = np.random.RandomState(seed)
+    frames = rs.randint(0, 256, size=(capacity + 3, 3, 84, 84), dtype=np.uint8)
+    actions = rs.uniform(-1, 1, size=(capacity, A)).astype(np.float32)
+    rewards = rs.randn(capacity, 1).astype(np.float32)
+    not_dones = np.ones((capacity, 1), dtype=np.float32)
+    pool = rs.randint(0, 256, size=(POOL_N, 3, 84, 84), dtype=np.uint8)
+    return frames, actions, rewards, not_dones, pool
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d["hbm_gbs"], d["bf16_tflops"], d.get("bf16_tflops_sustained", d["bf16_tflops"]), "measured"
+    return 6650.0, 1590.0, 1400.0, "fallback"
+
+
+# ----------------------------------------------------------------------------- reference arm / cpu baseline
+def time_oracle(steps, warmup, budget_s, B=PER_GPU_BATCH):
+    """Times the oracle port of SGSAC.update on the host cores (config 1 of BASELINE.json)."""
+    from oracle import sgsac_oracle as O
+    from oracle.pin_rnd import make_rnd
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    args = O.Args(algorithm="sgsac", sgqn_quantile=0.95, batch_size=B)
+    rs = np.random.RandomState(0)
+    rep = O.synthetic_replay(1000, 2, seed=0)
+    pool = torch.as_tensor(rs.randint(0, 256, size=(256, 3, 84, 84), dtype=np.uint8))
+    orc = O.make_oracle((9, 84, 84), (2,), args, seed=0)
+    orc.pool = pool
+    L = NullLog()
+    step = 1
+    for _ in range(warmup):
+        orc.update_from_batch(rep.sample(rs.randint(0, 1000, size=B)), make_rnd(rs, B, 2, 256), L, step); step += 1
+    times = []
+    t_start = time.time()
+    for i in range(steps):
+        t0 = time.time()
+        orc.update_from_batch(rep.sample(rs.randint(0, 1000, size=B)), make_rnd(rs, B, 2, 256), L, step); step += 1
+        times.append(time.time() - t0)
+        if time.time() - t_start > budget_s and len(times) >= 2 and len(times) % 2 == 0:
+            break
+    odd = [t for i, t in enumerate(times) if (warmup + 1 + i) % 2 == 1]
+    even = [t for i, t in enumerate(times) if (warmup + 1 + i) % 2 == 0]
+    mean = 0.5 * (np.mean(odd) + np.mean(even)) if odd and even else float(np.mean(times))
+    return 1.0 / mean, cores, f"{len(times)} consecutive oracle-port updates (B={B}, config 1, {len(even)} even + {len(odd)} odd) after {warmup} warm-up"
+
+
+def run_reference(a):
+    rank = env_int("RANK", 0)
+    if rank != 0:
+        return
+    v, cores, sample = time_oracle(a.steps, min(a.warmup, 2), 150.0)
+    line = {"impl": "reference", "metric": "SGSAC updates/sec (batch 128, 9x84x84)", "value": v, "unit": "updates/s",
+            "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1000.0 / v, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "SGSAC full update loop, batch 128, 9x84x84 (BASELINE configs[1] shapes) on host CPU cores"},
+            "cpu_baseline": {"value": v, "unit": "updates/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": v, "unit": "updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------- B200 arm
+def profile_kernels(agent, rb, nsteps=4):
+    """Per-ABI-call CUDA-event timing over `nsteps` updates -> {family: (total_ms, calls)}."""
+    from sgqn_carla_b200 import _lib
+    api = _lib.K
+    recs = []
+    names = list(_lib.SIGNATURES.keys())
+    saved = {}
+    for full in names:
+        n = full[len("sgqn_"):]
+        fn = getattr(api, n)
+        saved[n] = fn
+
+        def wrap(*args, _fn=fn, _n=n):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            _fn(*args)
+            e1.record()
+            recs.append((_n, args, e0, e1))
+        setattr(api, n, wrap)
+    try:
+        L = NullLog()
+        for s in range(1, nsteps + 1):
+            agent.update(rb, L, s)
+        torch.cuda.synchronize()
+    finally:
+        for n, fn in saved.items():
+            setattr(api, n, fn)
+    fam = {}
+    for n, args, e0, e1 in recs:
+        key = n
+        if n in ("conv_fwd", "conv_dgrad", "conv_wgrad"):
+            cin, cout = (args[7], args[8])
+            key = f"{n}[{cin}->{cout}]"
+        t = e0.elapsed_time(e1)
+        tot, cnt, flops = fam.get(key, (0.0, 0, 0.0))
+        fl = 0.0
+        if n == "conv_fwd":
+            B, Hs, Ws, Cin, Cout, pad, up = args[4], args[5], args[6], args[7], args[8], args[9], args[10]
+            Ho = Hs * up + 2 * pad - 2
+            fl = 2.0 * B * Ho * Ho * 9 * Cin * (9 if Cout == 16 else Cout)
+        elif n == "conv_dgrad":
+            B, Hl, Wl, Cin, Cout, pad = args[4], args[5], args[6], args[7], args[8], args[9]
+            Ho = Hl + 2 * pad - 2
+            fl = 2.0 * B * Ho * Ho * 9 * Cin * (9 if Cout == 16 else Cout)
+        elif n == "conv_wgrad":
+            B, Hs, Ws, Cin, Cout, pad, up = args[4], args[5], args[6], args[7], args[8], args[9], args[10]
+            Ho = Hs * up + 2 * pad - 2
+            fl = 2.0 * B * Ho * Ho * 9 * Cin * (9 if Cout == 16 else Cout)
+        fam[key] = (tot + t, cnt + 1, flops + fl)
+    return fam, nsteps
+
+
+def run_b200(a):
+    import torch.distributed as dist
+    import sgqn_carla_b200 as S
+    from sgqn_carla_b200 import _lib
+    from sgqn_carla_b200.dist import GradSync
+
+    world, rank, local = env_int("WORLD_SIZE", 1), env_int("RANK", 0), env_int("LOCAL_RANK", 0)
+    torch.cuda.set_device(local)
+    sync = None
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        sync = GradSync()
+    B = PER_GPU_BATCH
+    Bg = B * world
+    args = S.default_args(algorithm="sgsac", batch_size=B, sgqn_quantile=0.95, seed=1 + rank)
+    frames, actions, rewards, not_dones, pool = synthetic(CAPACITY, 2, seed=rank)
+
+    def make(storage):
+        ag = S.make_agent((9, 84, 84), (2,), args, dist=sync, global_batch=Bg)
+        ag.engine.seed = 1234 + rank
+        if world > 1:                       # identical replicated parameters
+            dist.broadcast(ag.engine.params, 0); dist.broadcast(ag.engine.target, 0)
+        ag.set_overlay_pool(pool)
+        rb = S.ReplayBuffer((9, 84, 84), (2,), CAPACITY, B, storage=storage, frame_capacity=CAPACITY + 8)
+        rb.load_ring(frames, actions, rewards, not_dones)
+        return ag, rb
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(agent, rb, L, steps, warmup, s0=1):
+        step = s0
+        for _ in range(warmup):
+            agent.update(rb, L, step); step += 1
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        c0 = _lib.launch_count
+        e0.record()
+        for _ in range(steps):
+            agent.update(rb, L, step); step += 1
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MAX); ms = float(t)
+        return ms, _lib.launch_count - c0
+
+    # ---- device-resident run (value)
+    agent, rb = make("device")
+    L = NullLog()
+    sampler = ClockSampler(local)
+    sampler.start()
+    ms, launches = timed(agent, rb, L, a.steps, a.warmup)
+    sampler.stop_flag = True
+    last = {k: float(v) for k, v in L.last.items()}
+    assert all(np.isfinite(v) for v in last.values()), last
+    ups = a.steps / (ms / 1000.0)
+    value = ups * (Bg / PER_GPU_BATCH)
+
+    # ---- kernel-family profile + roofline of the dominant family (rank 0)
+    roof, fam_rows = None, None
+    if rank == 0:
+        fam, nst = profile_kernels(agent, rb, 4)
+        tot = sum(v[0] for v in fam.values())
+        fam_rows = sorted(((k, v[0] / nst, v[1] // nst, v[2] / nst) for k, v in fam.items()), key=lambda r: -r[1])
+        hbm, tf_burst, tf_sus, how = peaks()
+        top = next(r for r in fam_rows if r[3] > 0)
+        achieved = top[3] / (top[1] * 1e-3) / 1e12
+        peak = tf_sus / 2.0                                  # TF32 dense = bf16 / 2 (derived from measured bf16, sustained)
+        roof = {"bound": "tensor", "kernel": top[0], "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                "frac": achieved / peak, "traffic": None, "share_of_step": top[1] / (tot / nst),
+                "peak_source": f"bf16 sustained {tf_sus} TF/s ({how}) / 2 = TF32 dense, derived",
+                "launches_per_step": top[2], "ms_per_step_in_kernel": top[1]}
+    if world > 1:
+        barrier()
+
+    # ---- end-to-end run: host-resident replay ring (pinned), loss read-back every step
+    del rb
+    agent2, rb2 = make("pinned")
+    agent2.defer_logs = True
+    L2 = NullLog()
+    ms2, _ = timed(agent2, rb2, L2, a.steps, a.warmup)
+    _ = {k: float(v) for k, v in L2.last.items()}
+    e2e_v = a.steps / (ms2 / 1000.0) * (Bg / PER_GPU_BATCH)
+    h2d = 2 * B * 9 * 84 * 84 + B * 8 * 2 + 8                 # sampled uint8 stacks pulled from pinned host memory (+ nothing else: actions etc. live on device)
+    d2h = 8 * 4
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    cpu = None
+    if world == 1 and not a.no_cpu_baseline:
+        v, cores, sample = time_oracle(4, 1, 40.0)
+        cpu = {"value": v, "unit": "updates/s", "cores": cores, "kind": "port", "sample": sample}
+    gflop = 0.5 * (GFLOP_ODD + GFLOP_EVEN) * Bg
+    line = {
+        "metric": "SGSAC updates/sec (batch 128, 9x84x84)", "value": value, "unit": "updates/s", "n_gpus": world,
+        "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "SGSAC full update loop (critic + attribution mask consistency + actor/alpha + target EMA + overlay aux), "
+                               "9x84x84 uint8 stacks, A=2, sgqn_quantile=0.95, reference init, steps alternate odd/even",
+                   "per_gpu_batch": B, "global_batch": Bg, "parallelism": f"dp{world}" if world > 1 else "single",
+                   "replay_capacity": CAPACITY, "l2_policy": "inputs larger than L2 (423 MB frame ring, random gather; ~390 MB activations per encoder pass)",
+                   "value_definition": "global updates/s x (global_batch/128)"},
+        "e2e": {"value": e2e_v, "unit": "updates/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "how": "agent.update(replay_buffer, L, step) with the replay frame ring in pinned HOST memory (gather kernel pulls the "
+                       "sampled stacks host->device every step) and the loss vector copied device->host every step"},
+        "gpu_launches": launches, "clocks": sampler.summary(), "roofline": roof, "cpu_baseline": cpu,
+        "algorithmic_gflop_per_update": gflop, "achieved_tflops_whole_step": gflop * ups / 1e3,
+        "kernel_families_ms_per_step": [[r[0], round(r[1], 4), r[2]] for r in (fam_rows or [])[:12]],
+        "losses_last_step": last,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=40)
+    ap.add_argument("--warmup", type=int, default=4)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    a = ap.parse_args()
+    a.warmup = max(a.warmup, 3)
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_b200(a)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,116 @@
+/* sgqn_b200.h -- C ABI of libsgqn_b200.so: the sm_100a kernels behind the SGSAC update path.
+ *
+ * The reference (gferraro2019/SGQN-CARLA) has no FFI: its boundary is the Python agent API
+ * (`make_agent(...)` -> `update(replay_buffer, L, step)`, `select_action`, `sample_action`;
+ * src/algorithms/factory.py:22-23, sac.py:95-105,160-169, sgsac.py:169-185).  The host-side mirror of
+ * that API lives in `sgqn-carla_b200/` (Python, like the reference) and drives these entry points
+ * through ctypes.  Every function:
+ *   - takes raw DEVICE pointers, sizes and scalars only (no torch types), plus a `cudaStream_t` as `void*`;
+ *   - launches asynchronously on that stream, allocates nothing, never synchronises the host;
+ *   - returns 0 or the `cudaError_t` of the launch.
+ * Citations `file:line` are relative to /root/reference/src and name what each entry point replaces.
+ *
+ * Layout conventions: observations are fp32 NCHW (B,9,H,W) with values 0..255 (what
+ * ReplayBuffer.sample returns, utils.py:185-198); every feature map after the first conv is fp32 NHWC;
+ * 3x3 conv weights (layers 2..11 of SharedCNN and the decoder convs) are stored [Cout][ky][kx][Cin]; the first
+ * conv keeps the reference layout [Cout][Cin][ky][kx]; Linear weights keep the reference layout [out][in].
+ */
+#ifndef SGQN_B200_H
+#define SGQN_B200_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+int sgqn_abi_version(void);
+
+/* ---- replay sampling: ReplayBuffer.sample / sample_drq (utils.py:124-135,158-171,185-198) with
+ *      augmentations.random_crop (augmentations.py:236-264, mode 0) or random_shift (:229-233, mode 1) fused.
+ *      frames: uint8 ring [F][3][Hs][Hs]; fidx: int32 [capacity][6] = frame slots of (obs f0..f2, next f0..f2);
+ *      idxs: int64 [B]; offs: int32 [2][B][2] (row, col) offsets for obs / next_obs, or NULL. */
+int sgqn_replay_gather(const uint8_t* frames, const int32_t* fidx, const int64_t* idxs, const int32_t* offs, float* obs,
+                       float* next_obs, int B, int Hs, int Ho, int mode, int pad, void* stream);
+int sgqn_take_rows(const float* src, const int64_t* idxs, float* dst, int B, int width, void* stream);
+/* random_crop / random_shift on a materialised fp32 batch; offs int32 [B][2] */
+int sgqn_crop_shift(const float* x, const int32_t* offs, float* y, int B, int C, int Hs, int Ho, int mode, int pad, void* stream);
+int sgqn_zero(void* p, long long bytes, void* stream);
+
+/* ---- Linear layers (modules.py:107,194-198,239-243,318).  Strides (ld*, *bs) in elements; `batch` runs
+ *      independent problems (the Q1/Q2 pair) through one launch.
+ *      fwd:   y[M,N] = act(x)[M,K] * w[N,K]^T + bias      (relu_in: ReLU applied to x while loading;
+ *             splitk != 0: split-K with atomic accumulation, y must be zero-filled by the caller)
+ *      dgrad: dx[M,K] = dy[M,N] * w[N,K], optionally masked by zmask (mode 1: *1[z>0]; mode 2 guided:
+ *             relu(.)*1[z>0], captum GuidedBackprop, rl_utils.py:35-39); accumulate != 0: atomic +=
+ *      wgrad: dw[N,K] += dy^T * act(x);  db[N] += colsum(dy)   (atomic; caller zero-fills) */
+int sgqn_linear_fwd(const float* x, int ldx, long long xbs, const float* w, long long wbs, const float* bias, long long bbs,
+                    float* y, int ldy, long long ybs, int M, int N, int K, int relu_in, int batch, int splitk, void* stream);
+int sgqn_linear_dgrad(const float* dy, int lddy, long long dybs, const float* w, long long wbs, const float* zmask, int ldm,
+                      long long mbs, float* dx, int lddx, long long dxbs, int M, int N, int K, int mode, int accumulate,
+                      int batch, void* stream);
+int sgqn_linear_wgrad(const float* x, int ldx, long long xbs, const float* dy, int lddy, long long dybs, float* dw,
+                      long long dwbs, float* db, long long dbbs, int M, int N, int K, int relu_in, int batch, void* stream);
+int sgqn_colsum(const float* x, int ld, int M, int N, float* out, void* stream);
+
+/* ---- 3x3 convolutions on NHWC fp32 (SharedCNN layers 2..11: modules.py:144-146, valid, stride 1; decoder
+ *      convs: modules.py:319-326, pad 1, nearest x2 upsample of the input fused via up=2).
+ *      fwd:   y[B][Ho][Wo][Cout] = conv(act(up(x))) + bias,  Ho = Hs*up + 2*pad - 2
+ *      dgrad: dx[B][Hl][Wl][Cin] gradient w.r.t. the conv's logical input, masked per `mode` by `mask`
+ *      wgrad: dw[Cout][3][3][Cin] += ..., db[Cout] += ...     (atomic; caller zero-fills) */
+int sgqn_conv_fwd(const float* x, const float* w, const float* bias, float* y, int B, int Hs, int Ws, int Cin, int Cout,
+                  int pad, int up, int relu_in, void* stream);
+int sgqn_conv_dgrad(const float* dy, const float* w, const float* mask, float* dx, int B, int Hl, int Wl, int Cin, int Cout,
+                    int pad, int mode, void* stream);
+int sgqn_conv_wgrad(const float* x, const float* dy, float* dw, float* db, int B, int Hs, int Ws, int Cin, int Cout, int pad,
+                    int up, int relu_in, void* stream);
+/* first encoder conv (modules.py:139-142: CenterCrop(84) -> x/255 -> Conv2d(Cin,Cout,3,stride=2)) on NCHW obs */
+int sgqn_conv1_fwd(const float* obs, const float* w, const float* bias, float* y, int B, int Hin, int Cin, int Cout, void* stream);
+int sgqn_conv1_wgrad(const float* obs, const float* dy, float* dw, float* db, int B, int Hin, int Cin, int Cout, void* stream);
+int sgqn_conv1_dgrad(const float* dy, const float* w, float* dobs, int B, int Cin, int Cout, void* stream);
+/* backward of F.upsample(x, 2) followed by ReLU mask of the pre-upsample activation (modules.py:333-337) */
+int sgqn_upsample2_bwd(const float* dup, const float* act, float* dx, int B, int Hs, int Ws, int C, void* stream);
+
+/* ---- saliency: compute_attribution_mask (rl_utils.py:76-82) fused with the mask application of
+ *      update_critic (sgsac.py:67-70); mask uint8 [B][3][HW] (frame mask, the reference repeats it over the 3
+ *      channels of a frame); masked_obs may be NULL (mask only).  minmax: 2 floats, u: 1 float (device). */
+int sgqn_minmax(const float* x, long long n, float* scratch /* >= 592 floats */, float* out2, void* stream);
+int sgqn_attribution_mask(const float* grad, const float* obs, const float* minmax, const float* u, float quantile,
+                          uint8_t* mask, float* masked_obs, int B, int HW, void* stream);
+/* random_overlay (augmentations.py:79-99): 'carla' pool of uint8 frames [N][3][HW] / float places batch [B][3][HW] */
+int sgqn_overlay_u8(const float* obs, const uint8_t* pool, const int64_t* ids, float one_minus_alpha, float alpha, float* out,
+                    int B, int HW, void* stream);
+int sgqn_overlay_f32(const float* obs, const float* imgs, float one_minus_alpha, float alpha, float* out, int B, int HW,
+                     void* stream);
+
+/* ---- heads and losses */
+int sgqn_ln_tanh_fwd(const float* z, const float* gamma, const float* beta, float* h, int ldh, int M, int P, void* stream);
+int sgqn_ln_tanh_bwd(const float* dh, int lddh, const float* z, const float* h, int ldh, const float* gamma, float* dz,
+                     float* dgamma, float* dbeta, int M, int P, void* stream);
+int sgqn_set_cols(float* dst, int ld, int col0, const float* src, int lds, int M, int n, void* stream);
+int sgqn_actor_head_fwd(const float* raw, const float* noise, float lmin, float lmax, float* mu_t, float* pi_t, int ldpi,
+                        float* log_pi, float* log_std, int M, int A, void* stream);
+int sgqn_actor_head_bwd(const float* raw, const float* noise, const float* dpi, int lddpi, const double* log_alpha, float lmin,
+                        float lmax, float* draw, int M, int A, void* stream);
+int sgqn_critic_loss(const float* q, long long qs, const float* tq1, const float* tq2, const float* next_log_pi,
+                     const float* reward, const float* not_done, const double* log_alpha, float discount, int mode, float wa,
+                     float wb, float* target_q, float* dq, float* loss, int B, int Bg, void* stream);
+int sgqn_actor_loss(const float* q, long long qs, const float* log_pi, const double* log_alpha, float target_entropy, float* dq,
+                    float* out3, double* alpha_grad, int B, int Bg, void* stream);
+int sgqn_bce(const float* logits, const uint8_t* mask, float* loss, float* dlogits, int B, int HW, int Cs, int Bg, void* stream);
+
+/* ---- optimiser: torch.optim.Adam (sac.py:60-68, sgsac.py:35-39) over a flat range, soft target update
+ *      (utils.py:31-33, sac.py:153-158) fused when target != NULL */
+int sgqn_adam_prep(int* step, float* bc, double b1, double b2, void* stream);
+int sgqn_adam(float* p, const float* g, float* m, float* v, long long n, const float* bc, float lr, float one_minus_b1, float b2,
+              float one_minus_b2, float eps, float* target, long long n_tau0, float tau0, float tau1, void* stream);
+int sgqn_ema(const float* p, float* target, long long n, long long n_tau0, float tau0, float tau1, void* stream);
+int sgqn_alpha_adam(double* log_alpha, const double* grad, double* st, int* step, double lr, double b1, double b2, double eps,
+                    void* stream);
+/* all random draws of one update (numpy idxs utils.py:127, python random sgsac.py:68 / augmentations.py:70, torch
+ * randn_like modules.py:219, crop offsets augmentations.py:255-256) from one Philox launch */
+int sgqn_rng_step(unsigned long long seed, unsigned long long* counter, const int* n_valid, int64_t* idxs, int64_t* overlay_ids,
+                  int pool_n, int32_t* offs, int off_n, float* noise_next, float* noise_pi, float* u, int B, int A, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

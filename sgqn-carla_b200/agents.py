@@ -1,0 +1,326 @@
+"""Drop-in agents with the reference's API (src/algorithms/{factory,sac,sgsac,svea,rad,drq}.py):
+
+    agent = make_agent(obs_shape, action_shape, args)
+    agent.update(replay_buffer, L, step[, count]); agent.select_action(obs); agent.sample_action(obs)
+    agent.train(bool) / agent.eval() / agent.training / agent.alpha
+    agent.actor / agent.critic / agent.attribution_predictor  -> .state_dict() with the reference's keys
+
+Everything underneath runs on the hand-written sm_100a kernels of libsgqn_b200.so (engine.py); there is no
+PyTorch-op fallback for the update path.
+"""
+from collections import OrderedDict
+
+import numpy as np
+import torch
+
+from . import init as _init
+from ._lib import K
+from .engine import UpdateEngine, _ptr
+from .layout import reference_key_map
+from .lazylog import LazyScalar, _Ring
+from .replay import ReplayBuffer
+
+
+class _ModuleView(object):
+    """Stands in for `agent.actor` / `.critic` / `.critic_target` / `.attribution_predictor`: state_dict
+    interchange with reference checkpoints (train.py:206-219), `parameters()`, `train()`."""
+
+    def __init__(self, agent, module, target=False):
+        self._agent, self._module, self._target = agent, module, target
+        self.training = True
+
+    def _names(self):
+        m = "critic" if self._target else self._module
+        return [(n, key) for n, refs in reference_key_map().items() for mod, key in refs if mod == m]
+
+    def state_dict(self):
+        eng = self._agent.engine
+        lay = eng.lay
+        c0 = lay.ranges["critic"][0]
+        out = OrderedDict()
+        for n, key in self._names():
+            flat = eng.target if self._target else eng.params
+            base = c0 if self._target else 0
+            o, st, _ = lay.entries[n]
+            out[key] = lay.from_stored(n, flat[o - base:o - base + st])
+        return out
+
+    def load_state_dict(self, sd, strict=True):
+        eng = self._agent.engine
+        lay = eng.lay
+        c0 = lay.ranges["critic"][0]
+        for n, key in self._names():
+            if key not in sd:
+                if strict:
+                    raise KeyError(key)
+                continue
+            flat = eng.target if self._target else eng.params
+            base = c0 if self._target else 0
+            o, st, _ = lay.entries[n]
+            flat[o - base:o - base + st].copy_(lay.to_stored(n, sd[key]).to(flat.device))
+
+    def parameters(self):
+        return list(self.state_dict().values())
+
+    def train(self, mode=True):
+        self.training = mode
+        return self
+
+    def eval(self):
+        return self.train(False)
+
+
+class SAC(object):
+    """sac.py:21-169"""
+    algorithm = "sac"
+    critic_mode = 0
+    sample_mode = "crop"            # replay_buffer.sample() (sac.py:161)
+
+    def __init__(self, obs_shape, action_shape, args, device="cuda", dist=None, global_batch=None):
+        self.args = args
+        self.obs_shape, self.action_shape = tuple(obs_shape), tuple(action_shape)
+        self.discount = args.discount
+        self.critic_tau, self.encoder_tau = args.critic_tau, args.encoder_tau
+        self.actor_update_freq = args.actor_update_freq
+        self.critic_target_update_freq = args.critic_target_update_freq
+        self.batch_size = int(args.batch_size)
+        self.engine = UpdateEngine(action_shape[0], args, self.batch_size, device=device, algorithm=self.algorithm,
+                                   dist=dist, global_batch=global_batch)
+        self.set_parameters(_init.init_params(action_shape[0], args))
+        self.actor = _ModuleView(self, "actor")
+        self.critic = _ModuleView(self, "critic")
+        self.critic_target = _ModuleView(self, "critic", target=True)
+        self.target_entropy = self.engine.target_entropy
+        self._ring = _Ring()
+        self._supplied = None
+        self.defer_logs = True
+        self.train()
+
+    # ---- parameters
+    def set_parameters(self, canonical, sync_target=True):
+        """canonical: name -> tensor in the reference's shapes (layout.reference_key_map names)."""
+        eng = self.engine
+        eng.lay.pack(canonical, eng.params)
+        if sync_target:                                            # deepcopy(critic), sac.py:54
+            c0, c1 = eng.lay.ranges["critic"]
+            eng.target.copy_(eng.params[c0:c1])
+        if "log_alpha" in canonical:
+            eng.log_alpha.copy_(torch.as_tensor(canonical["log_alpha"], dtype=torch.float64).reshape(1))
+
+    def get_parameters(self):
+        eng = self.engine
+        out = eng.lay.unpack(eng.params)
+        c0, c1 = eng.lay.ranges["critic"]
+        crit = [n for n in eng.lay.entries if c0 <= eng.lay.off(n) < c1]
+        for n, t in eng.lay.unpack(eng.target, crit, base=c0).items():
+            out["t_" + n] = t
+        out["log_alpha"] = eng.log_alpha.clone().reshape(())
+        return out
+
+    def train(self, training=True):
+        self.training = training
+        self.actor.train(training)
+        self.critic.train(training)
+
+    def eval(self):
+        self.train(False)
+
+    @property
+    def alpha(self):
+        return self.engine.log_alpha.exp().reshape(())
+
+    @property
+    def log_alpha(self):
+        return self.engine.log_alpha.reshape(())
+
+    # ---- acting (sac.py:86-105)
+    def _obs_to_input(self, obs):
+        _obs = np.asarray(obs)
+        return torch.as_tensor(_obs, dtype=torch.float32).to(self.engine.dev).unsqueeze(0)
+
+    def select_action(self, obs):
+        x = self._obs_to_input(obs)
+        return self.engine.act(x, x.shape[-1], sample=False).cpu().numpy().flatten()
+
+    def sample_action(self, obs, noise=None):
+        x = self._obs_to_input(obs)
+        if noise is not None:
+            noise = torch.as_tensor(noise, dtype=torch.float32).to(self.engine.dev).reshape(1, -1)
+        return self.engine.act(x, x.shape[-1], sample=True, noise=noise).cpu().numpy().flatten()
+
+    # ---- one step's randomness
+    def supply(self, idxs=None, noise_next=None, noise_pi=None, u=None, overlay_ids=None, offs=None, places=None):
+        """Host-supplied randomness for the NEXT update (parity runs; SURVEY.md 5 'RNG').  Anything left None is
+        drawn on the device."""
+        self._supplied = dict(idxs=idxs, noise_next=noise_next, noise_pi=noise_pi, u=u, overlay_ids=overlay_ids,
+                              offs=offs, places=places)
+
+    def _draw(self, replay_buffer):
+        eng, B = self.engine, self.batch_size
+        pool_n = eng.overlay_pool.shape[0] if eng.overlay_pool is not None else 1
+        off_n = 9 if self.sample_mode == "shift" else max(1, getattr(replay_buffer, "Hs", 84) - 84)
+        n_valid = replay_buffer.n_valid if isinstance(replay_buffer, ReplayBuffer) else eng.rng_counter.to(torch.int32)
+        K.rng_step(eng.seed, _ptr(eng.rng_counter), _ptr(n_valid), _ptr(eng.idxs), _ptr(eng.overlay_ids), pool_n,
+                   _ptr(eng.offs), off_n, _ptr(eng.noise_next), _ptr(eng.noise_pi), _ptr(eng.u), B, eng.A, eng.st)
+        s, self._supplied = self._supplied, None
+        if s:
+            dev = eng.dev
+            if s["idxs"] is not None:
+                eng.idxs.copy_(torch.as_tensor(np.asarray(s["idxs"]), dtype=torch.int64))
+            if s["overlay_ids"] is not None:
+                eng.overlay_ids.copy_(torch.as_tensor(np.asarray(s["overlay_ids"]), dtype=torch.int64))
+            if s["offs"] is not None:
+                eng.offs.copy_(torch.as_tensor(np.asarray(s["offs"]), dtype=torch.int32).reshape(2, B, 2))
+            if s["noise_next"] is not None:
+                eng.noise_next.copy_(torch.as_tensor(s["noise_next"], dtype=torch.float32))
+            if s["noise_pi"] is not None:
+                eng.noise_pi.copy_(torch.as_tensor(s["noise_pi"], dtype=torch.float32))
+            if s["u"] is not None:
+                eng.u.fill_(float(np.float32(s["u"])))
+            if s["places"] is not None and hasattr(eng, "places"):
+                eng.places.copy_(torch.as_tensor(s["places"], dtype=torch.float32).reshape(B, 3, -1))
+
+    def _sample_into_engine(self, replay_buffer):
+        eng, B = self.engine, self.batch_size
+        if isinstance(replay_buffer, ReplayBuffer):
+            hs = replay_buffer.Hs
+            if self.sample_mode == "shift":
+                mode, offs = 1, eng.offs
+            else:
+                mode, offs = 0, (eng.offs if hs > 84 else None)
+            replay_buffer.gather_into(eng.idxs, eng.obs2[:B], eng.next_obs, eng.action, eng.reward, eng.not_done,
+                                      offs, mode, 4, 84)
+        else:       # a foreign buffer with the reference's surface: use its own sample*() (CUDA fp32 tensors)
+            fn = replay_buffer.sample_drq if self.sample_mode == "shift" else replay_buffer.sample
+            obs, a, r, nxt, nd = fn()
+            eng.obs2[:B].copy_(obs); eng.next_obs.copy_(nxt); eng.action.copy_(a); eng.reward.copy_(r); eng.not_done.copy_(nd)
+
+    def _emit_logs(self, L, step, cols):
+        if L is None:
+            return
+        slot, serial = self._ring.push(self.engine.logs)
+        for key, col in cols:
+            v = LazyScalar([(self._ring, slot, serial, col, 1.0)])
+            L.log(key, v if self.defer_logs else float(v), step)
+
+    def _log_cols(self, step):
+        cols = [("train_critic/loss", 0)]
+        if step % self.actor_update_freq == 0:
+            cols += [("train_actor/loss", 1), ("train_alpha/loss", 2), ("train_alpha/value", 3)]
+        return cols
+
+    def update(self, replay_buffer, L, step, count=0):
+        self.count = count
+        self._draw(replay_buffer)
+        self._sample_into_engine(replay_buffer)
+        self.engine.update_sac(step, self.critic_mode)
+        self._emit_logs(L, step, self._log_cols(step))
+
+
+class RAD(SAC):
+    """rad.py:11-13: SAC on 100x100 frames with sample()'s random crop to 84."""
+    algorithm = "rad"
+
+
+class DrQ(SAC):
+    """drq.py:11-24: SAC with sample_drq() (random shift, K=1, M=1)."""
+    algorithm = "drq"
+    sample_mode = "shift"
+
+
+class SVEA(SAC):
+    """svea.py:12-63: critic on cat(obs, random_overlay(obs)); places365 images are host-supplied / pooled."""
+    algorithm = "svea"
+    critic_mode = 2
+    sample_mode = "shift"
+
+    def __init__(self, obs_shape, action_shape, args, **kw):
+        super().__init__(obs_shape, action_shape, args, **kw)
+        self.svea_alpha, self.svea_beta = args.svea_alpha, args.svea_beta
+        self.places_pool = None         # float (N,3,84,84) in [0,1] on the device (what _get_places_batch yields)
+
+    def set_places_pool(self, imgs):
+        self.places_pool = torch.as_tensor(imgs, dtype=torch.float32).to(self.engine.dev)
+
+    def update(self, replay_buffer, L, step, count=0):
+        eng, B = self.engine, self.batch_size
+        supplied_places = self._supplied is not None and self._supplied.get("places") is not None
+        self._draw(replay_buffer)
+        if not supplied_places:
+            if self.places_pool is None:
+                raise RuntimeError("SVEA needs an overlay image pool: agent.set_places_pool(float images (N,3,84,84) in [0,1])")
+            eng.places.copy_(self.places_pool[eng.overlay_ids % self.places_pool.shape[0]].reshape(B, 3, -1))
+        self._sample_into_engine(replay_buffer)
+        eng.update_sac(step, 2)
+        self._emit_logs(L, step, self._log_cols(step))
+
+
+class SGSAC(SAC):
+    """sgsac.py:24-185"""
+    algorithm = "sgsac"
+    critic_mode = 1
+
+    def __init__(self, obs_shape, action_shape, args, **kw):
+        super().__init__(obs_shape, action_shape, args, **kw)
+        self.attribution_predictor = _ModuleView(self, "attribution_predictor")
+        self.quantile = args.sgqn_quantile
+        self.aux_update_freq = args.aux_update_freq
+        self.consistency = args.consistency
+        self.alpha_blending = args.alpha_blending
+        self.count = 0
+        self.writer = None              # tensorboard image logging (sgsac.py:104-161) is out of scope
+
+    def set_overlay_pool(self, frames_u8):
+        """uint8 (N,3,84,84) frames: what `datasets/carla/*.npy` hold (utils.py:325-327), loaded once to the device
+        instead of B `np.load`s per aux update (augmentations.py:65-76)."""
+        t = torch.as_tensor(frames_u8)
+        assert t.dtype == torch.uint8 and t.shape[1:] == (3, 84, 84)
+        self.engine.overlay_pool = t.to(self.engine.dev).reshape(t.shape[0], 3, -1).contiguous()
+
+    def load_overlay_dir(self, path, limit=None):
+        import os
+        files = sorted(f for f in os.listdir(path) if f.endswith(".npy"))[:limit]
+        self.set_overlay_pool(np.stack([np.load(os.path.join(path, f)) for f in files]))
+
+    def _log_cols(self, step):
+        cols = super()._log_cols(step)
+        if step % self.aux_update_freq == 0:
+            cols.append(("train/aux_loss", 4))
+        return cols
+
+    def update(self, replay_buffer, L, step, count=0):
+        self.count = count
+        if step % self.aux_update_freq == 0 and self.engine.overlay_pool is None:
+            raise RuntimeError("SGSAC.update_aux needs the overlay pool: agent.set_overlay_pool(uint8 frames (N,3,84,84))")
+        self._draw(replay_buffer)
+        self._sample_into_engine(replay_buffer)
+        self.engine.update_sgsac(step)
+        self._emit_logs(L, step, self._log_cols(step))
+
+    # stage-wise entry points mirroring rl_utils (used by the parity tests and by eval-time visualisation)
+    def compute_attribution(self, obs, action):
+        """rl_utils.compute_attribution(self.critic, obs, action): (B,9,84,84) guided-backprop attribution."""
+        eng, B = self.engine, self.batch_size
+        assert obs.shape[0] == B
+        eng.obs2[:B].copy_(obs); eng.action.copy_(action)
+        eng.shared_obs_fwd()
+        eng.attribution2(want_mask=False)
+        return eng.obs_grad.clone()
+
+    def compute_attribution_mask(self, obs_grad, quantile=None):
+        """rl_utils.compute_attribution_mask: bool (B,9,84,84)."""
+        eng, B = self.engine, obs_grad.shape[0]
+        g = obs_grad.contiguous().float()
+        mask = torch.empty(B, 3, 84 * 84, dtype=torch.uint8, device=eng.dev)
+        K.attribution_mask(_ptr(g), 0, 0, 0, float(self.quantile if quantile is None else quantile), _ptr(mask), 0, B, 84 * 84, eng.st)
+        return mask.reshape(B, 3, 1, 84, 84).expand(B, 3, 3, 84, 84).reshape(B, 9, 84, 84).bool()
+
+
+algorithm = {"sac": SAC, "rad": RAD, "drq": DrQ, "svea": SVEA, "sgsac": SGSAC}
+
+
+def make_agent(obs_shape, action_shape, args, **kw):
+    """factory.py:22-23"""
+    if args.algorithm not in algorithm:
+        raise KeyError(f'algorithm "{args.algorithm}" is outside the B200 hot-path scope (SURVEY.md 8): {sorted(algorithm)}')
+    return algorithm[args.algorithm](obs_shape, action_shape, args, **kw)

@@ -1,0 +1,193 @@
+// Dense ops of the SGSAC update on the fp32 CUDA-core tile GEMM (gemm_simt.cuh):
+// Linear fwd/dgrad/wgrad (RLProjection, Actor/Critic MLPs, decoder proj: modules.py:102-113,187-261,315-341),
+// 3x3 conv fwd/dgrad/wgrad on NHWC activations (SharedCNN layers 2..11 and the AttributionDecoder
+// convs: modules.py:132-152,315-341) and the stride-2 first conv on NCHW observations.
+#include "gemm_simt.cuh"
+#include "../../include/sgqn_b200.h"
+
+using namespace sgqn;
+
+static inline int aligned16(const void* p) { return (((uintptr_t)p) & 15) == 0; }
+
+// ---------------------------------------------------------------- column sums (bias gradients)
+__global__ void colsum_kernel(const float* __restrict__ x, int ld, int M, int N, float* __restrict__ out, int rows_per_block) {
+    // block: 256 threads = 8 row-lanes x 32 columns
+    __shared__ float sh[8][33];
+    int col = blockIdx.y * 32 + (threadIdx.x & 31);
+    int rl = threadIdx.x >> 5;
+    int r0 = blockIdx.x * rows_per_block, r1 = min(M, r0 + rows_per_block);
+    float s = 0.f;
+    if (col < N)
+        for (int r = r0 + rl; r < r1; r += 8) s += __ldg(x + (size_t)r * ld + col);
+    sh[rl][threadIdx.x & 31] = s;
+    __syncthreads();
+    if (rl == 0 && col < N) {
+        float t = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) t += sh[i][threadIdx.x];
+        atomicAdd(out + col, t);
+    }
+}
+
+static int launch_colsum(const float* x, int ld, int M, int N, float* out, cudaStream_t st) {
+    if (M <= 0 || N <= 0) return 0;
+    int ctas_y = cdiv(N, 32);
+    int want = cdiv(296, ctas_y);
+    int rpb = cdiv(M, want);
+    if (rpb < 64) rpb = 64;
+    dim3 grid(cdiv(M, rpb), ctas_y);
+    colsum_kernel<<<grid, 256, 0, st>>>(x, ld, M, N, out, rpb);
+    return SGQN_CHECK_LAUNCH();
+}
+
+extern "C" int sgqn_colsum(const float* x, int ld, int M, int N, float* out, void* stream) {
+    return launch_colsum(x, ld, M, N, out, (cudaStream_t)stream);
+}
+
+// ---------------------------------------------------------------- Linear
+extern "C" int sgqn_linear_fwd(const float* x, int ldx, long long xbs, const float* w, long long wbs, const float* bias,
+                               long long bbs, float* y, int ldy, long long ybs, int M, int N, int K, int relu_in,
+                               int batch, int splitk, void* stream) {
+    RowMajorC a{x, ldx, xbs, relu_in, aligned16(x) && (ldx % 4 == 0) && (xbs % 4 == 0)};
+    RowMajorC b{w, K, wbs, 0, aligned16(w) && (K % 4 == 0) && (wbs % 4 == 0)};
+    EpStore ep{y, ldy, ybs, bias, bbs, nullptr, 0, 0, 0, splitk ? 1 : 0, 1.0f};
+    return launch_gemm<64, 64, 16, 4, 4>(a, b, ep, M, N, K, batch, splitk ? 64 : 1, (cudaStream_t)stream);
+}
+
+extern "C" int sgqn_linear_dgrad(const float* dy, int lddy, long long dybs, const float* w, long long wbs,
+                                 const float* zmask, int ldm, long long mbs, float* dx, int lddx, long long dxbs, int M,
+                                 int N, int K, int mode, int accumulate, int batch, void* stream) {
+    // dx[M,K] = dy[M,N] * W[N,K]   (contraction over the N output features)
+    RowMajorC a{dy, lddy, dybs, 0, aligned16(dy) && (lddy % 4 == 0) && (dybs % 4 == 0)};
+    ColMajorR b{w, K, wbs, 0, aligned16(w) && (K % 4 == 0) && (wbs % 4 == 0)};
+    EpStore ep{dx, lddx, dxbs, nullptr, 0, zmask, ldm, mbs, mode, accumulate ? 1 : 0, 1.0f};
+    return launch_gemm<64, 64, 16, 4, 4>(a, b, ep, M, K, N, batch, 1, (cudaStream_t)stream);
+}
+
+extern "C" int sgqn_linear_wgrad(const float* x, int ldx, long long xbs, const float* dy, int lddy, long long dybs,
+                                 float* dw, long long dwbs, float* db, long long dbbs, int M, int N, int K, int relu_in,
+                                 int batch, void* stream) {
+    // dw[N,K] += dy^T[N,M] * act(x)[M,K] ; db[N] += colsum(dy)
+    ColMajorR a{dy, lddy, dybs, 0, aligned16(dy) && (lddy % 4 == 0) && (dybs % 4 == 0)};
+    ColMajorR b{x, ldx, xbs, relu_in, aligned16(x) && (ldx % 4 == 0) && (xbs % 4 == 0)};
+    EpStore ep{dw, K, dwbs, nullptr, 0, nullptr, 0, 0, 0, 1, 1.0f};
+    int rc = launch_gemm<64, 64, 16, 4, 4>(a, b, ep, N, K, M, batch, 64, (cudaStream_t)stream);
+    if (rc) return rc;
+    if (db)
+        for (int bi = 0; bi < batch; ++bi) {
+            rc = launch_colsum(dy + bi * dybs, lddy, M, N, db + bi * dbbs, (cudaStream_t)stream);
+            if (rc) return rc;
+        }
+    return 0;
+}
+
+// ---------------------------------------------------------------- 3x3 conv, NHWC, weights [Cout][9][Cin]
+extern "C" int sgqn_conv_fwd(const float* x, const float* w, const float* bias, float* y, int B, int Hs, int Ws, int Cin,
+                             int Cout, int pad, int up, int relu_in, void* stream) {
+    if ((Cin & 3) || (Cout & 3) || (up != 1 && up != 2)) return (int)cudaErrorInvalidValue;
+    int Ho = Hs * up + 2 * pad - 2, Wo = Ws * up + 2 * pad - 2;
+    ConvGeom g{Hs, Ws, up, Ho, Wo, 1, pad, 0, Cin};
+    ConvPixC a{x, g, relu_in};
+    RowMajorC b{w, 9 * Cin, 0, 0, aligned16(w)};
+    EpStore ep{y, Cout, 0, bias, 0, nullptr, 0, 0, 0, 0, 1.0f};
+    int M = B * Ho * Wo, K = 9 * Cin;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (Cout <= 16) return launch_gemm<128, 16, 32, 4, 4>(a, b, ep, M, Cout, K, 1, 1, st);
+    if (Cout <= 32) return launch_gemm<128, 32, 32, 8, 4>(a, b, ep, M, Cout, K, 1, 1, st);
+    return launch_gemm<128, 64, 32, 8, 4>(a, b, ep, M, Cout, K, 1, 1, st);
+}
+
+extern "C" int sgqn_conv_dgrad(const float* dy, const float* w, const float* mask, float* dx, int B, int Hl, int Wl,
+                               int Cin, int Cout, int pad, int mode, void* stream) {
+    // dx[B][Hl][Wl][Cin]: gradient w.r.t. the conv's logical input (after ReLU / upsample), optionally
+    // masked by `mask` (same shape): mode 1 plain ReLU backward, mode 2 guided (captum GuidedBackprop).
+    if ((Cin & 3) || (Cout & 3)) return (int)cudaErrorInvalidValue;
+    int Ho = Hl + 2 * pad - 2, Wo = Wl + 2 * pad - 2;
+    ConvGeom g{Ho, Wo, 1, Hl, Wl, 1, pad, 1, Cout};
+    ConvPixC a{dy, g, 0};
+    ConvWdgradR b{w, Cin, Cout};
+    EpStore ep{dx, Cin, 0, nullptr, 0, mask, Cin, 0, mode, 0, 1.0f};
+    int M = B * Hl * Wl, K = 9 * Cout;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (Cin <= 32) return launch_gemm<128, 32, 32, 8, 4>(a, b, ep, M, Cin, K, 1, 1, st);
+    return launch_gemm<128, 64, 32, 8, 4>(a, b, ep, M, Cin, K, 1, 1, st);
+}
+
+extern "C" int sgqn_conv_wgrad(const float* x, const float* dy, float* dw, float* db, int B, int Hs, int Ws, int Cin,
+                               int Cout, int pad, int up, int relu_in, void* stream) {
+    // dw[Cout][9][Cin] += sum_pix dy[pix][co] * act(x)[src(pix,tap)][ci] ; db[Cout] += sum_pix dy
+    if ((Cin & 3) || (Cout & 3)) return (int)cudaErrorInvalidValue;
+    int Ho = Hs * up + 2 * pad - 2, Wo = Ws * up + 2 * pad - 2;
+    ConvGeom g{Hs, Ws, up, Ho, Wo, 1, pad, 0, Cin};
+    int P = B * Ho * Wo;
+    ColMajorR a{dy, Cout, 0, 0, aligned16(dy)};
+    ConvPixR b{x, g, relu_in};
+    EpStore ep{dw, 9 * Cin, 0, nullptr, 0, nullptr, 0, 0, 0, 1, 1.0f};
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc;
+    if (Cout <= 32) rc = launch_gemm<32, 64, 16, 4, 4>(a, b, ep, Cout, 9 * Cin, P, 1, 4096, st);
+    else rc = launch_gemm<64, 64, 16, 4, 4>(a, b, ep, Cout, 9 * Cin, P, 1, 4096, st);
+    if (rc) return rc;
+    return db ? launch_colsum(dy, Cout, P, Cout, db, st) : 0;
+}
+
+// ---------------------------------------------------------------- first encoder conv (modules.py:142): NCHW obs, 9 -> 32, stride 2
+extern "C" int sgqn_conv1_fwd(const float* obs, const float* w, const float* bias, float* y, int B, int Hin, int Cin,
+                              int Cout, void* stream) {
+    int crop = (Hin - 84) / 2;                               // CenterCrop(84), modules.py:70-83
+    int Ho = (84 - 3) / 2 + 1;
+    Conv1ObsC a{{obs, Hin, Ho, crop, Cin}};
+    RowMajorC b{w, 9 * Cin, 0, 0, 0};
+    EpStore ep{y, Cout, 0, bias, 0, nullptr, 0, 0, 0, 0, 1.0f};
+    return launch_gemm<128, 32, 16, 8, 4>(a, b, ep, B * Ho * Ho, Cout, 9 * Cin, 1, 1, (cudaStream_t)stream);
+}
+
+extern "C" int sgqn_conv1_wgrad(const float* obs, const float* dy, float* dw, float* db, int B, int Hin, int Cin, int Cout,
+                                void* stream) {
+    int crop = (Hin - 84) / 2, Ho = 41, P = B * Ho * Ho;
+    ColMajorR a{dy, Cout, 0, 0, aligned16(dy) && (Cout % 4 == 0)};
+    Conv1ObsR b{{obs, Hin, Ho, crop, Cin}};
+    EpStore ep{dw, 9 * Cin, 0, nullptr, 0, nullptr, 0, 0, 0, 1, 1.0f};
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = launch_gemm<32, 64, 16, 4, 4>(a, b, ep, Cout, 9 * Cin, P, 1, 4096, st);
+    if (rc) return rc;
+    return db ? launch_colsum(dy, Cout, P, Cout, db, st) : 0;
+}
+
+extern "C" int sgqn_conv1_dgrad(const float* dy, const float* w, float* dobs, int B, int Cin, int Cout, void* stream) {
+    // d obs (NCHW, 84x84) = conv1^T(dy) / 255 ; only the attribution path needs it (rl_utils.py:35-39)
+    ConvGeom g{41, 41, 1, 84, 84, 2, 0, 1, Cout};
+    ConvPixC a{dy, g, 0};
+    Conv1WdgradR b{w, Cin, Cout};
+    EpObsGrad ep{dobs, 84, Cin};
+    return launch_gemm<128, 16, 32, 4, 4>(a, b, ep, B * 84 * 84, Cin, 9 * Cout, 1, 1, (cudaStream_t)stream);
+}
+
+// ---------------------------------------------------------------- nearest-upsample backward (+ ReLU mask of the pre-upsample activation)
+__global__ void upsample2_bwd_kernel(const float4* __restrict__ dup, const float4* __restrict__ act, float4* __restrict__ dx,
+                                     int Hs, int Ws, int C4, long long total) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    int c = (int)(i % C4); long long t = i / C4;
+    int x = (int)(t % Ws); t /= Ws;
+    int y = (int)(t % Hs); int b = (int)(t / Hs);
+    int Wl = 2 * Ws;
+    size_t base = (((size_t)b * 2 * Hs + 2 * y) * Wl + 2 * x) * C4 + c;
+    float4 a0 = __ldg(dup + base), a1 = __ldg(dup + base + C4), a2 = __ldg(dup + base + (size_t)Wl * C4),
+           a3 = __ldg(dup + base + (size_t)Wl * C4 + C4);
+    float4 m = __ldg(act + i);
+    float4 r;
+    r.x = m.x > 0.f ? (a0.x + a1.x) + (a2.x + a3.x) : 0.f;
+    r.y = m.y > 0.f ? (a0.y + a1.y) + (a2.y + a3.y) : 0.f;
+    r.z = m.z > 0.f ? (a0.z + a1.z) + (a2.z + a3.z) : 0.f;
+    r.w = m.w > 0.f ? (a0.w + a1.w) + (a2.w + a3.w) : 0.f;
+    dx[i] = r;
+}
+
+extern "C" int sgqn_upsample2_bwd(const float* dup, const float* act, float* dx, int B, int Hs, int Ws, int C, void* stream) {
+    if (C & 3) return (int)cudaErrorInvalidValue;
+    long long total = (long long)B * Hs * Ws * (C / 4);
+    upsample2_bwd_kernel<<<(unsigned)cdivll(total, 256), 256, 0, (cudaStream_t)stream>>>(
+        (const float4*)dup, (const float4*)act, (float4*)dx, Hs, Ws, C / 4, total);
+    return SGQN_CHECK_LAUNCH();
+}

@@ -1,0 +1,257 @@
+// Head and loss kernels of the SGSAC update: RLProjection LayerNorm+Tanh (modules.py:102-113), the Actor's
+// squashed-Gaussian head (modules.py:20-33,212-232), critic TD / consistency loss (sgsac.py:52-74, svea.py:19-47),
+// actor + alpha loss (sac.py:125-151) and the mask BCE (sgsac.py:163-167).  Tiny tensors: latency bound.
+#include "common.cuh"
+#include "../../include/sgqn_b200.h"
+
+// ---------------------------------------------------------------- LayerNorm + tanh, one warp per row (P <= 1024)
+__global__ void __launch_bounds__(256)
+ln_tanh_fwd_kernel(const float* __restrict__ z, const float* __restrict__ gamma, const float* __restrict__ beta,
+                   float* __restrict__ h, int ldh, int M, int P) {
+    int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (row >= M) return;
+    const float* zr = z + (size_t)row * P;
+    float s = 0.f;
+    for (int i = lane; i < P; i += 32) s += zr[i];
+    float mean = warp_sum(s) / (float)P;
+    float v = 0.f;
+    for (int i = lane; i < P; i += 32) { float d = zr[i] - mean; v += d * d; }
+    float rstd = rsqrtf(warp_sum(v) / (float)P + 1e-5f);
+    for (int i = lane; i < P; i += 32)
+        h[(size_t)row * ldh + i] = tanhf((zr[i] - mean) * rstd * gamma[i] + beta[i]);
+}
+
+extern "C" int sgqn_ln_tanh_fwd(const float* z, const float* gamma, const float* beta, float* h, int ldh, int M, int P,
+                                void* stream) {
+    if (M <= 0) return 0;
+    ln_tanh_fwd_kernel<<<cdiv(M, 8), 256, 0, (cudaStream_t)stream>>>(z, gamma, beta, h, ldh, M, P);
+    return SGQN_CHECK_LAUNCH();
+}
+
+// dz = LN^T( dh * (1 - h^2) ), dgamma / dbeta accumulated with atomics (pass nullptr to skip)
+__global__ void __launch_bounds__(256)
+ln_tanh_bwd_kernel(const float* __restrict__ dh, int lddh, const float* __restrict__ z, const float* __restrict__ h, int ldh,
+                   const float* __restrict__ gamma, float* __restrict__ dz, float* __restrict__ dgamma,
+                   float* __restrict__ dbeta, int M, int P) {
+    int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (row >= M) return;
+    const float* zr = z + (size_t)row * P;
+    float s = 0.f;
+    for (int i = lane; i < P; i += 32) s += zr[i];
+    float mean = warp_sum(s) / (float)P;
+    float v = 0.f;
+    for (int i = lane; i < P; i += 32) { float d = zr[i] - mean; v += d * d; }
+    float rstd = rsqrtf(warp_sum(v) / (float)P + 1e-5f);
+    float s1 = 0.f, s2 = 0.f;
+    for (int i = lane; i < P; i += 32) {
+        float hv = h[(size_t)row * ldh + i];
+        float dt = dh[(size_t)row * lddh + i] * (1.f - hv * hv);
+        float xh = (zr[i] - mean) * rstd;
+        float dxh = dt * gamma[i];
+        s1 += dxh; s2 += dxh * xh;
+        if (dgamma) { atomicAdd(dgamma + i, dt * xh); atomicAdd(dbeta + i, dt); }
+    }
+    s1 = warp_sum(s1) / (float)P; s2 = warp_sum(s2) / (float)P;
+    for (int i = lane; i < P; i += 32) {
+        float hv = h[(size_t)row * ldh + i];
+        float dt = dh[(size_t)row * lddh + i] * (1.f - hv * hv);
+        float xh = (zr[i] - mean) * rstd;
+        dz[(size_t)row * P + i] = rstd * (dt * gamma[i] - s1 - xh * s2);
+    }
+}
+
+extern "C" int sgqn_ln_tanh_bwd(const float* dh, int lddh, const float* z, const float* h, int ldh, const float* gamma,
+                                float* dz, float* dgamma, float* dbeta, int M, int P, void* stream) {
+    if (M <= 0) return 0;
+    ln_tanh_bwd_kernel<<<cdiv(M, 8), 256, 0, (cudaStream_t)stream>>>(dh, lddh, z, h, ldh, gamma, dz, dgamma, dbeta, M, P);
+    return SGQN_CHECK_LAUNCH();
+}
+
+// dst[:, col0:col0+n] = src[:, :n]
+__global__ void set_cols_kernel(float* __restrict__ dst, int ld, int col0, const float* __restrict__ src, int lds, int M, int n) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= M * n) return;
+    int r = i / n, c = i - r * n;
+    dst[(size_t)r * ld + col0 + c] = src[(size_t)r * lds + c];
+}
+extern "C" int sgqn_set_cols(float* dst, int ld, int col0, const float* src, int lds, int M, int n, void* stream) {
+    if (M * n <= 0) return 0;
+    set_cols_kernel<<<cdiv(M * n, 256), 256, 0, (cudaStream_t)stream>>>(dst, ld, col0, src, lds, M, n);
+    return SGQN_CHECK_LAUNCH();
+}
+
+// ---------------------------------------------------------------- Actor head
+// raw (M, 2A) = [mu | log_std_raw]; outputs tanh(mu), tanh(pi), log_pi, log_std   (modules.py:212-232)
+__global__ void actor_head_fwd_kernel(const float* __restrict__ raw, const float* __restrict__ noise, float lmin, float lmax,
+                                      float* __restrict__ mu_t, float* __restrict__ pi_t, int ldpi, float* __restrict__ log_pi,
+                                      float* __restrict__ log_std, int M, int A) {
+    int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= M) return;
+    float resid = 0.f, corr = 0.f;
+    for (int a = 0; a < A; ++a) {
+        float mu = raw[(size_t)r * 2 * A + a];
+        float ls = tanhf(raw[(size_t)r * 2 * A + A + a]);
+        ls = lmin + 0.5f * (lmax - lmin) * (ls + 1.f);
+        if (log_std) log_std[(size_t)r * A + a] = ls;
+        if (mu_t) mu_t[(size_t)r * A + a] = tanhf(mu);
+        if (noise) {
+            float n = noise[(size_t)r * A + a];
+            float p = tanhf(mu + n * expf(ls));
+            if (pi_t) pi_t[(size_t)r * ldpi + a] = p;
+            resid += -0.5f * n * n - ls;
+            corr += logf(fmaxf(1.f - p * p, 0.f) + 1e-6f);
+        }
+    }
+    if (log_pi && noise) log_pi[r] = resid - 0.5f * 1.8378770664093453f * (float)A - corr;
+}
+
+extern "C" int sgqn_actor_head_fwd(const float* raw, const float* noise, float lmin, float lmax, float* mu_t, float* pi_t,
+                                   int ldpi, float* log_pi, float* log_std, int M, int A, void* stream) {
+    if (M <= 0) return 0;
+    actor_head_fwd_kernel<<<cdiv(M, 128), 128, 0, (cudaStream_t)stream>>>(raw, noise, lmin, lmax, mu_t, pi_t, ldpi, log_pi, log_std, M, A);
+    return SGQN_CHECK_LAUNCH();
+}
+
+// d raw given dL/d pi_t (from the Q heads) and dL/d log_pi = alpha / M  (sac.py:129-130)
+__global__ void actor_head_bwd_kernel(const float* __restrict__ raw, const float* __restrict__ noise,
+                                      const float* __restrict__ dpi, int lddpi, const double* __restrict__ log_alpha, float lmin,
+                                      float lmax, float* __restrict__ draw, int M, int A) {
+    int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= M) return;
+    float glp = (float)exp(*log_alpha) / (float)M;
+    for (int a = 0; a < A; ++a) {
+        float mu = raw[(size_t)r * 2 * A + a];
+        float t = tanhf(raw[(size_t)r * 2 * A + A + a]);
+        float ls = lmin + 0.5f * (lmax - lmin) * (t + 1.f);
+        float sd = expf(ls), n = noise[(size_t)r * A + a];
+        float p = tanhf(mu + n * sd);
+        float om = 1.f - p * p;
+        float g = dpi[(size_t)r * lddpi + a];
+        if (om > 0.f) g += glp * 2.f * p / (om + 1e-6f);          // - d/dpi log(relu(1-pi^2)+1e-6)
+        float gpre = g * om;                                       // tanh'
+        draw[(size_t)r * 2 * A + a] = gpre;
+        float gls = gpre * n * sd - glp;                           // via pi and via gaussian_logprob
+        draw[(size_t)r * 2 * A + A + a] = gls * 0.5f * (lmax - lmin) * (1.f - t * t);
+    }
+}
+
+extern "C" int sgqn_actor_head_bwd(const float* raw, const float* noise, const float* dpi, int lddpi, const double* log_alpha,
+                                   float lmin, float lmax, float* draw, int M, int A, void* stream) {
+    if (M <= 0) return 0;
+    actor_head_bwd_kernel<<<cdiv(M, 128), 128, 0, (cudaStream_t)stream>>>(raw, noise, dpi, lddpi, log_alpha, lmin, lmax, draw, M, A);
+    return SGQN_CHECK_LAUNCH();
+}
+
+// ---------------------------------------------------------------- critic loss
+// q: [2 heads][R] (head stride qs).  Bg = global batch the means are taken over (data-parallel shards pass the
+// global B and sum gradients across ranks).
+// mode 0 (sac.py:114-117)   R = B      : mse(q1,tq)+mse(q2,tq)
+// mode 1 (sgsac.py:59-74)   R = 2B     : rows [clean | masked]: + 0.5*(mse(q1,mq1)+mse(q2,mq2)), grads to both branches
+// mode 2 (svea.py:25-45)    R = 2B     : rows [obs | aug]: wa*(mse on obs rows) + wb*(mse on aug rows)
+__global__ void __launch_bounds__(256)
+critic_loss_kernel(const float* __restrict__ q, long long qs, const float* __restrict__ tq1, const float* __restrict__ tq2,
+                   const float* __restrict__ next_log_pi, const float* __restrict__ reward, const float* __restrict__ not_done,
+                   const double* __restrict__ log_alpha, float discount, int mode, float wa, float wb, float* __restrict__ target_q,
+                   float* __restrict__ dq, float* __restrict__ loss, int B, int Bg) {
+    __shared__ float sh[33];
+    float alpha = (float)exp(*log_alpha);
+    float acc = 0.f;
+    const float invB = 1.f / (float)Bg;
+    for (int b = threadIdx.x; b < B; b += blockDim.x) {
+        float tv = fminf(tq1[b], tq2[b]) - alpha * next_log_pi[b];
+        float tq = reward[b] + not_done[b] * discount * tv;
+        target_q[b] = tq;
+        for (int hd = 0; hd < 2; ++hd) {
+            const float* qh = q + hd * qs; float* dqh = dq + hd * qs;
+            float e = qh[b] - tq;
+            if (mode == 0) { acc += e * e; dqh[b] = 2.f * invB * e; }
+            else if (mode == 1) {
+                float c = qh[b] - qh[B + b];
+                acc += e * e + 0.5f * c * c;
+                dqh[b] = 2.f * invB * e + invB * c;
+                dqh[B + b] = -invB * c;
+            } else {
+                float e2 = qh[B + b] - tq;
+                acc += wa * e * e + wb * e2 * e2;
+                dqh[b] = 2.f * invB * wa * e; dqh[B + b] = 2.f * invB * wb * e2;
+            }
+        }
+    }
+    float tot = block_sum(acc, sh);
+    if (threadIdx.x == 0) *loss = tot * invB;
+}
+
+extern "C" int sgqn_critic_loss(const float* q, long long qs, const float* tq1, const float* tq2, const float* next_log_pi,
+                                const float* reward, const float* not_done, const double* log_alpha, float discount, int mode,
+                                float wa, float wb, float* target_q, float* dq, float* loss, int B, int Bg, void* stream) {
+    critic_loss_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(q, qs, tq1, tq2, next_log_pi, reward, not_done, log_alpha, discount,
+                                                            mode, wa, wb, target_q, dq, loss, B, Bg);
+    return SGQN_CHECK_LAUNCH();
+}
+
+// ---------------------------------------------------------------- actor + alpha loss (sac.py:125-151)
+// out[0] = actor_loss, out[1] = alpha_loss, out[2] = alpha ; alpha_grad (fp64) = d alpha_loss / d log_alpha
+__global__ void __launch_bounds__(256)
+actor_loss_kernel(const float* __restrict__ q, long long qs, const float* __restrict__ log_pi, const double* __restrict__ log_alpha,
+                  float target_entropy, float* __restrict__ dq, float* __restrict__ out, double* __restrict__ alpha_grad, int B,
+                  int Bg) {
+    __shared__ float sh[33];
+    double alpha_d = exp(*log_alpha);
+    float alpha = (float)alpha_d;
+    const float invB = 1.f / (float)Bg;
+    float a1 = 0.f, a2 = 0.f;
+    for (int b = threadIdx.x; b < B; b += blockDim.x) {
+        float q1 = q[b], q2 = q[qs + b];
+        a1 += alpha * log_pi[b] - fminf(q1, q2);
+        a2 += -log_pi[b] - target_entropy;
+        float g1 = q1 < q2 ? 1.f : (q1 == q2 ? 0.5f : 0.f);
+        dq[b] = -invB * g1; dq[qs + b] = -invB * (1.f - g1);
+    }
+    float s1 = block_sum(a1, sh);
+    float s2 = block_sum(a2, sh);
+    if (threadIdx.x == 0) {
+        out[0] = s1 * invB;
+        out[1] = alpha * s2 * invB;
+        out[2] = alpha;
+        *alpha_grad = (double)(s2 * invB) * alpha_d;
+    }
+}
+
+extern "C" int sgqn_actor_loss(const float* q, long long qs, const float* log_pi, const double* log_alpha, float target_entropy,
+                               float* dq, float* out, double* alpha_grad, int B, int Bg, void* stream) {
+    actor_loss_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(q, qs, log_pi, log_alpha, target_entropy, dq, out, alpha_grad, B, Bg);
+    return SGQN_CHECK_LAUNCH();
+}
+
+// ---------------------------------------------------------------- BCE-with-logits against the attribution mask (sgsac.py:163-167)
+// logits NHWC [B][HW][Cs] (Cs >= 9 stored channels, extra ones are padding); mask [B][3][HW] uint8 (frame f covers channels 3f..3f+2)
+__global__ void __launch_bounds__(256)
+bce_kernel(const float* __restrict__ logits, const uint8_t* __restrict__ mask, float* __restrict__ loss,
+           float* __restrict__ dlogits, int HW, int Cs, long long npix, float inv_n) {
+    __shared__ float sh[33];
+    float acc = 0.f;
+    for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < npix; p += (long long)gridDim.x * blockDim.x) {
+        int b = (int)(p / HW), i = (int)(p - (long long)b * HW);
+        const float* x = logits + (size_t)p * Cs;
+        float* d = dlogits + (size_t)p * Cs;
+        for (int c = 0; c < Cs; ++c) {
+            if (c >= 9) { d[c] = 0.f; continue; }
+            float y = (float)mask[((size_t)b * 3 + c / 3) * HW + i];
+            float v = x[c];
+            acc += fmaxf(v, 0.f) - v * y + log1pf(expf(-fabsf(v)));
+            d[c] = (1.f / (1.f + expf(-v)) - y) * inv_n;
+        }
+    }
+    float tot = block_sum(acc, sh);
+    if (threadIdx.x == 0) atomicAdd(loss, tot * inv_n);
+}
+
+extern "C" int sgqn_bce(const float* logits, const uint8_t* mask, float* loss, float* dlogits, int B, int HW, int Cs, int Bg,
+                        void* stream) {
+    long long npix = (long long)B * HW;
+    if (npix <= 0) return 0;
+    float inv_n = 1.0f / ((float)Bg * 9.0f * (float)HW);
+    int grid = (int)(cdivll(npix, 256) < 1184 ? cdivll(npix, 256) : 1184);
+    bce_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(logits, mask, loss, dlogits, HW, Cs, npix, inv_n);
+    return SGQN_CHECK_LAUNCH();
+}

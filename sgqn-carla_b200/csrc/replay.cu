@@ -1,0 +1,92 @@
+// Replay sampling (utils.py:124-135,185-198): gather 3-frame uint8 stacks of the sampled transitions out of the
+// device-resident frame ring and emit fp32 NCHW batches, with random_crop (augmentations.py:236-264) or
+// random_shift (augmentations.py:229-233 == clamp-gather) fused into the read.  HBM-bound byte work.
+#include "common.cuh"
+#include "../../include/sgqn_b200.h"
+
+// grid: (6*B) blocks; block -> (sample b, which in {obs,next}, frame j); 3 channels x Ho x Ho outputs per block
+__global__ void __launch_bounds__(256)
+replay_gather_kernel(const uint8_t* __restrict__ frames, const int32_t* __restrict__ fidx, const int64_t* __restrict__ idxs,
+                     const int32_t* __restrict__ offs, float* __restrict__ obs, float* __restrict__ next_obs, int B, int Hs,
+                     int Ho, int mode, int pad) {
+    int blk = blockIdx.x;
+    int j = blk % 3; int t = blk / 3; int which = t & 1; int b = t >> 1;
+    long long tr = idxs[b];
+    int slot = fidx[tr * 6 + which * 3 + j];
+    const uint8_t* src = frames + (size_t)slot * 3 * Hs * Hs;
+    float* dst = (which ? next_obs : obs) + ((size_t)b * 9 + 3 * j) * Ho * Ho;
+    int oy = 0, ox = 0;
+    if (offs) { oy = offs[(which * B + b) * 2 + 0]; ox = offs[(which * B + b) * 2 + 1]; }
+    if (mode == 1) { oy -= pad; ox -= pad; }
+    const int W4 = Ho >> 2;                    // Ho % 4 == 0 (84)
+    const int n4 = 3 * Ho * W4;
+    for (int i = threadIdx.x; i < n4; i += blockDim.x) {
+        int x4 = i % W4; int r = i / W4; int y = r % Ho; int c = r / Ho;
+        int sy = y + oy;
+        if (mode == 1) sy = min(max(sy, 0), Hs - 1);
+        const uint8_t* row = src + ((size_t)c * Hs + sy) * Hs;
+        int sx = x4 * 4 + ox;
+        float4 v;
+        if (mode == 1) {
+            v.x = (float)__ldg(row + min(max(sx, 0), Hs - 1));
+            v.y = (float)__ldg(row + min(max(sx + 1, 0), Hs - 1));
+            v.z = (float)__ldg(row + min(max(sx + 2, 0), Hs - 1));
+            v.w = (float)__ldg(row + min(max(sx + 3, 0), Hs - 1));
+        } else if ((((uintptr_t)(row + sx)) & 3) == 0) {
+            uchar4 u = __ldg(reinterpret_cast<const uchar4*>(row + sx));
+            v = make_float4((float)u.x, (float)u.y, (float)u.z, (float)u.w);
+        } else {
+            v.x = (float)__ldg(row + sx); v.y = (float)__ldg(row + sx + 1);
+            v.z = (float)__ldg(row + sx + 2); v.w = (float)__ldg(row + sx + 3);
+        }
+        reinterpret_cast<float4*>(dst)[i] = v;
+    }
+}
+
+extern "C" int sgqn_replay_gather(const uint8_t* frames, const int32_t* fidx, const int64_t* idxs, const int32_t* offs,
+                                  float* obs, float* next_obs, int B, int Hs, int Ho, int mode, int pad, void* stream) {
+    if (B <= 0) return 0;
+    if (Ho & 3) return (int)cudaErrorInvalidValue;
+    if (mode == 0 && Ho > Hs) return (int)cudaErrorInvalidValue;
+    replay_gather_kernel<<<6 * B, 256, 0, (cudaStream_t)stream>>>(frames, fidx, idxs, offs, obs, next_obs, B, Hs, Ho, mode, pad);
+    return SGQN_CHECK_LAUNCH();
+}
+
+// actions / rewards / not_dones rows of the sampled transitions
+__global__ void take_rows_kernel(const float* __restrict__ src, const int64_t* __restrict__ idxs, float* __restrict__ dst,
+                                 int B, int width) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B * width) return;
+    int b = i / width, c = i - b * width;
+    dst[i] = __ldg(src + (size_t)idxs[b] * width + c);
+}
+
+extern "C" int sgqn_take_rows(const float* src, const int64_t* idxs, float* dst, int B, int width, void* stream) {
+    if (B * width <= 0) return 0;
+    take_rows_kernel<<<cdiv(B * width, 256), 256, 0, (cudaStream_t)stream>>>(src, idxs, dst, B, width);
+    return SGQN_CHECK_LAUNCH();
+}
+
+// crop / shift of an already materialised fp32 batch (public augmentations.random_crop / random_shift entry points)
+__global__ void crop_shift_kernel(const float* __restrict__ x, const int32_t* __restrict__ offs, float* __restrict__ y, int B,
+                                  int C, int Hs, int Ho, int mode, int pad, long long total) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    int xo = (int)(i % Ho); long long t = i / Ho; int yo = (int)(t % Ho); t /= Ho; int c = (int)(t % C); int b = (int)(t / C);
+    int sy = yo + offs[b * 2], sx = xo + offs[b * 2 + 1];
+    if (mode == 1) { sy = min(max(sy - pad, 0), Hs - 1); sx = min(max(sx - pad, 0), Hs - 1); }
+    y[i] = __ldg(x + (((size_t)b * C + c) * Hs + sy) * Hs + sx);
+}
+
+extern "C" int sgqn_crop_shift(const float* x, const int32_t* offs, float* y, int B, int C, int Hs, int Ho, int mode, int pad,
+                               void* stream) {
+    long long total = (long long)B * C * Ho * Ho;
+    if (total <= 0) return 0;
+    crop_shift_kernel<<<(unsigned)cdivll(total, 256), 256, 0, (cudaStream_t)stream>>>(x, offs, y, B, C, Hs, Ho, mode, pad, total);
+    return SGQN_CHECK_LAUNCH();
+}
+
+extern "C" int sgqn_zero(void* p, long long bytes, void* stream) {
+    if (bytes <= 0) return 0;
+    return (int)cudaMemsetAsync(p, 0, (size_t)bytes, (cudaStream_t)stream);
+}

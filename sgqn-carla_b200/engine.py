@@ -1,0 +1,449 @@
+"""Device-side engine of the SAC / SGSAC / SVEA update: owns the flat parameter / gradient / Adam arenas and the
+activation workspaces, and issues the kernel schedule of one update through the C ABI (include/sgqn_b200.h).
+
+Reference call stack being replaced: sgsac.py:169-185 `SGSAC.update` -> update_critic (:52-80),
+compute_attribution x2 (rl_utils.py:35-39,57-62), update_actor_and_alpha (sac.py:125-151),
+soft_update_critic_target (sac.py:153-158), update_aux (sgsac.py:82-102).
+
+Forward passes that the reference repeats on identical inputs and weights are shared:
+`critic(obs)` and attribution #1 share one encoder forward; attribution #2, `actor(obs, detach)` and
+`critic(obs, pi, detach)` share one.  The soft target update rides on the critic Adam launch of even steps
+(nothing reads the target or writes the critic in between).
+"""
+import math
+
+import numpy as np
+import torch
+
+from ._lib import K
+from .layout import DEC_C3, ENC_H, FEAT, ParamLayout
+
+
+def _ptr(t, off=0):
+    return t.data_ptr() + off * t.element_size()
+
+
+class _Opt:
+    def __init__(self, dev, n, lr, b1, b2=0.999, eps=1e-8):
+        self.m = torch.zeros(n, device=dev)
+        self.v = torch.zeros(n, device=dev)
+        self.step = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.bc = torch.zeros(2, device=dev)
+        self.lr, self.b1, self.b2, self.eps = float(lr), float(b1), float(b2), float(eps)
+
+
+class UpdateEngine:
+    LOG_KEYS = ("train_critic/loss", "train_actor/loss", "train_alpha/loss", "train_alpha/value", "train/aux_loss")
+
+    def __init__(self, action_dim, args, batch_size, device="cuda", algorithm="sgsac", dist=None, global_batch=None):
+        if not torch.cuda.is_available():
+            raise RuntimeError("sgqn-carla_b200 needs a CUDA device (B200, sm_100a); there is no CPU path")
+        self.dev = torch.device(device)
+        self.args, self.A, self.B = args, int(action_dim), int(batch_size)
+        self.Bg = int(global_batch) if global_batch else self.B
+        self.dist = dist
+        self.algorithm = algorithm
+        self.H = int(args.hidden_dim)
+        self.lay = ParamLayout(self.A, self.H, int(args.projection_dim), int(args.num_shared_layers), int(args.num_filters))
+        L, dev, B, A, H = self.lay, self.dev, self.B, self.A, self.H
+        self.params = torch.zeros(L.total, device=dev)
+        self.grads = torch.zeros(L.total, device=dev)
+        c0, c1 = L.ranges["critic"]
+        self.target = torch.zeros(c1 - c0, device=dev)
+        self.log_alpha = torch.tensor([math.log(args.init_temperature)], dtype=torch.float64, device=dev)
+        self.alpha_st = torch.zeros(2, dtype=torch.float64, device=dev)
+        self.alpha_step = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.alpha_grad = torch.zeros(1, dtype=torch.float64, device=dev)
+        self.target_entropy = -float(np.prod((A,)))
+        self.opt_critic = _Opt(dev, c1 - c0, args.critic_lr, args.critic_beta)
+        a0, a1 = L.ranges["actor"]
+        self.opt_actor = _Opt(dev, a1 - a0, args.actor_lr, args.actor_beta)
+        x0, x1 = L.ranges["aux"]
+        self.opt_aux = _Opt(dev, x1 - x0, getattr(args, "aux_lr", 3e-4), getattr(args, "aux_beta", 0.9))
+        self.quantile = float(getattr(args, "sgqn_quantile", 0.5))
+
+        R = 2 * B                                       # rows of the critic slot: [clean | masked] or [obs | aug]
+        f32 = lambda *s: torch.zeros(*s, device=dev)
+        self.obs2 = f32(R, 9, 84, 84)                   # [obs ; masked_obs / overlay-augmented obs]
+        self.next_obs = f32(B, 9, 84, 84)
+        self.action = f32(B, A); self.reward = f32(B, 1); self.not_done = f32(B, 1)
+        self.actS = [f32(R * h * h * 32) for h in ENC_H]       # critic slot activations (pre-ReLU, NHWC)
+        self.actT = [f32(B * h * h * 32) for h in ENC_H]       # transient slot
+        self.dbuf = [f32(R * 41 * 41 * 32), f32(R * 41 * 41 * 32)]
+        P1 = L.P + A
+        self.zS, self.haS, self.dzS, self.dhaS = f32(R, L.P), f32(R, P1), f32(R, L.P), f32(R, P1)
+        self.zT, self.haT, self.dzT, self.dhaT = f32(B, L.P), f32(B, P1), f32(B, L.P), f32(B, P1)
+        self.z_a, self.h_a, self.dz_a, self.dh_a = f32(B, L.P), f32(B, L.P), f32(B, L.P), f32(B, L.P)   # actor projection
+        self.q = f32(2, R); self.dq = f32(2, R)
+        self.z1 = f32(2, R, H); self.z2 = f32(2, R, H); self.dz1 = f32(2, R, H); self.dz2 = f32(2, R, H)
+        self.az1 = f32(B, H); self.az2 = f32(B, H); self.daz1 = f32(B, H); self.daz2 = f32(B, H)
+        self.raw = f32(B, 2 * A); self.draw = f32(B, 2 * A)
+        self.mu = f32(B, A); self.pi = f32(B, A); self.log_pi = f32(B); self.log_std = f32(B, A)
+        self.next_log_pi = f32(B); self.tq = f32(2, B); self.target_q = f32(B)
+        self.ones = torch.ones(B, device=dev)
+        self.obs_grad = f32(B, 9, 84, 84)
+        self.mask = torch.zeros(B, 3, 84 * 84, dtype=torch.uint8, device=dev)
+        self.mm = f32(2); self.mm_scratch = f32(1024)
+        self.logs = f32(8)          # critic_loss, actor_loss, alpha_loss, alpha, aux_loss
+        # host-suppliable randomness of one step (SURVEY.md 5 'RNG')
+        self.idxs = torch.zeros(B, dtype=torch.int64, device=dev)
+        self.overlay_ids = torch.zeros(B, dtype=torch.int64, device=dev)
+        self.offs = torch.zeros(2, B, 2, dtype=torch.int32, device=dev)
+        self.noise_next = f32(B, A); self.noise_pi = f32(B, A); self.u = f32(1)
+        self.rng_counter = torch.zeros(1, dtype=torch.int64, device=dev)
+        self.seed = int(getattr(args, "seed", 0))
+        if algorithm == "sgsac":
+            self.s_tilde = f32(B, 9, 84, 84)
+            self.dl = f32(B, FEAT); self.ddl = f32(B, FEAT)
+            self.d1 = f32(B * 21 * 21 * 128); self.dd1 = f32(B * 21 * 21 * 128)
+            self.d2 = f32(B * 42 * 42 * 64); self.dd2 = f32(B * 42 * 42 * 64)
+            self.lg = f32(B * 84 * 84 * DEC_C3); self.dlg = f32(B * 84 * 84 * DEC_C3)
+            self.dup3 = f32(B * 84 * 84 * 64); self.dup2 = f32(B * 42 * 42 * 128)
+        if algorithm == "svea":
+            self.places = f32(B, 3, 84 * 84)
+        self.overlay_pool = None       # uint8 (N,3,84*84) device pool for the 'carla' overlay
+        self._p = self.params.data_ptr(); self._g = self.grads.data_ptr(); self._t = self.target.data_ptr()
+        self._c0 = c0
+
+    # ------------------------------------------------------------------ pointers
+    def P(self, name):
+        return self._p + 4 * self.lay.off(name)
+
+    def G(self, name):
+        return self._g + 4 * self.lay.off(name)
+
+    def T(self, name):                                  # target copy of a critic-range parameter
+        return self._t + 4 * (self.lay.off(name) - self._c0)
+
+    @property
+    def st(self):
+        return torch.cuda.current_stream().cuda_stream
+
+    # ------------------------------------------------------------------ building blocks
+    def enc_fwd(self, x_ptr, n, acts, row0=0, target=False, hin=84):
+        """SharedCNN forward (modules.py:132-152): x (n,9,hin,hin) fp32 NCHW -> acts[0..10] rows [row0, row0+n)."""
+        W = self.T if target else self.P
+        st = self.st
+        K.conv1_fwd(x_ptr, W("cnn.0.weight"), W("cnn.0.bias"), _ptr(acts[0], row0 * 41 * 41 * 32), n, hin, 9, 32, st)
+        for l in range(1, 11):
+            hi, ho = ENC_H[l - 1], ENC_H[l]
+            K.conv_fwd(_ptr(acts[l - 1], row0 * hi * hi * 32), W(f"cnn.{l}.weight"), W(f"cnn.{l}.bias"),
+                       _ptr(acts[l], row0 * ho * ho * 32), n, hi, hi, 32, 32, 0, 1, 1, st)
+
+    def proj_fwd(self, feat_ptr, n, pre, z, h, ldh, target=False):
+        """RLProjection (modules.py:102-113): Linear(14112->100) (split-K) -> LayerNorm -> tanh, h row stride ldh."""
+        W = self.T if target else self.P
+        st = self.st
+        K.zero(z, 4 * n * self.lay.P, st)
+        K.linear_fwd(feat_ptr, FEAT, 0, W(f"{pre}.0.weight"), 0, W(f"{pre}.0.bias"), 0, z, self.lay.P, 0,
+                     n, self.lay.P, FEAT, 0, 1, 1, st)
+        K.ln_tanh_fwd(z, W(f"{pre}.1.weight"), W(f"{pre}.1.bias"), h, ldh, n, self.lay.P, st)
+
+    def q_fwd(self, ha, n, row0, nheads=2, target=False):
+        """Q1/Q2 trunks (modules.py:235-261) on ha (n, P+A); both heads in one launch per layer."""
+        W = self.T if target else self.P
+        L, H, R, st = self.lay, self.H, 2 * self.B, self.st
+        P1, qs = L.P + self.A, L.q_stride
+        z1, z2 = _ptr(self.z1, row0 * H), _ptr(self.z2, row0 * H)
+        out = _ptr(self.tq) if target else _ptr(self.q, row0)
+        obs_ = self.B if target else R
+        K.linear_fwd(ha, P1, 0, W("Q1.0.weight"), qs, W("Q1.0.bias"), qs, z1, H, R * H, n, H, P1, 0, nheads, 0, st)
+        K.linear_fwd(z1, H, R * H, W("Q1.2.weight"), qs, W("Q1.2.bias"), qs, z2, H, R * H, n, H, H, 1, nheads, 0, st)
+        K.linear_fwd(z2, H, R * H, W("Q1.4.weight"), qs, W("Q1.4.bias"), qs, out, 1, obs_, n, 1, H, 1, nheads, 0, st)
+
+    def q_dgrad(self, dq, dq_bs, n, row0, nheads, mode, dha):
+        """Backward of the Q trunks to their input (n, P+A), heads summed.  mode 1 plain, 2 guided."""
+        L, H, R, st = self.lay, self.H, 2 * self.B, self.st
+        P1, qs = L.P + self.A, L.q_stride
+        z1, z2 = _ptr(self.z1, row0 * H), _ptr(self.z2, row0 * H)
+        dz1, dz2 = _ptr(self.dz1, row0 * H), _ptr(self.dz2, row0 * H)
+        K.linear_dgrad(dq, 1, dq_bs, self.P("Q1.4.weight"), qs, z2, H, R * H, dz2, H, R * H, n, 1, H, mode, 0, nheads, st)
+        K.linear_dgrad(dz2, H, R * H, self.P("Q1.2.weight"), qs, z1, H, R * H, dz1, H, R * H, n, H, H, mode, 0, nheads, st)
+        K.zero(dha, 4 * n * P1, st)
+        K.linear_dgrad(dz1, H, R * H, self.P("Q1.0.weight"), qs, 0, 0, 0, dha, P1, 0, n, H, P1, 0, 1, nheads, st)
+
+    def q_wgrad(self, ha, dq, n, row0):
+        L, H, R, st = self.lay, self.H, 2 * self.B, self.st
+        P1, qs = L.P + self.A, L.q_stride
+        z1, z2 = _ptr(self.z1, row0 * H), _ptr(self.z2, row0 * H)
+        dz1, dz2 = _ptr(self.dz1, row0 * H), _ptr(self.dz2, row0 * H)
+        K.linear_wgrad(z2, H, R * H, dq, 1, R, self.G("Q1.4.weight"), qs, self.G("Q1.4.bias"), qs, n, 1, H, 1, 2, st)
+        K.linear_wgrad(z1, H, R * H, dz2, H, R * H, self.G("Q1.2.weight"), qs, self.G("Q1.2.bias"), qs, n, H, H, 1, 2, st)
+        K.linear_wgrad(ha, P1, 0, dz1, H, R * H, self.G("Q1.0.weight"), qs, self.G("Q1.0.bias"), qs, n, H, P1, 0, 2, st)
+
+    def proj_bwd(self, dh, lddh, n, z, h, ldh, pre, dz, feat_ptr=0, dfeat=0, wgrad=True):
+        st, P = self.st, self.lay.P
+        K.ln_tanh_bwd(dh, lddh, z, h, ldh, self.P(f"{pre}.1.weight"), dz,
+                      self.G(f"{pre}.1.weight") if wgrad else 0, self.G(f"{pre}.1.bias") if wgrad else 0, n, P, st)
+        if wgrad:
+            K.linear_wgrad(feat_ptr, FEAT, 0, dz, P, 0, self.G(f"{pre}.0.weight"), 0, self.G(f"{pre}.0.bias"), 0,
+                           n, P, FEAT, 0, 1, st)
+        if dfeat:
+            K.linear_dgrad(dz, P, 0, self.P(f"{pre}.0.weight"), 0, 0, 0, 0, dfeat, FEAT, 0, n, P, FEAT, 0, 0, 1, st)
+
+    def enc_bwd(self, dfeat, n, acts, row0, x_ptr, mode, wgrad, dobs=0):
+        """Backward through SharedCNN.  dfeat: (n,21,21,32).  mode 1: plain ReLU backward (+ wgrad into the grad
+        arena); mode 2: guided backprop to the observation (rl_utils.py:35-39)."""
+        st = self.st
+        d = dfeat
+        for l in range(10, 0, -1):
+            hi = ENC_H[l - 1]
+            a_in = _ptr(acts[l - 1], row0 * hi * hi * 32)
+            if wgrad:
+                K.conv_wgrad(a_in, d, self.G(f"cnn.{l}.weight"), self.G(f"cnn.{l}.bias"), n, hi, hi, 32, 32, 0, 1, 1, st)
+            dx = _ptr(self.dbuf[l & 1])
+            K.conv_dgrad(d, self.P(f"cnn.{l}.weight"), a_in, dx, n, hi, hi, 32, 32, 0, mode, st)
+            d = dx
+        if wgrad:
+            K.conv1_wgrad(x_ptr, d, self.G("cnn.0.weight"), self.G("cnn.0.bias"), n, 84, 9, 32, st)
+        if dobs:
+            K.conv1_dgrad(d, self.P("cnn.0.weight"), dobs, n, 9, 32, st)
+
+    def attribution(self, acts, row0, ha, z, obs_grad):
+        """compute_attribution (rl_utils.py:57-62): guided backprop of sum_b Q1[b] to the observation, re-using the
+        forward activations of critic(obs) (acts / z / ha / z1 / z2 rows [row0, row0+B))."""
+        B, L, st = self.B, self.lay, self.st
+        self.q_dgrad(_ptr(self.ones), 0, B, row0, 1, 2, _ptr(self.dhaT))
+        K.ln_tanh_bwd(_ptr(self.dhaT), L.P + self.A, z, ha, L.P + self.A, self.P("critic_proj.1.weight"), _ptr(self.dzT),
+                      0, 0, B, L.P, st)
+        dfeat = _ptr(self.dbuf[1])
+        K.linear_dgrad(_ptr(self.dzT), L.P, 0, self.P("critic_proj.0.weight"), 0, 0, 0, 0, dfeat, FEAT, 0, B, L.P, FEAT,
+                       0, 0, 1, st)
+        self.enc_bwd(dfeat, B, acts, row0, 0, 2, False, dobs=obs_grad)
+
+    def adam(self, opt, rng, target=None, n_tau0=0, tau0=0.0, tau1=0.0):
+        st = self.st
+        o0, o1 = rng
+        K.adam_prep(_ptr(opt.step), _ptr(opt.bc), opt.b1, opt.b2, st)
+        K.adam(self._p + 4 * o0, self._g + 4 * o0, _ptr(opt.m), _ptr(opt.v), o1 - o0, _ptr(opt.bc), opt.lr,
+               float(np.float32(1 - opt.b1)), opt.b2, float(np.float32(1 - opt.b2)), opt.eps,
+               target if target else 0, n_tau0, tau0, tau1, st)
+
+    def allreduce_grads(self, rng):
+        if self.dist is not None:
+            self.dist.all_reduce_sum(self.grads[rng[0]:rng[1]])
+
+    # ------------------------------------------------------------------ the update
+    def target_q_pass(self):
+        """sac.py:108-112 / sgsac.py:53-57 (no grad): actor(next_obs), critic_target(next_obs, a')."""
+        B, A, L, st = self.B, self.A, self.lay, self.st
+        a = self.args
+        nx = _ptr(self.next_obs)
+        self.enc_fwd(nx, B, self.actT)
+        self.proj_fwd(_ptr(self.actT[10]), B, "actor_proj", _ptr(self.z_a), _ptr(self.h_a), L.P)
+        self.actor_mlp_fwd(B)
+        K.actor_head_fwd(_ptr(self.raw), _ptr(self.noise_next), float(a.actor_log_std_min), float(a.actor_log_std_max),
+                         0, _ptr(self.haT, L.P), L.P + A, _ptr(self.next_log_pi), 0, B, A, st)
+        self.enc_fwd(nx, B, self.actT, target=True)
+        self.proj_fwd(_ptr(self.actT[10]), B, "critic_proj", _ptr(self.zT), _ptr(self.haT), L.P + A, target=True)
+        self.q_fwd(_ptr(self.haT), B, 0, 2, target=True)
+
+    def actor_mlp_fwd(self, n):
+        L, H, A, st = self.lay, self.H, self.A, self.st
+        K.linear_fwd(_ptr(self.h_a), L.P, 0, self.P("actor_mlp.0.weight"), 0, self.P("actor_mlp.0.bias"), 0,
+                     _ptr(self.az1), H, 0, n, H, L.P, 0, 1, 0, st)
+        K.linear_fwd(_ptr(self.az1), H, 0, self.P("actor_mlp.2.weight"), 0, self.P("actor_mlp.2.bias"), 0,
+                     _ptr(self.az2), H, 0, n, H, H, 1, 1, 0, st)
+        K.linear_fwd(_ptr(self.az2), H, 0, self.P("actor_mlp.4.weight"), 0, self.P("actor_mlp.4.bias"), 0,
+                     _ptr(self.raw), 2 * A, 0, n, 2 * A, H, 1, 1, 0, st)
+
+    def critic_fwd_rows(self, row0, n):
+        """critic(obs2[row0:row0+n], action) with activations kept in the critic slot."""
+        L, A, st = self.lay, self.A, self.st
+        P1 = L.P + A
+        self.enc_fwd(_ptr(self.obs2, row0 * 9 * 84 * 84), n, self.actS, row0)
+        K.set_cols(_ptr(self.haS, row0 * P1), P1, L.P, _ptr(self.action), A, n, A, st)
+        self.proj_fwd(_ptr(self.actS[10], row0 * FEAT), n, "critic_proj", _ptr(self.zS, row0 * L.P),
+                      _ptr(self.haS, row0 * P1), P1)
+        self.q_fwd(_ptr(self.haS, row0 * P1), n, row0)
+
+    def update_critic(self, mode):
+        """mode 0: SAC (sac.py:107-123); 1: SGSAC with consistency (sgsac.py:52-80); 2: SVEA (svea.py:19-52)."""
+        B, A, L, st, a = self.B, self.A, self.lay, self.st, self.args
+        P1 = L.P + A
+        self.target_q_pass()
+        self.critic_fwd_rows(0, B)
+        R = B
+        if mode == 1:
+            self.attribution(self.actS, 0, _ptr(self.haS), _ptr(self.zS), _ptr(self.obs_grad))
+            K.minmax(_ptr(self.obs2), B * 9 * 84 * 84, _ptr(self.mm_scratch), _ptr(self.mm), st)
+            if self.dist is not None:
+                self.dist.all_reduce_minmax(self.mm)
+            K.attribution_mask(_ptr(self.obs_grad), _ptr(self.obs2), _ptr(self.mm), _ptr(self.u), self.quantile,
+                               _ptr(self.mask), _ptr(self.obs2, B * 9 * 84 * 84), B, 84 * 84, st)
+            self.critic_fwd_rows(B, B)
+            R = 2 * B
+        elif mode == 2:
+            al = 0.2                                             # augmentations.py:79 default (svea.py:26 passes none)
+            K.overlay_f32(_ptr(self.obs2), _ptr(self.places), float(np.float32(1 - al)), float(np.float32(al)),
+                          _ptr(self.obs2, B * 9 * 84 * 84), B, 84 * 84, st)
+            self.critic_fwd_rows(B, B)
+            R = 2 * B
+        wa, wb = float(getattr(a, "svea_alpha", 0.5)), float(getattr(a, "svea_beta", 0.5))
+        K.critic_loss(_ptr(self.q), 2 * B, _ptr(self.tq), _ptr(self.tq, B), _ptr(self.next_log_pi), _ptr(self.reward),
+                      _ptr(self.not_done), _ptr(self.log_alpha), float(a.discount), mode, wa, wb, _ptr(self.target_q),
+                      _ptr(self.dq), _ptr(self.logs, 0), B, self.Bg, st)
+        # backward over all R rows at once
+        c0, c1 = L.ranges["critic"]
+        K.zero(self._g + 4 * c0, 4 * (c1 - c0), st)
+        self.q_dgrad(_ptr(self.dq), 2 * B, R, 0, 2, 1, _ptr(self.dhaS))
+        self.q_wgrad(_ptr(self.haS), _ptr(self.dq), R, 0)
+        dfeat = _ptr(self.dbuf[1])
+        self.proj_bwd(_ptr(self.dhaS), P1, R, _ptr(self.zS), _ptr(self.haS), P1, "critic_proj", _ptr(self.dzS),
+                      feat_ptr=_ptr(self.actS[10]), dfeat=dfeat)
+        self.enc_bwd(dfeat, R, self.actS, 0, _ptr(self.obs2), 1, True)
+        self.allreduce_grads((c0, c1))
+
+    def critic_step(self, with_ema):
+        L, a = self.lay, self.args
+        c0, c1 = L.ranges["critic"]
+        q0, q1 = L.ranges["critic_q"]
+        self.adam(self.opt_critic, (c0, c1), target=self._t if with_ema else None, n_tau0=q1 - q0,
+                  tau0=float(a.critic_tau), tau1=float(a.encoder_tau))
+
+    def shared_obs_fwd(self):
+        """One encoder forward of obs with the updated critic weights, shared by attribution #2 (sgsac.py:175),
+        actor(obs, detach) and critic(obs, pi, detach) (sac.py:126-127)."""
+        B, A, L, st = self.B, self.A, self.lay, self.st
+        P1 = L.P + A
+        self.enc_fwd(_ptr(self.obs2), B, self.actT)
+        K.set_cols(_ptr(self.haT), P1, L.P, _ptr(self.action), A, B, A, st)
+        self.proj_fwd(_ptr(self.actT[10]), B, "critic_proj", _ptr(self.zT), _ptr(self.haT), P1)
+
+    def attribution2(self, want_mask):
+        B, st = self.B, self.st
+        self.q_fwd(_ptr(self.haT), B, 0, 1)
+        self.attribution(self.actT, 0, _ptr(self.haT), _ptr(self.zT), _ptr(self.obs_grad))
+        if want_mask:
+            K.attribution_mask(_ptr(self.obs_grad), 0, 0, 0, self.quantile, _ptr(self.mask), 0, B, 84 * 84, st)
+
+    def update_actor_and_alpha(self):
+        """sac.py:125-151; expects shared_obs_fwd() state in the transient slot."""
+        B, A, L, H, st, a = self.B, self.A, self.lay, self.H, self.st, self.args
+        P1 = L.P + A
+        lmin, lmax = float(a.actor_log_std_min), float(a.actor_log_std_max)
+        self.proj_fwd(_ptr(self.actT[10]), B, "actor_proj", _ptr(self.z_a), _ptr(self.h_a), L.P)
+        self.actor_mlp_fwd(B)
+        K.actor_head_fwd(_ptr(self.raw), _ptr(self.noise_pi), lmin, lmax, 0, _ptr(self.haT, L.P), P1, _ptr(self.log_pi),
+                         0, B, A, st)
+        self.q_fwd(_ptr(self.haT), B, 0, 2)
+        K.actor_loss(_ptr(self.q), 2 * B, _ptr(self.log_pi), _ptr(self.log_alpha), self.target_entropy, _ptr(self.dq),
+                     _ptr(self.logs, 1), _ptr(self.alpha_grad), B, self.Bg, st)
+        self.q_dgrad(_ptr(self.dq), 2 * B, B, 0, 2, 1, _ptr(self.dhaT))
+        K.actor_head_bwd(_ptr(self.raw), _ptr(self.noise_pi), _ptr(self.dhaT, L.P), P1, _ptr(self.log_alpha), lmin, lmax,
+                         _ptr(self.draw), B, A, st)
+        a0, a1 = L.ranges["actor"]
+        K.zero(self._g + 4 * a0, 4 * (a1 - a0), st)
+        # actor MLP backward
+        K.linear_dgrad(_ptr(self.draw), 2 * A, 0, self.P("actor_mlp.4.weight"), 0, _ptr(self.az2), H, 0, _ptr(self.daz2), H, 0,
+                       B, 2 * A, H, 1, 0, 1, st)
+        K.linear_dgrad(_ptr(self.daz2), H, 0, self.P("actor_mlp.2.weight"), 0, _ptr(self.az1), H, 0, _ptr(self.daz1), H, 0,
+                       B, H, H, 1, 0, 1, st)
+        K.linear_dgrad(_ptr(self.daz1), H, 0, self.P("actor_mlp.0.weight"), 0, 0, 0, 0, _ptr(self.dh_a), L.P, 0,
+                       B, H, L.P, 0, 0, 1, st)
+        K.linear_wgrad(_ptr(self.az2), H, 0, _ptr(self.draw), 2 * A, 0, self.G("actor_mlp.4.weight"), 0,
+                       self.G("actor_mlp.4.bias"), 0, B, 2 * A, H, 1, 1, st)
+        K.linear_wgrad(_ptr(self.az1), H, 0, _ptr(self.daz2), H, 0, self.G("actor_mlp.2.weight"), 0,
+                       self.G("actor_mlp.2.bias"), 0, B, H, H, 1, 1, st)
+        K.linear_wgrad(_ptr(self.h_a), L.P, 0, _ptr(self.daz1), H, 0, self.G("actor_mlp.0.weight"), 0,
+                       self.G("actor_mlp.0.bias"), 0, B, H, L.P, 0, 1, st)
+        self.proj_bwd(_ptr(self.dh_a), L.P, B, _ptr(self.z_a), _ptr(self.h_a), L.P, "actor_proj", _ptr(self.dz_a),
+                      feat_ptr=_ptr(self.actT[10]), dfeat=0)
+        self.allreduce_grads((a0, a1))
+        if self.dist is not None:
+            self.dist.all_reduce_sum(self.alpha_grad)
+        self.adam(self.opt_actor, (a0, a1))
+        K.alpha_adam(_ptr(self.log_alpha), _ptr(self.alpha_grad), _ptr(self.alpha_st), _ptr(self.alpha_step),
+                     float(a.alpha_lr), float(a.alpha_beta), 0.999, 1e-8, st)
+
+    def update_aux(self):
+        """sgsac.py:82-102,163-167: overlay -> attribution predictor -> BCE vs mask of attribution #2."""
+        B, A, L, st, a = self.B, self.A, self.lay, self.st, self.args
+        P1 = L.P + A
+        al = float(getattr(a, "alpha_blending", 0.2))
+        K.overlay_u8(_ptr(self.obs2), _ptr(self.overlay_pool), _ptr(self.overlay_ids), float(np.float32(1 - al)),
+                     float(np.float32(al)), _ptr(self.s_tilde), B, 84 * 84, st)
+        self.enc_fwd(_ptr(self.s_tilde), B, self.actT)
+        K.set_cols(_ptr(self.haT), P1, L.P, _ptr(self.action), A, B, A, st)
+        self.proj_fwd(_ptr(self.actT[10]), B, "critic_proj", _ptr(self.zT), _ptr(self.haT), P1)
+        Wp, G = self.P, self.G
+        K.linear_fwd(_ptr(self.haT), P1, 0, Wp("dec.proj.weight"), 0, Wp("dec.proj.bias"), 0, _ptr(self.dl), FEAT, 0,
+                     B, FEAT, P1, 0, 1, 0, st)
+        K.conv_fwd(_ptr(self.dl), Wp("dec.conv1.weight"), Wp("dec.conv1.bias"), _ptr(self.d1), B, 21, 21, 32, 128, 1, 1, 1, st)
+        K.conv_fwd(_ptr(self.d1), Wp("dec.conv2.weight"), Wp("dec.conv2.bias"), _ptr(self.d2), B, 21, 21, 128, 64, 1, 2, 1, st)
+        K.conv_fwd(_ptr(self.d2), Wp("dec.conv3.weight"), Wp("dec.conv3.bias"), _ptr(self.lg), B, 42, 42, 64, DEC_C3, 1, 2, 1, st)
+        K.zero(_ptr(self.logs, 4), 4, st)
+        K.bce(_ptr(self.lg), _ptr(self.mask), _ptr(self.logs, 4), _ptr(self.dlg), B, 84 * 84, DEC_C3, self.Bg, st)
+        x0, x1 = L.ranges["aux"]
+        K.zero(self._g + 4 * x0, 4 * (x1 - x0), st)
+        K.conv_wgrad(_ptr(self.d2), _ptr(self.dlg), G("dec.conv3.weight"), G("dec.conv3.bias"), B, 42, 42, 64, DEC_C3, 1, 2, 1, st)
+        K.conv_dgrad(_ptr(self.dlg), Wp("dec.conv3.weight"), 0, _ptr(self.dup3), B, 84, 84, 64, DEC_C3, 1, 0, st)
+        K.upsample2_bwd(_ptr(self.dup3), _ptr(self.d2), _ptr(self.dd2), B, 42, 42, 64, st)
+        K.conv_wgrad(_ptr(self.d1), _ptr(self.dd2), G("dec.conv2.weight"), G("dec.conv2.bias"), B, 21, 21, 128, 64, 1, 2, 1, st)
+        K.conv_dgrad(_ptr(self.dd2), Wp("dec.conv2.weight"), 0, _ptr(self.dup2), B, 42, 42, 128, 64, 1, 0, st)
+        K.upsample2_bwd(_ptr(self.dup2), _ptr(self.d1), _ptr(self.dd1), B, 21, 21, 128, st)
+        K.conv_wgrad(_ptr(self.dl), _ptr(self.dd1), G("dec.conv1.weight"), G("dec.conv1.bias"), B, 21, 21, 32, 128, 1, 1, 1, st)
+        K.conv_dgrad(_ptr(self.dd1), Wp("dec.conv1.weight"), _ptr(self.dl), _ptr(self.ddl), B, 21, 21, 32, 128, 1, 1, st)
+        K.linear_wgrad(_ptr(self.haT), P1, 0, _ptr(self.ddl), FEAT, 0, G("dec.proj.weight"), 0, G("dec.proj.bias"), 0,
+                       B, FEAT, P1, 0, 1, st)
+        K.linear_dgrad(_ptr(self.ddl), FEAT, 0, Wp("dec.proj.weight"), 0, 0, 0, 0, _ptr(self.dhaT), P1, 0, B, FEAT, P1, 0, 0, 1, st)
+        dfeat = _ptr(self.dbuf[1])
+        self.proj_bwd(_ptr(self.dhaT), P1, B, _ptr(self.zT), _ptr(self.haT), P1, "critic_proj", _ptr(self.dzT),
+                      feat_ptr=_ptr(self.actT[10]), dfeat=dfeat)
+        self.enc_bwd(dfeat, B, self.actT, 0, _ptr(self.s_tilde), 1, True)
+        self.allreduce_grads((x0, x1))
+        self.adam(self.opt_aux, (x0, x1))
+
+    def update_sgsac(self, step):
+        """sgsac.py:169-185 after the sample (obs2[:B], next_obs, action, reward, not_done and the step's randomness
+        are already in place)."""
+        a = self.args
+        do_actor = step % a.actor_update_freq == 0
+        do_target = step % a.critic_target_update_freq == 0
+        do_aux = step % a.aux_update_freq == 0
+        self.update_critic(1 if a.consistency else 0)
+        self.critic_step(with_ema=do_target)
+        if do_actor or do_aux:
+            self.shared_obs_fwd()
+        if do_aux:
+            # attribution #2 with the updated critic feeds only update_aux's mask (sgsac.py:175-176,83); on steps
+            # without an aux update the reference computes it and discards it (no side effects).
+            self.attribution2(want_mask=True)
+        if do_actor:
+            self.update_actor_and_alpha()
+        if do_aux:
+            self.update_aux()
+        self._finish_logs()
+
+    def update_sac(self, step, mode=0):
+        """sac.py:160-169 (SAC / RAD / DrQ) and svea.py:54-63 (mode 2)."""
+        a = self.args
+        do_actor = step % a.actor_update_freq == 0
+        do_target = step % a.critic_target_update_freq == 0
+        self.update_critic(mode)
+        self.critic_step(with_ema=do_target)
+        if do_actor:
+            self.shared_obs_fwd()
+            self.update_actor_and_alpha()
+        self._finish_logs()
+
+    def _finish_logs(self):
+        if self.dist is not None:
+            self.dist.all_reduce_logs(self.logs)
+
+    # ------------------------------------------------------------------ acting (sac.py:86-105)
+    def act(self, obs_dev, hin, sample, noise=None):
+        """obs_dev: (1,9,hin,hin) fp32 device tensor -> (A,) device tensor tanh(mu) or tanh(pi)."""
+        L, A, st, a = self.lay, self.A, self.st, self.args
+        self.enc_fwd(_ptr(obs_dev), 1, self.actT, hin=hin)
+        self.proj_fwd(_ptr(self.actT[10]), 1, "actor_proj", _ptr(self.z_a), _ptr(self.h_a), L.P)
+        self.actor_mlp_fwd(1)
+        if sample:
+            if noise is None:
+                noise = torch.randn(1, A, device=self.dev)
+            K.actor_head_fwd(_ptr(self.raw), _ptr(noise), float(a.actor_log_std_min), float(a.actor_log_std_max),
+                             _ptr(self.mu), _ptr(self.pi), A, 0, 0, 1, A, st)
+            return self.pi[0]
+        K.actor_head_fwd(_ptr(self.raw), 0, float(a.actor_log_std_min), float(a.actor_log_std_max),
+                         _ptr(self.mu), 0, A, 0, 0, 1, A, st)
+        return self.mu[0]

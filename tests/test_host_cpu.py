@@ -1,0 +1,129 @@
+"""CPU-side checks: the C-ABI library loads and exports every symbol include/sgqn_b200.h declares with the
+argument lists the ctypes binding uses; parameter layout round-trips; lazy logging arithmetic."""
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import ROOT
+import sgqn_carla_b200 as S
+from sgqn_carla_b200 import _lib
+from sgqn_carla_b200.layout import ParamLayout, reference_key_map, FEAT
+
+
+def _header_protos():
+    src = open(os.path.join(ROOT, "include", "sgqn_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    protos = {}
+    for m in re.finditer(r"\bint\s+(sgqn_\w+)\s*\(([^)]*)\)\s*;", src):
+        args = [a.strip() for a in m.group(2).split(",") if a.strip() and a.strip() != "void"]
+        protos[m.group(1)] = args
+    return protos
+
+
+def test_library_exports_every_declared_symbol():
+    lib = _lib.load()
+    protos = _header_protos()
+    assert len(protos) >= 30
+    for name in protos:
+        assert hasattr(lib, name), name
+    assert lib.sgqn_abi_version() == _lib.ABI_VERSION
+
+
+def test_ctypes_signatures_match_header():
+    import ctypes as C
+    protos = _header_protos()
+    assert set(_lib.SIGNATURES) == set(protos) - {"sgqn_abi_version"}
+    for name, args in protos.items():
+        if name == "sgqn_abi_version":
+            continue
+        sig = _lib.SIGNATURES[name]
+        assert len(sig) == len(args), name
+        for ct, a in zip(sig, args):
+            if "*" in a:
+                want = C.c_void_p
+            elif a.startswith("unsigned long long"):
+                want = C.c_ulonglong
+            elif a.startswith("long long"):
+                want = C.c_longlong
+            elif a.startswith("float"):
+                want = C.c_float
+            elif a.startswith("double"):
+                want = C.c_double
+            else:
+                assert a.startswith("int"), (name, a)
+                want = C.c_int
+            assert ct is want, (name, a)
+
+
+def test_missing_library_fails_loudly(monkeypatch):
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "LIB_PATH", "/nonexistent/libsgqn_b200.so")
+    with pytest.raises(_lib.KernelError):
+        _lib.load()
+
+
+def test_engine_refuses_cpu():
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    with pytest.raises(RuntimeError):
+        S.make_agent((9, 84, 84), (2,), S.default_args())
+
+
+def test_layout_roundtrip_and_ranges():
+    lay = ParamLayout(2)
+    g = torch.Generator().manual_seed(0)
+    params = {n: torch.randn(*shape, generator=g) for n, (_, _, shape) in lay.entries.items()}
+    flat = torch.zeros(lay.total)
+    lay.pack(params, flat)
+    back = lay.unpack(flat)
+    for n in params:
+        assert torch.equal(back[n], params[n]), n
+    for n, (o, st, _) in lay.entries.items():
+        assert o % 4 == 0, n                                    # 16-byte aligned segments
+    c0, c1 = lay.ranges["critic"]
+    crit = sum(int(np.prod(s)) for n, (_, _, s) in lay.entries.items() if n.startswith(("Q1.", "Q2.", "cnn.", "critic_proj.")))
+    assert crit == 3818798
+    assert c1 - c0 >= crit and lay.ranges["Q2"][0] - lay.ranges["Q1"][0] == lay.q_stride
+    # NHWC permutation of the projection columns: feature (c,y,x) -> (y,x,c)
+    w = params["critic_proj.0.weight"]
+    o = lay.off("critic_proj.0.weight")
+    stored = flat[o:o + 100 * FEAT].reshape(100, 441, 32)
+    assert torch.equal(stored[7, 5, 3], w[7, 3 * 441 + 5])
+    keys = reference_key_map()
+    assert set(keys) == set(lay.entries)
+
+
+def test_lazy_scalar_arithmetic_without_device():
+    from sgqn_carla_b200.lazylog import LazyScalar
+
+    class FakeRing:
+        def read(self, slot, serial, col):
+            return [1.5, 2.5][slot]
+
+    a = LazyScalar([(FakeRing(), 0, 0, 0, 1.0)])
+    b = LazyScalar([(FakeRing(), 1, 1, 0, 1.0)])
+    s = 0
+    s += a
+    s += b
+    assert isinstance(s, LazyScalar) and abs(s / 2 - 2.0) < 1e-12 and abs(float(a) - 1.5) < 1e-12
+    assert "%.04f" % s == "4.0000"
+
+
+def test_default_args_match_reference_defaults():
+    a = S.default_args()
+    assert (a.batch_size, a.hidden_dim, a.projection_dim, a.num_shared_layers) == (128, 1024, 100, 11)
+    assert (a.critic_tau, a.encoder_tau, a.aux_lr, a.alpha_blending, a.sgqn_quantile) == (0.01, 0.05, 3e-4, 0.2, 0.5)
+    assert S.default_args(algorithm="rad").image_size == 100
+
+
+@pytest.mark.ref
+def test_default_args_against_reference_argparse():
+    from oracle import ref_shim as R
+    ref = vars(R.parse_args([]))
+    mine = vars(S.default_args())
+    for k, v in mine.items():
+        if k in ref:
+            assert ref[k] == v, k

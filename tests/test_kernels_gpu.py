@@ -1,0 +1,424 @@
+"""Per-kernel parity (B200): every C-ABI entry point against a plain fp32 torch restatement of the same op,
+the oracle's integer/byte semantics bit-exactly, and the golden vectors generated from the reference."""
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from conftest import GOLDEN
+
+pytestmark = pytest.mark.gpu
+
+if torch.cuda.is_available():
+    from sgqn_carla_b200._lib import K
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+
+DEV = "cuda"
+
+
+def P(t, off=0):
+    return t.data_ptr() + off * t.element_size()
+
+
+def ST():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def rnd(*shape, seed=0, scale=1.0):
+    g = torch.Generator().manual_seed(seed)
+    return (torch.randn(*shape, generator=g) * scale).to(DEV)
+
+
+def close(a, b, rtol=1e-4, atol=1e-5, what=""):
+    a, b = a.float().cpu(), b.float().cpu()
+    scale = b.abs().max().item() + 1e-30
+    err = (a - b).abs().max().item()
+    assert err <= atol * max(scale, 1.0) + rtol * scale, f"{what}: max err {err:.3e} vs scale {scale:.3e}"
+
+
+def nhwc(x):      # NCHW -> flat NHWC
+    return x.permute(0, 2, 3, 1).contiguous()
+
+
+def nchw(x, B, H, W, C):
+    return x.reshape(B, H, W, C).permute(0, 3, 1, 2).contiguous()
+
+
+def wk(w):        # [Cout][Cin][3][3] -> [Cout][3][3][Cin]
+    return w.permute(0, 2, 3, 1).contiguous()
+
+
+# ------------------------------------------------------------------ Linear
+@pytest.mark.parametrize("M,N,K_,relu,split", [(128, 1024, 102, 0, 0), (37, 100, 14112, 0, 1), (256, 1, 1024, 1, 0),
+                                               (5, 4, 1024, 1, 0), (130, 14112, 102, 0, 0), (1, 1024, 100, 0, 0)])
+def test_linear_fwd(M, N, K_, relu, split):
+    x, w, b = rnd(M, K_, seed=1), rnd(N, K_, seed=2, scale=0.05), rnd(N, seed=3)
+    y = torch.zeros(M, N, device=DEV)
+    K.linear_fwd(P(x), K_, 0, P(w), 0, P(b), 0, P(y), N, 0, M, N, K_, relu, 1, split, ST())
+    ref = F.linear(F.relu(x) if relu else x, w, b)
+    close(y, ref, what="linear_fwd")
+
+
+def test_linear_fwd_batched_heads():
+    M, N, K_ = 64, 1024, 102
+    x, w, b = rnd(M, K_, seed=1), rnd(2, N, K_, seed=2, scale=0.1), rnd(2, N, seed=3)
+    y = torch.zeros(2, M, N, device=DEV)
+    K.linear_fwd(P(x), K_, 0, P(w), N * K_, P(b), N, P(y), N, M * N, M, N, K_, 0, 2, 0, ST())
+    for h in range(2):
+        close(y[h], F.linear(x, w[h], b[h]), what=f"head{h}")
+
+
+@pytest.mark.parametrize("M,N,K_,mode", [(128, 1024, 1024, 1), (64, 1, 1024, 2), (200, 100, 14112, 0), (33, 1024, 102, 0)])
+def test_linear_dgrad(M, N, K_, mode):
+    dy, w, z = rnd(M, N, seed=1), rnd(N, K_, seed=2, scale=0.05), rnd(M, K_, seed=3)
+    dx = torch.zeros(M, K_, device=DEV)
+    K.linear_dgrad(P(dy), N, 0, P(w), 0, P(z) if mode else 0, K_, 0, P(dx), K_, 0, M, N, K_, mode, 0, 1, ST())
+    ref = dy @ w
+    if mode == 1:
+        ref = ref * (z > 0)
+    if mode == 2:
+        ref = F.relu(ref) * (z > 0)
+    close(dx, ref, what="linear_dgrad")
+
+
+@pytest.mark.parametrize("M,N,K_,relu", [(256, 1024, 1024, 1), (128, 100, 14112, 0), (64, 1, 1024, 1), (77, 1024, 102, 0), (128, 14112, 102, 0)])
+def test_linear_wgrad(M, N, K_, relu):
+    x, dy = rnd(M, K_, seed=1), rnd(M, N, seed=2)
+    dw = torch.zeros(N, K_, device=DEV); db = torch.zeros(N, device=DEV)
+    K.linear_wgrad(P(x), K_, 0, P(dy), N, 0, P(dw), 0, P(db), 0, M, N, K_, relu, 1, ST())
+    xa = F.relu(x) if relu else x
+    close(dw, dy.t() @ xa, rtol=2e-4, what="linear_wgrad")
+    close(db, dy.sum(0), rtol=2e-4, what="linear_bgrad")
+
+
+# ------------------------------------------------------------------ convs (NHWC)
+CONVS = [  # B, Hs, Cin, Cout(real), Cout(stored), pad, up
+    (3, 41, 32, 32, 32, 0, 1), (2, 23, 32, 32, 32, 0, 1), (2, 21, 32, 128, 128, 1, 1), (2, 21, 128, 64, 64, 1, 2),
+    (2, 42, 64, 9, 16, 1, 2)]
+
+
+@pytest.mark.parametrize("B,Hs,Cin,Co,Cs,pad,up", CONVS)
+def test_conv_fwd_dgrad_wgrad(B, Hs, Cin, Co, Cs, pad, up):
+    x = rnd(B, Cin, Hs, Hs, seed=1)
+    w = rnd(Co, Cin, 3, 3, seed=2, scale=0.1); b = rnd(Co, seed=3)
+    ws = torch.zeros(Cs, Cin, 3, 3, device=DEV); ws[:Co] = w
+    bs = torch.zeros(Cs, device=DEV); bs[:Co] = b
+    xr = x.clone().requires_grad_(True); wr = w.clone().requires_grad_(True); br = b.clone().requires_grad_(True)
+    xin = F.relu(xr)
+    if up == 2:
+        xin = F.interpolate(xin, scale_factor=2)
+    xin.retain_grad()
+    yr = F.conv2d(xin, wr, br, padding=pad)
+    Ho = yr.shape[-1]
+    y = torch.zeros(B * Ho * Ho * Cs, device=DEV)
+    xh, wsk = nhwc(x), wk(ws)            # keep the NHWC copies alive while kernels read them
+    K.conv_fwd(P(xh), P(wsk), P(bs), P(y), B, Hs, Hs, Cin, Cs, pad, up, 1, ST())
+    close(nchw(y, B, Ho, Ho, Cs)[:, :Co], yr, what="conv_fwd")
+    dy = rnd(B, Co, Ho, Ho, seed=4)
+    yr.backward(dy)
+    dys = torch.zeros(B, Cs, Ho, Ho, device=DEV); dys[:, :Co] = dy
+    dw = torch.zeros(Cs * 9 * Cin, device=DEV); db = torch.zeros(Cs, device=DEV)
+    dyh = nhwc(dys)
+    K.conv_wgrad(P(xh), P(dyh), P(dw), P(db), B, Hs, Hs, Cin, Cs, pad, up, 1, ST())
+    close(dw.reshape(Cs, 3, 3, Cin).permute(0, 3, 1, 2)[:Co], wr.grad, rtol=3e-4, what="conv_wgrad")
+    close(db[:Co], br.grad, rtol=3e-4, what="conv_bgrad")
+    Hl = Hs * up
+    dxl = torch.zeros(B * Hl * Hl * Cin, device=DEV)
+    K.conv_dgrad(P(dyh), P(wsk), 0, P(dxl), B, Hl, Hl, Cin, Cs, pad, 0, ST())
+    close(nchw(dxl, B, Hl, Hl, Cin), xin.grad, rtol=3e-4, what="conv_dgrad(logical input)")
+    if up == 1:
+        for mode in (1, 2):
+            K.conv_dgrad(P(dyh), P(wsk), P(xh), P(dxl), B, Hl, Hl, Cin, Cs, pad, mode, ST())
+            ref = xin.grad * (x > 0) if mode == 1 else F.relu(xin.grad) * (x > 0)
+            close(nchw(dxl, B, Hl, Hl, Cin), ref, rtol=3e-4, what=f"conv_dgrad mode {mode}")
+    else:
+        dx = torch.zeros(B * Hs * Hs * Cin, device=DEV)
+        K.upsample2_bwd(P(dxl), P(xh), P(dx), B, Hs, Hs, Cin, ST())
+        close(nchw(dx, B, Hs, Hs, Cin), xr.grad, rtol=3e-4, what="upsample2_bwd")
+
+
+@pytest.mark.parametrize("B,Hin", [(3, 84), (2, 100)])
+def test_conv1(B, Hin):
+    g = torch.Generator().manual_seed(5)
+    obs = torch.randint(0, 256, (B, 9, Hin, Hin), generator=g).float().to(DEV)
+    w = rnd(32, 9, 3, 3, seed=2, scale=0.2); b = rnd(32, seed=3)
+    c = (Hin - 84) // 2
+    xr = obs[:, :, c:c + 84, c:c + 84].clone().requires_grad_(True)
+    wr = w.clone().requires_grad_(True); br = b.clone().requires_grad_(True)
+    yr = F.conv2d(xr / 255.0, wr, br, stride=2)
+    y = torch.zeros(B * 41 * 41 * 32, device=DEV)
+    K.conv1_fwd(P(obs), P(w), P(b), P(y), B, Hin, 9, 32, ST())
+    close(nchw(y, B, 41, 41, 32), yr, what="conv1_fwd")
+    dy = rnd(B, 32, 41, 41, seed=4)
+    yr.backward(dy)
+    dw = torch.zeros(32 * 81, device=DEV); db = torch.zeros(32, device=DEV)
+    dyh = nhwc(dy)
+    K.conv1_wgrad(P(obs), P(dyh), P(dw), P(db), B, Hin, 9, 32, ST())
+    close(dw.reshape(32, 9, 3, 3), wr.grad, rtol=3e-4, what="conv1_wgrad")
+    close(db, br.grad, rtol=3e-4, what="conv1_bgrad")
+    if Hin == 84:
+        dobs = torch.zeros(B, 9, 84, 84, device=DEV)
+        K.conv1_dgrad(P(dyh), P(w), P(dobs), B, 9, 32, ST())
+        close(dobs, xr.grad, rtol=3e-4, what="conv1_dgrad")
+        assert float(dobs[:, :, 83].abs().max()) == 0.0 and float(dobs[:, :, :, 83].abs().max()) == 0.0
+
+
+# ------------------------------------------------------------------ heads / losses
+def test_ln_tanh_fwd_bwd():
+    M, Pd = 67, 100
+    z = rnd(M, Pd, seed=1, scale=2.0); gam = rnd(Pd, seed=2) + 1; bet = rnd(Pd, seed=3)
+    zr, gr, br = z.clone().requires_grad_(True), gam.clone().requires_grad_(True), bet.clone().requires_grad_(True)
+    hr = torch.tanh(F.layer_norm(zr, (Pd,), gr, br, 1e-5))
+    h = torch.zeros(M, Pd + 2, device=DEV)
+    K.ln_tanh_fwd(P(z), P(gam), P(bet), P(h), Pd + 2, M, Pd, ST())
+    close(h[:, :Pd], hr, what="ln_tanh_fwd")
+    dh = rnd(M, Pd + 2, seed=4)
+    hr.backward(dh[:, :Pd])
+    dz = torch.zeros(M, Pd, device=DEV); dg = torch.zeros(Pd, device=DEV); dbt = torch.zeros(Pd, device=DEV)
+    K.ln_tanh_bwd(P(dh), Pd + 2, P(z), P(h), Pd + 2, P(gam), P(dz), P(dg), P(dbt), M, Pd, ST())
+    close(dz, zr.grad, rtol=3e-4, what="ln dz"); close(dg, gr.grad, rtol=3e-4, what="ln dgamma"); close(dbt, br.grad, rtol=3e-4, what="ln dbeta")
+
+
+def _actor_head_ref(raw, noise, lmin, lmax):
+    A = noise.shape[1]
+    mu, ls = raw.chunk(2, dim=-1)
+    ls = torch.tanh(ls); ls = lmin + 0.5 * (lmax - lmin) * (ls + 1)
+    pi = mu + noise * ls.exp()
+    logp = (-0.5 * noise.pow(2) - ls).sum(-1, keepdim=True) - 0.5 * np.log(2 * np.pi) * A
+    mu_t, pi_t = torch.tanh(mu), torch.tanh(pi)
+    logp = logp - torch.log(F.relu(1 - pi_t.pow(2)) + 1e-6).sum(-1, keepdim=True)
+    return mu_t, pi_t, logp, ls
+
+
+@pytest.mark.parametrize("A", [1, 2, 6])
+def test_actor_head_fwd_bwd(A):
+    M = 50
+    raw, noise = rnd(M, 2 * A, seed=1), rnd(M, A, seed=2)
+    rr = raw.clone().requires_grad_(True)
+    mu_r, pi_r, lp_r, ls_r = _actor_head_ref(rr, noise, -10.0, 2.0)
+    mu = torch.zeros(M, A, device=DEV); pi = torch.zeros(M, A + 3, device=DEV); lp = torch.zeros(M, device=DEV); ls = torch.zeros(M, A, device=DEV)
+    K.actor_head_fwd(P(raw), P(noise), -10.0, 2.0, P(mu), P(pi), A + 3, P(lp), P(ls), M, A, ST())
+    close(mu, mu_r, what="mu"); close(pi[:, :A], pi_r, what="pi"); close(lp, lp_r[:, 0], rtol=2e-4, what="log_pi"); close(ls, ls_r, what="log_std")
+    log_alpha = torch.tensor([np.log(0.3)], dtype=torch.float64, device=DEV)
+    dpi = rnd(M, A + 3, seed=3)
+    loss = (pi_r * dpi[:, :A]).sum() + (0.3 / M) * lp_r.sum()
+    loss.backward()
+    draw = torch.zeros(M, 2 * A, device=DEV)
+    K.actor_head_bwd(P(raw), P(noise), P(dpi), A + 3, P(log_alpha), -10.0, 2.0, P(draw), M, A, ST())
+    close(draw, rr.grad, rtol=5e-4, what="actor_head_bwd")
+
+
+@pytest.mark.parametrize("mode", [0, 1, 2])
+def test_critic_loss(mode):
+    B = 37
+    R = B if mode == 0 else 2 * B
+    q = rnd(2, 2 * B, seed=1); tq = rnd(2, B, seed=2); nlp = rnd(B, seed=3); r = rnd(B, seed=4)
+    nd = (rnd(B, seed=5) > -1).float(); la = torch.tensor([np.log(0.2)], dtype=torch.float64, device=DEV)
+    qr = q.clone().requires_grad_(True)
+    t = r + nd * 0.99 * (torch.min(tq[0], tq[1]) - 0.2 * nlp)
+    if mode == 0:
+        ref = F.mse_loss(qr[0, :B], t) + F.mse_loss(qr[1, :B], t)
+    elif mode == 1:
+        ref = F.mse_loss(qr[0, :B], t) + F.mse_loss(qr[1, :B], t) + 0.5 * (F.mse_loss(qr[0, :B], qr[0, B:]) + F.mse_loss(qr[1, :B], qr[1, B:]))
+    else:
+        t2 = torch.cat([t, t])
+        ref = (0.5 + 0.5) * (F.mse_loss(qr[0], t2) + F.mse_loss(qr[1], t2))
+    ref.backward()
+    dq = torch.zeros(2, 2 * B, device=DEV); loss = torch.zeros(1, device=DEV); tqo = torch.zeros(B, device=DEV)
+    K.critic_loss(P(q), 2 * B, P(tq), P(tq, B), P(nlp), P(r), P(nd), P(la), 0.99, mode, 0.5, 0.5, P(tqo), P(dq), P(loss), B, B, ST())
+    close(loss, ref.detach().reshape(1), what="critic loss"); close(tqo, t, what="target_q")
+    close(dq[:, :R], qr.grad[:, :R], rtol=2e-4, what="dq")
+
+
+def test_actor_loss():
+    B = 41
+    q = rnd(2, 2 * B, seed=1); lp = rnd(B, seed=2); la = torch.tensor([np.log(0.15)], dtype=torch.float64, device=DEV)
+    qr = q.clone().requires_grad_(True); lar = la.clone().requires_grad_(True)
+    actor = (0.15 * lp - torch.min(qr[0, :B], qr[1, :B])).mean()
+    alpha_loss = (lar.exp() * (-lp - (-2.0))).mean()
+    actor.backward(); alpha_loss.backward()
+    dq = torch.zeros(2, 2 * B, device=DEV); out = torch.zeros(3, device=DEV); ag = torch.zeros(1, dtype=torch.float64, device=DEV)
+    K.actor_loss(P(q), 2 * B, P(lp), P(la), -2.0, P(dq), P(out), P(ag), B, B, ST())
+    close(out[0:1], actor.detach().reshape(1), what="actor loss"); close(out[1:2], alpha_loss.detach().float().reshape(1), what="alpha loss")
+    close(out[2:3], torch.tensor([0.15]), what="alpha"); close(dq[:, :B], qr.grad[:, :B], what="dq")
+    close(ag, lar.grad, what="alpha grad")
+
+
+def test_bce():
+    B, HW, Cs = 3, 84 * 84, 16
+    lg = rnd(B, HW, Cs, seed=1, scale=2.0)
+    mask = (rnd(B, 3, HW, seed=2) > 0.8).to(torch.uint8)
+    x = lg[:, :, :9].permute(0, 2, 1).clone().requires_grad_(True)          # (B,9,HW)
+    y = mask.float().repeat_interleave(3, dim=1)
+    ref = F.binary_cross_entropy_with_logits(x, y)
+    ref.backward()
+    loss = torch.zeros(1, device=DEV); d = torch.ones(B, HW, Cs, device=DEV)
+    K.bce(P(lg), P(mask), P(loss), P(d), B, HW, Cs, B, ST())
+    close(loss, ref.detach().reshape(1), what="bce loss")
+    close(d[:, :, :9].permute(0, 2, 1), x.grad, rtol=2e-4, what="bce grad")
+    assert float(d[:, :, 9:].abs().max()) == 0.0
+
+
+# ------------------------------------------------------------------ saliency / augmentation / replay: bit-exact
+def _mask_gpu(grad, q, obs=None, mm=None, u=None):
+    B = grad.shape[0]
+    mask = torch.zeros(B, 3, 84 * 84, dtype=torch.uint8, device=DEV)
+    masked = torch.zeros(B, 9, 84, 84, device=DEV) if obs is not None else None
+    K.attribution_mask(P(grad), P(obs) if obs is not None else 0, P(mm) if mm is not None else 0, P(u) if u is not None else 0,
+                       float(q), P(mask), P(masked) if masked is not None else 0, B, 84 * 84, ST())
+    full = mask.reshape(B, 3, 1, 84, 84).expand(B, 3, 3, 84, 84).reshape(B, 9, 84, 84).bool()
+    return full, masked
+
+
+def test_attribution_mask_golden_bit_exact():
+    gold = np.load(os.path.join(GOLDEN, "masks.npz"))
+    g = torch.Generator().manual_seed(77)
+    base = torch.randn(4, 9, 84, 84, generator=g)
+    base[1, :3] = 0.0
+    base[2, 3:6] = (torch.rand(3, 84, 84, generator=g) < 0.03).float() * base[2, 3:6]
+    base[3, 6:9] = torch.round(base[3, 6:9] * 2) / 2
+    for q in (0.5, 0.9, 0.95, 0.98, 0.999):
+        m, _ = _mask_gpu(base.to(DEV), q)
+        assert np.array_equal(np.packbits(m.cpu().numpy().reshape(-1)), gold[f"q{q}"]), q
+
+
+@pytest.mark.parametrize("q", [0.0, 0.5, 0.95, 0.98, 1.0])
+def test_attribution_mask_vs_oracle_and_fill(q):
+    from oracle import sgsac_oracle as O
+    g = torch.Generator().manual_seed(3)
+    grad = torch.randn(6, 9, 84, 84, generator=g) * 1e-3
+    grad[0, :3] = 0; grad[1, 3:6, :80] = 0; grad[2] = torch.round(grad[2] * 4000) / 4000
+    obs = torch.randint(0, 256, (6, 9, 84, 84), generator=g).float()
+    ref = O.compute_attribution_mask(grad, q)
+    mm = torch.zeros(2, device=DEV); scratch = torch.zeros(1024, device=DEV)
+    obs_d = obs.to(DEV)
+    K.minmax(P(obs_d), obs.numel(), P(scratch), P(mm), ST())
+    assert mm.cpu().tolist() == [float(obs.min()), float(obs.max())]
+    u = torch.tensor([0.37], device=DEV)
+    m, masked = _mask_gpu(grad.to(DEV), q, obs_d, mm, u)
+    assert torch.equal(m.cpu(), ref)
+    fill = obs.min() + (obs.max() - obs.min()) * 0.37
+    ref_masked = obs * ref
+    ref_masked[ref < 1] = fill
+    assert torch.equal(masked.cpu(), ref_masked)
+
+
+def test_overlay_and_crop_shift_golden():
+    gold = np.load(os.path.join(GOLDEN, "aug.npz"))
+    rs = np.random.RandomState(11)
+    x100 = torch.as_tensor(rs.randint(0, 256, size=(3, 9, 100, 100)).astype(np.float32)).to(DEV)
+    w1 = rs.randint(0, 16, size=3); h1 = rs.randint(0, 16, size=3)
+    offs = torch.as_tensor(np.stack([w1, h1], 1), dtype=torch.int32).to(DEV).contiguous()
+    y = torch.zeros(3, 9, 84, 84, device=DEV)
+    K.crop_shift(P(x100), P(offs), P(y), 3, 9, 100, 84, 0, 0, ST())
+    assert np.array_equal(y.cpu().numpy().astype(np.uint8), gold["crop"])
+    x84 = torch.as_tensor(rs.randint(0, 256, size=(3, 9, 84, 84)).astype(np.float32)).to(DEV)
+    dy = rs.randint(0, 9, size=3); dx = rs.randint(0, 9, size=3)
+    offs = torch.as_tensor(np.stack([dy, dx], 1), dtype=torch.int32).to(DEV).contiguous()
+    K.crop_shift(P(x84), P(offs), P(y), 3, 9, 84, 84, 1, 4, ST())
+    assert np.array_equal(y.cpu().numpy().astype(np.uint8), gold["shift"])
+    pool = torch.as_tensor(rs.randint(0, 256, size=(8, 3, 84, 84), dtype=np.uint8)).to(DEV)
+    ids = torch.as_tensor(rs.randint(0, 8, size=3), dtype=torch.int64).to(DEV)
+    K.overlay_u8(P(x84), P(pool), P(ids), float(np.float32(0.8)), float(np.float32(0.2)), P(y), 3, 84 * 84, ST())
+    np.testing.assert_allclose(y.cpu().numpy(), gold["overlay"], rtol=1e-6, atol=1e-4)
+
+
+@pytest.mark.parametrize("size,mode", [(84, 0), (84, 1), (100, 0)])
+def test_replay_gather_bit_exact(size, mode):
+    from oracle import sgsac_oracle as O
+    import sgqn_carla_b200 as S
+    cap, B = 64, 16
+    rep = O.synthetic_replay(cap, 2, size=size, seed=3)
+    rb = S.ReplayBuffer((9, size, size), (2,), cap, B)
+    rb.load_ring(rep.frames, rep.actions, rep.rewards, rep.not_dones)
+    rs = np.random.RandomState(0)
+    idxs = rs.randint(0, cap, size=B)
+    if mode == 1:
+        offs = rs.randint(0, 9, size=(2, B, 2))
+        ref = rep.sample_drq(idxs, (offs[0, :, 0], offs[0, :, 1], offs[1, :, 0], offs[1, :, 1]))
+        got = rb.sample_drq(idxs=idxs, offs=offs)
+    elif size == 100:
+        offs = rs.randint(0, 16, size=(2, B, 2))
+        ref = rep.sample(idxs, (offs[0, :, 0], offs[0, :, 1], offs[1, :, 0], offs[1, :, 1]))
+        got = rb.sample(idxs=idxs, offs=offs)
+    else:
+        ref = rep.sample(idxs)
+        got = rb.sample(idxs=idxs)
+    for a, b in zip(got, ref):
+        assert torch.equal(a.cpu(), b)
+
+
+def test_replay_add_dedups_lazyframes_and_matches_oracle_stacks():
+    import sgqn_carla_b200 as S
+    rs = np.random.RandomState(1)
+    frames = [rs.randint(0, 256, size=(3, 84, 84), dtype=np.uint8) for _ in range(40)]
+    rb = S.ReplayBuffer((9, 84, 84), (2,), 16, 4, frame_capacity=64)
+    for i in range(30):          # wraps the 16-transition ring
+        rb.add(S.LazyFrames(frames[i:i + 3]), rs.rand(2), float(i), S.LazyFrames(frames[i + 1:i + 4]), False)
+    assert rb._next_frame <= 30 + 3 + 1 or rb.F == 64       # ~1 new frame per transition, not 6
+    idxs = np.array([0, 5, 13, 15])
+    obs, a, r, nxt, nd = rb.sample(idxs=idxs)
+    for j, i in enumerate(idxs):
+        t = 16 + i if i < 14 else i                           # slot i holds transition 16+i after the wrap (i<14)
+        assert np.array_equal(obs[j].cpu().numpy().astype(np.uint8), np.concatenate(frames[t:t + 3]))
+        assert np.array_equal(nxt[j].cpu().numpy().astype(np.uint8), np.concatenate(frames[t + 1:t + 4]))
+        assert float(r[j]) == float(t)
+
+
+# ------------------------------------------------------------------ optimiser
+def test_adam_and_ema_vs_oracle():
+    from oracle import sgsac_oracle as O
+    n = 4096 + 8
+    g = torch.Generator().manual_seed(0)
+    p0 = torch.randn(n, generator=g); tgt0 = torch.randn(n, generator=g)
+    p = {"w": p0.clone()}
+    opt = O.Adam(["w"], 1e-3, 0.9)
+    pd, m, v = p0.clone().to(DEV), torch.zeros(n, device=DEV), torch.zeros(n, device=DEV)
+    tgt = tgt0.clone().to(DEV)
+    step = torch.zeros(1, dtype=torch.int32, device=DEV); bc = torch.zeros(2, device=DEV)
+    tref = tgt0.clone()
+    for it in range(5):
+        gr = torch.randn(n, generator=g) * (10.0 ** (it - 3))
+        opt.step(p, {"w": gr})
+        tref[:1024] = 0.01 * p["w"][:1024] + (1 - 0.01) * tref[:1024]
+        tref[1024:] = 0.05 * p["w"][1024:] + (1 - 0.05) * tref[1024:]
+        gd = gr.to(DEV)
+        K.adam_prep(P(step), P(bc), 0.9, 0.999, ST())
+        K.adam(P(pd), P(gd), P(m), P(v), n, P(bc), 1e-3, float(np.float32(0.1)), 0.999, float(np.float32(0.001)), 1e-8,
+               P(tgt), 1024, 0.01, 0.05, ST())
+    assert int(step) == 5
+    np.testing.assert_allclose(pd.cpu().numpy(), p["w"].numpy(), rtol=0, atol=2e-6)
+    np.testing.assert_allclose(m.cpu().numpy(), opt.m["w"].numpy(), rtol=1e-5, atol=1e-9)
+    np.testing.assert_allclose(v.cpu().numpy(), opt.v["w"].numpy(), rtol=1e-5, atol=1e-12)
+    np.testing.assert_allclose(tgt.cpu().numpy(), tref.numpy(), rtol=0, atol=2e-6)
+
+
+def test_alpha_adam_fp64():
+    la = torch.tensor([np.log(0.1)], dtype=torch.float64, device=DEV); st = torch.zeros(2, dtype=torch.float64, device=DEV)
+    step = torch.zeros(1, dtype=torch.int32, device=DEV)
+    ref = torch.tensor(np.log(0.1), dtype=torch.float64, requires_grad=True)
+    opt = torch.optim.Adam([ref], lr=1e-4, betas=(0.5, 0.999))
+    for gval in (0.3, -1.2, 0.05):
+        ref.grad = torch.tensor(gval, dtype=torch.float64)
+        opt.step()
+        gd = torch.tensor([gval], dtype=torch.float64, device=DEV)
+        K.alpha_adam(P(la), P(gd), P(st), P(step), 1e-4, 0.5, 0.999, 1e-8, ST())
+    assert abs(float(la) - float(ref)) < 1e-12
+
+
+def test_rng_step_statistics():
+    B, A = 512, 2
+    ctr = torch.zeros(1, dtype=torch.int64, device=DEV); nv = torch.tensor([1000], dtype=torch.int32, device=DEV)
+    idxs = torch.zeros(B, dtype=torch.int64, device=DEV); ov = torch.zeros(B, dtype=torch.int64, device=DEV)
+    offs = torch.zeros(2, B, 2, dtype=torch.int32, device=DEV)
+    n1 = torch.zeros(B, A, device=DEV); n2 = torch.zeros(B, A, device=DEV); u = torch.zeros(1, device=DEV)
+    K.rng_step(7, P(ctr), P(nv), P(idxs), P(ov), 256, P(offs), 9, P(n1), P(n2), P(u), B, A, ST())
+    first = idxs.clone()
+    K.rng_step(7, P(ctr), P(nv), P(idxs), P(ov), 256, P(offs), 9, P(n1), P(n2), P(u), B, A, ST())
+    assert int(ctr) == 2 and not torch.equal(first, idxs)
+    assert 0 <= int(idxs.min()) and int(idxs.max()) < 1000 and int(ov.max()) < 256 and int(offs.max()) <= 8 and int(offs.min()) >= 0
+    z = torch.cat([n1.flatten(), n2.flatten()])
+    assert abs(float(z.mean())) < 0.15 and abs(float(z.std()) - 1.0) < 0.1 and 0.0 <= float(u) < 1.0
