@@ -101,6 +101,7 @@ class UpdateEngine:
             self.dup3 = f32(B * 84 * 84 * 64); self.dup2 = f32(B * 42 * 42 * 128)
         if algorithm == "svea":
             self.places = f32(B, 3, 84 * 84)
+        self.debug_masked_obs = None
         self.overlay_pool = None       # uint8 (N,3,84*84) device pool for the 'carla' overlay
         self._p = self.params.data_ptr(); self._g = self.grads.data_ptr(); self._t = self.target.data_ptr()
         self._c0 = c0
@@ -271,6 +272,9 @@ class UpdateEngine:
                 self.dist.all_reduce_minmax(self.mm)
             K.attribution_mask(_ptr(self.obs_grad), _ptr(self.obs2), _ptr(self.mm), _ptr(self.u), self.quantile,
                                _ptr(self.mask), _ptr(self.obs2, B * 9 * 84 * 84), B, 84 * 84, st)
+            if self.debug_masked_obs is not None:           # parity tests: feed the oracle's masked obs forward
+                self.obs2[B:].copy_(self.debug_masked_obs)
+                self.debug_masked_obs = None
             self.critic_fwd_rows(B, B)
             R = 2 * B
         elif mode == 2:
