@@ -175,7 +175,6 @@ def profile_kernels(agent, rb, nsteps=4):
             cin, cout = (args[7], args[8])
             key = f"{n}[{cin}->{cout}]"
         t = e0.elapsed_time(e1)
-        tot, cnt, flops = fam.get(key, (0.0, 0, 0.0))
         fl = 0.0
         if n == "conv_fwd":
             B, Hs, Ws, Cin, Cout, pad, up = args[4], args[5], args[6], args[7], args[8], args[9], args[10]
@@ -185,10 +184,18 @@ def profile_kernels(agent, rb, nsteps=4):
             B, Hl, Wl, Cin, Cout, pad = args[4], args[5], args[6], args[7], args[8], args[9]
             Ho = Hl + 2 * pad - 2
             fl = 2.0 * B * Ho * Ho * 9 * Cin * (9 if Cout == 16 else Cout)
+        elif n == "conv_tc":
+            B, Hv = args[5], args[8]
+            fl = 2.0 * B * Hv * Hv * 9 * 32 * 32
+            key = "conv_tc[32->32 " + ("dgrad" if args[10] else "fwd") + "]"
+        elif n == "conv_wgrad_tc":
+            B, Wp = args[3], args[5]
+            fl = 2.0 * B * (Wp - 2) * (Wp - 2) * 9 * 32 * 32
         elif n == "conv_wgrad":
             B, Hs, Ws, Cin, Cout, pad, up = args[4], args[5], args[6], args[7], args[8], args[9], args[10]
             Ho = Hs * up + 2 * pad - 2
             fl = 2.0 * B * Ho * Ho * 9 * Cin * (9 if Cout == 16 else Cout)
+        tot, cnt, flops = fam.get(key, (0.0, 0, 0.0))
         fam[key] = (tot + t, cnt + 1, flops + fl)
     return fam, nsteps
 

@@ -57,15 +57,30 @@ int sgqn_colsum(const float* x, int ld, int M, int N, float* out, void* stream);
  *      dgrad: dx[B][Hl][Wl][Cin] gradient w.r.t. the conv's logical input, masked per `mode` by `mask`
  *      wgrad: dw[Cout][3][3][Cin] += ..., db[Cout] += ...     (atomic; caller zero-fills) */
 int sgqn_conv_fwd(const float* x, const float* w, const float* bias, float* y, int B, int Hs, int Ws, int Cin, int Cout,
-                  int pad, int up, int relu_in, void* stream);
+                  int pad, int up, int relu_in, int flags /* bit0: ReLU on the output, bit1: round it to TF32 */, void* stream);
 int sgqn_conv_dgrad(const float* dy, const float* w, const float* mask, float* dx, int B, int Hl, int Wl, int Cin, int Cout,
                     int pad, int mode, void* stream);
 int sgqn_conv_wgrad(const float* x, const float* dy, float* dw, float* db, int B, int Hs, int Ws, int Cin, int Cout, int pad,
-                    int up, int relu_in, void* stream);
+                    int up, int relu_in, int dy_border, void* stream);
 /* first encoder conv (modules.py:139-142: CenterCrop(84) -> x/255 -> Conv2d(Cin,Cout,3,stride=2)) on NCHW obs */
-int sgqn_conv1_fwd(const float* obs, const float* w, const float* bias, float* y, int B, int Hin, int Cin, int Cout, void* stream);
+int sgqn_conv1_fwd(const float* obs, const float* w, const float* bias, float* y, int B, int Hin, int Cin, int Cout,
+                   int flags /* bit0 ReLU, bit1 TF32 round, bit2: 2 extra (untouched) rows per sample in y */, void* stream);
 int sgqn_conv1_wgrad(const float* obs, const float* dy, float* dw, float* db, int B, int Hin, int Cin, int Cout, void* stream);
 int sgqn_conv1_dgrad(const float* dy, const float* w, float* dobs, int B, int Cin, int Cout, void* stream);
+/* ---- tcgen05 / TMEM / TMA implicit-GEMM 3x3 conv, 32 -> 32 channels, TF32 (SharedCNN layers 2..11, forward and data
+ *      gradient; conv_tc.cu).  x [B][Hr][Wp][32] pitch-linear; w: TF32-rounded operand copy [32][9][32] made by
+ *      sgqn_conv_weights_prep (wf: forward, wd: flipped+transposed for the data gradient).  Output (b,y,x), y < Hv,
+ *      x < Wv = sum over taps of x-row q + ky*Wp + kx + shift, q = (b*Hr + y)*Wp + x; it goes to
+ *      out[((b*Hq + y+oy)*Wq + x+ox)*32].  flags: bit0 ReLU, bit1 round output to TF32, bits 2-3 mask mode (1 plain ReLU
+ *      backward, 2 guided) with the mask value of (b,y,x) at mask[((b*Hm + y)*Wm + x)*32]. */
+int sgqn_conv_tc(const float* x, const float* w, const float* bias, const float* mask, float* out, int B, int Hr, int Wp, int Hv,
+                 int Wv, int shift, int Hq, int Wq, int oy, int ox, int Hm, int Wm, int flags, void* stream);
+/*      weight gradient of the same convs on tcgen05 (MN-major TF32 operands, reduction over pixels, one
+ *      red.global.add per CTA and element): x, dy [B][Hr][Wp][32] share one geometry, dy zero outside its valid region */
+int sgqn_conv_wgrad_tc(const float* x, const float* dy, float* dw, int B, int Hr, int Wp, void* stream);
+int sgqn_conv_weights_prep(const float* w, long long lstride, float* wf, float* wd, int n_layers, void* stream);
+int sgqn_pad_copy(const float* src, float* dst, int B, int H, int W, int C, int Hq, int Wq, int oy, int ox, int round_out,
+                  void* stream);
 /* backward of F.upsample(x, 2) followed by ReLU mask of the pre-upsample activation (modules.py:333-337) */
 int sgqn_upsample2_bwd(const float* dup, const float* act, float* dx, int B, int Hs, int Ws, int C, void* stream);
 

@@ -5,8 +5,8 @@ sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(
 from test_update_parity_gpu import _mk, _rnd, _supply, _relerr
 from oracle import sgsac_oracle as O
 B, A = 8, 2
-for feed in (False, True):
-    agent, rb, orc, rep, args = _mk(B=B, dense=0.05, quantile=0.95)
+for feed, prec in ((False, 'fp32'), (False, 'tf32'), (True, 'tf32')):
+    agent, rb, orc, rep, args = _mk(B=B, dense=0.05, quantile=0.95, precision=prec)
     eng = agent.engine
     rs = np.random.RandomState(2)
     idxs = rs.randint(0, 48, size=B); rnd = _rnd(rs, B, A, "sgsac")
@@ -24,7 +24,7 @@ for feed in (False, True):
     eng.update_critic(1)
     torch.cuda.synchronize()
     g_ref = tr["obs_grad1"]
-    print("feed", feed, "attr maxerr", float((eng.obs_grad.cpu() - g_ref).abs().max()), "max", float(g_ref.abs().max()), "relnorm", _relerr(eng.obs_grad, g_ref))
+    print("feed", feed, prec, "attr maxerr", float((eng.obs_grad.cpu() - g_ref).abs().max()), "max", float(g_ref.abs().max()), "relnorm", _relerr(eng.obs_grad, g_ref))
     mask = eng.mask.reshape(B, 3, 1, 84, 84).expand(B, 3, 3, 84, 84).reshape(B, 9, 84, 84).bool().cpu()
     print(" mask mismatches", int((mask != tr["mask1"]).sum()) // 3, "of", B * 3 * 7056, "kept", int(mask.sum()) // 3, int(tr["mask1"].sum()) // 3)
     print(" loss", float(eng.logs[0]), float(loss))

@@ -19,10 +19,14 @@ SIGNATURES = {
     "sgqn_linear_dgrad": [_p, _i, _ll, _p, _ll, _p, _i, _ll, _p, _i, _ll, _i, _i, _i, _i, _i, _i, _p],
     "sgqn_linear_wgrad": [_p, _i, _ll, _p, _i, _ll, _p, _ll, _p, _ll, _i, _i, _i, _i, _i, _p],
     "sgqn_colsum": [_p, _i, _i, _i, _p, _p],
-    "sgqn_conv_fwd": [_p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p],
+    "sgqn_conv_fwd": [_p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p],
     "sgqn_conv_dgrad": [_p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p],
-    "sgqn_conv_wgrad": [_p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p],
-    "sgqn_conv1_fwd": [_p, _p, _p, _p, _i, _i, _i, _i, _p],
+    "sgqn_conv_wgrad": [_p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p],
+    "sgqn_conv1_fwd": [_p, _p, _p, _p, _i, _i, _i, _i, _i, _p],
+    "sgqn_conv_tc": [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p],
+    "sgqn_conv_wgrad_tc": [_p, _p, _p, _i, _i, _i, _p],
+    "sgqn_conv_weights_prep": [_p, _ll, _p, _p, _i, _p],
+    "sgqn_pad_copy": [_p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p],
     "sgqn_conv1_wgrad": [_p, _p, _p, _p, _i, _i, _i, _i, _p],
     "sgqn_conv1_dgrad": [_p, _p, _p, _i, _i, _i, _p],
     "sgqn_upsample2_bwd": [_p, _p, _p, _i, _i, _i, _i, _p],

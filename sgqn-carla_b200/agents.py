@@ -58,6 +58,7 @@ class _ModuleView(object):
             base = c0 if self._target else 0
             o, st, _ = lay.entries[n]
             flat[o - base:o - base + st].copy_(lay.to_stored(n, sd[key]).to(flat.device))
+        eng.prep_conv_weights(target=self._target)
 
     def parameters(self):
         return list(self.state_dict().values())
@@ -76,7 +77,7 @@ class SAC(object):
     critic_mode = 0
     sample_mode = "crop"            # replay_buffer.sample() (sac.py:161)
 
-    def __init__(self, obs_shape, action_shape, args, device="cuda", dist=None, global_batch=None):
+    def __init__(self, obs_shape, action_shape, args, device="cuda", dist=None, global_batch=None, precision="tf32"):
         self.args = args
         self.obs_shape, self.action_shape = tuple(obs_shape), tuple(action_shape)
         self.discount = args.discount
@@ -85,7 +86,7 @@ class SAC(object):
         self.critic_target_update_freq = args.critic_target_update_freq
         self.batch_size = int(args.batch_size)
         self.engine = UpdateEngine(action_shape[0], args, self.batch_size, device=device, algorithm=self.algorithm,
-                                   dist=dist, global_batch=global_batch)
+                                   dist=dist, global_batch=global_batch, precision=precision)
         self.set_parameters(_init.init_params(action_shape[0], args))
         self.actor = _ModuleView(self, "actor")
         self.critic = _ModuleView(self, "critic")
@@ -106,6 +107,8 @@ class SAC(object):
             eng.target.copy_(eng.params[c0:c1])
         if "log_alpha" in canonical:
             eng.log_alpha.copy_(torch.as_tensor(canonical["log_alpha"], dtype=torch.float64).reshape(1))
+        eng.prep_conv_weights()
+        eng.prep_conv_weights(target=True)
 
     def get_parameters(self):
         eng = self.engine

@@ -1,0 +1,501 @@
+// tcgen05 / TMEM / TMA implicit-GEMM 3x3 convolution (32 -> 32 channels, stride 1, valid) for the SharedCNN layers
+// 2..11 (modules.py:144-146): forward and data-gradient.  TF32 operands, fp32 accumulation in TMEM.
+//
+// Formulation ("pitch-linear implicit GEMM"): activations are NHWC fp32, so one pixel = 32 channels = 128 B = one
+// SWIZZLE_128B row.  Number the output positions in INPUT pitch coordinates, q = (b*Hp + y)*Wp + x; then for filter
+// tap (ky,kx) the A-operand row of output q is input row q + ky*Wp + kx -- for a tile of 128 consecutive q the A tile of
+// each tap is 128 CONSECUTIVE input rows, i.e. one plain 2-D TMA box {32 ch, 128 rows}.  Positions with x >= Wp-2 or
+// y >= Hp-2 are computed and dropped in the epilogue (5-17 % of the rows).  K loop: 9 taps x 4 UMMA_K(=8) steps,
+// D[128 x 32] accumulates in 32 TMEM columns; two accumulator buffers overlap the epilogue with the next tile.
+// The data-gradient is the same kernel on a zero-bordered (pad 2) gradient buffer with flipped / transposed weights
+// and a ReLU-mask (plain or guided, rl_utils.py:35-39) epilogue writing into the interior of the next padded buffer.
+//
+// Warp roles (192 threads): warp 0 = TMA producer (one lane), warp 1 = TMEM allocator + MMA issuer (one lane),
+// warps 2..5 = epilogue (TMEM -> registers -> bias / ReLU / mask / TF32 round -> global).
+#include <cuda.h>
+#include <cstdio>
+#include "common.cuh"
+#include "../../include/sgqn_b200.h"
+
+namespace {
+
+constexpr int kStages = 6;
+constexpr int kTileM = 128;
+constexpr int kABytes = kTileM * 128;          // 16 KB per tap tile
+constexpr int kWBytes = 9 * 32 * 128;          // 36 KB: 9 taps x [32 n][32 k] fp32
+constexpr int kSmemBytes = kStages * kABytes + kWBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+
+struct TcParams {
+    int total_q;            // B * Hr * Wp virtual output positions (input-pitch coordinates)
+    int Hr, Wp;             // rows per sample and row pitch of the INPUT buffer
+    int Hv, Wv;             // valid output extent: positions with y < Hv and x < Wv are written
+    int shift;              // A row of tap (ky,kx) for position q = q + ky*Wp + kx + shift
+    int Hq, Wq, oy, ox;     // output buffer: rows per sample, pitch, offset of output (0,0)
+    int Hm, Wm;             // mask buffer: rows per sample, pitch (mask of output (y,x) at row y, col x)
+    int num_tiles;
+    const float* bias;
+    const float* mask;
+    float* out;
+    int relu_out, round_out, mask_mode;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+// bounded wait: a protocol bug must trap (sticky error, the host sees it) instead of hanging the GPU
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done = 0;
+    for (uint32_t it = 0; it < (1u << 26); ++it) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+        if (done) return;
+    }
+    printf("sgqn conv_tc: mbarrier timeout (block %d thread %d bar %u parity %u)\n", blockIdx.x, threadIdx.x, bar, parity);
+    __trap();
+}
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* tm, uint32_t bar, uint32_t dst, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(dst), "l"((unsigned long long)tm), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// K-major, SWIZZLE_128B operand tile: rows of 128 B, 8-row atoms 1024 B apart (cute::UMMA::SmemDescriptor, version 1)
+__device__ __forceinline__ uint64_t make_desc_sw128(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFF);            // start address
+    d |= (uint64_t)1 << 16;                            // leading byte offset (unused for swizzled K-major) = 1
+    d |= (uint64_t)(1024 >> 4) << 32;                  // stride byte offset between 8-row groups
+    d |= (uint64_t)1 << 46;                            // descriptor version (Blackwell)
+    d |= (uint64_t)2 << 61;                            // SWIZZLE_128B
+    return d;
+}
+// kind::tf32, D fp32, A/B TF32 K-major, M = 128, N = 32 (cute::UMMA::InstrDescriptor)
+constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((32u >> 3) << 17) | ((128u >> 4) << 24);
+
+__device__ __forceinline__ float round_tf32(float v) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+    return __uint_as_float(r);
+}
+
+__global__ void __launch_bounds__(192, 1)
+conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, TcParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t a_sm = base;
+    const uint32_t w_sm = base + kStages * kABytes;
+    const uint32_t bars = w_sm + kWBytes;                         // 8-byte mbarriers
+    const uint32_t full0 = bars, empty0 = bars + 8 * kStages, wbar = bars + 16 * kStages;
+    const uint32_t tfull0 = wbar + 8, tempty0 = tfull0 + 16;
+    const uint32_t tmem_slot = tempty0 + 16;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"((unsigned long long)&tmA) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"((unsigned long long)&tmW) : "memory");
+        for (int s = 0; s < kStages; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
+        mbar_init(wbar, 1);
+        for (int a = 0; a < 2; ++a) { mbar_init(tfull0 + 8 * a, 1); mbar_init(tempty0 + 8 * a, 128); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(64) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    uint32_t tmem_base;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+    if (warp == 0) {
+        if (lane == 0) {
+            mbar_expect_tx(wbar, kWBytes);
+            for (int t = 0; t < 9; ++t) tma_load_2d(&tmW, wbar, w_sm + t * 4096, t * 32, 0);
+            int stage = 0; uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+                const int q0 = tile * kTileM;
+                for (int t = 0; t < 9; ++t) {
+                    mbar_wait(empty0 + 8 * stage, phase ^ 1u);
+                    mbar_expect_tx(full0 + 8 * stage, kABytes);
+                    tma_load_2d(&tmA, full0 + 8 * stage, a_sm + stage * kABytes, 0, q0 + (t / 3) * p.Wp + (t % 3) + p.shift);
+                    if (++stage == kStages) { stage = 0; phase ^= 1u; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            mbar_wait(wbar, 0);
+            tc_fence_after();
+            int stage = 0; uint32_t phase = 0; int acc = 0; uint32_t acc_phase = 0;
+            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+                mbar_wait(tempty0 + 8 * acc, acc_phase ^ 1u);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * 32);
+                for (int t = 0; t < 9; ++t) {
+                    mbar_wait(full0 + 8 * stage, phase);
+                    tc_fence_after();
+                    const uint64_t ad = make_desc_sw128(a_sm + stage * kABytes);
+                    const uint64_t bd = make_desc_sw128(w_sm + t * 4096);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)          // advance 8 TF32 = 32 B inside the swizzle atom: +2 in the >>4 address field
+                        tc_mma_tf32(d_tmem, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), kIdesc, (t | k) != 0);
+                    tc_commit(empty0 + 8 * stage);       // smem slot free once these MMAs retire
+                    if (++stage == kStages) { stage = 0; phase ^= 1u; }
+                }
+                tc_commit(tfull0 + 8 * acc);             // accumulator complete -> epilogue
+                if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+            }
+        }
+    } else {
+        const int quarter = warp & 3;                    // TMEM lane quarter this warp may access
+        const int row = quarter * 32 + lane;
+        int acc = 0; uint32_t acc_phase = 0;
+        const int HW = p.Hr * p.Wp;
+        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+            mbar_wait(tfull0 + 8 * acc, acc_phase);
+            tc_fence_after();
+            uint32_t v[32];
+            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * 32);
+            asm volatile(
+                "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                  "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+                  "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+                  "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                : "r"(taddr) : "memory");
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            tc_fence_before();
+            mbar_arrive(tempty0 + 8 * acc);              // accumulator drained: MMA warp may reuse it
+            if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+
+            const int q = tile * kTileM + row;
+            if (q >= p.total_q) continue;
+            const int b = q / HW; const int r2 = q - b * HW; const int y = r2 / p.Wp; const int x = r2 - y * p.Wp;
+            if (y >= p.Hv || x >= p.Wv) continue;
+            float* dst = p.out + ((size_t)(b * p.Hq + y + p.oy) * p.Wq + x + p.ox) * 32;
+            const float4* mk = p.mask_mode ? reinterpret_cast<const float4*>(p.mask + ((size_t)(b * p.Hm + y) * p.Wm + x) * 32) : nullptr;
+#pragma unroll
+            for (int c4 = 0; c4 < 8; ++c4) {
+                float o[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    float f = __uint_as_float(v[4 * c4 + e]);
+                    if (p.bias) f += __ldg(p.bias + 4 * c4 + e);
+                    if (p.relu_out) f = fmaxf(f, 0.f);
+                    o[e] = f;
+                }
+                if (p.mask_mode) {
+                    const float4 m = __ldg(mk + c4);
+                    const float mm[4] = {m.x, m.y, m.z, m.w};
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        if (p.mask_mode == 2) o[e] = fmaxf(o[e], 0.f);
+                        o[e] = mm[e] > 0.f ? o[e] : 0.f;
+                    }
+                }
+                if (p.round_out) {
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) o[e] = round_tf32(o[e]);
+                }
+                reinterpret_cast<float4*>(dst)[c4] = make_float4(o[0], o[1], o[2], o[3]);
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(64) : "memory");
+    }
+}
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point lookup: libcuda is NOT a link dependency, so the
+// library still loads (and exports its symbols) on a CPU-only build box.
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)p;
+    }
+    return fn;
+}
+
+int make_map_2d(CUtensorMap* tm, const float* ptr, uint64_t cols, uint64_t rows, uint32_t box_cols, uint32_t box_rows,
+                CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
+    EncodeTiledFn cuTensorMapEncodeTiled = get_encode_fn();
+    if (!cuTensorMapEncodeTiled) return (int)cudaErrorNotSupported;
+    cuuint64_t dims[2] = {cols, rows};
+    cuuint64_t strides[1] = {cols * sizeof(float)};
+    cuuint32_t box[2] = {box_cols, box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = cuTensorMapEncodeTiled(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)ptr, dims, strides, box, estr,
+                                        CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
+                                        CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? 0 : 900 + (int)r;
+}
+
+}  // namespace
+
+// x: [B][Hr][Wp][32]; w: [32 n][9 taps][32 k] (TF32-rounded copy).  Output (b,y,x), y < Hv, x < Wv, is the 3x3 window sum
+// over input rows q + ky*Wp + kx + shift (q = (b*Hr + y)*Wp + x) and goes to out[((b*Hq + y+oy)*Wq + x+ox)*32].
+// flags: bit0 ReLU on the output, bit1 round the output to TF32 (it feeds another TF32 conv), bits 2-3 mask mode
+// (1 plain ReLU backward, 2 guided) with the mask of (b,y,x) at mask[((b*Hm + y)*Wm + x)*32].
+extern "C" int sgqn_conv_tc(const float* x, const float* w, const float* bias, const float* mask, float* out, int B, int Hr,
+                            int Wp, int Hv, int Wv, int shift, int Hq, int Wq, int oy, int ox, int Hm, int Wm, int flags,
+                            void* stream) {
+    if (B <= 0) return 0;
+    static int smem_set = 0;
+    static int num_sms = 0;
+    if (!smem_set) {
+        cudaError_t e = cudaFuncSetAttribute(conv3x3_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+        if (e != cudaSuccess) return (int)e;
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+        smem_set = 1;
+    }
+    TcParams p;
+    p.total_q = B * Hr * Wp; p.Hr = Hr; p.Wp = Wp; p.Hv = Hv; p.Wv = Wv; p.shift = shift;
+    p.Hq = Hq; p.Wq = Wq; p.oy = oy; p.ox = ox; p.Hm = Hm; p.Wm = Wm;
+    p.num_tiles = (p.total_q + kTileM - 1) / kTileM;
+    p.bias = bias; p.mask = mask; p.out = out;
+    p.relu_out = flags & 1; p.round_out = (flags >> 1) & 1; p.mask_mode = (flags >> 2) & 3;
+    if (p.mask_mode && !mask) return (int)cudaErrorInvalidValue;
+    CUtensorMap tmA, tmW;
+    int rc = make_map_2d(&tmA, x, 32, (uint64_t)p.total_q, 32, kTileM);
+    if (rc) return rc;
+    rc = make_map_2d(&tmW, w, 288, 32, 32, 32);
+    if (rc) return rc;
+    int grid = p.num_tiles < num_sms ? p.num_tiles : num_sms;
+    conv3x3_tc_kernel<<<grid, 192, kSmemBytes, (cudaStream_t)stream>>>(tmA, tmW, p);
+    return SGQN_CHECK_LAUNCH();
+}
+
+// TF32-rounded operand copies of the 32->32 conv weights, refreshed after every optimiser step that touches them:
+// wf[l][n=co][t][k=ci] = rna(w[l][co][t][ci]) (forward), wd[l][n=ci][t][k=co] = rna(w[l][co][8-t][ci]) (data gradient:
+// flipped taps, transposed channels).  `lstride` = distance between consecutive layers' weights in `w` (floats).
+__global__ void conv_weights_prep_kernel(const float* __restrict__ w, long long lstride, float* __restrict__ wf,
+                                         float* __restrict__ wd, int n_layers) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_layers * 9216) return;
+    int l = i / 9216, r = i - l * 9216;
+    int co = r / 288, t = (r / 32) % 9, ci = r & 31;
+    float v = round_tf32(w[(size_t)l * lstride + r]);
+    wf[i] = v;
+    wd[(size_t)l * 9216 + ci * 288 + (8 - t) * 32 + co] = v;
+}
+extern "C" int sgqn_conv_weights_prep(const float* w, long long lstride, float* wf, float* wd, int n_layers, void* stream) {
+    int n = n_layers * 9216;
+    if (n <= 0) return 0;
+    conv_weights_prep_kernel<<<cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>(w, lstride, wf, wd, n_layers);
+    return SGQN_CHECK_LAUNCH();
+}
+
+// compact [B][H][W][C] -> rows [oy, oy+H), cols [ox, ox+W) of a zero-initialised [B][Hq][Wq][C] buffer
+__global__ void pad_copy_kernel(const float4* __restrict__ src, float4* __restrict__ dst, int H, int W, int C4, int Hq, int Wq,
+                                int oy, int ox, int round_out, long long total) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    int c = (int)(i % C4); long long t = i / C4;
+    int x = (int)(t % W); t /= W; int y = (int)(t % H); int b = (int)(t / H);
+    float4 v = __ldg(src + i);
+    if (round_out) { v.x = round_tf32(v.x); v.y = round_tf32(v.y); v.z = round_tf32(v.z); v.w = round_tf32(v.w); }
+    dst[(((size_t)b * Hq + y + oy) * Wq + x + ox) * C4 + c] = v;
+}
+extern "C" int sgqn_pad_copy(const float* src, float* dst, int B, int H, int W, int C, int Hq, int Wq, int oy, int ox,
+                             int round_out, void* stream) {
+    if (C & 3) return (int)cudaErrorInvalidValue;
+    long long total = (long long)B * H * W * (C / 4);
+    if (total <= 0) return 0;
+    pad_copy_kernel<<<(unsigned)cdivll(total, 256), 256, 0, (cudaStream_t)stream>>>((const float4*)src, (float4*)dst, H, W,
+                                                                                   C / 4, Hq, Wq, oy, ox, round_out, total);
+    return SGQN_CHECK_LAUNCH();
+}
+
+// =====================================================================================================================
+// Weight gradient of the 32->32 convs on tcgen05:  dW[co][tap][ci] += sum_q dY[q][co] * X[q + (ky-2)*Wp + kx][ci].
+// X (post-ReLU activations of the previous layer) and dY (zero-bordered gradient of this layer's output) share one
+// pitch-linear geometry [B][Hr][Wp][32], so every tap's operand for a block of 64 consecutive q is again one 2-D TMA box.
+// GEMM view: D[M = (tap, ci)][N = co] with the reduction over pixels: both operands are "MN-major" (the pixel index runs
+// over the 128-byte rows of the SWIZZLE_128B tile, channels are contiguous), UMMA_K = 8 pixels = two 512-byte swizzle
+// atoms (SWIZZLE_128B_BASE32B, the only MN-major layout for TF32).  M = 128 packs 4 taps (4 atoms LBO = one tile apart); 9 taps = 3 accumulators of 32 TMEM columns (the third one
+// computes 3 unused row groups).  Each CTA reduces a contiguous range of pixel blocks in TMEM and adds its 9216 partial
+// sums to dW with red.global.add.f32 once at the end.
+namespace {
+
+constexpr int kWgRows = 64;
+constexpr int kWgTile = kWgRows * 128;                 // 8 KB
+constexpr int kWgStageBytes = 10 * kWgTile;            // 9 X tap tiles + 1 dY tile
+constexpr int kWgStages = 2;
+constexpr int kWgSmem = kWgStages * kWgStageBytes + 2 * kWgTile /*overrun of the 3rd accumulator's unused atoms*/ + 1024 + 256;
+constexpr uint32_t kIdescMN = kIdesc | (1u << 15) | (1u << 16);      // A and B MN-major
+
+// MN-major TF32 operands only exist in the SWIZZLE_128B_BASE32B layout (cute::UMMA::Layout_MN_SW128_32B_Atom: rows of
+// 128 B = 32 channels, 32-byte chunks XOR-ed with row % 4, K atom = 4 rows = 512 B); TMA writes it with
+// CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B.
+__device__ __forceinline__ uint64_t make_desc_mn_sw128(uint32_t saddr, uint32_t lbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;   // stride between 32-channel atoms along M / N
+    d |= (uint64_t)(512 >> 4) << 32;                    // stride between 4-pixel atoms along K
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)1 << 61;                             // SWIZZLE_128B_BASE32B
+    return d;
+}
+
+struct WgParams { int total_q, Wp, kb_total, kb_per_cta; float* dw; };
+
+__global__ void __launch_bounds__(192, 1)
+conv3x3_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmD, WgParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t bars = base + kWgStages * kWgStageBytes + 2 * kWgTile;
+    const uint32_t full0 = bars, empty0 = bars + 8 * kWgStages, done_bar = bars + 16 * kWgStages, tmem_slot = done_bar + 8;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int kb0 = blockIdx.x * p.kb_per_cta;
+    const int kb1 = min(p.kb_total, kb0 + p.kb_per_cta);
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"((unsigned long long)&tmX) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"((unsigned long long)&tmD) : "memory");
+        for (int s = 0; s < kWgStages; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
+        mbar_init(done_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(128) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    uint32_t tmem_base;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            for (int kb = kb0; kb < kb1; ++kb) {
+                const int q0 = kb * kWgRows;
+                const uint32_t sb = base + stage * kWgStageBytes;
+                mbar_wait(empty0 + 8 * stage, phase ^ 1u);
+                mbar_expect_tx(full0 + 8 * stage, kWgStageBytes);
+                for (int t = 0; t < 9; ++t)
+                    tma_load_2d(&tmX, full0 + 8 * stage, sb + t * kWgTile, 0, q0 + (t / 3 - 2) * p.Wp + (t % 3));
+                tma_load_2d(&tmD, full0 + 8 * stage, sb + 9 * kWgTile, 0, q0);
+                if (++stage == kWgStages) { stage = 0; phase ^= 1u; }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            for (int kb = kb0; kb < kb1; ++kb) {
+                const uint32_t sb = base + stage * kWgStageBytes;
+                mbar_wait(full0 + 8 * stage, phase);
+                tc_fence_after();
+#pragma unroll 1
+                for (int j = 0; j < kWgRows / 8; ++j) {
+                    const uint64_t bd = make_desc_mn_sw128(sb + 9 * kWgTile + j * 1024, kWgTile);
+#pragma unroll
+                    for (int g = 0; g < 3; ++g) {
+                        const uint64_t ad = make_desc_mn_sw128(sb + g * 4 * kWgTile + j * 1024, kWgTile);
+                        tc_mma_tf32(tmem_base + (uint32_t)(g * 32), ad, bd, kIdescMN, (kb != kb0 || j != 0) ? 1u : 0u);
+                    }
+                }
+                tc_commit(empty0 + 8 * stage);
+                if (++stage == kWgStages) { stage = 0; phase ^= 1u; }
+            }
+            tc_commit(done_bar);
+        }
+    } else if (kb1 > kb0) {
+        const int quarter = warp & 3;
+        mbar_wait(done_bar, 0);
+        tc_fence_after();
+        for (int g = 0; g < 3; ++g) {
+            uint32_t v[32];
+            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(g * 32);
+            asm volatile(
+                "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                  "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+                  "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+                  "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                : "r"(taddr) : "memory");
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            const int tap = g * 4 + quarter;               // accumulator row m = (tap - 4g)*32 + ci, ci = lane
+            if (tap < 9) {
+                float* dst = p.dw + tap * 32 + lane;
+#pragma unroll
+                for (int co = 0; co < 32; ++co) atomicAdd(dst + co * 288, __uint_as_float(v[co]));
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(128) : "memory");
+    }
+}
+
+}  // namespace
+
+// x, dy: [B][Hr][Wp][32] (same geometry; dy zero outside its valid region, x finite everywhere);
+// dw[32 co][9][32 ci] += sum_q dy[q][co] * x[q + (ky-2)*Wp + kx][ci]   (atomic; caller zero-fills)
+extern "C" int sgqn_conv_wgrad_tc(const float* x, const float* dy, float* dw, int B, int Hr, int Wp, void* stream) {
+    if (B <= 0) return 0;
+    static int inited = 0, num_sms = 0;
+    if (!inited) {
+        cudaError_t e = cudaFuncSetAttribute(conv3x3_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWgSmem);
+        if (e != cudaSuccess) return (int)e;
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+        inited = 1;
+    }
+    WgParams p;
+    p.total_q = B * Hr * Wp; p.Wp = Wp; p.dw = dw;
+    p.kb_total = (p.total_q + kWgRows - 1) / kWgRows;
+    int grid = p.kb_total < num_sms ? p.kb_total : num_sms;
+    p.kb_per_cta = (p.kb_total + grid - 1) / grid;
+    grid = (p.kb_total + p.kb_per_cta - 1) / p.kb_per_cta;
+    CUtensorMap tmX, tmD;
+    int rc = make_map_2d(&tmX, x, 32, (uint64_t)p.total_q, 32, kWgRows, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+    if (rc) return rc;
+    rc = make_map_2d(&tmD, dy, 32, (uint64_t)p.total_q, 32, kWgRows, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+    if (rc) return rc;
+    conv3x3_wgrad_tc_kernel<<<grid, 192, kWgSmem, (cudaStream_t)stream>>>(tmX, tmD, p);
+    return SGQN_CHECK_LAUNCH();
+}

@@ -50,7 +50,7 @@ extern "C" int sgqn_linear_fwd(const float* x, int ldx, long long xbs, const flo
                                int batch, int splitk, void* stream) {
     RowMajorC a{x, ldx, xbs, relu_in, aligned16(x) && (ldx % 4 == 0) && (xbs % 4 == 0)};
     RowMajorC b{w, K, wbs, 0, aligned16(w) && (K % 4 == 0) && (wbs % 4 == 0)};
-    EpStore ep{y, ldy, ybs, bias, bbs, nullptr, 0, 0, 0, splitk ? 1 : 0, 1.0f};
+    EpStore ep{y, ldy, ybs, bias, bbs, nullptr, 0, 0, 0, splitk ? 1 : 0, 1.0f, 0, 0, 0};
     return launch_gemm<64, 64, 16, 4, 4>(a, b, ep, M, N, K, batch, splitk ? 64 : 1, (cudaStream_t)stream);
 }
 
@@ -60,7 +60,7 @@ extern "C" int sgqn_linear_dgrad(const float* dy, int lddy, long long dybs, cons
     // dx[M,K] = dy[M,N] * W[N,K]   (contraction over the N output features)
     RowMajorC a{dy, lddy, dybs, 0, aligned16(dy) && (lddy % 4 == 0) && (dybs % 4 == 0)};
     ColMajorR b{w, K, wbs, 0, aligned16(w) && (K % 4 == 0) && (wbs % 4 == 0)};
-    EpStore ep{dx, lddx, dxbs, nullptr, 0, zmask, ldm, mbs, mode, accumulate ? 1 : 0, 1.0f};
+    EpStore ep{dx, lddx, dxbs, nullptr, 0, zmask, ldm, mbs, mode, accumulate ? 1 : 0, 1.0f, 0, 0, 0};
     return launch_gemm<64, 64, 16, 4, 4>(a, b, ep, M, K, N, batch, 1, (cudaStream_t)stream);
 }
 
@@ -70,7 +70,7 @@ extern "C" int sgqn_linear_wgrad(const float* x, int ldx, long long xbs, const f
     // dw[N,K] += dy^T[N,M] * act(x)[M,K] ; db[N] += colsum(dy)
     ColMajorR a{dy, lddy, dybs, 0, aligned16(dy) && (lddy % 4 == 0) && (dybs % 4 == 0)};
     ColMajorR b{x, ldx, xbs, relu_in, aligned16(x) && (ldx % 4 == 0) && (xbs % 4 == 0)};
-    EpStore ep{dw, K, dwbs, nullptr, 0, nullptr, 0, 0, 0, 1, 1.0f};
+    EpStore ep{dw, K, dwbs, nullptr, 0, nullptr, 0, 0, 0, 1, 1.0f, 0, 0, 0};
     int rc = launch_gemm<64, 64, 16, 4, 4>(a, b, ep, N, K, M, batch, 64, (cudaStream_t)stream);
     if (rc) return rc;
     if (db)
@@ -83,13 +83,13 @@ extern "C" int sgqn_linear_wgrad(const float* x, int ldx, long long xbs, const f
 
 // ---------------------------------------------------------------- 3x3 conv, NHWC, weights [Cout][9][Cin]
 extern "C" int sgqn_conv_fwd(const float* x, const float* w, const float* bias, float* y, int B, int Hs, int Ws, int Cin,
-                             int Cout, int pad, int up, int relu_in, void* stream) {
+                             int Cout, int pad, int up, int relu_in, int flags, void* stream) {
     if ((Cin & 3) || (Cout & 3) || (up != 1 && up != 2)) return (int)cudaErrorInvalidValue;
     int Ho = Hs * up + 2 * pad - 2, Wo = Ws * up + 2 * pad - 2;
     ConvGeom g{Hs, Ws, up, Ho, Wo, 1, pad, 0, Cin};
     ConvPixC a{x, g, relu_in};
     RowMajorC b{w, 9 * Cin, 0, 0, aligned16(w)};
-    EpStore ep{y, Cout, 0, bias, 0, nullptr, 0, 0, 0, 0, 1.0f};
+    EpStore ep{y, Cout, 0, bias, 0, nullptr, 0, 0, 0, 0, 1.0f, flags & 3, 0, 0};
     int M = B * Ho * Wo, K = 9 * Cin;
     cudaStream_t st = (cudaStream_t)stream;
     if (Cout <= 16) return launch_gemm<128, 16, 32, 4, 4>(a, b, ep, M, Cout, K, 1, 1, st);
@@ -106,7 +106,7 @@ extern "C" int sgqn_conv_dgrad(const float* dy, const float* w, const float* mas
     ConvGeom g{Ho, Wo, 1, Hl, Wl, 1, pad, 1, Cout};
     ConvPixC a{dy, g, 0};
     ConvWdgradR b{w, Cin, Cout};
-    EpStore ep{dx, Cin, 0, nullptr, 0, mask, Cin, 0, mode, 0, 1.0f};
+    EpStore ep{dx, Cin, 0, nullptr, 0, mask, Cin, 0, mode, 0, 1.0f, 0, 0, 0};
     int M = B * Hl * Wl, K = 9 * Cout;
     cudaStream_t st = (cudaStream_t)stream;
     if (Cin <= 32) return launch_gemm<128, 32, 32, 8, 4>(a, b, ep, M, Cin, K, 1, 1, st);
@@ -114,17 +114,24 @@ extern "C" int sgqn_conv_dgrad(const float* dy, const float* w, const float* mas
 }
 
 extern "C" int sgqn_conv_wgrad(const float* x, const float* dy, float* dw, float* db, int B, int Hs, int Ws, int Cin,
-                               int Cout, int pad, int up, int relu_in, void* stream) {
+                               int Cout, int pad, int up, int relu_in, int dy_border, void* stream) {
     // dw[Cout][9][Cin] += sum_pix dy[pix][co] * act(x)[src(pix,tap)][ci] ; db[Cout] += sum_pix dy
     if ((Cin & 3) || (Cout & 3)) return (int)cudaErrorInvalidValue;
     int Ho = Hs * up + 2 * pad - 2, Wo = Ws * up + 2 * pad - 2;
     ConvGeom g{Hs, Ws, up, Ho, Wo, 1, pad, 0, Cin};
     int P = B * Ho * Wo;
-    ColMajorR a{dy, Cout, 0, 0, aligned16(dy)};
     ConvPixR b{x, g, relu_in};
-    EpStore ep{dw, 9 * Cin, 0, nullptr, 0, nullptr, 0, 0, 0, 1, 1.0f};
+    EpStore ep{dw, 9 * Cin, 0, nullptr, 0, nullptr, 0, 0, 0, 1, 1.0f, 0, 0, 0};
     cudaStream_t st = (cudaStream_t)stream;
     int rc;
+    if (dy_border > 0) {          // dy stored [B][Ho+2b][Wo+2b][Cout] with a zero border (tcgen05 dgrad layout)
+        PixRowsR a{dy, Cout, Ho, Wo, Ho + 2 * dy_border, Wo + 2 * dy_border, dy_border};
+        if (Cout <= 32) rc = launch_gemm<32, 64, 16, 4, 4>(a, b, ep, Cout, 9 * Cin, P, 1, 4096, st);
+        else rc = launch_gemm<64, 64, 16, 4, 4>(a, b, ep, Cout, 9 * Cin, P, 1, 4096, st);
+        if (rc) return rc;      // the border is zero, so the bias gradient may sum every stored row
+        return db ? launch_colsum(dy, Cout, B * (Ho + 2 * dy_border) * (Wo + 2 * dy_border), Cout, db, st) : 0;
+    }
+    ColMajorR a{dy, Cout, 0, 0, aligned16(dy)};
     if (Cout <= 32) rc = launch_gemm<32, 64, 16, 4, 4>(a, b, ep, Cout, 9 * Cin, P, 1, 4096, st);
     else rc = launch_gemm<64, 64, 16, 4, 4>(a, b, ep, Cout, 9 * Cin, P, 1, 4096, st);
     if (rc) return rc;
@@ -133,12 +140,12 @@ extern "C" int sgqn_conv_wgrad(const float* x, const float* dy, float* dw, float
 
 // ---------------------------------------------------------------- first encoder conv (modules.py:142): NCHW obs, 9 -> 32, stride 2
 extern "C" int sgqn_conv1_fwd(const float* obs, const float* w, const float* bias, float* y, int B, int Hin, int Cin,
-                              int Cout, void* stream) {
+                              int Cout, int flags, void* stream) {
     int crop = (Hin - 84) / 2;                               // CenterCrop(84), modules.py:70-83
     int Ho = (84 - 3) / 2 + 1;
     Conv1ObsC a{{obs, Hin, Ho, crop, Cin}};
     RowMajorC b{w, 9 * Cin, 0, 0, 0};
-    EpStore ep{y, Cout, 0, bias, 0, nullptr, 0, 0, 0, 0, 1.0f};
+    EpStore ep{y, Cout, 0, bias, 0, nullptr, 0, 0, 0, 0, 1.0f, flags & 3, (flags & 4) ? Ho * Ho : 0, 2 * Ho};
     return launch_gemm<128, 32, 16, 8, 4>(a, b, ep, B * Ho * Ho, Cout, 9 * Cin, 1, 1, (cudaStream_t)stream);
 }
 
@@ -147,7 +154,7 @@ extern "C" int sgqn_conv1_wgrad(const float* obs, const float* dy, float* dw, fl
     int crop = (Hin - 84) / 2, Ho = 41, P = B * Ho * Ho;
     ColMajorR a{dy, Cout, 0, 0, aligned16(dy) && (Cout % 4 == 0)};
     Conv1ObsR b{{obs, Hin, Ho, crop, Cin}};
-    EpStore ep{dw, 9 * Cin, 0, nullptr, 0, nullptr, 0, 0, 0, 1, 1.0f};
+    EpStore ep{dw, 9 * Cin, 0, nullptr, 0, nullptr, 0, 0, 0, 1, 1.0f, 0, 0, 0};
     cudaStream_t st = (cudaStream_t)stream;
     int rc = launch_gemm<32, 64, 16, 4, 4>(a, b, ep, Cout, 9 * Cin, P, 1, 4096, st);
     if (rc) return rc;

@@ -53,6 +53,24 @@ struct ColMajorR {            // element (row,c) at ptr[c*ld + row]
     }
 };
 
+// element (row = channel, c = compact pixel of [B][Ho][Wo]) of a pixel-major tensor stored with its own pitch:
+// ptr[((b*Hq + y + off)*Wq + x + off)*C + row]   (conv wgrad A operand when dY lives in a zero-bordered buffer)
+struct PixRowsR {
+    static constexpr bool kRowContig = true;
+    const float* ptr; int C, Ho, Wo, Hq, Wq, off;
+    __device__ __forceinline__ float4 fetch4(int row, int c, int rows, int cend, int) const {
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (row >= rows || c >= cend) return v;
+        int x = c % Wo; int t = c / Wo; int y = t % Ho; int b = t / Ho;
+        const float* p = ptr + ((size_t)(b * Hq + y + off) * Wq + x + off) * C + row;
+        if (row + 3 < rows) return __ldg(reinterpret_cast<const float4*>(p));
+        v.x = __ldg(p);
+        if (row + 1 < rows) v.y = __ldg(p + 1);
+        if (row + 2 < rows) v.z = __ldg(p + 2);
+        return v;
+    }
+};
+
 // ------------------------------------------------------------------ 3x3 conv geometry (NHWC, C % 4 == 0)
 struct ConvGeom {
     int Hs, Ws;      // stored source tensor [B][Hs][Ws][C]
@@ -177,6 +195,13 @@ struct EpStore {
     int mode;        // 0 none, 1 v *= (mask > 0), 2 guided: v = (mask > 0) ? max(v, 0) : 0
     int atomic;      // 1: atomicAdd into C (caller zero-fills / accumulates)
     float scale;
+    int post;        // bit0: ReLU on the output, bit1: round the output to TF32 (it feeds a tcgen05 TF32 conv)
+    int grp, gpad;   // grp > 0: output row r is stored at row r + (r / grp) * gpad (extra rows per sample in C)
+    __device__ __forceinline__ float finish(float v) const {
+        if (post & 1) v = fmaxf(v, 0.f);
+        if (post & 2) { uint32_t r; asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v)); v = __uint_as_float(r); }
+        return v;
+    }
     template <int TM, int TN>
     __device__ __forceinline__ void store(float (&acc)[TM][TN], int i, int j, int M, int N, int batch, int split) const {
         float* Cb = C + (size_t)batch * bstride;
@@ -188,10 +213,11 @@ struct EpStore {
         for (int m = 0; m < TM; ++m) {
             int row = i + m;
             if (row >= M) break;
+            if (grp > 0) row += (row / grp) * gpad;
             if (vec) {
                 float v[4];
 #pragma unroll
-                for (int n = 0; n < 4; ++n) v[n] = acc[m][n] + (bb ? __ldg(bb + j + n) : 0.f);
+                for (int n = 0; n < 4; ++n) v[n] = finish(acc[m][n] + (bb ? __ldg(bb + j + n) : 0.f));
                 if (mode) {
                     float4 mk = __ldg(reinterpret_cast<const float4*>(mb + (size_t)row * ldm + j));
                     float mm[4] = {mk.x, mk.y, mk.z, mk.w};
@@ -211,6 +237,7 @@ struct EpStore {
                 if (col >= N) continue;
                 float v = acc[m][n];
                 if (bb) v += __ldg(bb + col);
+                v = finish(v);
                 if (mode) {
                     float mk = __ldg(mb + (size_t)row * ldm + col);
                     if (mode == 2) v = fmaxf(v, 0.f);

@@ -35,7 +35,13 @@ class _Opt:
 class UpdateEngine:
     LOG_KEYS = ("train_critic/loss", "train_actor/loss", "train_alpha/loss", "train_alpha/value", "train/aux_loss")
 
-    def __init__(self, action_dim, args, batch_size, device="cuda", algorithm="sgsac", dist=None, global_batch=None):
+    def __init__(self, action_dim, args, batch_size, device="cuda", algorithm="sgsac", dist=None, global_batch=None,
+                 precision="tf32"):
+        # precision: "tf32" = tcgen05 TF32 tensor-core convs for SharedCNN layers 2..11 (the product path; the reference
+        # runs cuDNN with allow_tf32=True); "fp32" = the same schedule on the fp32 CUDA-core conv kernels (used by the
+        # parity tests to check the schedule to 1e-3 without TF32 rounding / ReLU sign flips in the way).
+        assert precision in ("tf32", "fp32")
+        self.precision = precision
         if not torch.cuda.is_available():
             raise RuntimeError("sgqn-carla_b200 needs a CUDA device (B200, sm_100a); there is no CPU path")
         self.dev = torch.device(device)
@@ -67,9 +73,15 @@ class UpdateEngine:
         self.obs2 = f32(R, 9, 84, 84)                   # [obs ; masked_obs / overlay-augmented obs]
         self.next_obs = f32(B, 9, 84, 84)
         self.action = f32(B, A); self.reward = f32(B, 1); self.not_done = f32(B, 1)
-        self.actS = [f32(R * h * h * 32) for h in ENC_H]       # critic slot activations (pre-ReLU, NHWC)
-        self.actT = [f32(B * h * h * 32) for h in ENC_H]       # transient slot
+        # activations: NHWC, post-ReLU; layers 0..9 carry 2 spare zero rows per sample ([n][h+2][h][32], tcgen05 path)
+        self.actS = [f32(R * (h + 2) * h * 32) for h in ENC_H]  # critic slot
+        self.actT = [f32(B * (h + 2) * h * 32) for h in ENC_H]  # transient slot
         self.dbuf = [f32(R * 41 * 41 * 32), f32(R * 41 * 41 * 32)]
+        # tcgen05 conv path (conv_tc.cu): TF32-rounded operand copies of the 32->32 conv weights (forward; flipped +
+        # transposed for the data gradient; forward copy of the target net) and one zero-bordered (pad 2) gradient
+        # buffer per layer -- borders are written once here (zeros) and never again.
+        self.wf, self.wd, self.wf_t, self.wd_t = f32(10 * 9216), f32(10 * 9216), f32(10 * 9216), f32(10 * 9216)
+        self.gpad = [None] + [f32(R * (h + 4) * (h + 2) * 32) for h in ENC_H[1:]]    # d(act_l): [n][h+4][h+2][32]
         P1 = L.P + A
         self.zS, self.haS, self.dzS, self.dhaS = f32(R, L.P), f32(R, P1), f32(R, L.P), f32(R, P1)
         self.zT, self.haT, self.dzT, self.dhaT = f32(B, L.P), f32(B, P1), f32(B, L.P), f32(B, P1)
@@ -124,12 +136,36 @@ class UpdateEngine:
     def enc_fwd(self, x_ptr, n, acts, row0=0, target=False, hin=84):
         """SharedCNN forward (modules.py:132-152): x (n,9,hin,hin) fp32 NCHW -> acts[0..10] rows [row0, row0+n)."""
         W = self.T if target else self.P
+        wf = self.wf_t if target else self.wf
         st = self.st
-        K.conv1_fwd(x_ptr, W("cnn.0.weight"), W("cnn.0.bias"), _ptr(acts[0], row0 * 41 * 41 * 32), n, hin, 9, 32, st)
-        for l in range(1, 11):
+        # activations are stored AFTER the ReLU that follows each conv (the last conv has none) and rounded to TF32,
+        # the operand format of the next layer's tcgen05 MMA; 1[x>0] for the backward is 1[relu(x)>0].
+        tc = self.precision == "tf32"
+        if tc:
+            # pitch-linear layout [n][h+2][h][32]: the 2 spare rows per sample stay zero (never written) so that the
+            # weight-gradient kernel can pair activations and the zero-bordered output gradient row by row
+            K.conv1_fwd(x_ptr, W("cnn.0.weight"), W("cnn.0.bias"), _ptr(acts[0], row0 * 43 * 41 * 32), n, hin, 9, 32, 7, st)
+            for l in range(1, 11):
+                hi, ho = ENC_H[l - 1], ENC_H[l]
+                last = l == 10                                  # the feature map that feeds the projection is compact
+                K.conv_tc(_ptr(acts[l - 1], row0 * (hi + 2) * hi * 32), _ptr(wf, (l - 1) * 9216), W(f"cnn.{l}.bias"), 0,
+                          _ptr(acts[l], row0 * (ho * ho if last else (ho + 2) * ho) * 32), n, hi + 2, hi, ho, ho, 0,
+                          ho if last else ho + 2, ho, 0, 0, 0, 0, 0 if last else 3, st)
+            return
+        K.conv1_fwd(x_ptr, W("cnn.0.weight"), W("cnn.0.bias"), _ptr(acts[0], row0 * 41 * 41 * 32), n, hin, 9, 32, 1, st)
+        for l in range(1, 11):                                  # fp32 CUDA-core path, compact [n][h][h][32] layout
             hi, ho = ENC_H[l - 1], ENC_H[l]
             K.conv_fwd(_ptr(acts[l - 1], row0 * hi * hi * 32), W(f"cnn.{l}.weight"), W(f"cnn.{l}.bias"),
-                       _ptr(acts[l], row0 * ho * ho * 32), n, hi, hi, 32, 32, 0, 1, 1, st)
+                       _ptr(acts[l], row0 * ho * ho * 32), n, hi, hi, 32, 32, 0, 1, 0, 1 if l < 10 else 0, st)
+
+    def prep_conv_weights(self, target=False):
+        """Refresh the TF32 operand copies after the 32->32 conv weights changed (optimiser step / EMA / load)."""
+        L = self.lay
+        ls = L.off("cnn.2.weight") - L.off("cnn.1.weight")
+        if target:
+            K.conv_weights_prep(self.T("cnn.1.weight"), ls, _ptr(self.wf_t), _ptr(self.wd_t), 10, self.st)
+        else:
+            K.conv_weights_prep(self.P("cnn.1.weight"), ls, _ptr(self.wf), _ptr(self.wd), 10, self.st)
 
     def proj_fwd(self, feat_ptr, n, pre, z, h, ldh, target=False):
         """RLProjection (modules.py:102-113): Linear(14112->100) (split-K) -> LayerNorm -> tanh, h row stride ldh."""
@@ -186,15 +222,36 @@ class UpdateEngine:
         """Backward through SharedCNN.  dfeat: (n,21,21,32).  mode 1: plain ReLU backward (+ wgrad into the grad
         arena); mode 2: guided backprop to the observation (rl_utils.py:35-39)."""
         st = self.st
-        d = dfeat
-        for l in range(10, 0, -1):
-            hi = ENC_H[l - 1]
-            a_in = _ptr(acts[l - 1], row0 * hi * hi * 32)
+        if self.precision != "tf32":
+            d = dfeat
+            for l in range(10, 0, -1):
+                hi = ENC_H[l - 1]
+                a_in = _ptr(acts[l - 1], row0 * hi * hi * 32)
+                if wgrad:
+                    K.conv_wgrad(a_in, d, self.G(f"cnn.{l}.weight"), self.G(f"cnn.{l}.bias"), n, hi, hi, 32, 32, 0, 1, 0, 0, st)
+                dx = _ptr(self.dbuf[l & 1])
+                K.conv_dgrad(d, self.P(f"cnn.{l}.weight"), a_in, dx, n, hi, hi, 32, 32, 0, mode, st)
+                d = dx
             if wgrad:
-                K.conv_wgrad(a_in, d, self.G(f"cnn.{l}.weight"), self.G(f"cnn.{l}.bias"), n, hi, hi, 32, 32, 0, 1, 1, st)
-            dx = _ptr(self.dbuf[l & 1])
-            K.conv_dgrad(d, self.P(f"cnn.{l}.weight"), a_in, dx, n, hi, hi, 32, 32, 0, mode, st)
-            d = dx
+                K.conv1_wgrad(x_ptr, d, self.G("cnn.0.weight"), self.G("cnn.0.bias"), n, 84, 9, 32, st)
+            if dobs:
+                K.conv1_dgrad(d, self.P("cnn.0.weight"), dobs, n, 9, 32, st)
+            return
+        K.pad_copy(dfeat, _ptr(self.gpad[10]), n, 21, 21, 32, 25, 23, 2, 0, 1, st)
+        for l in range(10, 0, -1):
+            hi, ho = ENC_H[l - 1], ENC_H[l]
+            a_in = _ptr(acts[l - 1], row0 * (hi + 2) * hi * 32)     # [n][hi+2][hi][32], post-ReLU
+            d = _ptr(self.gpad[l])                                  # d(act_l): [n][ho+4][ho+2][32] == [n][hi+2][hi][32]
+            if wgrad:
+                K.conv_wgrad_tc(a_in, d, self.G(f"cnn.{l}.weight"), n, hi + 2, hi, st)
+                K.colsum(d, 32, n * (hi + 2) * hi, 32, self.G(f"cnn.{l}.bias"), st)
+            if l > 1:
+                K.conv_tc(d, _ptr(self.wd, (l - 1) * 9216), 0, a_in, _ptr(self.gpad[l - 1]), n, ho + 4, ho + 2, hi, hi, -2,
+                          hi + 4, hi + 2, 2, 0, hi + 2, hi, 2 | (mode << 2), st)
+            else:                                       # d(act_0) compact: consumed by the CUDA-core first-conv kernels
+                K.conv_tc(d, _ptr(self.wd), 0, a_in, _ptr(self.dbuf[0]), n, ho + 4, ho + 2, hi, hi, -2,
+                          hi, hi, 0, 0, hi + 2, hi, mode << 2, st)
+        d = _ptr(self.dbuf[0])
         if wgrad:
             K.conv1_wgrad(x_ptr, d, self.G("cnn.0.weight"), self.G("cnn.0.bias"), n, 84, 9, 32, st)
         if dobs:
@@ -304,6 +361,9 @@ class UpdateEngine:
         q0, q1 = L.ranges["critic_q"]
         self.adam(self.opt_critic, (c0, c1), target=self._t if with_ema else None, n_tau0=q1 - q0,
                   tau0=float(a.critic_tau), tau1=float(a.encoder_tau))
+        self.prep_conv_weights()
+        if with_ema:
+            self.prep_conv_weights(target=True)
 
     def shared_obs_fwd(self):
         """One encoder forward of obs with the updated critic weights, shared by attribution #2 (sgsac.py:175),
@@ -373,20 +433,20 @@ class UpdateEngine:
         Wp, G = self.P, self.G
         K.linear_fwd(_ptr(self.haT), P1, 0, Wp("dec.proj.weight"), 0, Wp("dec.proj.bias"), 0, _ptr(self.dl), FEAT, 0,
                      B, FEAT, P1, 0, 1, 0, st)
-        K.conv_fwd(_ptr(self.dl), Wp("dec.conv1.weight"), Wp("dec.conv1.bias"), _ptr(self.d1), B, 21, 21, 32, 128, 1, 1, 1, st)
-        K.conv_fwd(_ptr(self.d1), Wp("dec.conv2.weight"), Wp("dec.conv2.bias"), _ptr(self.d2), B, 21, 21, 128, 64, 1, 2, 1, st)
-        K.conv_fwd(_ptr(self.d2), Wp("dec.conv3.weight"), Wp("dec.conv3.bias"), _ptr(self.lg), B, 42, 42, 64, DEC_C3, 1, 2, 1, st)
+        K.conv_fwd(_ptr(self.dl), Wp("dec.conv1.weight"), Wp("dec.conv1.bias"), _ptr(self.d1), B, 21, 21, 32, 128, 1, 1, 1, 0, st)
+        K.conv_fwd(_ptr(self.d1), Wp("dec.conv2.weight"), Wp("dec.conv2.bias"), _ptr(self.d2), B, 21, 21, 128, 64, 1, 2, 1, 0, st)
+        K.conv_fwd(_ptr(self.d2), Wp("dec.conv3.weight"), Wp("dec.conv3.bias"), _ptr(self.lg), B, 42, 42, 64, DEC_C3, 1, 2, 1, 0, st)
         K.zero(_ptr(self.logs, 4), 4, st)
         K.bce(_ptr(self.lg), _ptr(self.mask), _ptr(self.logs, 4), _ptr(self.dlg), B, 84 * 84, DEC_C3, self.Bg, st)
         x0, x1 = L.ranges["aux"]
         K.zero(self._g + 4 * x0, 4 * (x1 - x0), st)
-        K.conv_wgrad(_ptr(self.d2), _ptr(self.dlg), G("dec.conv3.weight"), G("dec.conv3.bias"), B, 42, 42, 64, DEC_C3, 1, 2, 1, st)
+        K.conv_wgrad(_ptr(self.d2), _ptr(self.dlg), G("dec.conv3.weight"), G("dec.conv3.bias"), B, 42, 42, 64, DEC_C3, 1, 2, 1, 0, st)
         K.conv_dgrad(_ptr(self.dlg), Wp("dec.conv3.weight"), 0, _ptr(self.dup3), B, 84, 84, 64, DEC_C3, 1, 0, st)
         K.upsample2_bwd(_ptr(self.dup3), _ptr(self.d2), _ptr(self.dd2), B, 42, 42, 64, st)
-        K.conv_wgrad(_ptr(self.d1), _ptr(self.dd2), G("dec.conv2.weight"), G("dec.conv2.bias"), B, 21, 21, 128, 64, 1, 2, 1, st)
+        K.conv_wgrad(_ptr(self.d1), _ptr(self.dd2), G("dec.conv2.weight"), G("dec.conv2.bias"), B, 21, 21, 128, 64, 1, 2, 1, 0, st)
         K.conv_dgrad(_ptr(self.dd2), Wp("dec.conv2.weight"), 0, _ptr(self.dup2), B, 42, 42, 128, 64, 1, 0, st)
         K.upsample2_bwd(_ptr(self.dup2), _ptr(self.d1), _ptr(self.dd1), B, 21, 21, 128, st)
-        K.conv_wgrad(_ptr(self.dl), _ptr(self.dd1), G("dec.conv1.weight"), G("dec.conv1.bias"), B, 21, 21, 32, 128, 1, 1, 1, st)
+        K.conv_wgrad(_ptr(self.dl), _ptr(self.dd1), G("dec.conv1.weight"), G("dec.conv1.bias"), B, 21, 21, 32, 128, 1, 1, 1, 0, st)
         K.conv_dgrad(_ptr(self.dd1), Wp("dec.conv1.weight"), _ptr(self.dl), _ptr(self.ddl), B, 21, 21, 32, 128, 1, 1, st)
         K.linear_wgrad(_ptr(self.haT), P1, 0, _ptr(self.ddl), FEAT, 0, G("dec.proj.weight"), 0, G("dec.proj.bias"), 0,
                        B, FEAT, P1, 0, 1, st)
@@ -397,6 +457,7 @@ class UpdateEngine:
         self.enc_bwd(dfeat, B, self.actT, 0, _ptr(self.s_tilde), 1, True)
         self.allreduce_grads((x0, x1))
         self.adam(self.opt_aux, (x0, x1))
+        self.prep_conv_weights()
 
     def update_sgsac(self, step):
         """sgsac.py:169-185 after the sample (obs2[:B], next_obs, action, reward, not_done and the step's randomness

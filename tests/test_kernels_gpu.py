@@ -115,14 +115,14 @@ def test_conv_fwd_dgrad_wgrad(B, Hs, Cin, Co, Cs, pad, up):
     Ho = yr.shape[-1]
     y = torch.zeros(B * Ho * Ho * Cs, device=DEV)
     xh, wsk = nhwc(x), wk(ws)            # keep the NHWC copies alive while kernels read them
-    K.conv_fwd(P(xh), P(wsk), P(bs), P(y), B, Hs, Hs, Cin, Cs, pad, up, 1, ST())
+    K.conv_fwd(P(xh), P(wsk), P(bs), P(y), B, Hs, Hs, Cin, Cs, pad, up, 1, 0, ST())
     close(nchw(y, B, Ho, Ho, Cs)[:, :Co], yr, what="conv_fwd")
     dy = rnd(B, Co, Ho, Ho, seed=4)
     yr.backward(dy)
     dys = torch.zeros(B, Cs, Ho, Ho, device=DEV); dys[:, :Co] = dy
     dw = torch.zeros(Cs * 9 * Cin, device=DEV); db = torch.zeros(Cs, device=DEV)
     dyh = nhwc(dys)
-    K.conv_wgrad(P(xh), P(dyh), P(dw), P(db), B, Hs, Hs, Cin, Cs, pad, up, 1, ST())
+    K.conv_wgrad(P(xh), P(dyh), P(dw), P(db), B, Hs, Hs, Cin, Cs, pad, up, 1, 0, ST())
     close(dw.reshape(Cs, 3, 3, Cin).permute(0, 3, 1, 2)[:Co], wr.grad, rtol=3e-4, what="conv_wgrad")
     close(db[:Co], br.grad, rtol=3e-4, what="conv_bgrad")
     Hl = Hs * up
@@ -150,7 +150,7 @@ def test_conv1(B, Hin):
     wr = w.clone().requires_grad_(True); br = b.clone().requires_grad_(True)
     yr = F.conv2d(xr / 255.0, wr, br, stride=2)
     y = torch.zeros(B * 41 * 41 * 32, device=DEV)
-    K.conv1_fwd(P(obs), P(w), P(b), P(y), B, Hin, 9, 32, ST())
+    K.conv1_fwd(P(obs), P(w), P(b), P(y), B, Hin, 9, 32, 0, ST())
     close(nchw(y, B, 41, 41, 32), yr, what="conv1_fwd")
     dy = rnd(B, 32, 41, 41, seed=4)
     yr.backward(dy)
@@ -422,3 +422,105 @@ def test_rng_step_statistics():
     assert 0 <= int(idxs.min()) and int(idxs.max()) < 1000 and int(ov.max()) < 256 and int(offs.max()) <= 8 and int(offs.min()) >= 0
     z = torch.cat([n1.flatten(), n2.flatten()])
     assert abs(float(z.mean())) < 0.15 and abs(float(z.std()) - 1.0) < 0.1 and 0.0 <= float(u) < 1.0
+
+
+# ------------------------------------------------------------------ tcgen05 TF32 conv (32 -> 32)
+def tf32_round(x):
+    """cvt.rna.tf32.f32 emulation: round-to-nearest (ties away) onto a 10-bit mantissa."""
+    i = x.contiguous().view(torch.int32)
+    return ((i + 0x1000) & ~0x1FFF).view(torch.float32)
+
+
+def rows_pad(x_nchw, extra):
+    """NCHW -> NHWC with `extra` zero rows appended to every sample ([B][H+extra][W][C], the tcgen05 conv layout)."""
+    B, C, H, W = x_nchw.shape
+    out = torch.zeros(B, H + extra, W, C, device=DEV)
+    out[:, :H] = x_nchw.permute(0, 2, 3, 1)
+    return out
+
+
+def prep_w(w):
+    wk_ = wk(w).reshape(1, -1).contiguous()
+    wf = torch.zeros(9216, device=DEV); wd = torch.zeros(9216, device=DEV)
+    K.conv_weights_prep(P(wk_), 9216, P(wf), P(wd), 1, ST())
+    return wf, wd
+
+
+@pytest.mark.parametrize("B,Hp", [(2, 23), (3, 41), (5, 25), (16, 39)])
+def test_conv_tc_forward(B, Hp):
+    x = tf32_round(F.relu(rnd(B, 32, Hp, Hp, seed=1)))
+    w = rnd(32, 32, 3, 3, seed=2, scale=0.1); b = rnd(32, seed=3)
+    wf, wd = prep_w(w)
+    assert torch.equal(wf.reshape(32, 3, 3, 32).permute(0, 3, 1, 2), tf32_round(w))
+    assert torch.equal(wd.reshape(32, 3, 3, 32).permute(3, 0, 1, 2), tf32_round(w).flip(2, 3))      # wd[ci][t'][co] = w[co][ci][8-t']
+    ref = F.conv2d(x.double(), tf32_round(w).double(), b.double())
+    xh = rows_pad(x, 2)                                   # [B][Hp+2][Hp][32]
+    Ho = Hp - 2
+    for flags in (0, 1, 3):
+        y = torch.full((B, Ho + 2, Ho, 32), 7.0, device=DEV)          # output with 2 extra rows per sample, never written
+        K.conv_tc(P(xh), P(wf), P(b), 0, P(y), B, Hp + 2, Hp, Ho, Ho, 0, Ho + 2, Ho, 0, 0, 0, 0, flags, ST())
+        torch.cuda.synchronize()
+        r = ref.clone()
+        if flags & 1:
+            r = F.relu(r)
+        got = y[:, :Ho].permute(0, 3, 1, 2)
+        assert float((y[:, Ho:] - 7.0).abs().max()) == 0.0
+        if flags & 2:
+            assert torch.equal(got, tf32_round(got))
+            close(got, r.float(), rtol=1e-3, what=f"conv_tc fwd flags={flags}")
+        else:
+            close(got, r.float(), rtol=2e-5, what=f"conv_tc fwd flags={flags}")
+
+
+@pytest.mark.parametrize("B,Hl,mode", [(2, 23, 1), (3, 41, 2), (4, 25, 0), (16, 39, 1)])
+def test_conv_tc_dgrad_and_wgrad(B, Hl, mode):
+    """Data gradient = 3x3 window sums over the zero-bordered dY buffer [B][Ho+4][Ho+2] (2 zero rows above/below, 2 zero
+    columns after each row doubling as the next row's left border) with flipped/transposed weights and the ReLU-mask
+    epilogue, written into the next layer's buffer of the same kind; weight gradient = tcgen05 reduction over pixels of
+    dY x shifted activations, both in the shared [B][Hl+2][Hl] geometry."""
+    Ho = Hl - 2
+    w = rnd(32, 32, 3, 3, seed=2, scale=0.1)
+    dy = tf32_round(rnd(B, 32, Ho, Ho, seed=4))
+    act = tf32_round(F.relu(rnd(B, 32, Hl, Hl, seed=5)))
+    wf, wd = prep_w(w)
+    dyp = torch.zeros(B, Ho + 4, Ho + 2, 32, device=DEV)
+    dyh = nhwc(dy)
+    K.pad_copy(P(dyh), P(dyp), B, Ho, Ho, 32, Ho + 4, Ho + 2, 2, 0, 1, ST())
+    assert torch.equal(dyp[:, 2:2 + Ho, :Ho].permute(0, 3, 1, 2), dy)
+    out = torch.zeros(B, Hl + 4, Hl + 2, 32, device=DEV)
+    acth = rows_pad(act, 2)                               # [B][Hl+2][Hl][32]
+    K.conv_tc(P(dyp), P(wd), 0, P(acth) if mode else 0, P(out), B, Ho + 4, Ho + 2, Hl, Hl, -2, Hl + 4, Hl + 2, 2, 0, Hl + 2, Hl,
+              (mode << 2), ST())
+    torch.cuda.synchronize()
+    ref = F.conv_transpose2d(dy.double(), tf32_round(w).double())
+    if mode == 1:
+        ref = ref * (act > 0)
+    if mode == 2:
+        ref = F.relu(ref) * (act > 0)
+    close(out[:, 2:2 + Hl, :Hl].permute(0, 3, 1, 2), ref.float(), rtol=2e-5, what="conv_tc dgrad")
+    border = out.clone(); border[:, 2:2 + Hl, :Hl] = 0
+    assert float(border.abs().max()) == 0.0
+    # weight gradient
+    dw = torch.zeros(9216, device=DEV)
+    K.conv_wgrad_tc(P(acth), P(dyp), P(dw), B, Hl + 2, Hl, ST())
+    torch.cuda.synchronize()
+    wr = w.clone().double().requires_grad_(True)
+    F.conv2d(act.double(), wr).backward(dy.double())
+    close(dw.reshape(32, 3, 3, 32).permute(0, 3, 1, 2), wr.grad.float(), rtol=2e-5, what="conv_wgrad_tc")
+    db = torch.zeros(32, device=DEV)
+    K.colsum(P(dyp), 32, B * (Ho + 4) * (Ho + 2), 32, P(db), ST())
+    close(db, dy.sum((0, 2, 3)), rtol=1e-5, what="bias grad over the bordered buffer")
+
+
+def test_conv1_fwd_pitched_output():
+    """conv1 writing post-ReLU, TF32-rounded activations with 2 spare rows per sample (what the tcgen05 layers read)."""
+    B = 3
+    g = torch.Generator().manual_seed(5)
+    obs = torch.randint(0, 256, (B, 9, 84, 84), generator=g).float().to(DEV)
+    w = rnd(32, 9, 3, 3, seed=2, scale=0.2); b = rnd(32, seed=3)
+    ref = F.relu(F.conv2d(obs / 255.0, w, b, stride=2))
+    y = torch.full((B, 43, 41, 32), -1.0, device=DEV)
+    K.conv1_fwd(P(obs), P(w), P(b), P(y), B, 84, 9, 32, 7, ST())
+    got = y[:, :41].permute(0, 3, 1, 2)
+    close(got, ref, rtol=1e-3, what="conv1 pitched")
+    assert torch.equal(got, tf32_round(got)) and float((y[:, 41:] + 1.0).abs().max()) == 0.0
