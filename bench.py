@@ -168,6 +168,10 @@ def profile_kernels(agent, rb, nsteps=4):
     finally:
         for n, fn in saved.items():
             setattr(api, n, fn)
+    dump = os.environ.get("SGQN_PROFILE_CALLS")
+    if dump:
+        rows = [[n, [a for a in args if isinstance(a, int) and abs(a) < (1 << 31)][:14], round(e0.elapsed_time(e1), 4)] for n, args, e0, e1 in recs]
+        json.dump(rows, open(dump, "w"))
     fam = {}
     for n, args, e0, e1 in recs:
         key = n
@@ -210,7 +214,8 @@ def run_b200(a):
     torch.cuda.set_device(local)
     sync = None
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        import datetime
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local), timeout=datetime.timedelta(seconds=120))
         sync = GradSync()
     B = PER_GPU_BATCH
     Bg = B * world
@@ -263,8 +268,8 @@ def run_b200(a):
 
     # ---- kernel-family profile + roofline of the dominant family (rank 0)
     roof, fam_rows = None, None
+    fam, nst = profile_kernels(agent, rb, 4)          # every rank runs it (the updates contain collectives)
     if rank == 0:
-        fam, nst = profile_kernels(agent, rb, 4)
         tot = sum(v[0] for v in fam.values())
         fam_rows = sorted(((k, v[0] / nst, v[1] // nst, v[2] / nst) for k, v in fam.items()), key=lambda r: -r[1])
         hbm, tf_burst, tf_sus, how = peaks()

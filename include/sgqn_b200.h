@@ -38,9 +38,10 @@ int sgqn_zero(void* p, long long bytes, void* stream);
 /* ---- Linear layers (modules.py:107,194-198,239-243,318).  Strides (ld*, *bs) in elements; `batch` runs
  *      independent problems (the Q1/Q2 pair) through one launch.
  *      fwd:   y[M,N] = act(x)[M,K] * w[N,K]^T + bias      (relu_in: ReLU applied to x while loading;
- *             splitk != 0: split-K with atomic accumulation, y must be zero-filled by the caller)
+ *             splitk 1: split-K with atomic accumulation into a caller-zeroed y; 2: y is zero-filled here first)
  *      dgrad: dx[M,K] = dy[M,N] * w[N,K], optionally masked by zmask (mode 1: *1[z>0]; mode 2 guided:
- *             relu(.)*1[z>0], captum GuidedBackprop, rl_utils.py:35-39); accumulate != 0: atomic +=
+ *             relu(.)*1[z>0], captum GuidedBackprop, rl_utils.py:35-39); accumulate 1: atomic += (split-K allowed);
+ *             2: dx zero-filled here, then split-K atomics (modes 0/1 only)
  *      wgrad: dw[N,K] += dy^T * act(x);  db[N] += colsum(dy)   (atomic; caller zero-fills) */
 int sgqn_linear_fwd(const float* x, int ldx, long long xbs, const float* w, long long wbs, const float* bias, long long bbs,
                     float* y, int ldy, long long ybs, int M, int N, int K, int relu_in, int batch, int splitk, void* stream);
@@ -67,6 +68,12 @@ int sgqn_conv1_fwd(const float* obs, const float* w, const float* bias, float* y
                    int flags /* bit0 ReLU, bit1 TF32 round, bit2: 2 extra (untouched) rows per sample in y */, void* stream);
 int sgqn_conv1_wgrad(const float* obs, const float* dy, float* dw, float* db, int B, int Hin, int Cin, int Cout, void* stream);
 int sgqn_conv1_dgrad(const float* dy, const float* w, float* dobs, int B, int Cin, int Cout, void* stream);
+/*      the same three through a materialised im2col matrix col[B*41*41][84] (81 real columns, /255 applied): the index
+ *      arithmetic is paid once per observation batch, forward / weight gradient / data gradient become plain GEMMs */
+int sgqn_conv1_im2col(const float* obs, float* col, int B, int Hin, void* stream);
+int sgqn_conv1_fwd_col(const float* col, const float* w, const float* bias, float* y, int B, int flags, void* stream);
+int sgqn_conv1_wgrad_col(const float* col, const float* dy, float* dw, float* db, int B, void* stream);
+int sgqn_conv1_dgrad_col(const float* dy, const float* w, float* dcol, float* dobs, int B, void* stream);
 /* ---- tcgen05 / TMEM / TMA implicit-GEMM 3x3 conv, 32 -> 32 channels, TF32 (SharedCNN layers 2..11, forward and data
  *      gradient; conv_tc.cu).  x [B][Hr][Wp][32] pitch-linear; w: TF32-rounded operand copy [32][9][32] made by
  *      sgqn_conv_weights_prep (wf: forward, wd: flipped+transposed for the data gradient).  Output (b,y,x), y < Hv,

@@ -29,6 +29,10 @@ SIGNATURES = {
     "sgqn_pad_copy": [_p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p],
     "sgqn_conv1_wgrad": [_p, _p, _p, _p, _i, _i, _i, _i, _p],
     "sgqn_conv1_dgrad": [_p, _p, _p, _i, _i, _i, _p],
+    "sgqn_conv1_im2col": [_p, _p, _i, _i, _p],
+    "sgqn_conv1_fwd_col": [_p, _p, _p, _p, _i, _i, _p],
+    "sgqn_conv1_wgrad_col": [_p, _p, _p, _p, _i, _p],
+    "sgqn_conv1_dgrad_col": [_p, _p, _p, _p, _i, _p],
     "sgqn_upsample2_bwd": [_p, _p, _p, _i, _i, _i, _i, _p],
     "sgqn_minmax": [_p, _ll, _p, _p, _p],
     "sgqn_attribution_mask": [_p, _p, _p, _p, _f, _p, _p, _i, _i, _p],

@@ -51,6 +51,11 @@ extern "C" int sgqn_linear_fwd(const float* x, int ldx, long long xbs, const flo
     RowMajorC a{x, ldx, xbs, relu_in, aligned16(x) && (ldx % 4 == 0) && (xbs % 4 == 0)};
     RowMajorC b{w, K, wbs, 0, aligned16(w) && (K % 4 == 0) && (wbs % 4 == 0)};
     EpStore ep{y, ldy, ybs, bias, bbs, nullptr, 0, 0, 0, splitk ? 1 : 0, 1.0f, 0, 0, 0};
+    if (splitk == 2)                 // zero-fill here (strided rows, per batch), then split-K with atomics
+        for (int bi = 0; bi < batch; ++bi) {
+            cudaError_t e = cudaMemset2DAsync(y + bi * ybs, (size_t)ldy * 4, 0, (size_t)N * 4, (size_t)M, (cudaStream_t)stream);
+            if (e != cudaSuccess) return (int)e;
+        }
     return launch_gemm<64, 64, 16, 4, 4>(a, b, ep, M, N, K, batch, splitk ? 64 : 1, (cudaStream_t)stream);
 }
 
@@ -61,7 +66,14 @@ extern "C" int sgqn_linear_dgrad(const float* dy, int lddy, long long dybs, cons
     RowMajorC a{dy, lddy, dybs, 0, aligned16(dy) && (lddy % 4 == 0) && (dybs % 4 == 0)};
     ColMajorR b{w, K, wbs, 0, aligned16(w) && (K % 4 == 0) && (wbs % 4 == 0)};
     EpStore ep{dx, lddx, dxbs, nullptr, 0, zmask, ldm, mbs, mode, accumulate ? 1 : 0, 1.0f, 0, 0, 0};
-    return launch_gemm<64, 64, 16, 4, 4>(a, b, ep, M, K, N, batch, 1, (cudaStream_t)stream);
+    if (accumulate == 2) {           // zero-fill here, then split-K with atomics (the plain ReLU mask distributes over the sum)
+        if (mode == 2) return (int)cudaErrorInvalidValue;
+        for (int bi = 0; bi < batch; ++bi) {
+            cudaError_t e = cudaMemset2DAsync(dx + bi * dxbs, (size_t)lddx * 4, 0, (size_t)K * 4, (size_t)M, (cudaStream_t)stream);
+            if (e != cudaSuccess) return (int)e;
+        }
+    }
+    return launch_gemm<64, 64, 16, 4, 4>(a, b, ep, M, K, N, batch, accumulate ? 64 : 1, (cudaStream_t)stream);
 }
 
 extern "C" int sgqn_linear_wgrad(const float* x, int ldx, long long xbs, const float* dy, int lddy, long long dybs,
@@ -196,5 +208,84 @@ extern "C" int sgqn_upsample2_bwd(const float* dup, const float* act, float* dx,
     long long total = (long long)B * Hs * Ws * (C / 4);
     upsample2_bwd_kernel<<<(unsigned)cdivll(total, 256), 256, 0, (cudaStream_t)stream>>>(
         (const float4*)dup, (const float4*)act, (float4*)dx, Hs, Ws, C / 4, total);
+    return SGQN_CHECK_LAUNCH();
+}
+
+// ---------------------------------------------------------------- first conv through a materialised im2col matrix
+// col[pix][84]: columns 0..80 = obs[b][ci][2y+ky+crop][2x+kx+crop] / 255 (c = ci*9 + ky*3 + kx), 81..83 = 0.
+// Forward, weight gradient and the attribution's data gradient of conv1 then are plain GEMMs over `col` (the
+// per-element index arithmetic of the direct kernels above is paid once per observation batch instead of per use).
+__global__ void conv1_im2col_kernel(const float* __restrict__ obs, float4* __restrict__ col, int Hin, int crop, long long total) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    int c4 = (int)(i % 21); long long pix = i / 21;
+    int x = (int)(pix % 41); long long t = pix / 41; int y = (int)(t % 41); int b = (int)(t / 41);
+    float v[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        int c = c4 * 4 + e;
+        if (c < 81) {
+            int ci = c / 9, r = c - ci * 9, ky = r / 3, kx = r - ky * 3;
+            v[e] = __fdiv_rn(__ldg(obs + ((size_t)(b * 9 + ci) * Hin + (2 * y + ky + crop)) * Hin + (2 * x + kx + crop)), 255.0f);
+        } else v[e] = 0.f;
+    }
+    col[i] = make_float4(v[0], v[1], v[2], v[3]);
+}
+
+extern "C" int sgqn_conv1_im2col(const float* obs, float* col, int B, int Hin, void* stream) {
+    long long total = (long long)B * 1681 * 21;
+    if (total <= 0) return 0;
+    conv1_im2col_kernel<<<(unsigned)cdivll(total, 256), 256, 0, (cudaStream_t)stream>>>(obs, (float4*)col, Hin, (Hin - 84) / 2, total);
+    return SGQN_CHECK_LAUNCH();
+}
+
+extern "C" int sgqn_conv1_fwd_col(const float* col, const float* w, const float* bias, float* y, int B, int flags, void* stream) {
+    RowMajorC a{col, 84, 0, 0, aligned16(col)};
+    RowMajorC b{w, 81, 0, 0, 0};
+    EpStore ep{y, 32, 0, bias, 0, nullptr, 0, 0, 0, 0, 1.0f, flags & 3, (flags & 4) ? 1681 : 0, 82};
+    return launch_gemm<128, 32, 16, 8, 4>(a, b, ep, B * 1681, 32, 81, 1, 1, (cudaStream_t)stream);
+}
+
+extern "C" int sgqn_conv1_wgrad_col(const float* col, const float* dy, float* dw, float* db, int B, void* stream) {
+    int P = B * 1681;
+    ColMajorR a{dy, 32, 0, 0, aligned16(dy)};
+    ColMajorR b{col, 84, 0, 0, aligned16(col)};
+    EpStore ep{dw, 81, 0, nullptr, 0, nullptr, 0, 0, 0, 1, 1.0f, 0, 0, 0};
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = launch_gemm<32, 64, 16, 4, 4>(a, b, ep, 32, 81, P, 1, 4096, st);
+    if (rc) return rc;
+    return db ? launch_colsum(dy, 32, P, 32, db, st) : 0;
+}
+
+// d obs[b][ci][Y][X] = (1/255) * sum over windows (y,x,ky,kx) with 2y+ky = Y, 2x+kx = X of dcol[(b,y,x)][ci*9+ky*3+kx]
+__global__ void conv1_col2im_kernel(const float* __restrict__ dcol, float* __restrict__ dobs, long long total) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    int X = (int)(i % 84); long long t = i / 84; int Y = (int)(t % 84); t /= 84; int ci = (int)(t % 9); int b = (int)(t / 9);
+    float s = 0.f;
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+        int yy = Y - ky;
+        if (yy < 0 || (yy & 1) || (yy >> 1) >= 41) continue;
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+            int xx = X - kx;
+            if (xx < 0 || (xx & 1) || (xx >> 1) >= 41) continue;
+            s += __ldg(dcol + ((size_t)(b * 41 + (yy >> 1)) * 41 + (xx >> 1)) * 84 + ci * 9 + ky * 3 + kx);
+        }
+    }
+    dobs[i] = __fdiv_rn(s, 255.0f);
+}
+
+extern "C" int sgqn_conv1_dgrad_col(const float* dy, const float* w, float* dcol, float* dobs, int B, void* stream) {
+    // dcol[pix][84] = dy[pix][32] * W1[32][81]  (cols 81..83 untouched), then gather back to the NCHW observation gradient
+    RowMajorC a{dy, 32, 0, 0, aligned16(dy)};
+    ColMajorR b{w, 81, 0, 0, 0};
+    EpStore ep{dcol, 84, 0, nullptr, 0, nullptr, 0, 0, 0, 0, 1.0f, 0, 0, 0};
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = launch_gemm<128, 32, 16, 8, 4>(a, b, ep, B * 1681, 81, 32, 1, 1, st);
+    if (rc) return rc;
+    long long total = (long long)B * 9 * 84 * 84;
+    conv1_col2im_kernel<<<(unsigned)cdivll(total, 256), 256, 0, st>>>(dcol, dobs, total);
     return SGQN_CHECK_LAUNCH();
 }

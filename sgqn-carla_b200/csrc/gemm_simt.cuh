@@ -271,21 +271,41 @@ struct EpObsGrad {            // conv1 dgrad: rows (b,Y,X) on H x H, cols ci -> 
 };
 
 // ------------------------------------------------------------------ the core
+// One shared-memory buffer per operand + register prefetch: the global loads of tile t+1 are in flight while tile t is
+// being multiplied (these kernels run at low occupancy, so the overlap has to come from inside the thread).
+template <int BR, int BK, int NT>
+struct TileRegs { static constexpr int G = (BR * BK / 4 + NT - 1) / NT; float4 v[G]; };
+
 template <int BR, int BK, int NT, class L>
-__device__ __forceinline__ void load_tile(float (*tile)[BR + 4], const L& ld, int r0, int c0, int rows, int cend,
-                                          int batch, int tid) {
-    if constexpr (!L::kRowContig) {
-        constexpr int G = BR * (BK / 4);
-        for (int g = tid; g < G; g += NT) {
+__device__ __forceinline__ void fetch_tile(TileRegs<BR, BK, NT>& t, const L& ld, int r0, int c0, int rows, int cend, int batch, int tid) {
+    constexpr int G = BR * BK / 4;
+#pragma unroll
+    for (int u = 0; u < TileRegs<BR, BK, NT>::G; ++u) {
+        int g = tid + u * NT;
+        if (G % NT != 0 && g >= G) break;
+        if constexpr (!L::kRowContig) {
             int r = g / (BK / 4), cg = g - r * (BK / 4);
-            float4 v = ld.fetch4(r0 + r, c0 + cg * 4, rows, cend, batch);
-            tile[cg * 4 + 0][r] = v.x; tile[cg * 4 + 1][r] = v.y; tile[cg * 4 + 2][r] = v.z; tile[cg * 4 + 3][r] = v.w;
-        }
-    } else {
-        constexpr int G = (BR / 4) * BK;
-        for (int g = tid; g < G; g += NT) {
+            t.v[u] = ld.fetch4(r0 + r, c0 + cg * 4, rows, cend, batch);
+        } else {
             int c = g / (BR / 4), rg = g - c * (BR / 4);
-            float4 v = ld.fetch4(r0 + rg * 4, c0 + c, rows, cend, batch);
+            t.v[u] = ld.fetch4(r0 + rg * 4, c0 + c, rows, cend, batch);
+        }
+    }
+}
+
+template <int BR, int BK, int NT, class L>
+__device__ __forceinline__ void store_tile(float (*tile)[BR + 4], const TileRegs<BR, BK, NT>& t, int tid) {
+    constexpr int G = BR * BK / 4;
+#pragma unroll
+    for (int u = 0; u < TileRegs<BR, BK, NT>::G; ++u) {
+        int g = tid + u * NT;
+        if (G % NT != 0 && g >= G) break;
+        const float4 v = t.v[u];
+        if constexpr (!L::kRowContig) {
+            int r = g / (BK / 4), cg = g - r * (BK / 4);
+            tile[cg * 4 + 0][r] = v.x; tile[cg * 4 + 1][r] = v.y; tile[cg * 4 + 2][r] = v.z; tile[cg * 4 + 3][r] = v.w;
+        } else {
+            int c = g / (BR / 4), rg = g - c * (BR / 4);
             *reinterpret_cast<float4*>(&tile[c][rg * 4]) = v;
         }
     }
@@ -310,10 +330,20 @@ gemm_simt_kernel(AL al, BL bl, EP ep, int M, int N, int K, int nsplit, int klen)
 #pragma unroll
         for (int n = 0; n < TN; ++n) acc[m][n] = 0.f;
 
+    TileRegs<BM, BK, NT> ra;
+    TileRegs<BN, BK, NT> rb;
+    if (kb < ke) {
+        fetch_tile<BM, BK, NT, AL>(ra, al, i0, kb, M, ke, batch, tid);
+        fetch_tile<BN, BK, NT, BL>(rb, bl, j0, kb, N, ke, batch, tid);
+    }
     for (int c0 = kb; c0 < ke; c0 += BK) {
-        load_tile<BM, BK, NT, AL>(As, al, i0, c0, M, ke, batch, tid);
-        load_tile<BN, BK, NT, BL>(Bs, bl, j0, c0, N, ke, batch, tid);
+        store_tile<BM, BK, NT, AL>(As, ra, tid);
+        store_tile<BN, BK, NT, BL>(Bs, rb, tid);
         __syncthreads();
+        if (c0 + BK < ke) {
+            fetch_tile<BM, BK, NT, AL>(ra, al, i0, c0 + BK, M, ke, batch, tid);
+            fetch_tile<BN, BK, NT, BL>(rb, bl, j0, c0 + BK, N, ke, batch, tid);
+        }
 #pragma unroll
         for (int k = 0; k < BK; ++k) {
             float a[TM], b[TN];
@@ -346,7 +376,7 @@ static int launch_gemm(const AL& al, const BL& bl, const EP& ep, int M, int N, i
     long long tiles = (long long)tm * tn * batch;
     int nsplit = 1;
     if (max_split > 1) {
-        nsplit = (int)cdivll(296, tiles);
+        nsplit = (int)cdivll(592, tiles);            // ~4 CTAs per SM: these kernels hide latency with occupancy only
         int kchunks = cdiv(K, BK * 2);                 // at least 2 BK steps per split
         if (nsplit > kchunks) nsplit = kchunks;
         if (nsplit > max_split) nsplit = max_split;

@@ -77,6 +77,9 @@ class UpdateEngine:
         self.actS = [f32(R * (h + 2) * h * 32) for h in ENC_H]  # critic slot
         self.actT = [f32(B * (h + 2) * h * 32) for h in ENC_H]  # transient slot
         self.dbuf = [f32(R * 41 * 41 * 32), f32(R * 41 * 41 * 32)]
+        # im2col matrices of the first conv (col[n*1681][84]) per slot: built once per observation batch by enc_fwd and
+        # re-used by that slot's weight gradient; dcol is the attribution's data-gradient workspace
+        self.colS, self.colT, self.dcol = f32(R * 1681 * 84), f32(B * 1681 * 84), f32(B * 1681 * 84)
         # tcgen05 conv path (conv_tc.cu): TF32-rounded operand copies of the 32->32 conv weights (forward; flipped +
         # transposed for the data gradient; forward copy of the target net) and one zero-bordered (pad 2) gradient
         # buffer per layer -- borders are written once here (zeros) and never again.
@@ -141,10 +144,12 @@ class UpdateEngine:
         # activations are stored AFTER the ReLU that follows each conv (the last conv has none) and rounded to TF32,
         # the operand format of the next layer's tcgen05 MMA; 1[x>0] for the backward is 1[relu(x)>0].
         tc = self.precision == "tf32"
+        col = _ptr(self.colS if acts is self.actS else self.colT, row0 * 1681 * 84)
+        K.conv1_im2col(x_ptr, col, n, hin, st)
         if tc:
             # pitch-linear layout [n][h+2][h][32]: the 2 spare rows per sample stay zero (never written) so that the
             # weight-gradient kernel can pair activations and the zero-bordered output gradient row by row
-            K.conv1_fwd(x_ptr, W("cnn.0.weight"), W("cnn.0.bias"), _ptr(acts[0], row0 * 43 * 41 * 32), n, hin, 9, 32, 7, st)
+            K.conv1_fwd_col(col, W("cnn.0.weight"), W("cnn.0.bias"), _ptr(acts[0], row0 * 43 * 41 * 32), n, 7, st)
             for l in range(1, 11):
                 hi, ho = ENC_H[l - 1], ENC_H[l]
                 last = l == 10                                  # the feature map that feeds the projection is compact
@@ -152,7 +157,7 @@ class UpdateEngine:
                           _ptr(acts[l], row0 * (ho * ho if last else (ho + 2) * ho) * 32), n, hi + 2, hi, ho, ho, 0,
                           ho if last else ho + 2, ho, 0, 0, 0, 0, 0 if last else 3, st)
             return
-        K.conv1_fwd(x_ptr, W("cnn.0.weight"), W("cnn.0.bias"), _ptr(acts[0], row0 * 41 * 41 * 32), n, hin, 9, 32, 1, st)
+        K.conv1_fwd_col(col, W("cnn.0.weight"), W("cnn.0.bias"), _ptr(acts[0], row0 * 41 * 41 * 32), n, 1, st)
         for l in range(1, 11):                                  # fp32 CUDA-core path, compact [n][h][h][32] layout
             hi, ho = ENC_H[l - 1], ENC_H[l]
             K.conv_fwd(_ptr(acts[l - 1], row0 * hi * hi * 32), W(f"cnn.{l}.weight"), W(f"cnn.{l}.bias"),
@@ -171,9 +176,8 @@ class UpdateEngine:
         """RLProjection (modules.py:102-113): Linear(14112->100) (split-K) -> LayerNorm -> tanh, h row stride ldh."""
         W = self.T if target else self.P
         st = self.st
-        K.zero(z, 4 * n * self.lay.P, st)
         K.linear_fwd(feat_ptr, FEAT, 0, W(f"{pre}.0.weight"), 0, W(f"{pre}.0.bias"), 0, z, self.lay.P, 0,
-                     n, self.lay.P, FEAT, 0, 1, 1, st)
+                     n, self.lay.P, FEAT, 0, 1, 2, st)
         K.ln_tanh_fwd(z, W(f"{pre}.1.weight"), W(f"{pre}.1.bias"), h, ldh, n, self.lay.P, st)
 
     def q_fwd(self, ha, n, row0, nheads=2, target=False):
@@ -185,8 +189,8 @@ class UpdateEngine:
         out = _ptr(self.tq) if target else _ptr(self.q, row0)
         obs_ = self.B if target else R
         K.linear_fwd(ha, P1, 0, W("Q1.0.weight"), qs, W("Q1.0.bias"), qs, z1, H, R * H, n, H, P1, 0, nheads, 0, st)
-        K.linear_fwd(z1, H, R * H, W("Q1.2.weight"), qs, W("Q1.2.bias"), qs, z2, H, R * H, n, H, H, 1, nheads, 0, st)
-        K.linear_fwd(z2, H, R * H, W("Q1.4.weight"), qs, W("Q1.4.bias"), qs, out, 1, obs_, n, 1, H, 1, nheads, 0, st)
+        K.linear_fwd(z1, H, R * H, W("Q1.2.weight"), qs, W("Q1.2.bias"), qs, z2, H, R * H, n, H, H, 1, nheads, 2, st)
+        K.linear_fwd(z2, H, R * H, W("Q1.4.weight"), qs, W("Q1.4.bias"), qs, out, 1, obs_, n, 1, H, 1, nheads, 2, st)
 
     def q_dgrad(self, dq, dq_bs, n, row0, nheads, mode, dha):
         """Backward of the Q trunks to their input (n, P+A), heads summed.  mode 1 plain, 2 guided."""
@@ -195,7 +199,8 @@ class UpdateEngine:
         z1, z2 = _ptr(self.z1, row0 * H), _ptr(self.z2, row0 * H)
         dz1, dz2 = _ptr(self.dz1, row0 * H), _ptr(self.dz2, row0 * H)
         K.linear_dgrad(dq, 1, dq_bs, self.P("Q1.4.weight"), qs, z2, H, R * H, dz2, H, R * H, n, 1, H, mode, 0, nheads, st)
-        K.linear_dgrad(dz2, H, R * H, self.P("Q1.2.weight"), qs, z1, H, R * H, dz1, H, R * H, n, H, H, mode, 0, nheads, st)
+        K.linear_dgrad(dz2, H, R * H, self.P("Q1.2.weight"), qs, z1, H, R * H, dz1, H, R * H, n, H, H, mode,
+                       2 if mode == 1 else 0, nheads, st)
         K.zero(dha, 4 * n * P1, st)
         K.linear_dgrad(dz1, H, R * H, self.P("Q1.0.weight"), qs, 0, 0, 0, dha, P1, 0, n, H, P1, 0, 1, nheads, st)
 
@@ -232,10 +237,7 @@ class UpdateEngine:
                 dx = _ptr(self.dbuf[l & 1])
                 K.conv_dgrad(d, self.P(f"cnn.{l}.weight"), a_in, dx, n, hi, hi, 32, 32, 0, mode, st)
                 d = dx
-            if wgrad:
-                K.conv1_wgrad(x_ptr, d, self.G("cnn.0.weight"), self.G("cnn.0.bias"), n, 84, 9, 32, st)
-            if dobs:
-                K.conv1_dgrad(d, self.P("cnn.0.weight"), dobs, n, 9, 32, st)
+            self._conv1_bwd(d, n, acts, row0, wgrad, dobs)
             return
         K.pad_copy(dfeat, _ptr(self.gpad[10]), n, 21, 21, 32, 25, 23, 2, 0, 1, st)
         for l in range(10, 0, -1):
@@ -251,11 +253,16 @@ class UpdateEngine:
             else:                                       # d(act_0) compact: consumed by the CUDA-core first-conv kernels
                 K.conv_tc(d, _ptr(self.wd), 0, a_in, _ptr(self.dbuf[0]), n, ho + 4, ho + 2, hi, hi, -2,
                           hi, hi, 0, 0, hi + 2, hi, mode << 2, st)
-        d = _ptr(self.dbuf[0])
+        self._conv1_bwd(_ptr(self.dbuf[0]), n, acts, row0, wgrad, dobs)
+
+    def _conv1_bwd(self, d, n, acts, row0, wgrad, dobs):
+        """Backward of the first conv from d = d(act_0) (compact [n][41][41][32]) through the slot's im2col matrix."""
+        st = self.st
+        col = _ptr(self.colS if acts is self.actS else self.colT, row0 * 1681 * 84)
         if wgrad:
-            K.conv1_wgrad(x_ptr, d, self.G("cnn.0.weight"), self.G("cnn.0.bias"), n, 84, 9, 32, st)
+            K.conv1_wgrad_col(col, d, self.G("cnn.0.weight"), self.G("cnn.0.bias"), n, st)
         if dobs:
-            K.conv1_dgrad(d, self.P("cnn.0.weight"), dobs, n, 9, 32, st)
+            K.conv1_dgrad_col(d, self.P("cnn.0.weight"), _ptr(self.dcol), dobs, n, st)
 
     def attribution(self, acts, row0, ha, z, obs_grad):
         """compute_attribution (rl_utils.py:57-62): guided backprop of sum_b Q1[b] to the observation, re-using the
@@ -301,9 +308,9 @@ class UpdateEngine:
         K.linear_fwd(_ptr(self.h_a), L.P, 0, self.P("actor_mlp.0.weight"), 0, self.P("actor_mlp.0.bias"), 0,
                      _ptr(self.az1), H, 0, n, H, L.P, 0, 1, 0, st)
         K.linear_fwd(_ptr(self.az1), H, 0, self.P("actor_mlp.2.weight"), 0, self.P("actor_mlp.2.bias"), 0,
-                     _ptr(self.az2), H, 0, n, H, H, 1, 1, 0, st)
+                     _ptr(self.az2), H, 0, n, H, H, 1, 1, 2, st)
         K.linear_fwd(_ptr(self.az2), H, 0, self.P("actor_mlp.4.weight"), 0, self.P("actor_mlp.4.bias"), 0,
-                     _ptr(self.raw), 2 * A, 0, n, 2 * A, H, 1, 1, 0, st)
+                     _ptr(self.raw), 2 * A, 0, n, 2 * A, H, 1, 1, 2, st)
 
     def critic_fwd_rows(self, row0, n):
         """critic(obs2[row0:row0+n], action) with activations kept in the critic slot."""
@@ -402,9 +409,9 @@ class UpdateEngine:
         K.linear_dgrad(_ptr(self.draw), 2 * A, 0, self.P("actor_mlp.4.weight"), 0, _ptr(self.az2), H, 0, _ptr(self.daz2), H, 0,
                        B, 2 * A, H, 1, 0, 1, st)
         K.linear_dgrad(_ptr(self.daz2), H, 0, self.P("actor_mlp.2.weight"), 0, _ptr(self.az1), H, 0, _ptr(self.daz1), H, 0,
-                       B, H, H, 1, 0, 1, st)
+                       B, H, H, 1, 2, 1, st)
         K.linear_dgrad(_ptr(self.daz1), H, 0, self.P("actor_mlp.0.weight"), 0, 0, 0, 0, _ptr(self.dh_a), L.P, 0,
-                       B, H, L.P, 0, 0, 1, st)
+                       B, H, L.P, 0, 2, 1, st)
         K.linear_wgrad(_ptr(self.az2), H, 0, _ptr(self.draw), 2 * A, 0, self.G("actor_mlp.4.weight"), 0,
                        self.G("actor_mlp.4.bias"), 0, B, 2 * A, H, 1, 1, st)
         K.linear_wgrad(_ptr(self.az1), H, 0, _ptr(self.daz2), H, 0, self.G("actor_mlp.2.weight"), 0,
@@ -450,7 +457,7 @@ class UpdateEngine:
         K.conv_dgrad(_ptr(self.dd1), Wp("dec.conv1.weight"), _ptr(self.dl), _ptr(self.ddl), B, 21, 21, 32, 128, 1, 1, st)
         K.linear_wgrad(_ptr(self.haT), P1, 0, _ptr(self.ddl), FEAT, 0, G("dec.proj.weight"), 0, G("dec.proj.bias"), 0,
                        B, FEAT, P1, 0, 1, st)
-        K.linear_dgrad(_ptr(self.ddl), FEAT, 0, Wp("dec.proj.weight"), 0, 0, 0, 0, _ptr(self.dhaT), P1, 0, B, FEAT, P1, 0, 0, 1, st)
+        K.linear_dgrad(_ptr(self.ddl), FEAT, 0, Wp("dec.proj.weight"), 0, 0, 0, 0, _ptr(self.dhaT), P1, 0, B, FEAT, P1, 0, 2, 1, st)
         dfeat = _ptr(self.dbuf[1])
         self.proj_bwd(_ptr(self.dhaT), P1, B, _ptr(self.zT), _ptr(self.haT), P1, "critic_proj", _ptr(self.dzT),
                       feat_ptr=_ptr(self.actT[10]), dfeat=dfeat)

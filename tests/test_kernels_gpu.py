@@ -53,7 +53,7 @@ def wk(w):        # [Cout][Cin][3][3] -> [Cout][3][3][Cin]
 
 # ------------------------------------------------------------------ Linear
 @pytest.mark.parametrize("M,N,K_,relu,split", [(128, 1024, 102, 0, 0), (37, 100, 14112, 0, 1), (256, 1, 1024, 1, 0),
-                                               (5, 4, 1024, 1, 0), (130, 14112, 102, 0, 0), (1, 1024, 100, 0, 0)])
+                                               (5, 4, 1024, 1, 0), (130, 14112, 102, 0, 0), (1, 1024, 100, 0, 0), (64, 4, 1024, 1, 2), (128, 1, 1024, 1, 2)])
 def test_linear_fwd(M, N, K_, relu, split):
     x, w, b = rnd(M, K_, seed=1), rnd(N, K_, seed=2, scale=0.05), rnd(N, seed=3)
     y = torch.zeros(M, N, device=DEV)
@@ -524,3 +524,27 @@ def test_conv1_fwd_pitched_output():
     got = y[:, :41].permute(0, 3, 1, 2)
     close(got, ref, rtol=1e-3, what="conv1 pitched")
     assert torch.equal(got, tf32_round(got)) and float((y[:, 41:] + 1.0).abs().max()) == 0.0
+
+
+def test_conv1_via_im2col_matches_direct_kernels():
+    B = 3
+    g = torch.Generator().manual_seed(5)
+    obs = torch.randint(0, 256, (B, 9, 100, 100), generator=g).float().to(DEV)
+    w = rnd(32, 9, 3, 3, seed=2, scale=0.2); b = rnd(32, seed=3)
+    col = torch.full((B * 1681, 84), 5.0, device=DEV)
+    K.conv1_im2col(P(obs), P(col), B, 100, ST())
+    assert float(col[:, 81:].abs().max()) == 0.0
+    y0 = torch.zeros(B * 1681 * 32, device=DEV); y1 = torch.zeros(B * 1681 * 32, device=DEV)
+    K.conv1_fwd(P(obs), P(w), P(b), P(y0), B, 100, 9, 32, 0, ST())
+    K.conv1_fwd_col(P(col), P(w), P(b), P(y1), B, 0, ST())
+    close(y1, y0, rtol=1e-6, what="conv1 fwd via col")
+    dy = rnd(B * 1681, 32, seed=4)
+    dw0 = torch.zeros(32 * 81, device=DEV); db0 = torch.zeros(32, device=DEV); dw1 = torch.zeros(32 * 81, device=DEV); db1 = torch.zeros(32, device=DEV)
+    K.conv1_wgrad(P(obs), P(dy), P(dw0), P(db0), B, 100, 9, 32, ST())
+    K.conv1_wgrad_col(P(col), P(dy), P(dw1), P(db1), B, ST())
+    close(dw1, dw0, rtol=1e-5, what="conv1 wgrad via col"); close(db1, db0, rtol=1e-5, what="conv1 bgrad via col")
+    obs84 = obs[:, :, 8:92, 8:92].contiguous()
+    d0 = torch.zeros(B, 9, 84, 84, device=DEV); d1 = torch.ones(B, 9, 84, 84, device=DEV); dcol = torch.zeros(B * 1681, 84, device=DEV)
+    K.conv1_dgrad(P(dy), P(w), P(d0), B, 9, 32, ST())
+    K.conv1_dgrad_col(P(dy), P(w), P(dcol), P(d1), B, ST())
+    close(d1, d0, rtol=1e-5, what="conv1 dgrad via col")
