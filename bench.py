@@ -160,12 +160,15 @@ def profile_kernels(agent, rb, nsteps=4):
             e1.record()
             recs.append((_n, args, e0, e1))
         setattr(api, n, wrap)
+    graphs = agent.use_cuda_graphs
+    agent.use_cuda_graphs = False                     # per-call timing needs the eager path
     try:
         L = NullLog()
         for s in range(1, nsteps + 1):
             agent.update(rb, L, s)
         torch.cuda.synchronize()
     finally:
+        agent.use_cuda_graphs = graphs
         for n, fn in saved.items():
             setattr(api, n, fn)
     dump = os.environ.get("SGQN_PROFILE_CALLS")
@@ -311,7 +314,8 @@ def run_b200(a):
                                "9x84x84 uint8 stacks, A=2, sgqn_quantile=0.95, reference init, steps alternate odd/even",
                    "per_gpu_batch": B, "global_batch": Bg, "parallelism": f"dp{world}" if world > 1 else "single",
                    "replay_capacity": CAPACITY, "l2_policy": "inputs larger than L2 (423 MB frame ring, random gather; ~390 MB activations per encoder pass)",
-                   "value_definition": "global updates/s x (global_batch/128)"},
+                   "value_definition": "global updates/s x (global_batch/128)",
+                   "cuda_graphs": bool(agent.use_cuda_graphs), "conv_precision": agent.engine.precision},
         "e2e": {"value": e2e_v, "unit": "updates/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "how": "agent.update(replay_buffer, L, step) with the replay frame ring in pinned HOST memory (gather kernel pulls the "
                        "sampled stacks host->device every step) and the loss vector copied device->host every step"},

@@ -14,6 +14,7 @@ import numpy as np
 import torch
 
 from . import init as _init
+from . import _lib
 from ._lib import K
 from .engine import UpdateEngine, _ptr
 from .layout import reference_key_map
@@ -95,6 +96,10 @@ class SAC(object):
         self._ring = _Ring()
         self._supplied = None
         self.defer_logs = True
+        # CUDA graphs: after one eager update of each kind (odd / even step pattern) the whole update -- device RNG,
+        # replay gather, ~200 kernels, optimiser steps -- is captured once and replayed with a single launch.
+        self.use_cuda_graphs = dist is None
+        self._graphs, self._eager_runs, self._graph_rb, self._graph_nodes = {}, {}, None, {}
         self.train()
 
     # ---- parameters
@@ -212,11 +217,50 @@ class SAC(object):
             cols += [("train_actor/loss", 1), ("train_alpha/loss", 2), ("train_alpha/value", 3)]
         return cols
 
-    def update(self, replay_buffer, L, step, count=0):
-        self.count = count
+    def _step_kind(self, step):
+        return (step % self.actor_update_freq == 0, step % self.critic_target_update_freq == 0)
+
+    def _run_update(self, replay_buffer, step):
         self._draw(replay_buffer)
         self._sample_into_engine(replay_buffer)
+        self._engine_update(step)
+
+    def _engine_update(self, step):
         self.engine.update_sac(step, self.critic_mode)
+
+    def _update_maybe_graphed(self, replay_buffer, step):
+        """Eager the first time a step kind is seen (and whenever randomness is host-supplied or the buffer is foreign);
+        afterwards one cudaGraphLaunch per update."""
+        kind = self._step_kind(step)
+        graphable = (self.use_cuda_graphs and self._supplied is None and isinstance(replay_buffer, ReplayBuffer)
+                     and self._graphable())
+        if not graphable:
+            self._run_update(replay_buffer, step)
+            return
+        if self._graph_rb is not replay_buffer:            # pointers are baked into the graphs
+            self._graphs.clear(); self._eager_runs.clear(); self._graph_rb = replay_buffer
+        g = self._graphs.get(kind)
+        if g is None:
+            if self._eager_runs.get(kind, 0) < 1:
+                self._eager_runs[kind] = self._eager_runs.get(kind, 0) + 1
+                self._run_update(replay_buffer, step)
+                return
+            g = torch.cuda.CUDAGraph()
+            c0 = _lib.launch_count
+            with torch.cuda.graph(g):
+                self._run_update(replay_buffer, step)
+            self._graphs[kind] = g
+            self._graph_nodes[kind] = _lib.launch_count - c0
+            _lib.launch_count = c0                          # capturing launched nothing
+        g.replay()
+        _lib.launch_count += self._graph_nodes[kind]        # kernels-launching ABI calls replayed by this graph
+
+    def _graphable(self):
+        return True
+
+    def update(self, replay_buffer, L, step, count=0):
+        self.count = count
+        self._update_maybe_graphed(replay_buffer, step)
         self._emit_logs(L, step, self._log_cols(step))
 
 
@@ -244,6 +288,9 @@ class SVEA(SAC):
 
     def set_places_pool(self, imgs):
         self.places_pool = torch.as_tensor(imgs, dtype=torch.float32).to(self.engine.dev)
+
+    def _graphable(self):
+        return False                    # the places batch is assembled with torch indexing per step
 
     def update(self, replay_buffer, L, step, count=0):
         eng, B = self.engine, self.batch_size
@@ -295,10 +342,14 @@ class SGSAC(SAC):
         self.count = count
         if step % self.aux_update_freq == 0 and self.engine.overlay_pool is None:
             raise RuntimeError("SGSAC.update_aux needs the overlay pool: agent.set_overlay_pool(uint8 frames (N,3,84,84))")
-        self._draw(replay_buffer)
-        self._sample_into_engine(replay_buffer)
-        self.engine.update_sgsac(step)
+        self._update_maybe_graphed(replay_buffer, step)
         self._emit_logs(L, step, self._log_cols(step))
+
+    def _step_kind(self, step):
+        return super()._step_kind(step) + (step % self.aux_update_freq == 0,)
+
+    def _engine_update(self, step):
+        self.engine.update_sgsac(step)
 
     # stage-wise entry points mirroring rl_utils (used by the parity tests and by eval-time visualisation)
     def compute_attribution(self, obs, action):

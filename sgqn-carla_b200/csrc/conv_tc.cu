@@ -19,11 +19,10 @@
 
 namespace {
 
-constexpr int kStages = 6;
+constexpr int kMaxStages = 6;
 constexpr int kTileM = 128;
-constexpr int kABytes = kTileM * 128;          // 16 KB per tap tile
 constexpr int kWBytes = 9 * 32 * 128;          // 36 KB: 9 taps x [32 n][32 k] fp32
-constexpr int kSmemBytes = kStages * kABytes + kWBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int kSmemBudget = 200 * 1024;        // dynamic shared memory we ask for
 
 struct TcParams {
     int total_q;            // B * Hr * Wp virtual output positions (input-pitch coordinates)
@@ -33,6 +32,7 @@ struct TcParams {
     int Hq, Wq, oy, ox;     // output buffer: rows per sample, pitch, offset of output (0,0)
     int Hm, Wm;             // mask buffer: rows per sample, pitch (mask of output (y,x) at row y, col x)
     int num_tiles;
+    int halo_rows, stage_bytes, stages;   // A stage = one halo tile: rows [q0+shift, q0+shift+halo_rows) serve all 9 taps
     const float* bias;
     const float* mask;
     float* out;
@@ -103,10 +103,11 @@ __global__ void __launch_bounds__(192, 1)
 conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, TcParams p) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const int kStages = p.stages;
     const uint32_t a_sm = base;
-    const uint32_t w_sm = base + kStages * kABytes;
+    const uint32_t w_sm = base + kStages * p.stage_bytes;
     const uint32_t bars = w_sm + kWBytes;                         // 8-byte mbarriers
-    const uint32_t full0 = bars, empty0 = bars + 8 * kStages, wbar = bars + 16 * kStages;
+    const uint32_t full0 = bars, empty0 = bars + 8 * kMaxStages, wbar = bars + 16 * kMaxStages;
     const uint32_t tfull0 = wbar + 8, tempty0 = tfull0 + 16;
     const uint32_t tmem_slot = tempty0 + 16;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -114,7 +115,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"((unsigned long long)&tmA) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"((unsigned long long)&tmW) : "memory");
-        for (int s = 0; s < kStages; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
+        for (int s = 0; s < kMaxStages; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
         mbar_init(wbar, 1);
         for (int a = 0; a < 2; ++a) { mbar_init(tfull0 + 8 * a, 1); mbar_init(tempty0 + 8 * a, 128); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -135,13 +136,11 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             for (int t = 0; t < 9; ++t) tma_load_2d(&tmW, wbar, w_sm + t * 4096, t * 32, 0);
             int stage = 0; uint32_t phase = 0;
             for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-                const int q0 = tile * kTileM;
-                for (int t = 0; t < 9; ++t) {
-                    mbar_wait(empty0 + 8 * stage, phase ^ 1u);
-                    mbar_expect_tx(full0 + 8 * stage, kABytes);
-                    tma_load_2d(&tmA, full0 + 8 * stage, a_sm + stage * kABytes, 0, q0 + (t / 3) * p.Wp + (t % 3) + p.shift);
-                    if (++stage == kStages) { stage = 0; phase ^= 1u; }
-                }
+                // one halo tile per output tile: the 9 tap operands are row-shifted views of it (9x less L2->SM traffic)
+                mbar_wait(empty0 + 8 * stage, phase ^ 1u);
+                mbar_expect_tx(full0 + 8 * stage, p.stage_bytes);
+                tma_load_2d(&tmA, full0 + 8 * stage, a_sm + stage * p.stage_bytes, 0, tile * kTileM + p.shift);
+                if (++stage == kStages) { stage = 0; phase ^= 1u; }
             }
         }
     } else if (warp == 1) {
@@ -153,17 +152,19 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 mbar_wait(tempty0 + 8 * acc, acc_phase ^ 1u);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)(acc * 32);
+                mbar_wait(full0 + 8 * stage, phase);
+                tc_fence_after();
                 for (int t = 0; t < 9; ++t) {
-                    mbar_wait(full0 + 8 * stage, phase);
-                    tc_fence_after();
-                    const uint64_t ad = make_desc_sw128(a_sm + stage * kABytes);
+                    // tap (ky,kx) = the halo tile shifted by ky*Wp + kx rows of 128 B; the 128B swizzle is a function of
+                    // the absolute shared-memory address, so a row-shifted start address reads what TMA wrote
+                    const uint64_t ad = make_desc_sw128(a_sm + stage * p.stage_bytes + ((t / 3) * p.Wp + (t % 3)) * 128);
                     const uint64_t bd = make_desc_sw128(w_sm + t * 4096);
 #pragma unroll
                     for (int k = 0; k < 4; ++k)          // advance 8 TF32 = 32 B inside the swizzle atom: +2 in the >>4 address field
                         tc_mma_tf32(d_tmem, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), kIdesc, (t | k) != 0);
-                    tc_commit(empty0 + 8 * stage);       // smem slot free once these MMAs retire
-                    if (++stage == kStages) { stage = 0; phase ^= 1u; }
                 }
+                tc_commit(empty0 + 8 * stage);           // smem slot free once these MMAs retire
+                if (++stage == kStages) { stage = 0; phase ^= 1u; }
                 tc_commit(tfull0 + 8 * acc);             // accumulator complete -> epilogue
                 if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
             }
@@ -277,7 +278,7 @@ extern "C" int sgqn_conv_tc(const float* x, const float* w, const float* bias, c
     static int smem_set = 0;
     static int num_sms = 0;
     if (!smem_set) {
-        cudaError_t e = cudaFuncSetAttribute(conv3x3_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+        cudaError_t e = cudaFuncSetAttribute(conv3x3_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget);
         if (e != cudaSuccess) return (int)e;
         int dev = 0;
         cudaGetDevice(&dev);
@@ -291,13 +292,19 @@ extern "C" int sgqn_conv_tc(const float* x, const float* w, const float* bias, c
     p.bias = bias; p.mask = mask; p.out = out;
     p.relu_out = flags & 1; p.round_out = (flags >> 1) & 1; p.mask_mode = (flags >> 2) & 3;
     if (p.mask_mode && !mask) return (int)cudaErrorInvalidValue;
+    p.halo_rows = (kTileM + 2 * Wp + 2 + 7) / 8 * 8;               // whole 1024-byte swizzle atoms
+    if (p.halo_rows > 256) return (int)cudaErrorInvalidValue;      // TMA box limit
+    p.stage_bytes = p.halo_rows * 128;
+    p.stages = (kSmemBudget - kWBytes - 1024 - 256) / p.stage_bytes;
+    if (p.stages > kMaxStages) p.stages = kMaxStages;
+    if (p.stages < 2) return (int)cudaErrorInvalidValue;
     CUtensorMap tmA, tmW;
-    int rc = make_map_2d(&tmA, x, 32, (uint64_t)p.total_q, 32, kTileM);
+    int rc = make_map_2d(&tmA, x, 32, (uint64_t)p.total_q, 32, (uint32_t)p.halo_rows);
     if (rc) return rc;
     rc = make_map_2d(&tmW, w, 288, 32, 32, 32);
     if (rc) return rc;
     int grid = p.num_tiles < num_sms ? p.num_tiles : num_sms;
-    conv3x3_tc_kernel<<<grid, 192, kSmemBytes, (cudaStream_t)stream>>>(tmA, tmW, p);
+    conv3x3_tc_kernel<<<grid, 192, kSmemBudget, (cudaStream_t)stream>>>(tmA, tmW, p);
     return SGQN_CHECK_LAUNCH();
 }
 

@@ -257,6 +257,26 @@ def test_device_rng_update_runs_and_is_finite():
     assert (6, "train/aux_loss") in vals and (5, "train/aux_loss") not in vals
 
 
+def test_cuda_graph_replay_equals_eager():
+    """Graph-captured updates (device RNG inside the graph) produce the same parameters as eager updates."""
+    outs = []
+    for graphs in (False, True):
+        agent, rb, orc, rep, args = _mk(B=8, precision="fp32")
+        agent.use_cuda_graphs = graphs
+        L = _L()
+        for step in range(1, 9):
+            agent.update(rb, L, step)
+        torch.cuda.synchronize()
+        assert (len(agent._graphs) == 2) == graphs
+        outs.append((agent.get_parameters(), {k: float(v) for k, v in L.rows.items()}))
+    (p0, l0), (p1, l1) = outs
+    for k in l0:
+        np.testing.assert_allclose(l1[k], l0[k], rtol=2e-2, atol=1e-4, err_msg=str(k))      # atomics reorder sums run to run
+    for n in p0:
+        d = float((p0[n].double() - p1[n].double()).abs().mean())
+        assert d <= 2e-4, (n, d)
+
+
 def test_foreign_replay_buffer_surface():
     """A buffer exposing only the reference's `sample()` (utils.py:185-198) still drives update()."""
     agent, rb, orc, rep, args = _mk(B=8)
