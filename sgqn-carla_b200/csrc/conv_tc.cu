@@ -10,8 +10,8 @@
 // The data-gradient is the same kernel on a zero-bordered (pad 2) gradient buffer with flipped / transposed weights
 // and a ReLU-mask (plain or guided, rl_utils.py:35-39) epilogue writing into the interior of the next padded buffer.
 //
-// Warp roles (192 threads): warp 0 = TMA producer (one lane), warp 1 = TMEM allocator + MMA issuer (one lane),
-// warps 2..5 = epilogue (TMEM -> registers -> bias / ReLU / mask / TF32 round -> global).
+// Warp roles (320 threads): warp 0 = TMA producer (one lane), warp 1 = TMEM allocator + MMA issuer (one lane),
+// warps 2..9 = epilogue (TMEM -> registers -> bias / ReLU / mask / TF32 round -> global), two warps per TMEM lane quarter.
 #include <cuda.h>
 #include <cstdio>
 #include "common.cuh"
@@ -99,7 +99,7 @@ __device__ __forceinline__ float round_tf32(float v) {
     return __uint_as_float(r);
 }
 
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(320, 1)
 conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, TcParams p) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -117,7 +117,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         asm volatile("prefetch.tensormap [%0];" ::"l"((unsigned long long)&tmW) : "memory");
         for (int s = 0; s < kMaxStages; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
         mbar_init(wbar, 1);
-        for (int a = 0; a < 2; ++a) { mbar_init(tfull0 + 8 * a, 1); mbar_init(tempty0 + 8 * a, 128); }
+        for (int a = 0; a < 2; ++a) { mbar_init(tfull0 + 8 * a, 1); mbar_init(tempty0 + 8 * a, 256); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -170,48 +170,53 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             }
         }
     } else {
+        // 8 epilogue warps: warp w works on TMEM lane quarter (w & 3) and on 16 of the 32 accumulator columns
         const int quarter = warp & 3;                    // TMEM lane quarter this warp may access
+        const int half = (warp - 2) >> 2;                // which 16 output channels
         const int row = quarter * 32 + lane;
         int acc = 0; uint32_t acc_phase = 0;
         const int HW = p.Hr * p.Wp;
+        float bias_r[16];
+#pragma unroll
+        for (int e = 0; e < 16; ++e) bias_r[e] = p.bias ? __ldg(p.bias + half * 16 + e) : 0.f;
         for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+            // output coordinates first (independent of the accumulator), so the mask load is in flight during the wait
+            const int q = tile * kTileM + row;
+            const int b = q / HW; const int r2 = q - b * HW; const int y = r2 / p.Wp; const int x = r2 - y * p.Wp;
+            const bool valid = q < p.total_q && y < p.Hv && x < p.Wv;
+            float4 mk[4];
+            if (p.mask_mode && valid) {
+                const float4* mp = reinterpret_cast<const float4*>(p.mask + ((size_t)(b * p.Hm + y) * p.Wm + x) * 32 + half * 16);
+#pragma unroll
+                for (int c4 = 0; c4 < 4; ++c4) mk[c4] = __ldg(mp + c4);
+            }
             mbar_wait(tfull0 + 8 * acc, acc_phase);
             tc_fence_after();
-            uint32_t v[32];
-            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * 32);
+            uint32_t v[16];
+            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * 32 + half * 16);
             asm volatile(
-                "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-                "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-                "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+                "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-                  "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
-                  "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
-                  "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                  "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
                 : "r"(taddr) : "memory");
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
             tc_fence_before();
             mbar_arrive(tempty0 + 8 * acc);              // accumulator drained: MMA warp may reuse it
             if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
-
-            const int q = tile * kTileM + row;
-            if (q >= p.total_q) continue;
-            const int b = q / HW; const int r2 = q - b * HW; const int y = r2 / p.Wp; const int x = r2 - y * p.Wp;
-            if (y >= p.Hv || x >= p.Wv) continue;
-            float* dst = p.out + ((size_t)(b * p.Hq + y + p.oy) * p.Wq + x + p.ox) * 32;
-            const float4* mk = p.mask_mode ? reinterpret_cast<const float4*>(p.mask + ((size_t)(b * p.Hm + y) * p.Wm + x) * 32) : nullptr;
+            if (!valid) continue;
+            float* dst = p.out + ((size_t)(b * p.Hq + y + p.oy) * p.Wq + x + p.ox) * 32 + half * 16;
 #pragma unroll
-            for (int c4 = 0; c4 < 8; ++c4) {
+            for (int c4 = 0; c4 < 4; ++c4) {
                 float o[4];
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
-                    float f = __uint_as_float(v[4 * c4 + e]);
-                    if (p.bias) f += __ldg(p.bias + 4 * c4 + e);
+                    float f = __uint_as_float(v[4 * c4 + e]) + bias_r[4 * c4 + e];
                     if (p.relu_out) f = fmaxf(f, 0.f);
                     o[e] = f;
                 }
                 if (p.mask_mode) {
-                    const float4 m = __ldg(mk + c4);
-                    const float mm[4] = {m.x, m.y, m.z, m.w};
+                    const float mm[4] = {mk[c4].x, mk[c4].y, mk[c4].z, mk[c4].w};
 #pragma unroll
                     for (int e = 0; e < 4; ++e) {
                         if (p.mask_mode == 2) o[e] = fmaxf(o[e], 0.f);
@@ -304,7 +309,7 @@ extern "C" int sgqn_conv_tc(const float* x, const float* w, const float* bias, c
     rc = make_map_2d(&tmW, w, 288, 32, 32, 32);
     if (rc) return rc;
     int grid = p.num_tiles < num_sms ? p.num_tiles : num_sms;
-    conv3x3_tc_kernel<<<grid, 192, kSmemBudget, (cudaStream_t)stream>>>(tmA, tmW, p);
+    conv3x3_tc_kernel<<<grid, 320, kSmemBudget, (cudaStream_t)stream>>>(tmA, tmW, p);
     return SGQN_CHECK_LAUNCH();
 }
 

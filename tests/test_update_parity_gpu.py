@@ -181,7 +181,10 @@ def test_sgsac_critic_stage(dense, quantile, precision):
 def test_full_updates_match_oracle(algorithm, precision):
     B, A = 8, 2
     tf = precision == "tf32"
-    agent, rb, orc, rep, args = _mk(algorithm=algorithm, B=B, precision=precision)
+    # fp32: dense N(0,0.05) weights (adversarial: every activation is live).  tf32: the reference's own initialisation
+    # (what training starts from); 10-bit-mantissa operands make a dense random 11-layer ReLU net drift by several %
+    # within a few Adam steps, which says nothing about the kernels.
+    agent, rb, orc, rep, args = _mk(algorithm=algorithm, B=B, precision=precision, dense=None if tf else 0.05)
     if algorithm == "svea":
         agent.set_places_pool(torch.rand(4, 3, 84, 84))
     rs = np.random.RandomState(9)
