@@ -195,6 +195,14 @@ def profile_kernels(agent, rb, nsteps=4):
             B, Hv = args[5], args[8]
             fl = 2.0 * B * Hv * Hv * 9 * 32 * 32
             key = "conv_tc[32->32 " + ("dgrad" if args[10] else "fwd") + "]"
+        elif n == "conv_tcg":
+            B, Cin, Cout, Hv = args[5], args[8], args[9], args[10]
+            fl = 2.0 * B * Hv * Hv * 9 * Cin * Cout
+            key = f"conv_tcg[{Cin}->{Cout}]"
+        elif n == "conv_wgrad_tcg":
+            B, Hr, Cin, Cout = args[3], args[4], args[6], args[7]
+            fl = 2.0 * B * (Hr - 2) * (Hr - 2) * 9 * Cin * Cout
+            key = f"conv_wgrad_tcg[{Cin}->{Cout}]"
         elif n == "conv_wgrad_tc":
             B, Wp = args[3], args[5]
             fl = 2.0 * B * (Wp - 2) * (Wp - 2) * 9 * 32 * 32

@@ -86,8 +86,18 @@ int sgqn_conv_tc(const float* x, const float* w, const float* bias, const float*
  *      red.global.add per CTA and element): x, dy [B][Hr][Wp][32] share one geometry, dy zero outside its valid region */
 int sgqn_conv_wgrad_tc(const float* x, const float* dy, float* dw, int B, int Hr, int Wp, void* stream);
 int sgqn_conv_weights_prep(const float* w, long long lstride, float* wf, float* wd, int n_layers, void* stream);
-int sgqn_pad_copy(const float* src, float* dst, int B, int H, int W, int C, int Hq, int Wq, int oy, int ox, int round_out,
-                  void* stream);
+int sgqn_pad_copy(const float* src, float* dst, int B, int H, int W, int C, int Hq, int Wq, int oy, int ox,
+                  int flags /* bit0 TF32 round, bit1 ReLU */, void* stream);
+/* ---- generalised tcgen05 convs for the AttributionDecoder (modules.py:319-326; conv_tcg.cu): Cin = 32*k, Cout in {32,64,128},
+ *      weights streamed per (channel chunk, tap); forward and data gradient through sgqn_conv_tcg (flags bit4: scatter every
+ *      output to the 2x2 block of the next layer's zero-bordered input = fused ReLU + nearest x2 upsample), weight gradient
+ *      through sgqn_conv_wgrad_tcg; sgqn_pool2_bwd is the backward of the fused upsample + ReLU. */
+int sgqn_conv_tcg(const float* x, const float* wop, const float* bias, const float* mask, float* out, int B, int Hr, int Wp, int Cin,
+                  int Cout, int Hv, int Wv, int shift, int Hq, int Wq, int oy, int ox, int Hm, int Wm, int flags, void* stream);
+int sgqn_conv_weights_prep_g(const float* w, float* wf, float* wd, int Cout, int Cin, int Cout_real, void* stream);
+int sgqn_conv_wgrad_tcg(const float* x, const float* dy, float* dw, int B, int Hr, int Wp, int Cin, int Cout, int ta, int tb,
+                        void* stream);
+int sgqn_pool2_bwd(const float* dup, const float* src, float* dst, int B, int H, int W, int C, void* stream);
 /* backward of F.upsample(x, 2) followed by ReLU mask of the pre-upsample activation (modules.py:333-337) */
 int sgqn_upsample2_bwd(const float* dup, const float* act, float* dx, int B, int Hs, int Ws, int C, void* stream);
 
@@ -117,7 +127,8 @@ int sgqn_critic_loss(const float* q, long long qs, const float* tq1, const float
                      float wb, float* target_q, float* dq, float* loss, int B, int Bg, void* stream);
 int sgqn_actor_loss(const float* q, long long qs, const float* log_pi, const double* log_alpha, float target_entropy, float* dq,
                     float* out3, double* alpha_grad, int B, int Bg, void* stream);
-int sgqn_bce(const float* logits, const uint8_t* mask, float* loss, float* dlogits, int B, int HW, int Cs, int Bg, void* stream);
+int sgqn_bce(const float* logits, const uint8_t* mask, float* loss, float* dlogits, int B, int H, int W, int Hq, int Wq, int oy,
+             int ox, int Cs, int Bg, int round_out, void* stream);
 
 /* ---- optimiser: torch.optim.Adam (sac.py:60-68, sgsac.py:35-39) over a flat range, soft target update
  *      (utils.py:31-33, sac.py:153-158) fused when target != NULL */

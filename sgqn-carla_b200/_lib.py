@@ -33,6 +33,10 @@ SIGNATURES = {
     "sgqn_conv1_fwd_col": [_p, _p, _p, _p, _i, _i, _p],
     "sgqn_conv1_wgrad_col": [_p, _p, _p, _p, _i, _p],
     "sgqn_conv1_dgrad_col": [_p, _p, _p, _p, _i, _p],
+    "sgqn_conv_tcg": [_p, _p, _p, _p, _p] + [_i] * 15 + [_p],
+    "sgqn_conv_weights_prep_g": [_p, _p, _p, _i, _i, _i, _p],
+    "sgqn_conv_wgrad_tcg": [_p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p],
+    "sgqn_pool2_bwd": [_p, _p, _p, _i, _i, _i, _i, _p],
     "sgqn_upsample2_bwd": [_p, _p, _p, _i, _i, _i, _i, _p],
     "sgqn_minmax": [_p, _ll, _p, _p, _p],
     "sgqn_attribution_mask": [_p, _p, _p, _p, _f, _p, _p, _i, _i, _p],
@@ -45,7 +49,7 @@ SIGNATURES = {
     "sgqn_actor_head_bwd": [_p, _p, _p, _i, _p, _f, _f, _p, _i, _i, _p],
     "sgqn_critic_loss": [_p, _ll, _p, _p, _p, _p, _p, _p, _f, _i, _f, _f, _p, _p, _p, _i, _i, _p],
     "sgqn_actor_loss": [_p, _ll, _p, _p, _f, _p, _p, _p, _i, _i, _p],
-    "sgqn_bce": [_p, _p, _p, _p, _i, _i, _i, _i, _p],
+    "sgqn_bce": [_p, _p, _p, _p] + [_i] * 10 + [_p],
     "sgqn_adam_prep": [_p, _p, _d, _d, _p],
     "sgqn_adam": [_p, _p, _p, _p, _ll, _p, _f, _f, _f, _f, _f, _p, _ll, _f, _f, _p],
     "sgqn_ema": [_p, _p, _ll, _ll, _f, _f, _p],

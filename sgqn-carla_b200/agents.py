@@ -60,6 +60,7 @@ class _ModuleView(object):
             o, st, _ = lay.entries[n]
             flat[o - base:o - base + st].copy_(lay.to_stored(n, sd[key]).to(flat.device))
         eng.prep_conv_weights(target=self._target)
+        eng.prep_dec_weights()
 
     def parameters(self):
         return list(self.state_dict().values())
@@ -114,6 +115,7 @@ class SAC(object):
             eng.log_alpha.copy_(torch.as_tensor(canonical["log_alpha"], dtype=torch.float64).reshape(1))
         eng.prep_conv_weights()
         eng.prep_conv_weights(target=True)
+        eng.prep_dec_weights()
 
     def get_parameters(self):
         eng = self.engine

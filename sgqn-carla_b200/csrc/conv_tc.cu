@@ -12,10 +12,10 @@
 //
 // Warp roles (320 threads): warp 0 = TMA producer (one lane), warp 1 = TMEM allocator + MMA issuer (one lane),
 // warps 2..9 = epilogue (TMEM -> registers -> bias / ReLU / mask / TF32 round -> global), two warps per TMEM lane quarter.
-#include <cuda.h>
-#include <cstdio>
-#include "common.cuh"
+#include "tc_common.cuh"
 #include "../../include/sgqn_b200.h"
+
+using namespace tc;
 
 namespace {
 
@@ -39,65 +39,8 @@ struct TcParams {
     int relu_out, round_out, mask_mode;
 };
 
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-// bounded wait: a protocol bug must trap (sticky error, the host sees it) instead of hanging the GPU
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    uint32_t done = 0;
-    for (uint32_t it = 0; it < (1u << 26); ++it) {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(done) : "r"(bar), "r"(parity) : "memory");
-        if (done) return;
-    }
-    printf("sgqn conv_tc: mbarrier timeout (block %d thread %d bar %u parity %u)\n", blockIdx.x, threadIdx.x, bar, parity);
-    __trap();
-}
-__device__ __forceinline__ void tma_load_2d(const CUtensorMap* tm, uint32_t bar, uint32_t dst, int c0, int c1) {
-    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-                 ::"r"(dst), "l"((unsigned long long)tm), "r"(bar), "r"(c0), "r"(c1) : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_commit(uint32_t bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void tc_mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
-}
-// K-major, SWIZZLE_128B operand tile: rows of 128 B, 8-row atoms 1024 B apart (cute::UMMA::SmemDescriptor, version 1)
-__device__ __forceinline__ uint64_t make_desc_sw128(uint32_t saddr) {
-    uint64_t d = 0;
-    d |= (uint64_t)((saddr >> 4) & 0x3FFF);            // start address
-    d |= (uint64_t)1 << 16;                            // leading byte offset (unused for swizzled K-major) = 1
-    d |= (uint64_t)(1024 >> 4) << 32;                  // stride byte offset between 8-row groups
-    d |= (uint64_t)1 << 46;                            // descriptor version (Blackwell)
-    d |= (uint64_t)2 << 61;                            // SWIZZLE_128B
-    return d;
-}
 // kind::tf32, D fp32, A/B TF32 K-major, M = 128, N = 32 (cute::UMMA::InstrDescriptor)
 constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((32u >> 3) << 17) | ((128u >> 4) << 24);
-
-__device__ __forceinline__ float round_tf32(float v) {
-    uint32_t r;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
-    return __uint_as_float(r);
-}
 
 __global__ void __launch_bounds__(320, 1)
 conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, TcParams p) {
@@ -239,37 +182,6 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
 }
 
-// cuTensorMapEncodeTiled through the runtime's driver entry point lookup: libcuda is NOT a link dependency, so the
-// library still loads (and exports its symbols) on a CPU-only build box.
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-EncodeTiledFn get_encode_fn() {
-    static EncodeTiledFn fn = nullptr;
-    if (!fn) {
-        void* p = nullptr;
-        cudaDriverEntryPointQueryResult qres;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
-            qres == cudaDriverEntryPointSuccess)
-            fn = (EncodeTiledFn)p;
-    }
-    return fn;
-}
-
-int make_map_2d(CUtensorMap* tm, const float* ptr, uint64_t cols, uint64_t rows, uint32_t box_cols, uint32_t box_rows,
-                CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
-    EncodeTiledFn cuTensorMapEncodeTiled = get_encode_fn();
-    if (!cuTensorMapEncodeTiled) return (int)cudaErrorNotSupported;
-    cuuint64_t dims[2] = {cols, rows};
-    cuuint64_t strides[1] = {cols * sizeof(float)};
-    cuuint32_t box[2] = {box_cols, box_rows};
-    cuuint32_t estr[2] = {1, 1};
-    CUresult r = cuTensorMapEncodeTiled(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)ptr, dims, strides, box, estr,
-                                        CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
-                                        CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    return r == CUDA_SUCCESS ? 0 : 900 + (int)r;
-}
-
 }  // namespace
 
 // x: [B][Hr][Wp][32]; w: [32 n][9 taps][32 k] (TF32-rounded copy).  Output (b,y,x), y < Hv, x < Wv, is the 3x3 window sum
@@ -341,7 +253,8 @@ __global__ void pad_copy_kernel(const float4* __restrict__ src, float4* __restri
     int c = (int)(i % C4); long long t = i / C4;
     int x = (int)(t % W); t /= W; int y = (int)(t % H); int b = (int)(t / H);
     float4 v = __ldg(src + i);
-    if (round_out) { v.x = round_tf32(v.x); v.y = round_tf32(v.y); v.z = round_tf32(v.z); v.w = round_tf32(v.w); }
+    if (round_out & 2) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+    if (round_out & 1) { v.x = round_tf32(v.x); v.y = round_tf32(v.y); v.z = round_tf32(v.z); v.w = round_tf32(v.w); }
     dst[(((size_t)b * Hq + y + oy) * Wq + x + ox) * C4 + c] = v;
 }
 extern "C" int sgqn_pad_copy(const float* src, float* dst, int B, int H, int W, int C, int Hq, int Wq, int oy, int ox,

@@ -1,0 +1,474 @@
+// Generalised tcgen05 / TMEM / TMA implicit-GEMM 3x3 convolution: Cin = 32*KC input channels, N = Cout in {32, 64, 128},
+// stride 1, TF32 operands, fp32 accumulation.  Used for the AttributionDecoder convs (modules.py:319-326), forward and
+// data gradient: conv1 32->128 @21x21, conv2 128->64 @42x42 (input = nearest x2 upsample of relu(conv1)), conv3 64->9(32)
+// @84x84 (input = nearest x2 upsample of relu(conv2)); padding 1 is a zero border in the pitch-linear input buffer.
+//
+// Same pitch-linear formulation as conv_tc.cu (one 2-D TMA halo tile per 128 consecutive output positions serves all 9
+// taps through row-shifted UMMA descriptors), with two differences: the K loop runs over channel chunks of 32 (one halo
+// tile per chunk, ring "A"), and the weights do not fit in shared memory, so the [N][32] weight tile of every
+// (chunk, tap) streams through its own TMA ring "W".  The epilogue can scatter every output pixel to the 2x2 block of
+// the next layer's zero-bordered input (ReLU + nearest upsample + TF32 rounding fused into the producer).
+#include "tc_common.cuh"
+#include "../../include/sgqn_b200.h"
+
+using namespace tc;
+
+namespace {
+
+constexpr int kTileM = 128;
+constexpr int kSmemBudget = 208 * 1024;
+constexpr int kMaxA = 4, kMaxW = 8;
+
+struct GParams {
+    int total_q, Hr, Wp, Hv, Wv, shift;
+    int Hq, Wq, oy, ox, Hm, Wm;
+    int num_tiles, kc, cin;
+    int a_bytes, piece_rows, pieces, a_stages, w_stages;
+    const float* bias;
+    const float* mask;
+    float* out;
+    int relu_out, round_out, mask_mode, upsample;
+};
+
+template <int N>
+__global__ void __launch_bounds__(320, 1)
+conv3x3_tcg_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, GParams p) {
+    constexpr int kWBytes = N * 128;
+    constexpr uint32_t kIdescN = idesc_tf32(N, false, false);
+    constexpr int kTmemCols = 2 * N < 32 ? 32 : 2 * N;               // 64 / 128 / 256: powers of two
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t a_sm = base;
+    const uint32_t w_sm = a_sm + p.a_stages * p.a_bytes;
+    const uint32_t bias_sm = w_sm + p.w_stages * kWBytes;
+    const uint32_t bars = bias_sm + N * 4;
+    const uint32_t afull0 = bars, aempty0 = afull0 + 8 * kMaxA, wfull0 = aempty0 + 8 * kMaxA, wempty0 = wfull0 + 8 * kMaxW;
+    const uint32_t tfull0 = wempty0 + 8 * kMaxW, tempty0 = tfull0 + 16, tmem_slot = tempty0 + 16;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"((unsigned long long)&tmA) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"((unsigned long long)&tmW) : "memory");
+        for (int s = 0; s < kMaxA; ++s) { mbar_init(afull0 + 8 * s, 1); mbar_init(aempty0 + 8 * s, 1); }
+        for (int s = 0; s < kMaxW; ++s) { mbar_init(wfull0 + 8 * s, 1); mbar_init(wempty0 + 8 * s, 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(tfull0 + 8 * a, 1); mbar_init(tempty0 + 8 * a, 256); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(kTmemCols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (warp >= 2) {
+        for (int i = threadIdx.x - 64; i < N; i += 256) {
+            float bv = p.bias ? __ldg(p.bias + i) : 0.f;
+            asm volatile("st.shared.f32 [%0], %1;" ::"r"(bias_sm + 4 * i), "f"(bv) : "memory");
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    uint32_t tmem_base;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int as = 0, ws = 0; uint32_t aph = 0, wph = 0;
+            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+                const int r0 = tile * kTileM + p.shift;
+                for (int c = 0; c < p.kc; ++c) {
+                    mbar_wait(aempty0 + 8 * as, aph ^ 1u);
+                    mbar_expect_tx(afull0 + 8 * as, p.a_bytes);
+                    for (int pc = 0; pc < p.pieces; ++pc)
+                        tma_load_2d(&tmA, afull0 + 8 * as, a_sm + as * p.a_bytes + pc * p.piece_rows * 128, c * 32, r0 + pc * p.piece_rows);
+                    if (++as == p.a_stages) { as = 0; aph ^= 1u; }
+                    for (int t = 0; t < 9; ++t) {
+                        mbar_wait(wempty0 + 8 * ws, wph ^ 1u);
+                        mbar_expect_tx(wfull0 + 8 * ws, kWBytes);
+                        tma_load_2d(&tmW, wfull0 + 8 * ws, w_sm + ws * kWBytes, t * p.cin + c * 32, 0);
+                        if (++ws == p.w_stages) { ws = 0; wph ^= 1u; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            int as = 0, ws = 0; uint32_t aph = 0, wph = 0; int acc = 0; uint32_t acc_phase = 0;
+            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+                mbar_wait(tempty0 + 8 * acc, acc_phase ^ 1u);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * N);
+                for (int c = 0; c < p.kc; ++c) {
+                    mbar_wait(afull0 + 8 * as, aph);
+                    tc_fence_after();
+                    const uint32_t a0 = a_sm + as * p.a_bytes;
+                    for (int t = 0; t < 9; ++t) {
+                        mbar_wait(wfull0 + 8 * ws, wph);
+                        tc_fence_after();
+                        const uint64_t ad = make_desc_sw128(a0 + ((t / 3) * p.Wp + (t % 3)) * 128);
+                        const uint64_t bd = make_desc_sw128(w_sm + ws * kWBytes);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                            tc_mma_tf32(d_tmem, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), kIdescN, (c | t | k) != 0);
+                        tc_commit(wempty0 + 8 * ws);
+                        if (++ws == p.w_stages) { ws = 0; wph ^= 1u; }
+                    }
+                    tc_commit(aempty0 + 8 * as);
+                    if (++as == p.a_stages) { as = 0; aph ^= 1u; }
+                }
+                tc_commit(tfull0 + 8 * acc);
+                if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+            }
+        }
+    } else {
+        constexpr int CPW = N / 2;                       // accumulator columns per epilogue warp
+        const int quarter = warp & 3;
+        const int half = (warp - 2) >> 2;
+        const int row = quarter * 32 + lane;
+        int acc = 0; uint32_t acc_phase = 0;
+        const int HW = p.Hr * p.Wp;
+        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+            const int q = tile * kTileM + row;
+            const int b = q / HW; const int r2 = q - b * HW; const int y = r2 / p.Wp; const int x = r2 - y * p.Wp;
+            const bool valid = q < p.total_q && y < p.Hv && x < p.Wv;
+            mbar_wait(tfull0 + 8 * acc, acc_phase);
+            tc_fence_after();
+            uint32_t v[CPW];
+#pragma unroll
+            for (int g = 0; g < CPW / 16; ++g) {
+                const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * N + half * CPW + g * 16);
+                asm volatile(
+                    "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+                    "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                    : "=r"(v[16 * g + 0]), "=r"(v[16 * g + 1]), "=r"(v[16 * g + 2]), "=r"(v[16 * g + 3]), "=r"(v[16 * g + 4]),
+                      "=r"(v[16 * g + 5]), "=r"(v[16 * g + 6]), "=r"(v[16 * g + 7]), "=r"(v[16 * g + 8]), "=r"(v[16 * g + 9]),
+                      "=r"(v[16 * g + 10]), "=r"(v[16 * g + 11]), "=r"(v[16 * g + 12]), "=r"(v[16 * g + 13]), "=r"(v[16 * g + 14]),
+                      "=r"(v[16 * g + 15])
+                    : "r"(taddr) : "memory");
+            }
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            tc_fence_before();
+            mbar_arrive(tempty0 + 8 * acc);
+            if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+            if (!valid) continue;
+            const int c0 = half * CPW;
+            const float* mk = p.mask_mode ? p.mask + ((size_t)(b * p.Hm + y) * p.Wm + x) * N + c0 : nullptr;
+            float* dst0;
+            if (p.upsample) dst0 = p.out + ((size_t)(b * p.Hq + 2 * y + p.oy) * p.Wq + 2 * x + p.ox) * N + c0;
+            else dst0 = p.out + ((size_t)(b * p.Hq + y + p.oy) * p.Wq + x + p.ox) * N + c0;
+#pragma unroll
+            for (int c4 = 0; c4 < CPW / 4; ++c4) {
+                float o[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    float bv;
+                    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(bv) : "r"(bias_sm + 4 * (c0 + 4 * c4 + e)));
+                    float f = __uint_as_float(v[4 * c4 + e]) + bv;
+                    if (p.relu_out) f = fmaxf(f, 0.f);
+                    o[e] = f;
+                }
+                if (p.mask_mode) {
+                    const float4 m = __ldg(reinterpret_cast<const float4*>(mk) + c4);
+                    const float mm[4] = {m.x, m.y, m.z, m.w};
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        if (p.mask_mode == 2) o[e] = fmaxf(o[e], 0.f);
+                        o[e] = mm[e] > 0.f ? o[e] : 0.f;
+                    }
+                }
+                if (p.round_out) {
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) o[e] = round_tf32(o[e]);
+                }
+                const float4 ov = make_float4(o[0], o[1], o[2], o[3]);
+                reinterpret_cast<float4*>(dst0)[c4] = ov;
+                if (p.upsample) {                        // nearest x2: the same value at (2y,2x+1), (2y+1,2x), (2y+1,2x+1)
+                    reinterpret_cast<float4*>(dst0 + N)[c4] = ov;
+                    reinterpret_cast<float4*>(dst0 + (size_t)p.Wq * N)[c4] = ov;
+                    reinterpret_cast<float4*>(dst0 + (size_t)p.Wq * N + N)[c4] = ov;
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+    }
+}
+
+template <int N>
+int launch_tcg(const CUtensorMap& tmA, const CUtensorMap& tmW, const GParams& p, int smem, cudaStream_t st) {
+    static int inited = 0, num_sms = 0;
+    if (!inited) {
+        cudaError_t e = cudaFuncSetAttribute(conv3x3_tcg_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget);
+        if (e != cudaSuccess) return (int)e;
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+        inited = 1;
+    }
+    int grid = p.num_tiles < num_sms ? p.num_tiles : num_sms;
+    conv3x3_tcg_kernel<N><<<grid, 320, smem, st>>>(tmA, tmW, p);
+    return SGQN_CHECK_LAUNCH();
+}
+
+}  // namespace
+
+// x: [B][Hr][Wp][Cin] pitch-linear (zero border where the conv pads); wop: TF32 operand copy [Cout][9][Cin] (forward) or
+// [Cin_orig][9 flipped][Cout_orig] (data gradient), made by sgqn_conv_weights_prep_g.  Output (b,y,x), y < Hv, x < Wv, is the
+// 3x3 window sum over input rows q + ky*Wp + kx + shift, q = (b*Hr + y)*Wp + x, and goes to
+// out[((b*Hq + y+oy)*Wq + x+ox)*Cout]; with flags bit4 it goes to the 2x2 block at (2y+oy, 2x+ox) (nearest upsample).
+// flags: bit0 ReLU, bit1 TF32 round, bits 2-3 mask mode against mask[((b*Hm + y)*Wm + x)*Cout], bit4 upsample.
+extern "C" int sgqn_conv_tcg(const float* x, const float* wop, const float* bias, const float* mask, float* out, int B, int Hr,
+                             int Wp, int Cin, int Cout, int Hv, int Wv, int shift, int Hq, int Wq, int oy, int ox, int Hm, int Wm,
+                             int flags, void* stream) {
+    if (B <= 0) return 0;
+    if ((Cin & 31) || (Cout != 32 && Cout != 64 && Cout != 128)) return (int)cudaErrorInvalidValue;
+    GParams p;
+    p.total_q = B * Hr * Wp; p.Hr = Hr; p.Wp = Wp; p.Hv = Hv; p.Wv = Wv; p.shift = shift;
+    p.Hq = Hq; p.Wq = Wq; p.oy = oy; p.ox = ox; p.Hm = Hm; p.Wm = Wm;
+    p.num_tiles = (p.total_q + kTileM - 1) / kTileM;
+    p.kc = Cin / 32; p.cin = Cin;
+    p.bias = bias; p.mask = mask; p.out = out;
+    p.relu_out = flags & 1; p.round_out = (flags >> 1) & 1; p.mask_mode = (flags >> 2) & 3; p.upsample = (flags >> 4) & 1;
+    if (p.mask_mode && !mask) return (int)cudaErrorInvalidValue;
+    int halo = kTileM + 2 * Wp + 2;
+    p.pieces = halo > 256 ? 2 : 1;
+    p.piece_rows = ((halo + p.pieces - 1) / p.pieces + 7) / 8 * 8;
+    if (p.piece_rows > 256) return (int)cudaErrorInvalidValue;
+    p.a_bytes = p.pieces * p.piece_rows * 128;
+    const int wb = Cout * 128;
+    p.w_stages = kMaxW;
+    while (p.w_stages > 2 && kSmemBudget - 4096 - p.w_stages * wb < 2 * p.a_bytes) --p.w_stages;
+    p.a_stages = (kSmemBudget - 4096 - p.w_stages * wb) / p.a_bytes;
+    if (p.a_stages > kMaxA) p.a_stages = kMaxA;
+    if (p.a_stages < 2) return (int)cudaErrorInvalidValue;
+    int smem = p.a_stages * p.a_bytes + p.w_stages * wb + Cout * 4 + 512 + 1024;
+    CUtensorMap tmA, tmW;
+    int rc = make_map_2d(&tmA, x, (uint64_t)Cin, (uint64_t)p.total_q, 32, (uint32_t)p.piece_rows);
+    if (rc) return rc;
+    rc = make_map_2d(&tmW, wop, (uint64_t)9 * Cin, (uint64_t)Cout, 32, (uint32_t)Cout);
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (Cout == 32) return launch_tcg<32>(tmA, tmW, p, smem, st);
+    if (Cout == 64) return launch_tcg<64>(tmA, tmW, p, smem, st);
+    return launch_tcg<128>(tmA, tmW, p, smem, st);
+}
+
+// TF32 operand copies of a [Cout][9][Cin] conv weight (Cout_real <= Cout rows are real, the rest of wf/wd is zero-filled):
+// wf[co][t][ci] = rna(w[co][t][ci]);  wd[ci][t][co] = rna(w[co][8-t][ci])
+__global__ void conv_weights_prep_g_kernel(const float* __restrict__ w, float* __restrict__ wf, float* __restrict__ wd, int Cout,
+                                           int Cin, int Cout_real) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= Cout * 9 * Cin) return;
+    int co = i / (9 * Cin), r = i - co * 9 * Cin, t = r / Cin, ci = r - t * Cin;
+    float v = co < Cout_real ? round_tf32(w[i]) : 0.f;
+    wf[i] = v;
+    wd[((size_t)ci * 9 + (8 - t)) * Cout + co] = v;
+}
+extern "C" int sgqn_conv_weights_prep_g(const float* w, float* wf, float* wd, int Cout, int Cin, int Cout_real, void* stream) {
+    int n = Cout * 9 * Cin;
+    if (n <= 0) return 0;
+    conv_weights_prep_g_kernel<<<cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>(w, wf, wd, Cout, Cin, Cout_real);
+    return SGQN_CHECK_LAUNCH();
+}
+
+// =====================================================================================================================
+// Generalised weight gradient:  dW[co][ky*3+kx][c*32+ci] += sum_q dY[q][co] * X[q + (ky+ta)*Wp + kx + tb][c*32+ci]
+// X: [rows][Cin = 32*KC], dY: [rows][N = 32*NA], both pitch-linear over the same position index q.
+// grid = (pixel ranges, 3): blockIdx.y = ky.  Per 64-position block a CTA loads, per channel chunk c, ONE X tile of 72 rows
+// starting at q0 + (ky+ta)*Wp + tb, and the NA dY tiles.  MN-major TF32 operands (SWIZZLE_128B_BASE32B).  One M=128
+// accumulator per chunk: its four 32-row atoms are the SAME tile shifted by kx = 0,1,2,(3 unused) rows -- the UMMA
+// descriptor's leading-byte-offset is simply 128 B.  N = Cout columns per accumulator (KC*N <= 512 TMEM columns).
+namespace {
+
+constexpr int kGwRows = 64;
+constexpr int kGwXRows = 72;
+constexpr int kGwStagesMax = 4;
+
+struct GwParams { int total_q, Wp, ta, tb, kc, cin, na, kb_total, kb_per_cta, stages, stage_bytes; float* dw; };
+
+__device__ __forceinline__ uint64_t make_desc_mn32(uint32_t saddr, uint32_t lbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)(512 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)1 << 61;                             // SWIZZLE_128B_BASE32B
+    return d;
+}
+
+template <int N>
+__global__ void __launch_bounds__(192, 1)
+conv3x3_wgrad_tcg_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmD, GwParams p) {
+    constexpr uint32_t kIdescMN = idesc_tf32(N, true, true);
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t bars = base + p.stages * p.stage_bytes + 1024;      // +1 KB: the unused 4th atom reads past the last X tile
+    const uint32_t full0 = bars, empty0 = bars + 8 * kGwStagesMax, done_bar = empty0 + 8 * kGwStagesMax, tmem_slot = done_bar + 8;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int ky = blockIdx.y;
+    const int kb0 = blockIdx.x * p.kb_per_cta;
+    const int kb1 = min(p.kb_total, kb0 + p.kb_per_cta);
+    const int tmem_cols = p.kc * N < 32 ? 32 : (p.kc * N <= 64 ? 64 : (p.kc * N <= 128 ? 128 : (p.kc * N <= 256 ? 256 : 512)));
+    const uint32_t xtile = kGwXRows * 128, dtile = kGwRows * 128;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"((unsigned long long)&tmX) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"((unsigned long long)&tmD) : "memory");
+        for (int s = 0; s < kGwStagesMax; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
+        mbar_init(done_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(tmem_cols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    uint32_t tmem_base;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            for (int kb = kb0; kb < kb1; ++kb) {
+                const int q0 = kb * kGwRows;
+                const uint32_t sb = base + stage * p.stage_bytes;
+                mbar_wait(empty0 + 8 * stage, phase ^ 1u);
+                mbar_expect_tx(full0 + 8 * stage, p.kc * xtile + p.na * dtile);
+                for (int c = 0; c < p.kc; ++c)
+                    tma_load_2d(&tmX, full0 + 8 * stage, sb + c * xtile, c * 32, q0 + (ky + p.ta) * p.Wp + p.tb);
+                for (int a = 0; a < p.na; ++a)
+                    tma_load_2d(&tmD, full0 + 8 * stage, sb + p.kc * xtile + a * dtile, a * 32, q0);
+                if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            for (int kb = kb0; kb < kb1; ++kb) {
+                const uint32_t sb = base + stage * p.stage_bytes;
+                mbar_wait(full0 + 8 * stage, phase);
+                tc_fence_after();
+#pragma unroll 1
+                for (int j = 0; j < kGwRows / 8; ++j) {
+                    const uint64_t bd = make_desc_mn32(sb + p.kc * xtile + j * 1024, dtile);
+                    for (int c = 0; c < p.kc; ++c) {
+                        const uint64_t ad = make_desc_mn32(sb + c * xtile + j * 1024, 128);    // atoms = row shifts kx = 0..3
+                        tc_mma_tf32(tmem_base + (uint32_t)(c * N), ad, bd, kIdescMN, (kb != kb0 || j != 0) ? 1u : 0u);
+                    }
+                }
+                tc_commit(empty0 + 8 * stage);
+                if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+            }
+            tc_commit(done_bar);
+        }
+    } else if (kb1 > kb0) {
+        const int kx = warp & 3;                          // TMEM lane quarter = accumulator rows of tap kx
+        mbar_wait(done_bar, 0);
+        tc_fence_after();
+        for (int c = 0; c < p.kc; ++c) {
+#pragma unroll 1
+            for (int g = 0; g < N / 16; ++g) {
+                uint32_t v[16];
+                const uint32_t taddr = tmem_base + ((uint32_t)(kx * 32) << 16) + (uint32_t)(c * N + g * 16);
+                asm volatile(
+                    "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+                    "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                    : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                      "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                    : "r"(taddr) : "memory");
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                if (kx < 3) {
+                    float* dst = p.dw + (size_t)(ky * 3 + kx) * p.cin + c * 32 + lane;
+#pragma unroll
+                    for (int e = 0; e < 16; ++e) atomicAdd(dst + (size_t)(g * 16 + e) * 9 * p.cin, __uint_as_float(v[e]));
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
+    }
+}
+
+template <int N>
+int launch_wgrad_tcg(const CUtensorMap& tmX, const CUtensorMap& tmD, GwParams& p, cudaStream_t st) {
+    static int inited = 0, num_sms = 0;
+    if (!inited) {
+        cudaError_t e = cudaFuncSetAttribute(conv3x3_wgrad_tcg_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget);
+        if (e != cudaSuccess) return (int)e;
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+        inited = 1;
+    }
+    int gx = (num_sms + 2) / 3;
+    if (gx > p.kb_total) gx = p.kb_total;
+    p.kb_per_cta = (p.kb_total + gx - 1) / gx;
+    gx = (p.kb_total + p.kb_per_cta - 1) / p.kb_per_cta;
+    int smem = p.stages * p.stage_bytes + 1024 + 1024 + 256;
+    conv3x3_wgrad_tcg_kernel<N><<<dim3(gx, 3), 192, smem, st>>>(tmX, tmD, p);
+    return SGQN_CHECK_LAUNCH();
+}
+
+}  // namespace
+
+// x: [rows][Cin], dy: [rows][Cout] over the same B*Hr*Wp positions; dw[Cout][9][Cin] += ... (atomic; caller zero-fills).
+// (ta, tb): the activation row paired with dy row q for tap (ky,kx) is q + (ky+ta)*Wp + kx + tb.
+extern "C" int sgqn_conv_wgrad_tcg(const float* x, const float* dy, float* dw, int B, int Hr, int Wp, int Cin, int Cout, int ta,
+                                   int tb, void* stream) {
+    if (B <= 0) return 0;
+    if ((Cin & 31) || (Cout != 32 && Cout != 64 && Cout != 128) || (Cin / 32) * Cout > 512) return (int)cudaErrorInvalidValue;
+    GwParams p;
+    p.total_q = B * Hr * Wp; p.Wp = Wp; p.ta = ta; p.tb = tb; p.kc = Cin / 32; p.cin = Cin; p.na = Cout / 32; p.dw = dw;
+    p.kb_total = (p.total_q + kGwRows - 1) / kGwRows;
+    p.stage_bytes = p.kc * kGwXRows * 128 + p.na * kGwRows * 128;
+    p.stages = (kSmemBudget - 4096) / p.stage_bytes;
+    if (p.stages > kGwStagesMax) p.stages = kGwStagesMax;
+    if (p.stages < 2) return (int)cudaErrorInvalidValue;
+    CUtensorMap tmX, tmD;
+    int rc = make_map_2d(&tmX, x, (uint64_t)Cin, (uint64_t)p.total_q, 32, kGwXRows, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+    if (rc) return rc;
+    rc = make_map_2d(&tmD, dy, (uint64_t)Cout, (uint64_t)p.total_q, 32, kGwRows, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (Cout == 32) return launch_wgrad_tcg<32>(tmX, tmD, p, st);
+    if (Cout == 64) return launch_wgrad_tcg<64>(tmX, tmD, p, st);
+    return launch_wgrad_tcg<128>(tmX, tmD, p, st);
+}
+
+// backward of "nearest x2 upsample of relu(x)": dst(b,y,x) = (sum of the 2x2 block of dup) * 1[src(2y,2x) > 0]
+// dup compact [B][2H][2W][C]; src = the upsampled, zero-bordered forward buffer [B][2H+2][2W+2][C] (value of (Y,X) at row Y+1,
+// col X); dst = zero-bordered gradient buffer [B][H+2][W+2][C] (value of (y,x) at row y+1, col x), TF32-rounded.
+__global__ void pool2_bwd_kernel(const float4* __restrict__ dup, const float4* __restrict__ src, float4* __restrict__ dst, int H, int W,
+                                 int C4, long long total) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    int c = (int)(i % C4); long long t = i / C4;
+    int x = (int)(t % W); t /= W; int y = (int)(t % H); int b = (int)(t / H);
+    const int W2 = 2 * W;
+    size_t d0 = (((size_t)b * 2 * H + 2 * y) * W2 + 2 * x) * C4 + c;
+    float4 a0 = __ldg(dup + d0), a1 = __ldg(dup + d0 + C4), a2 = __ldg(dup + d0 + (size_t)W2 * C4), a3 = __ldg(dup + d0 + (size_t)W2 * C4 + C4);
+    float4 m = __ldg(src + (((size_t)b * (2 * H + 2) + 2 * y + 1) * (W2 + 2) + 2 * x) * C4 + c);
+    float4 r;
+    r.x = m.x > 0.f ? round_tf32((a0.x + a1.x) + (a2.x + a3.x)) : 0.f;
+    r.y = m.y > 0.f ? round_tf32((a0.y + a1.y) + (a2.y + a3.y)) : 0.f;
+    r.z = m.z > 0.f ? round_tf32((a0.z + a1.z) + (a2.z + a3.z)) : 0.f;
+    r.w = m.w > 0.f ? round_tf32((a0.w + a1.w) + (a2.w + a3.w)) : 0.f;
+    dst[(((size_t)b * (H + 2) + y + 1) * (W + 2) + x) * C4 + c] = r;
+}
+extern "C" int sgqn_pool2_bwd(const float* dup, const float* src, float* dst, int B, int H, int W, int C, void* stream) {
+    if (C & 3) return (int)cudaErrorInvalidValue;
+    long long total = (long long)B * H * W * (C / 4);
+    if (total <= 0) return 0;
+    pool2_bwd_kernel<<<(unsigned)cdivll(total, 256), 256, 0, (cudaStream_t)stream>>>((const float4*)dup, (const float4*)src,
+                                                                                    (float4*)dst, H, W, C / 4, total);
+    return SGQN_CHECK_LAUNCH();
+}

@@ -224,34 +224,41 @@ extern "C" int sgqn_actor_loss(const float* q, long long qs, const float* log_pi
 }
 
 // ---------------------------------------------------------------- BCE-with-logits against the attribution mask (sgsac.py:163-167)
-// logits NHWC [B][HW][Cs] (Cs >= 9 stored channels, extra ones are padding); mask [B][3][HW] uint8 (frame f covers channels 3f..3f+2)
+// logits NHWC with Cs >= 9 stored channels (extra ones are padding) in a [B][Hq][Wq][Cs] buffer, pixel (y,x) at row y+oy,
+// col x+ox; mask [B][3][H*W] uint8 (frame f covers channels 3f..3f+2).  dlogits has the logits' layout.
 __global__ void __launch_bounds__(256)
 bce_kernel(const float* __restrict__ logits, const uint8_t* __restrict__ mask, float* __restrict__ loss,
-           float* __restrict__ dlogits, int HW, int Cs, long long npix, float inv_n) {
+           float* __restrict__ dlogits, int H, int W, int Hq, int Wq, int oy, int ox, int Cs, long long npix, float inv_n,
+           int round_out) {
     __shared__ float sh[33];
     float acc = 0.f;
+    const int HW = H * W;
     for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < npix; p += (long long)gridDim.x * blockDim.x) {
         int b = (int)(p / HW), i = (int)(p - (long long)b * HW);
-        const float* x = logits + (size_t)p * Cs;
-        float* d = dlogits + (size_t)p * Cs;
+        int y = i / W, xx = i - y * W;
+        size_t o = (((size_t)b * Hq + y + oy) * Wq + xx + ox) * Cs;
+        const float* x = logits + o;
+        float* d = dlogits + o;
         for (int c = 0; c < Cs; ++c) {
             if (c >= 9) { d[c] = 0.f; continue; }
-            float y = (float)mask[((size_t)b * 3 + c / 3) * HW + i];
+            float yv = (float)mask[((size_t)b * 3 + c / 3) * HW + i];
             float v = x[c];
-            acc += fmaxf(v, 0.f) - v * y + log1pf(expf(-fabsf(v)));
-            d[c] = (1.f / (1.f + expf(-v)) - y) * inv_n;
+            acc += fmaxf(v, 0.f) - v * yv + log1pf(expf(-fabsf(v)));
+            float g = (1.f / (1.f + expf(-v)) - yv) * inv_n;
+            if (round_out) { uint32_t r; asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(g)); g = __uint_as_float(r); }
+            d[c] = g;
         }
     }
     float tot = block_sum(acc, sh);
     if (threadIdx.x == 0) atomicAdd(loss, tot * inv_n);
 }
 
-extern "C" int sgqn_bce(const float* logits, const uint8_t* mask, float* loss, float* dlogits, int B, int HW, int Cs, int Bg,
-                        void* stream) {
-    long long npix = (long long)B * HW;
+extern "C" int sgqn_bce(const float* logits, const uint8_t* mask, float* loss, float* dlogits, int B, int H, int W, int Hq, int Wq,
+                        int oy, int ox, int Cs, int Bg, int round_out, void* stream) {
+    long long npix = (long long)B * H * W;
     if (npix <= 0) return 0;
-    float inv_n = 1.0f / ((float)Bg * 9.0f * (float)HW);
+    float inv_n = 1.0f / ((float)Bg * 9.0f * (float)(H * W));
     int grid = (int)(cdivll(npix, 256) < 1184 ? cdivll(npix, 256) : 1184);
-    bce_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(logits, mask, loss, dlogits, HW, Cs, npix, inv_n);
+    bce_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(logits, mask, loss, dlogits, H, W, Hq, Wq, oy, ox, Cs, npix, inv_n, round_out);
     return SGQN_CHECK_LAUNCH();
 }

@@ -112,8 +112,18 @@ class UpdateEngine:
             self.dl = f32(B, FEAT); self.ddl = f32(B, FEAT)
             self.d1 = f32(B * 21 * 21 * 128); self.dd1 = f32(B * 21 * 21 * 128)
             self.d2 = f32(B * 42 * 42 * 64); self.dd2 = f32(B * 42 * 42 * 64)
-            self.lg = f32(B * 84 * 84 * DEC_C3); self.dlg = f32(B * 84 * 84 * DEC_C3)
+            self.lg = f32(B * 86 * 86 * DEC_C3); self.dlg = f32(B * 86 * 86 * DEC_C3)
             self.dup3 = f32(B * 84 * 84 * 64); self.dup2 = f32(B * 42 * 42 * 128)
+            if precision == "tf32":
+                # tcgen05 decoder: zero-bordered pitch-linear buffers [B][H+2][W+2][C], image at rows [1,H+1), cols [0,W)
+                # (borders are zero from this allocation on; kernels only ever write the interior)
+                self.xin1 = f32(B * 23 * 23 * 32)        # relu(proj output)
+                self.xin2 = f32(B * 44 * 44 * 128)       # up2(relu(conv1))
+                self.xin3 = f32(B * 86 * 86 * 64)        # up2(relu(conv2))
+                self.dd2g = f32(B * 44 * 44 * 64)        # d conv2 output
+                self.dd1g = f32(B * 23 * 23 * 128)       # d conv1 output
+                self.dwf = [f32(128 * 9 * 32), f32(64 * 9 * 128), f32(DEC_C3 * 9 * 64)]     # TF32 operand copies (forward)
+                self.dwd = [f32(128 * 9 * 32), f32(64 * 9 * 128), f32(DEC_C3 * 9 * 64)]     # ... (data gradient)
         if algorithm == "svea":
             self.places = f32(B, 3, 84 * 84)
         self.debug_masked_obs = None
@@ -162,6 +172,13 @@ class UpdateEngine:
             hi, ho = ENC_H[l - 1], ENC_H[l]
             K.conv_fwd(_ptr(acts[l - 1], row0 * hi * hi * 32), W(f"cnn.{l}.weight"), W(f"cnn.{l}.bias"),
                        _ptr(acts[l], row0 * ho * ho * 32), n, hi, hi, 32, 32, 0, 1, 0, 1 if l < 10 else 0, st)
+
+    def prep_dec_weights(self):
+        if self.algorithm != "sgsac" or self.precision != "tf32":
+            return
+        for i, (name, co, ci, cr) in enumerate((("dec.conv1.weight", 128, 32, 128), ("dec.conv2.weight", 64, 128, 64),
+                                                ("dec.conv3.weight", DEC_C3, 64, 9))):
+            K.conv_weights_prep_g(self.P(name), _ptr(self.dwf[i]), _ptr(self.dwd[i]), co, ci, cr, self.st)
 
     def prep_conv_weights(self, target=False):
         """Refresh the TF32 operand copies after the 32->32 conv weights changed (optimiser step / EMA / load)."""
@@ -440,21 +457,11 @@ class UpdateEngine:
         Wp, G = self.P, self.G
         K.linear_fwd(_ptr(self.haT), P1, 0, Wp("dec.proj.weight"), 0, Wp("dec.proj.bias"), 0, _ptr(self.dl), FEAT, 0,
                      B, FEAT, P1, 0, 1, 0, st)
-        K.conv_fwd(_ptr(self.dl), Wp("dec.conv1.weight"), Wp("dec.conv1.bias"), _ptr(self.d1), B, 21, 21, 32, 128, 1, 1, 1, 0, st)
-        K.conv_fwd(_ptr(self.d1), Wp("dec.conv2.weight"), Wp("dec.conv2.bias"), _ptr(self.d2), B, 21, 21, 128, 64, 1, 2, 1, 0, st)
-        K.conv_fwd(_ptr(self.d2), Wp("dec.conv3.weight"), Wp("dec.conv3.bias"), _ptr(self.lg), B, 42, 42, 64, DEC_C3, 1, 2, 1, 0, st)
-        K.zero(_ptr(self.logs, 4), 4, st)
-        K.bce(_ptr(self.lg), _ptr(self.mask), _ptr(self.logs, 4), _ptr(self.dlg), B, 84 * 84, DEC_C3, self.Bg, st)
         x0, x1 = L.ranges["aux"]
-        K.zero(self._g + 4 * x0, 4 * (x1 - x0), st)
-        K.conv_wgrad(_ptr(self.d2), _ptr(self.dlg), G("dec.conv3.weight"), G("dec.conv3.bias"), B, 42, 42, 64, DEC_C3, 1, 2, 1, 0, st)
-        K.conv_dgrad(_ptr(self.dlg), Wp("dec.conv3.weight"), 0, _ptr(self.dup3), B, 84, 84, 64, DEC_C3, 1, 0, st)
-        K.upsample2_bwd(_ptr(self.dup3), _ptr(self.d2), _ptr(self.dd2), B, 42, 42, 64, st)
-        K.conv_wgrad(_ptr(self.d1), _ptr(self.dd2), G("dec.conv2.weight"), G("dec.conv2.bias"), B, 21, 21, 128, 64, 1, 2, 1, 0, st)
-        K.conv_dgrad(_ptr(self.dd2), Wp("dec.conv2.weight"), 0, _ptr(self.dup2), B, 42, 42, 128, 64, 1, 0, st)
-        K.upsample2_bwd(_ptr(self.dup2), _ptr(self.d1), _ptr(self.dd1), B, 21, 21, 128, st)
-        K.conv_wgrad(_ptr(self.dl), _ptr(self.dd1), G("dec.conv1.weight"), G("dec.conv1.bias"), B, 21, 21, 32, 128, 1, 1, 1, 0, st)
-        K.conv_dgrad(_ptr(self.dd1), Wp("dec.conv1.weight"), _ptr(self.dl), _ptr(self.ddl), B, 21, 21, 32, 128, 1, 1, st)
+        if self.precision == "tf32":
+            self._decoder_tc(B, st, Wp, G, x0, x1)
+        else:
+            self._decoder_simt(B, st, Wp, G, x0, x1)
         K.linear_wgrad(_ptr(self.haT), P1, 0, _ptr(self.ddl), FEAT, 0, G("dec.proj.weight"), 0, G("dec.proj.bias"), 0,
                        B, FEAT, P1, 0, 1, st)
         K.linear_dgrad(_ptr(self.ddl), FEAT, 0, Wp("dec.proj.weight"), 0, 0, 0, 0, _ptr(self.dhaT), P1, 0, B, FEAT, P1, 0, 2, 1, st)
@@ -465,6 +472,56 @@ class UpdateEngine:
         self.allreduce_grads((x0, x1))
         self.adam(self.opt_aux, (x0, x1))
         self.prep_conv_weights()
+        self.prep_dec_weights()
+
+    def _decoder_simt(self, B, st, Wp, G, x0, x1):
+        """AttributionDecoder convs + BCE + their backward on the fp32 CUDA-core kernels (compact NHWC buffers)."""
+        K.conv_fwd(_ptr(self.dl), Wp("dec.conv1.weight"), Wp("dec.conv1.bias"), _ptr(self.d1), B, 21, 21, 32, 128, 1, 1, 1, 0, st)
+        K.conv_fwd(_ptr(self.d1), Wp("dec.conv2.weight"), Wp("dec.conv2.bias"), _ptr(self.d2), B, 21, 21, 128, 64, 1, 2, 1, 0, st)
+        K.conv_fwd(_ptr(self.d2), Wp("dec.conv3.weight"), Wp("dec.conv3.bias"), _ptr(self.lg), B, 42, 42, 64, DEC_C3, 1, 2, 1, 0, st)
+        K.zero(_ptr(self.logs, 4), 4, st)
+        K.bce(_ptr(self.lg), _ptr(self.mask), _ptr(self.logs, 4), _ptr(self.dlg), B, 84, 84, 84, 84, 0, 0, DEC_C3, self.Bg, 0, st)
+        K.zero(self._g + 4 * x0, 4 * (x1 - x0), st)
+        K.conv_wgrad(_ptr(self.d2), _ptr(self.dlg), G("dec.conv3.weight"), G("dec.conv3.bias"), B, 42, 42, 64, DEC_C3, 1, 2, 1, 0, st)
+        K.conv_dgrad(_ptr(self.dlg), Wp("dec.conv3.weight"), 0, _ptr(self.dup3), B, 84, 84, 64, DEC_C3, 1, 0, st)
+        K.upsample2_bwd(_ptr(self.dup3), _ptr(self.d2), _ptr(self.dd2), B, 42, 42, 64, st)
+        K.conv_wgrad(_ptr(self.d1), _ptr(self.dd2), G("dec.conv2.weight"), G("dec.conv2.bias"), B, 21, 21, 128, 64, 1, 2, 1, 0, st)
+        K.conv_dgrad(_ptr(self.dd2), Wp("dec.conv2.weight"), 0, _ptr(self.dup2), B, 42, 42, 128, 64, 1, 0, st)
+        K.upsample2_bwd(_ptr(self.dup2), _ptr(self.d1), _ptr(self.dd1), B, 21, 21, 128, st)
+        K.conv_wgrad(_ptr(self.dl), _ptr(self.dd1), G("dec.conv1.weight"), G("dec.conv1.bias"), B, 21, 21, 32, 128, 1, 1, 1, 0, st)
+        K.conv_dgrad(_ptr(self.dd1), Wp("dec.conv1.weight"), _ptr(self.dl), _ptr(self.ddl), B, 21, 21, 32, 128, 1, 1, st)
+
+    def _decoder_tc(self, B, st, Wp, G, x0, x1):
+        """The same on the generalised tcgen05 kernels (conv_tcg.cu).  Every conv reads a zero-bordered pitch-linear
+        buffer [B][H+2][W+2][C] (image at rows [1,H+1), cols [0,W)); conv1 / conv2 write ReLU + nearest-x2 upsample + TF32
+        rounding of their output straight into the next conv's input buffer (modules.py:327-337 fused into the producer)."""
+        wf, wd = self.dwf, self.dwd
+        RU = 1 | 2 | 16                                       # ReLU, TF32 round, 2x2 upsample scatter
+        K.pad_copy(_ptr(self.dl), _ptr(self.xin1), B, 21, 21, 32, 23, 23, 1, 0, 3, st)
+        K.conv_tcg(_ptr(self.xin1), _ptr(wf[0]), Wp("dec.conv1.bias"), 0, _ptr(self.xin2), B, 23, 23, 32, 128, 21, 21, -1,
+                   44, 44, 1, 0, 0, 0, RU, st)
+        K.conv_tcg(_ptr(self.xin2), _ptr(wf[1]), Wp("dec.conv2.bias"), 0, _ptr(self.xin3), B, 44, 44, 128, 64, 42, 42, -1,
+                   86, 86, 1, 0, 0, 0, RU, st)
+        K.conv_tcg(_ptr(self.xin3), _ptr(wf[2]), Wp("dec.conv3.bias"), 0, _ptr(self.lg), B, 86, 86, 64, DEC_C3, 84, 84, -1,
+                   86, 86, 1, 0, 0, 0, 0, st)
+        K.zero(_ptr(self.logs, 4), 4, st)
+        K.bce(_ptr(self.lg), _ptr(self.mask), _ptr(self.logs, 4), _ptr(self.dlg), B, 84, 84, 86, 86, 1, 0, DEC_C3, self.Bg, 1, st)
+        K.zero(self._g + 4 * x0, 4 * (x1 - x0), st)
+        # conv3 backward
+        K.conv_wgrad_tcg(_ptr(self.xin3), _ptr(self.dlg), G("dec.conv3.weight"), B, 86, 86, 64, DEC_C3, -1, -1, st)
+        K.colsum(_ptr(self.dlg), DEC_C3, B * 86 * 86, DEC_C3, G("dec.conv3.bias"), st)
+        K.conv_tcg(_ptr(self.dlg), _ptr(wd[2]), 0, 0, _ptr(self.dup3), B, 86, 86, DEC_C3, 64, 84, 84, -1, 84, 84, 0, 0, 0, 0, 0, st)
+        K.pool2_bwd(_ptr(self.dup3), _ptr(self.xin3), _ptr(self.dd2g), B, 42, 42, 64, st)
+        # conv2 backward
+        K.conv_wgrad_tcg(_ptr(self.xin2), _ptr(self.dd2g), G("dec.conv2.weight"), B, 44, 44, 128, 64, -1, -1, st)
+        K.colsum(_ptr(self.dd2g), 64, B * 44 * 44, 64, G("dec.conv2.bias"), st)
+        K.conv_tcg(_ptr(self.dd2g), _ptr(wd[1]), 0, 0, _ptr(self.dup2), B, 44, 44, 64, 128, 42, 42, -1, 42, 42, 0, 0, 0, 0, 0, st)
+        K.pool2_bwd(_ptr(self.dup2), _ptr(self.xin2), _ptr(self.dd1g), B, 21, 21, 128, st)
+        # conv1 backward (ReLU mask of the projection output)
+        K.conv_wgrad_tcg(_ptr(self.xin1), _ptr(self.dd1g), G("dec.conv1.weight"), B, 23, 23, 32, 128, -1, -1, st)
+        K.colsum(_ptr(self.dd1g), 128, B * 23 * 23, 128, G("dec.conv1.bias"), st)
+        K.conv_tcg(_ptr(self.dd1g), _ptr(wd[0]), 0, _ptr(self.dl), _ptr(self.ddl), B, 23, 23, 128, 32, 21, 21, -1, 21, 21, 0, 0,
+                   21, 21, 1 << 2, st)
 
     def update_sgsac(self, step):
         """sgsac.py:169-185 after the sample (obs2[:B], next_obs, action, reward, not_done and the step's randomness

@@ -22,7 +22,7 @@ import torch
 
 FEAT = 32 * 21 * 21
 ENC_H = [41, 39, 37, 35, 33, 31, 29, 27, 25, 23, 21]      # spatial size after each SharedCNN conv (84x84 input)
-DEC_C3 = 16                                               # stored output channels of decoder.conv3 (9 real)
+DEC_C3 = 32                                               # stored output channels of decoder.conv3 (9 real; tcgen05 N)
 
 
 def _al4(n):

@@ -256,7 +256,7 @@ def test_bce():
     ref = F.binary_cross_entropy_with_logits(x, y)
     ref.backward()
     loss = torch.zeros(1, device=DEV); d = torch.ones(B, HW, Cs, device=DEV)
-    K.bce(P(lg), P(mask), P(loss), P(d), B, HW, Cs, B, ST())
+    K.bce(P(lg), P(mask), P(loss), P(d), B, 84, 84, 84, 84, 0, 0, Cs, B, 0, ST())
     close(loss, ref.detach().reshape(1), what="bce loss")
     close(d[:, :, :9].permute(0, 2, 1), x.grad, rtol=2e-4, what="bce grad")
     assert float(d[:, :, 9:].abs().max()) == 0.0
@@ -548,3 +548,86 @@ def test_conv1_via_im2col_matches_direct_kernels():
     K.conv1_dgrad(P(dy), P(w), P(d0), B, 9, 32, ST())
     K.conv1_dgrad_col(P(dy), P(w), P(dcol), P(d1), B, ST())
     close(d1, d0, rtol=1e-5, what="conv1 dgrad via col")
+
+
+# ------------------------------------------------------------------ generalised tcgen05 convs (decoder shapes)
+def bordered(x_nchw, Hq, Wq, oy, ox):
+    """NCHW -> zero-initialised NHWC buffer [B][Hq][Wq][C] with the image at rows [oy, oy+H), cols [ox, ox+W)."""
+    B, C, H, W = x_nchw.shape
+    out = torch.zeros(B, Hq, Wq, C, device=DEV)
+    out[:, oy:oy + H, ox:ox + W] = x_nchw.permute(0, 2, 3, 1)
+    return out
+
+
+def prep_wg(w, cs):
+    """w (Cout_real, Cin, 3, 3) -> stored [cs][9][Cin] + TF32 operand copies wf [cs][9][Cin], wd [Cin][9][cs]."""
+    co, ci = w.shape[:2]
+    ws = torch.zeros(cs, ci, 3, 3, device=DEV); ws[:co] = w
+    wk_ = wk(ws).contiguous()
+    wf = torch.zeros(cs * 9 * ci, device=DEV); wd = torch.zeros(cs * 9 * ci, device=DEV)
+    K.conv_weights_prep_g(P(wk_), P(wf), P(wd), cs, ci, co, ST())
+    return wf, wd
+
+
+DEC = [(2, 21, 32, 128, 128), (2, 42, 128, 64, 64), (1, 84, 64, 9, 32), (3, 23, 64, 32, 32)]
+
+
+@pytest.mark.parametrize("B,H,Cin,Co,Cs", DEC)
+def test_conv_tcg_forward_dgrad_wgrad(B, H, Cin, Co, Cs):
+    x = tf32_round(F.relu(rnd(B, Cin, H, H, seed=1)))
+    w = rnd(Co, Cin, 3, 3, seed=2, scale=0.05); b = rnd(Co, seed=3)
+    bs = torch.zeros(Cs, device=DEV); bs[:Co] = b
+    wf, wd = prep_wg(w, Cs)
+    wt = tf32_round(w)
+    xin = bordered(x, H + 2, H + 2, 1, 0)
+    # forward, compact output
+    y = torch.full((B, H, H, Cs), 3.0, device=DEV)
+    K.conv_tcg(P(xin), P(wf), P(bs), 0, P(y), B, H + 2, H + 2, Cin, Cs, H, H, -1, H, H, 0, 0, 0, 0, 0, ST())
+    torch.cuda.synchronize()
+    ref = F.conv2d(x.double(), wt.double(), b.double(), padding=1).float()
+    close(y.permute(0, 3, 1, 2)[:, :Co], ref, rtol=3e-5, what="conv_tcg fwd")
+    if Cs > Co:
+        assert float(y[..., Co:].abs().max()) == 0.0
+    # forward with fused ReLU + nearest x2 upsample + TF32 round into the next layer's zero-bordered input
+    up = torch.zeros(B, 2 * H + 2, 2 * H + 2, Cs, device=DEV)
+    K.conv_tcg(P(xin), P(wf), P(bs), 0, P(up), B, H + 2, H + 2, Cin, Cs, H, H, -1, 2 * H + 2, 2 * H + 2, 1, 0, 0, 0, 1 | 2 | 16, ST())
+    torch.cuda.synchronize()
+    refu = tf32_round(F.interpolate(F.relu(ref), scale_factor=2))
+    close(up[:, 1:2 * H + 1, :2 * H].permute(0, 3, 1, 2)[:, :Co], refu, rtol=1e-3, what="conv_tcg fwd upsample")
+    bz = up.clone(); bz[:, 1:2 * H + 1, :2 * H] = 0
+    assert float(bz.abs().max()) == 0.0
+    # data gradient (no mask / ReLU mask)
+    dy = tf32_round(rnd(B, Co, H, H, seed=4))
+    dys = torch.zeros(B, Cs, H, H, device=DEV); dys[:, :Co] = dy
+    dyb = bordered(dys, H + 2, H + 2, 1, 0)
+    refd = F.conv_transpose2d(dy.double(), wt.double(), padding=1).float()
+    if Cin in (32, 64, 128):
+        dx = torch.zeros(B, H, H, Cin, device=DEV)
+        K.conv_tcg(P(dyb), P(wd), 0, 0, P(dx), B, H + 2, H + 2, Cs, Cin, H, H, -1, H, H, 0, 0, 0, 0, 0, ST())
+        torch.cuda.synchronize()
+        close(dx.permute(0, 3, 1, 2), refd, rtol=3e-5, what="conv_tcg dgrad")
+        xm = nhwc(x)
+        K.conv_tcg(P(dyb), P(wd), 0, P(xm), P(dx), B, H + 2, H + 2, Cs, Cin, H, H, -1, H, H, 0, 0, H, H, 4, ST())
+        torch.cuda.synchronize()
+        close(dx.permute(0, 3, 1, 2), refd * (x > 0), rtol=3e-5, what="conv_tcg dgrad masked")
+    # weight gradient
+    dw = torch.zeros(Cs * 9 * Cin, device=DEV)
+    K.conv_wgrad_tcg(P(xin), P(dyb), P(dw), B, H + 2, H + 2, Cin, Cs, -1, -1, ST())
+    torch.cuda.synchronize()
+    wr = w.clone().double().requires_grad_(True)
+    F.conv2d(x.double(), wr, padding=1).backward(dy.double())
+    close(dw.reshape(Cs, 3, 3, Cin).permute(0, 3, 1, 2)[:Co], wr.grad.float(), rtol=3e-5, what="conv_wgrad_tcg")
+
+
+def test_pool2_bwd():
+    B, H, C = 2, 21, 128
+    dup = rnd(B, 2 * H, 2 * H, C, seed=1)
+    low = rnd(B, C, H, H, seed=2)
+    src = torch.zeros(B, 2 * H + 2, 2 * H + 2, C, device=DEV)
+    src[:, 1:2 * H + 1, :2 * H] = F.interpolate(F.relu(low), scale_factor=2).permute(0, 2, 3, 1)
+    dst = torch.zeros(B, H + 2, H + 2, C, device=DEV)
+    K.pool2_bwd(P(dup), P(src), P(dst), B, H, H, C, ST())
+    ref = F.avg_pool2d(dup.permute(0, 3, 1, 2), 2) * 4 * (low > 0)
+    close(dst[:, 1:H + 1, :H].permute(0, 3, 1, 2), tf32_round(ref), rtol=1e-3, what="pool2_bwd")
+    bz = dst.clone(); bz[:, 1:H + 1, :H] = 0
+    assert float(bz.abs().max()) == 0.0

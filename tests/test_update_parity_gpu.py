@@ -209,7 +209,8 @@ def test_full_updates_match_oracle(algorithm, precision):
         rt = (5e-3 if tf else 2e-3) if step == 2 else (5e-2 if tf else 2e-2)
         for k in keys:
             # alpha_loss = alpha*mean(-log_pi - target_entropy) is a small difference of O(1) numbers: absolute floor
-            np.testing.assert_allclose(float(L.rows[(step, k)]), float(Lo.rows[(step, k)]), rtol=rt, atol=3e-3 if tf else 1e-4,
+            np.testing.assert_allclose(float(L.rows[(step, k)]), float(Lo.rows[(step, k)]), rtol=rt,
+                                       atol=(3e-3 if step == 2 else 5e-2) if tf else 1e-4,
                                        err_msg=f"{step} {k}")
         mine = agent.get_parameters()
         nup = step - 1
