@@ -26,6 +26,7 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+os.environ["NCCL_DEBUG"] = os.environ.get("SGQN_NCCL_DEBUG", "WARN")     # keep stdout to the one JSON line
 
 import numpy as np  # noqa: E402
 import torch  # noqa: E402
@@ -35,6 +36,8 @@ CAPACITY = 20000            # transitions; 20003 frames x 21 KB = 423 MB > 126 M
 POOL_N = 2048               # overlay frames (43 MB)
 # algorithmic FLOPs per sample (minimal / de-duplicated schedule), FLOP = 2*MAC
 GFLOP_ODD, GFLOP_EVEN = 1.671, 3.712
+WORKLOAD = ("SGSAC full update loop (critic + attribution mask consistency + actor/alpha + target EMA + overlay aux), "
+            "batch 128 per GPU, 9x84x84 uint8 stacks, A=2, sgqn_quantile=0.95, reference init, steps alternate odd/even")
 
 
 def env_int(k, d):
@@ -134,10 +137,11 @@ def run_reference(a):
     line = {"impl": "reference", "metric": "SGSAC updates/sec (batch 128, 9x84x84)", "value": v, "unit": "updates/s",
             "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1000.0 / v, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "SGSAC full update loop, batch 128, 9x84x84 (BASELINE configs[1] shapes) on host CPU cores"},
+            "config": {"workload": WORKLOAD, "per_gpu_batch": PER_GPU_BATCH, "global_batch": PER_GPU_BATCH, "parallelism": "host-cpu",
+                       "note": "oracle port of the reference's SGSAC.update (bit-exact with the reference in the build container) on the host cores"},
             "cpu_baseline": {"value": v, "unit": "updates/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": v, "unit": "updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ----------------------------------------------------------------------------- B200 arm
@@ -306,8 +310,7 @@ def run_b200(a):
     d2h = 8 * 4
 
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
+        _finish(world)
         return
     cpu = None
     if world == 1 and not a.no_cpu_baseline:
@@ -318,8 +321,7 @@ def run_b200(a):
         "metric": "SGSAC updates/sec (batch 128, 9x84x84)", "value": value, "unit": "updates/s", "n_gpus": world,
         "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "SGSAC full update loop (critic + attribution mask consistency + actor/alpha + target EMA + overlay aux), "
-                               "9x84x84 uint8 stacks, A=2, sgqn_quantile=0.95, reference init, steps alternate odd/even",
+        "config": {"workload": WORKLOAD,
                    "per_gpu_batch": B, "global_batch": Bg, "parallelism": f"dp{world}" if world > 1 else "single",
                    "replay_capacity": CAPACITY, "l2_policy": "inputs larger than L2 (423 MB frame ring, random gather; ~390 MB activations per encoder pass)",
                    "value_definition": "global updates/s x (global_batch/128)",
@@ -332,12 +334,53 @@ def run_b200(a):
         "kernel_families_ms_per_step": [[r[0], round(r[1], 4), r[2]] for r in (fam_rows or [])[:12]],
         "losses_last_step": last,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
+    _finish(world)
+
+
+def _finish(world):
+    """Multi-rank exit: captured CUDA graphs that contain NCCL kernels can deadlock destroy_process_group(); leave together
+    after a barrier and let process exit tear the communicators down."""
     if world > 1:
-        dist.destroy_process_group()
+        import torch.distributed as dist
+        torch.cuda.synchronize()
+        dist.barrier()
+        torch.cuda.synchronize()
+        sys.stdout.flush(); sys.stderr.flush()
+        os._exit(0)
+
+
+class _StdoutToStderr(object):
+    """Everything any library prints to fd 1 while the benchmark runs (NCCL's version banner, ...) goes to stderr, so
+    stdout carries exactly the one JSON line."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+        return self
+
+    def restore(self):
+        sys.stdout.flush()
+        os.dup2(self.saved, 1)
+
+    def __exit__(self, *a):
+        self.restore()
+        return False
+
+
+_REDIRECT = None
+
+
+def emit(line):
+    if _REDIRECT is not None:
+        _REDIRECT.restore()
+    print(json.dumps(line), flush=True)
 
 
 def main():
+    global _REDIRECT
+    _REDIRECT = _StdoutToStderr().__enter__()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=40)

@@ -8,6 +8,7 @@
 Everything underneath runs on the hand-written sm_100a kernels of libsgqn_b200.so (engine.py); there is no
 PyTorch-op fallback for the update path.
 """
+import os
 from collections import OrderedDict
 
 import numpy as np
@@ -99,7 +100,8 @@ class SAC(object):
         self.defer_logs = True
         # CUDA graphs: after one eager update of each kind (odd / even step pattern) the whole update -- device RNG,
         # replay gather, ~200 kernels, optimiser steps -- is captured once and replayed with a single launch.
-        self.use_cuda_graphs = dist is None
+        # (the NCCL all-reduces of the sharded configuration are captured too; SGQN_DIST_GRAPHS=0 keeps that case eager)
+        self.use_cuda_graphs = dist is None or os.environ.get("SGQN_DIST_GRAPHS", "1") == "1"
         self._graphs, self._eager_runs, self._graph_rb, self._graph_nodes = {}, {}, None, {}
         self.train()
 
