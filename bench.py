@@ -199,6 +199,10 @@ def profile_kernels(agent, rb, nsteps=4):
             B, Hv = args[5], args[8]
             fl = 2.0 * B * Hv * Hv * 9 * 32 * 32
             key = "conv_tc[32->32 " + ("dgrad" if args[10] else "fwd") + "]"
+        elif n == "conv_tcg_taps":
+            B, Cin, Cout, Hv = args[5], args[8], args[9], args[10]
+            fl = 2.0 * B * Hv * Hv * 81 * Cout
+            key = "conv1_tcg[fwd]"
         elif n == "conv_tcg":
             B, Cin, Cout, Hv = args[5], args[8], args[9], args[10]
             fl = 2.0 * B * Hv * Hv * 9 * Cin * Cout

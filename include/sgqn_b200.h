@@ -71,6 +71,8 @@ int sgqn_conv1_dgrad(const float* dy, const float* w, float* dobs, int B, int Ci
 /*      the same three through a materialised im2col matrix col[B*41*41][84] (81 real columns, /255 applied): the index
  *      arithmetic is paid once per observation batch, forward / weight gradient / data gradient become plain GEMMs */
 int sgqn_conv1_im2col(const float* obs, float* col, int B, int Hin, void* stream);
+int sgqn_conv1_im2col96(const float* obs, float* col, int B, int Hin, void* stream);   /* col[.][96], TF32-rounded (tcgen05 path) */
+int sgqn_conv1_weights_prep(const float* w, float* wp /* [32][96] */, void* stream);
 int sgqn_conv1_fwd_col(const float* col, const float* w, const float* bias, float* y, int B, int flags, void* stream);
 int sgqn_conv1_wgrad_col(const float* col, const float* dy, float* dw, float* db, int B, void* stream);
 int sgqn_conv1_dgrad_col(const float* dy, const float* w, float* dcol, float* dobs, int B, void* stream);
@@ -94,6 +96,11 @@ int sgqn_pad_copy(const float* src, float* dst, int B, int H, int W, int C, int 
  *      through sgqn_conv_wgrad_tcg; sgqn_pool2_bwd is the backward of the fused upsample + ReLU. */
 int sgqn_conv_tcg(const float* x, const float* wop, const float* bias, const float* mask, float* out, int B, int Hr, int Wp, int Cin,
                   int Cout, int Hv, int Wv, int shift, int Hq, int Wq, int oy, int ox, int Hm, int Wm, int flags, void* stream);
+int sgqn_conv_tcg_taps(const float* x, const float* wop, const float* bias, const float* mask, float* out, int B, int Hr, int Wp,
+                       int Cin, int Cout, int Hv, int Wv, int shift, int Hq, int Wq, int oy, int ox, int Hm, int Wm, int flags,
+                       int ntaps /* 9: 3x3 conv, 1: per-position GEMM (the first conv on its im2col matrix) */, void* stream);
+int sgqn_gemm_wgrad_tcg(const float* x, const float* dy, float* dw, int B, int Hr, int Wp, int Cin, int Cout, int ta, int tb,
+                        int ntaps, int kvalid, void* stream);
 int sgqn_conv_weights_prep_g(const float* w, float* wf, float* wd, int Cout, int Cin, int Cout_real, void* stream);
 int sgqn_conv_wgrad_tcg(const float* x, const float* dy, float* dw, int B, int Hr, int Wp, int Cin, int Cout, int ta, int tb,
                         void* stream);

@@ -13,6 +13,10 @@
 
 using namespace tc;
 
+extern "C" int sgqn_conv_tcg_taps(const float*, const float*, const float*, const float*, float*, int, int, int, int, int, int, int, int,
+                                  int, int, int, int, int, int, int, int, void*);
+extern "C" int sgqn_gemm_wgrad_tcg(const float*, const float*, float*, int, int, int, int, int, int, int, int, int, void*);
+
 namespace {
 
 constexpr int kTileM = 128;
@@ -22,7 +26,7 @@ constexpr int kMaxA = 4, kMaxW = 8;
 struct GParams {
     int total_q, Hr, Wp, Hv, Wv, shift;
     int Hq, Wq, oy, ox, Hm, Wm;
-    int num_tiles, kc, cin;
+    int num_tiles, kc, cin, ntaps;
     int a_bytes, piece_rows, pieces, a_stages, w_stages;
     const float* bias;
     const float* mask;
@@ -81,7 +85,7 @@ conv3x3_tcg_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                     for (int pc = 0; pc < p.pieces; ++pc)
                         tma_load_2d(&tmA, afull0 + 8 * as, a_sm + as * p.a_bytes + pc * p.piece_rows * 128, c * 32, r0 + pc * p.piece_rows);
                     if (++as == p.a_stages) { as = 0; aph ^= 1u; }
-                    for (int t = 0; t < 9; ++t) {
+                    for (int t = 0; t < p.ntaps; ++t) {
                         mbar_wait(wempty0 + 8 * ws, wph ^ 1u);
                         mbar_expect_tx(wfull0 + 8 * ws, kWBytes);
                         tma_load_2d(&tmW, wfull0 + 8 * ws, w_sm + ws * kWBytes, t * p.cin + c * 32, 0);
@@ -101,10 +105,10 @@ conv3x3_tcg_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                     mbar_wait(afull0 + 8 * as, aph);
                     tc_fence_after();
                     const uint32_t a0 = a_sm + as * p.a_bytes;
-                    for (int t = 0; t < 9; ++t) {
+                    for (int t = 0; t < p.ntaps; ++t) {
                         mbar_wait(wfull0 + 8 * ws, wph);
                         tc_fence_after();
-                        const uint64_t ad = make_desc_sw128(a0 + ((t / 3) * p.Wp + (t % 3)) * 128);
+                        const uint64_t ad = make_desc_sw128(a0 + (p.ntaps == 9 ? ((t / 3) * p.Wp + (t % 3)) * 128 : 0));
                         const uint64_t bd = make_desc_sw128(w_sm + ws * kWBytes);
 #pragma unroll
                         for (int k = 0; k < 4; ++k)
@@ -223,17 +227,26 @@ int launch_tcg(const CUtensorMap& tmA, const CUtensorMap& tmW, const GParams& p,
 extern "C" int sgqn_conv_tcg(const float* x, const float* wop, const float* bias, const float* mask, float* out, int B, int Hr,
                              int Wp, int Cin, int Cout, int Hv, int Wv, int shift, int Hq, int Wq, int oy, int ox, int Hm, int Wm,
                              int flags, void* stream) {
+    return sgqn_conv_tcg_taps(x, wop, bias, mask, out, B, Hr, Wp, Cin, Cout, Hv, Wv, shift, Hq, Wq, oy, ox, Hm, Wm, flags, 9, stream);
+}
+
+// ntaps = 9: 3x3 conv (above); ntaps = 1: per-position GEMM out[q][Cout] = x[q][Cin] * wop[Cout][Cin]^T (1x1 conv) -- the
+// first encoder conv on its im2col matrix (col[q][96], 81 real columns).
+extern "C" int sgqn_conv_tcg_taps(const float* x, const float* wop, const float* bias, const float* mask, float* out, int B, int Hr,
+                                  int Wp, int Cin, int Cout, int Hv, int Wv, int shift, int Hq, int Wq, int oy, int ox, int Hm,
+                                  int Wm, int flags, int ntaps, void* stream) {
     if (B <= 0) return 0;
     if ((Cin & 31) || (Cout != 32 && Cout != 64 && Cout != 128)) return (int)cudaErrorInvalidValue;
     GParams p;
     p.total_q = B * Hr * Wp; p.Hr = Hr; p.Wp = Wp; p.Hv = Hv; p.Wv = Wv; p.shift = shift;
     p.Hq = Hq; p.Wq = Wq; p.oy = oy; p.ox = ox; p.Hm = Hm; p.Wm = Wm;
     p.num_tiles = (p.total_q + kTileM - 1) / kTileM;
-    p.kc = Cin / 32; p.cin = Cin;
+    p.kc = Cin / 32; p.cin = Cin; p.ntaps = ntaps;
+    if (ntaps != 1 && ntaps != 9) return (int)cudaErrorInvalidValue;
     p.bias = bias; p.mask = mask; p.out = out;
     p.relu_out = flags & 1; p.round_out = (flags >> 1) & 1; p.mask_mode = (flags >> 2) & 3; p.upsample = (flags >> 4) & 1;
     if (p.mask_mode && !mask) return (int)cudaErrorInvalidValue;
-    int halo = kTileM + 2 * Wp + 2;
+    int halo = ntaps == 9 ? kTileM + 2 * Wp + 2 : kTileM;
     p.pieces = halo > 256 ? 2 : 1;
     p.piece_rows = ((halo + p.pieces - 1) / p.pieces + 7) / 8 * 8;
     if (p.piece_rows > 256) return (int)cudaErrorInvalidValue;
@@ -248,7 +261,7 @@ extern "C" int sgqn_conv_tcg(const float* x, const float* wop, const float* bias
     CUtensorMap tmA, tmW;
     int rc = make_map_2d(&tmA, x, (uint64_t)Cin, (uint64_t)p.total_q, 32, (uint32_t)p.piece_rows);
     if (rc) return rc;
-    rc = make_map_2d(&tmW, wop, (uint64_t)9 * Cin, (uint64_t)Cout, 32, (uint32_t)Cout);
+    rc = make_map_2d(&tmW, wop, (uint64_t)ntaps * Cin, (uint64_t)Cout, 32, (uint32_t)Cout);
     if (rc) return rc;
     cudaStream_t st = (cudaStream_t)stream;
     if (Cout == 32) return launch_tcg<32>(tmA, tmW, p, smem, st);
@@ -287,7 +300,7 @@ constexpr int kGwRows = 64;
 constexpr int kGwXRows = 72;
 constexpr int kGwStagesMax = 4;
 
-struct GwParams { int total_q, Wp, ta, tb, kc, cin, na, kb_total, kb_per_cta, stages, stage_bytes; float* dw; };
+struct GwParams { int total_q, Wp, ta, tb, kc, cin, na, kb_total, kb_per_cta, stages, stage_bytes, ntaps, kvalid; float* dw; };
 
 __device__ __forceinline__ uint64_t make_desc_mn32(uint32_t saddr, uint32_t lbo_bytes) {
     uint64_t d = 0;
@@ -382,10 +395,16 @@ conv3x3_wgrad_tcg_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_c
                       "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
                     : "r"(taddr) : "memory");
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                if (kx < 3) {
-                    float* dst = p.dw + (size_t)(ky * 3 + kx) * p.cin + c * 32 + lane;
+                if (p.ntaps == 9) {
+                    if (kx < 3) {
+                        float* dst = p.dw + (size_t)(ky * 3 + kx) * p.cin + c * 32 + lane;
 #pragma unroll
-                    for (int e = 0; e < 16; ++e) atomicAdd(dst + (size_t)(g * 16 + e) * 9 * p.cin, __uint_as_float(v[e]));
+                        for (int e = 0; e < 16; ++e) atomicAdd(dst + (size_t)(g * 16 + e) * 9 * p.cin, __uint_as_float(v[e]));
+                    }
+                } else if (kx == 0 && c * 32 + lane < p.kvalid) {      // per-position GEMM: dw[co][kvalid], only the unshifted atom
+                    float* dst = p.dw + c * 32 + lane;
+#pragma unroll
+                    for (int e = 0; e < 16; ++e) atomicAdd(dst + (size_t)(g * 16 + e) * p.kvalid, __uint_as_float(v[e]));
                 }
             }
         }
@@ -409,12 +428,13 @@ int launch_wgrad_tcg(const CUtensorMap& tmX, const CUtensorMap& tmD, GwParams& p
         cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
         inited = 1;
     }
-    int gx = (num_sms + 2) / 3;
+    const int gy = p.ntaps == 9 ? 3 : 1;
+    int gx = (num_sms + gy - 1) / gy;
     if (gx > p.kb_total) gx = p.kb_total;
     p.kb_per_cta = (p.kb_total + gx - 1) / gx;
     gx = (p.kb_total + p.kb_per_cta - 1) / p.kb_per_cta;
     int smem = p.stages * p.stage_bytes + 1024 + 1024 + 256;
-    conv3x3_wgrad_tcg_kernel<N><<<dim3(gx, 3), 192, smem, st>>>(tmX, tmD, p);
+    conv3x3_wgrad_tcg_kernel<N><<<dim3(gx, gy), 192, smem, st>>>(tmX, tmD, p);
     return SGQN_CHECK_LAUNCH();
 }
 
@@ -424,10 +444,18 @@ int launch_wgrad_tcg(const CUtensorMap& tmX, const CUtensorMap& tmD, GwParams& p
 // (ta, tb): the activation row paired with dy row q for tap (ky,kx) is q + (ky+ta)*Wp + kx + tb.
 extern "C" int sgqn_conv_wgrad_tcg(const float* x, const float* dy, float* dw, int B, int Hr, int Wp, int Cin, int Cout, int ta,
                                    int tb, void* stream) {
+    return sgqn_gemm_wgrad_tcg(x, dy, dw, B, Hr, Wp, Cin, Cout, ta, tb, 9, 0, stream);
+}
+
+// ntaps = 1: dw[Cout][kvalid] += dy^T[Cout][rows] * x[rows][:kvalid]  (weight gradient of a per-position GEMM; Wp/ta/tb unused)
+extern "C" int sgqn_gemm_wgrad_tcg(const float* x, const float* dy, float* dw, int B, int Hr, int Wp, int Cin, int Cout, int ta,
+                                   int tb, int ntaps, int kvalid, void* stream) {
     if (B <= 0) return 0;
+    if (ntaps != 1 && ntaps != 9) return (int)cudaErrorInvalidValue;
     if ((Cin & 31) || (Cout != 32 && Cout != 64 && Cout != 128) || (Cin / 32) * Cout > 512) return (int)cudaErrorInvalidValue;
     GwParams p;
-    p.total_q = B * Hr * Wp; p.Wp = Wp; p.ta = ta; p.tb = tb; p.kc = Cin / 32; p.cin = Cin; p.na = Cout / 32; p.dw = dw;
+    p.total_q = B * Hr * Wp; p.Wp = ntaps == 9 ? Wp : 0; p.ta = ntaps == 9 ? ta : 0; p.tb = ntaps == 9 ? tb : 0;
+    p.kc = Cin / 32; p.cin = Cin; p.na = Cout / 32; p.dw = dw; p.ntaps = ntaps; p.kvalid = kvalid;
     p.kb_total = (p.total_q + kGwRows - 1) / kGwRows;
     p.stage_bytes = p.kc * kGwXRows * 128 + p.na * kGwRows * 128;
     p.stages = (kSmemBudget - 4096) / p.stage_bytes;

@@ -215,10 +215,11 @@ extern "C" int sgqn_upsample2_bwd(const float* dup, const float* act, float* dx,
 // col[pix][84]: columns 0..80 = obs[b][ci][2y+ky+crop][2x+kx+crop] / 255 (c = ci*9 + ky*3 + kx), 81..83 = 0.
 // Forward, weight gradient and the attribution's data gradient of conv1 then are plain GEMMs over `col` (the
 // per-element index arithmetic of the direct kernels above is paid once per observation batch instead of per use).
-__global__ void conv1_im2col_kernel(const float* __restrict__ obs, float4* __restrict__ col, int Hin, int crop, long long total) {
+__global__ void conv1_im2col_kernel(const float* __restrict__ obs, float4* __restrict__ col, int Hin, int crop, long long total,
+                                    int nc4, int round_out) {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= total) return;
-    int c4 = (int)(i % 21); long long pix = i / 21;
+    int c4 = (int)(i % nc4); long long pix = i / nc4;
     int x = (int)(pix % 41); long long t = pix / 41; int y = (int)(t % 41); int b = (int)(t / 41);
     float v[4];
 #pragma unroll
@@ -228,6 +229,7 @@ __global__ void conv1_im2col_kernel(const float* __restrict__ obs, float4* __res
             int ci = c / 9, r = c - ci * 9, ky = r / 3, kx = r - ky * 3;
             v[e] = __fdiv_rn(__ldg(obs + ((size_t)(b * 9 + ci) * Hin + (2 * y + ky + crop)) * Hin + (2 * x + kx + crop)), 255.0f);
         } else v[e] = 0.f;
+        if (round_out) { uint32_t r; asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v[e])); v[e] = __uint_as_float(r); }
     }
     col[i] = make_float4(v[0], v[1], v[2], v[3]);
 }
@@ -235,7 +237,29 @@ __global__ void conv1_im2col_kernel(const float* __restrict__ obs, float4* __res
 extern "C" int sgqn_conv1_im2col(const float* obs, float* col, int B, int Hin, void* stream) {
     long long total = (long long)B * 1681 * 21;
     if (total <= 0) return 0;
-    conv1_im2col_kernel<<<(unsigned)cdivll(total, 256), 256, 0, (cudaStream_t)stream>>>(obs, (float4*)col, Hin, (Hin - 84) / 2, total);
+    conv1_im2col_kernel<<<(unsigned)cdivll(total, 256), 256, 0, (cudaStream_t)stream>>>(obs, (float4*)col, Hin, (Hin - 84) / 2, total, 21, 0);
+    return SGQN_CHECK_LAUNCH();
+}
+
+// tcgen05 variant: col[pix][96] (three 32-channel chunks), values rounded to TF32
+extern "C" int sgqn_conv1_im2col96(const float* obs, float* col, int B, int Hin, void* stream) {
+    long long total = (long long)B * 1681 * 24;
+    if (total <= 0) return 0;
+    conv1_im2col_kernel<<<(unsigned)cdivll(total, 256), 256, 0, (cudaStream_t)stream>>>(obs, (float4*)col, Hin, (Hin - 84) / 2, total, 24, 1);
+    return SGQN_CHECK_LAUNCH();
+}
+
+// TF32 operand copy of the first conv's weights for the per-position GEMM: wp[32][96] = rna(w[32][81]), zero padded
+__global__ void conv1_weights_prep_kernel(const float* __restrict__ w, float* __restrict__ wp) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= 32 * 96) return;
+    int co = i / 96, c = i - co * 96;
+    float v = c < 81 ? w[co * 81 + c] : 0.f;
+    uint32_t r; asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+    wp[i] = __uint_as_float(r);
+}
+extern "C" int sgqn_conv1_weights_prep(const float* w, float* wp, void* stream) {
+    conv1_weights_prep_kernel<<<12, 256, 0, (cudaStream_t)stream>>>(w, wp);
     return SGQN_CHECK_LAUNCH();
 }
 

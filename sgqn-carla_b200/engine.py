@@ -79,7 +79,8 @@ class UpdateEngine:
         self.dbuf = [f32(R * 41 * 41 * 32), f32(R * 41 * 41 * 32)]
         # im2col matrices of the first conv (col[n*1681][84]) per slot: built once per observation batch by enc_fwd and
         # re-used by that slot's weight gradient; dcol is the attribution's data-gradient workspace
-        self.colS, self.colT, self.dcol = f32(R * 1681 * 84), f32(B * 1681 * 84), f32(B * 1681 * 84)
+        self.colS, self.colT, self.dcol = f32(R * 1681 * 96), f32(B * 1681 * 96), f32(B * 1681 * 84)
+        self.w1p, self.w1p_t = f32(32 * 96), f32(32 * 96)          # TF32 operand copies of cnn.0 ([32][96]) / target
         # tcgen05 conv path (conv_tc.cu): TF32-rounded operand copies of the 32->32 conv weights (forward; flipped +
         # transposed for the data gradient; forward copy of the target net) and one zero-bordered (pad 2) gradient
         # buffer per layer -- borders are written once here (zeros) and never again.
@@ -154,12 +155,16 @@ class UpdateEngine:
         # activations are stored AFTER the ReLU that follows each conv (the last conv has none) and rounded to TF32,
         # the operand format of the next layer's tcgen05 MMA; 1[x>0] for the backward is 1[relu(x)>0].
         tc = self.precision == "tf32"
-        col = _ptr(self.colS if acts is self.actS else self.colT, row0 * 1681 * 84)
-        K.conv1_im2col(x_ptr, col, n, hin, st)
+        col = _ptr(self.colS if acts is self.actS else self.colT, row0 * 1681 * (96 if tc else 84))
+        if tc:
+            K.conv1_im2col96(x_ptr, col, n, hin, st)
+        else:
+            K.conv1_im2col(x_ptr, col, n, hin, st)
         if tc:
             # pitch-linear layout [n][h+2][h][32]: the 2 spare rows per sample stay zero (never written) so that the
             # weight-gradient kernel can pair activations and the zero-bordered output gradient row by row
-            K.conv1_fwd_col(col, W("cnn.0.weight"), W("cnn.0.bias"), _ptr(acts[0], row0 * 43 * 41 * 32), n, 7, st)
+            K.conv_tcg_taps(col, _ptr(self.w1p_t if target else self.w1p), W("cnn.0.bias"), 0, _ptr(acts[0], row0 * 43 * 41 * 32),
+                            n, 41, 41, 96, 32, 41, 41, 0, 43, 41, 0, 0, 0, 0, 3, 1, st)
             for l in range(1, 11):
                 hi, ho = ENC_H[l - 1], ENC_H[l]
                 last = l == 10                                  # the feature map that feeds the projection is compact
@@ -186,8 +191,10 @@ class UpdateEngine:
         ls = L.off("cnn.2.weight") - L.off("cnn.1.weight")
         if target:
             K.conv_weights_prep(self.T("cnn.1.weight"), ls, _ptr(self.wf_t), _ptr(self.wd_t), 10, self.st)
+            K.conv1_weights_prep(self.T("cnn.0.weight"), _ptr(self.w1p_t), self.st)
         else:
             K.conv_weights_prep(self.P("cnn.1.weight"), ls, _ptr(self.wf), _ptr(self.wd), 10, self.st)
+            K.conv1_weights_prep(self.P("cnn.0.weight"), _ptr(self.w1p), self.st)
 
     def proj_fwd(self, feat_ptr, n, pre, z, h, ldh, target=False):
         """RLProjection (modules.py:102-113): Linear(14112->100) (split-K) -> LayerNorm -> tanh, h row stride ldh."""
@@ -269,14 +276,18 @@ class UpdateEngine:
                           hi + 4, hi + 2, 2, 0, hi + 2, hi, 2 | (mode << 2), st)
             else:                                       # d(act_0) compact: consumed by the CUDA-core first-conv kernels
                 K.conv_tc(d, _ptr(self.wd), 0, a_in, _ptr(self.dbuf[0]), n, ho + 4, ho + 2, hi, hi, -2,
-                          hi, hi, 0, 0, hi + 2, hi, mode << 2, st)
+                          hi, hi, 0, 0, hi + 2, hi, 2 | (mode << 2), st)
         self._conv1_bwd(_ptr(self.dbuf[0]), n, acts, row0, wgrad, dobs)
 
     def _conv1_bwd(self, d, n, acts, row0, wgrad, dobs):
         """Backward of the first conv from d = d(act_0) (compact [n][41][41][32]) through the slot's im2col matrix."""
         st = self.st
-        col = _ptr(self.colS if acts is self.actS else self.colT, row0 * 1681 * 84)
-        if wgrad:
+        tc = self.precision == "tf32"
+        col = _ptr(self.colS if acts is self.actS else self.colT, row0 * 1681 * (96 if tc else 84))
+        if wgrad and tc:
+            K.gemm_wgrad_tcg(col, d, self.G("cnn.0.weight"), n, 41, 41, 96, 32, 0, 0, 1, 81, st)
+            K.colsum(d, 32, n * 1681, 32, self.G("cnn.0.bias"), st)
+        elif wgrad:
             K.conv1_wgrad_col(col, d, self.G("cnn.0.weight"), self.G("cnn.0.bias"), n, st)
         if dobs:
             K.conv1_dgrad_col(d, self.P("cnn.0.weight"), _ptr(self.dcol), dobs, n, st)

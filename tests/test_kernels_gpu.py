@@ -631,3 +631,29 @@ def test_pool2_bwd():
     close(dst[:, 1:H + 1, :H].permute(0, 3, 1, 2), tf32_round(ref), rtol=1e-3, what="pool2_bwd")
     bz = dst.clone(); bz[:, 1:H + 1, :H] = 0
     assert float(bz.abs().max()) == 0.0
+
+
+def test_conv1_tcgen05_path_matches_cuda_core_path():
+    """First conv as a per-position tcgen05 GEMM over col[.][96] (forward, weight gradient) vs the fp32 im2col kernels."""
+    B = 5
+    g = torch.Generator().manual_seed(5)
+    obs = torch.randint(0, 256, (B, 9, 84, 84), generator=g).float().to(DEV)
+    w = rnd(32, 9, 3, 3, seed=2, scale=0.2); b = rnd(32, seed=3)
+    col = torch.zeros(B * 1681, 84, device=DEV); col96 = torch.full((B * 1681, 96), 9.0, device=DEV)
+    K.conv1_im2col(P(obs), P(col), B, 84, ST()); K.conv1_im2col96(P(obs), P(col96), B, 84, ST())
+    assert torch.equal(col96[:, :81], tf32_round(col[:, :81])) and float(col96[:, 81:].abs().max()) == 0.0
+    wp = torch.zeros(32 * 96, device=DEV)
+    K.conv1_weights_prep(P(w), P(wp), ST())
+    assert torch.equal(wp.reshape(32, 96)[:, :81], tf32_round(w.reshape(32, 81)))
+    y0 = torch.zeros(B, 43, 41, 32, device=DEV); y1 = torch.zeros(B, 43, 41, 32, device=DEV)
+    K.conv1_fwd_col(P(col), P(w), P(b), P(y0), B, 7, ST())
+    K.conv_tcg_taps(P(col96), P(wp), P(b), 0, P(y1), B, 41, 41, 96, 32, 41, 41, 0, 43, 41, 0, 0, 0, 0, 3, 1, ST())
+    torch.cuda.synchronize()
+    close(y1, y0, rtol=2e-3, what="conv1 tcgen05 fwd")
+    assert float(y1[:, 41:].abs().max()) == 0.0
+    dy = tf32_round(rnd(B * 1681, 32, seed=4))
+    dw0 = torch.zeros(32 * 81, device=DEV); db0 = torch.zeros(32, device=DEV); dw1 = torch.zeros(32 * 81, device=DEV)
+    K.conv1_wgrad_col(P(col), P(dy), P(dw0), P(db0), B, ST())
+    K.gemm_wgrad_tcg(P(col96), P(dy), P(dw1), B, 41, 41, 96, 32, 0, 0, 1, 81, ST())
+    torch.cuda.synchronize()
+    close(dw1, dw0, rtol=2e-3, what="conv1 tcgen05 wgrad")
