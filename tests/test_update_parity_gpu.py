@@ -229,7 +229,7 @@ def test_full_updates_match_oracle(algorithm, precision):
             if not tf:       # TF32 gradients differ at the percent level on this dense random net -> only the mean is bounded
                 assert bad <= max(2, 0.10 * d.numel()), (step, n, bad, d.numel())
             assert float(d.mean()) <= (0.3 if tf else 0.03) * lr * nup, (step, n, float(d.mean()))
-        assert abs(float(mine["log_alpha"]) - float(orc.log_alpha)) < 1e-7
+        assert abs(float(mine["log_alpha"]) - float(orc.log_alpha)) < (2e-5 if tf else 1e-7)      # alpha_lr = 1e-4 per step
 
 
 def test_rad_crop_and_actions_at_100():
