@@ -104,15 +104,17 @@ conv3x3_tcg_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                 for (int c = 0; c < p.kc; ++c) {
                     mbar_wait(afull0 + 8 * as, aph);
                     tc_fence_after();
-                    const uint32_t a0 = a_sm + as * p.a_bytes;
+                    const uint64_t a0 = make_desc_sw128(a_sm + as * p.a_bytes);
+                    const uint32_t rowq = (uint32_t)p.Wp * 8u;
                     for (int t = 0; t < p.ntaps; ++t) {
                         mbar_wait(wfull0 + 8 * ws, wph);
                         tc_fence_after();
-                        const uint64_t ad = make_desc_sw128(a0 + (p.ntaps == 9 ? ((t / 3) * p.Wp + (t % 3)) * 128 : 0));
+                        const uint64_t ad = a0 + (uint64_t)(p.ntaps == 9 ? (t / 3) * rowq + (t % 3) * 8u : 0u);
                         const uint64_t bd = make_desc_sw128(w_sm + ws * kWBytes);
+                        if ((c | t) == 0) tc_mma_tf32_zero(d_tmem, ad, bd, kIdescN);
+                        else tc_mma_tf32_acc(d_tmem, ad, bd, kIdescN);
 #pragma unroll
-                        for (int k = 0; k < 4; ++k)
-                            tc_mma_tf32(d_tmem, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), kIdescN, (c | t | k) != 0);
+                        for (int k = 1; k < 4; ++k) tc_mma_tf32_acc(d_tmem, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), kIdescN);
                         tc_commit(wempty0 + 8 * ws);
                         if (++ws == p.w_stages) { ws = 0; wph ^= 1u; }
                     }

@@ -64,6 +64,22 @@ __device__ __forceinline__ float round_tf32(float v) {
 }
 
 
+// accumulate flag as an immediate predicate: no setp / register traffic on the single MMA-issuing thread
+__device__ __forceinline__ void tc_mma_tf32_acc(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.eq.u32 p, 1, 1;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc) : "memory");
+}
+__device__ __forceinline__ void tc_mma_tf32_zero(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.eq.u32 p, 1, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc) : "memory");
+}
+
 // instruction descriptor of tcgen05.mma kind::tf32 (cute::UMMA::InstrDescriptor): D fp32, A/B TF32, M = 128
 __host__ __device__ constexpr uint32_t idesc_tf32(int n, bool a_mn_major, bool b_mn_major) {
     return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
