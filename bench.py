@@ -36,6 +36,8 @@ CAPACITY = 20000            # transitions; 20003 frames x 21 KB = 423 MB > 126 M
 POOL_N = 2048               # overlay frames (43 MB)
 # algorithmic FLOPs per sample (minimal / de-duplicated schedule), FLOP = 2*MAC
 GFLOP_ODD, GFLOP_EVEN = 1.671, 3.712
+# dram__bytes_read.sum + dram__bytes_write.sum per launch, from the committed `ncu --set full` captures under profiles/
+NCU_TRAFFIC = {"conv_tc_fwd_l1": 28961024 + 49920}
 WORKLOAD = ("SGSAC full update loop (critic + attribution mask consistency + actor/alpha + target EMA + overlay aux), "
             "batch 128 per GPU, 9x84x84 uint8 stacks, A=2, sgqn_quantile=0.95, reference init, steps alternate odd/even")
 
@@ -220,6 +222,9 @@ def profile_kernels(agent, rb, nsteps=4):
             fl = 2.0 * B * Ho * Ho * 9 * Cin * (9 if Cout == 16 else Cout)
         tot, cnt, flops = fam.get(key, (0.0, 0, 0.0))
         fam[key] = (tot + t, cnt + 1, flops + fl)
+        if n == "conv_tc" and args[10] == 0 and args[6] == 43:      # largest forward layer (41x41 -> 39x39), see NCU_TRAFFIC
+            t0, c0 = fam.get("_conv_tc_fwd_l1", (0.0, 0, 0.0))[:2]
+            fam["_conv_tc_fwd_l1"] = (t0 + t, c0 + 1, fl)
     return fam, nsteps
 
 
@@ -292,6 +297,8 @@ def run_b200(a):
         tot = sum(v[0] for v in fam.values())
         fam_rows = sorted(((k, v[0] / nst, v[1] // nst, v[2] / nst) for k, v in fam.items()), key=lambda r: -r[1])
         hbm, tf_burst, tf_sus, how = peaks()
+        l1 = fam.pop("_conv_tc_fwd_l1", None)
+        fam_rows = [r for r in fam_rows if not r[0].startswith("_")]
         top = next(r for r in fam_rows if r[3] > 0)
         achieved = top[3] / (top[1] * 1e-3) / 1e12
         peak = tf_sus / 2.0                                  # TF32 dense = bf16 / 2 (derived from measured bf16, sustained)
@@ -299,6 +306,13 @@ def run_b200(a):
                 "frac": achieved / peak, "traffic": None, "share_of_step": top[1] / (tot / nst),
                 "peak_source": f"bf16 sustained {tf_sus} TF/s ({how}) / 2 = TF32 dense, derived",
                 "launches_per_step": top[2], "ms_per_step_in_kernel": top[1]}
+        if l1 is not None and top[0].startswith("conv_tc"):
+            # per-launch view of the family's largest launch: algorithmic FLOPs / its own CUDA-event time, and the DRAM
+            # traffic ncu measured for exactly this launch (profiles/prof_r1_convtc_fwd.md)
+            us = l1[0] / l1[1] * 1e3
+            roof.update({"launch": "conv3x3_tc_kernel forward, layer 41x41->39x39, B=128 (largest launch of the family)",
+                         "launch_us": us, "launch_achieved": l1[2] / (us * 1e-6) / 1e12, "launch_frac": l1[2] / (us * 1e-6) / 1e12 / peak,
+                         "traffic": NCU_TRAFFIC["conv_tc_fwd_l1"], "algorithmic_bytes": 128 * (43 * 41 + 41 * 39) * 128})
     if world > 1:
         barrier()
 
