@@ -198,9 +198,9 @@ def profile_kernels(agent, rb, nsteps=4):
             Ho = Hl + 2 * pad - 2
             fl = 2.0 * B * Ho * Ho * 9 * Cin * (9 if Cout == 16 else Cout)
         elif n == "conv_tc":
-            B, Hv = args[5], args[8]
+            B, Hv = args[6], args[9]
             fl = 2.0 * B * Hv * Hv * 9 * 32 * 32
-            key = "conv_tc[32->32 " + ("dgrad" if args[10] else "fwd") + "]"
+            key = "conv_tc[32->32 " + ("dgrad" if args[11] else "fwd") + "]"
         elif n == "conv_tcg_taps":
             B, Cin, Cout, Hv = args[5], args[8], args[9], args[10]
             fl = 2.0 * B * Hv * Hv * 81 * Cout
@@ -222,7 +222,7 @@ def profile_kernels(agent, rb, nsteps=4):
             fl = 2.0 * B * Ho * Ho * 9 * Cin * (9 if Cout == 16 else Cout)
         tot, cnt, flops = fam.get(key, (0.0, 0, 0.0))
         fam[key] = (tot + t, cnt + 1, flops + fl)
-        if n == "conv_tc" and args[10] == 0 and args[6] == 43:      # largest forward layer (41x41 -> 39x39), see NCU_TRAFFIC
+        if n == "conv_tc" and args[11] == 0 and args[7] == 43:      # largest forward layer (41x41 -> 39x39), see NCU_TRAFFIC
             t0, c0 = fam.get("_conv_tc_fwd_l1", (0.0, 0, 0.0))[:2]
             fam["_conv_tc_fwd_l1"] = (t0 + t, c0 + 1, fl)
     return fam, nsteps

@@ -82,8 +82,9 @@ int sgqn_conv1_dgrad_col(const float* dy, const float* w, float* dcol, float* do
  *      x < Wv = sum over taps of x-row q + ky*Wp + kx + shift, q = (b*Hr + y)*Wp + x; it goes to
  *      out[((b*Hq + y+oy)*Wq + x+ox)*32].  flags: bit0 ReLU, bit1 round output to TF32, bits 2-3 mask mode (1 plain ReLU
  *      backward, 2 guided) with the mask value of (b,y,x) at mask[((b*Hm + y)*Wm + x)*32]. */
-int sgqn_conv_tc(const float* x, const float* w, const float* bias, const float* mask, float* out, int B, int Hr, int Wp, int Hv,
-                 int Wv, int shift, int Hq, int Wq, int oy, int ox, int Hm, int Wm, int flags, void* stream);
+int sgqn_conv_tc(const float* x, const float* w, const float* bias, const float* mask, float* out,
+                 float* dbias /* optional: dbias[32] += per-channel sum of the outputs written (atomic) */, int B, int Hr, int Wp,
+                 int Hv, int Wv, int shift, int Hq, int Wq, int oy, int ox, int Hm, int Wm, int flags, void* stream);
 /*      weight gradient of the same convs on tcgen05 (MN-major TF32 operands, reduction over pixels, one
  *      red.global.add per CTA and element): x, dy [B][Hr][Wp][32] share one geometry, dy zero outside its valid region */
 int sgqn_conv_wgrad_tc(const float* x, const float* dy, float* dw, int B, int Hr, int Wp, void* stream);

@@ -10,5 +10,5 @@ wf, wd = prep_w(w)
 xh = rows_pad(x, 2); Ho = Hp - 2
 y = torch.zeros(B, Ho + 2, Ho, 32, device=DEV)
 for i in range(3):
-    K.conv_tc(P(xh), P(wf), P(b), 0, P(y), B, Hp + 2, Hp, Ho, Ho, 0, Ho + 2, Ho, 0, 0, 0, 0, 3, ST())
+    K.conv_tc(P(xh), P(wf), P(b), 0, P(y), 0, B, Hp + 2, Hp, Ho, Ho, 0, Ho + 2, Ho, 0, 0, 0, 0, 3, ST())
 torch.cuda.synchronize()

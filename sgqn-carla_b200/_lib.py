@@ -23,7 +23,7 @@ SIGNATURES = {
     "sgqn_conv_dgrad": [_p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p],
     "sgqn_conv_wgrad": [_p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p],
     "sgqn_conv1_fwd": [_p, _p, _p, _p, _i, _i, _i, _i, _i, _p],
-    "sgqn_conv_tc": [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p],
+    "sgqn_conv_tc": [_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p],
     "sgqn_conv_wgrad_tc": [_p, _p, _p, _i, _i, _i, _p],
     "sgqn_conv_weights_prep": [_p, _ll, _p, _p, _i, _p],
     "sgqn_pad_copy": [_p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p],

@@ -36,6 +36,7 @@ struct TcParams {
     const float* bias;
     const float* mask;
     float* out;
+    float* dbias;            // optional: += per-channel sum of the written outputs (bias gradient of the layer below)
     int relu_out, round_out, mask_mode;
 };
 
@@ -122,6 +123,9 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         float bias_r[16];
 #pragma unroll
         for (int e = 0; e < 16; ++e) bias_r[e] = p.bias ? __ldg(p.bias + half * 16 + e) : 0.f;
+        float csum[16];
+#pragma unroll
+        for (int e = 0; e < 16; ++e) csum[e] = 0.f;
         for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
             // output coordinates first (independent of the accumulator), so the mask load is in flight during the wait
             const int q = tile * kTileM + row;
@@ -171,6 +175,15 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                     for (int e = 0; e < 4; ++e) o[e] = round_tf32(o[e]);
                 }
                 reinterpret_cast<float4*>(dst)[c4] = make_float4(o[0], o[1], o[2], o[3]);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) csum[4 * c4 + e] += o[e];
+            }
+        }
+        if (p.dbias) {                                   // one warp reduction + 16 atomics per warp for the whole launch
+#pragma unroll
+            for (int e = 0; e < 16; ++e) {
+                float t = warp_sum(csum[e]);
+                if (lane == 0) atomicAdd(p.dbias + half * 16 + e, t);
             }
         }
     }
@@ -188,8 +201,10 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 // over input rows q + ky*Wp + kx + shift (q = (b*Hr + y)*Wp + x) and goes to out[((b*Hq + y+oy)*Wq + x+ox)*32].
 // flags: bit0 ReLU on the output, bit1 round the output to TF32 (it feeds another TF32 conv), bits 2-3 mask mode
 // (1 plain ReLU backward, 2 guided) with the mask of (b,y,x) at mask[((b*Hm + y)*Wm + x)*32].
-extern "C" int sgqn_conv_tc(const float* x, const float* w, const float* bias, const float* mask, float* out, int B, int Hr,
-                            int Wp, int Hv, int Wv, int shift, int Hq, int Wq, int oy, int ox, int Hm, int Wm, int flags,
+// dbias (optional): dbias[32] += sum over the written outputs (atomic) -- in the data-gradient chain this is the bias
+// gradient of the layer below, for free.
+extern "C" int sgqn_conv_tc(const float* x, const float* w, const float* bias, const float* mask, float* out, float* dbias, int B,
+                            int Hr, int Wp, int Hv, int Wv, int shift, int Hq, int Wq, int oy, int ox, int Hm, int Wm, int flags,
                             void* stream) {
     if (B <= 0) return 0;
     static int smem_set = 0;
@@ -206,7 +221,7 @@ extern "C" int sgqn_conv_tc(const float* x, const float* w, const float* bias, c
     p.total_q = B * Hr * Wp; p.Hr = Hr; p.Wp = Wp; p.Hv = Hv; p.Wv = Wv; p.shift = shift;
     p.Hq = Hq; p.Wq = Wq; p.oy = oy; p.ox = ox; p.Hm = Hm; p.Wm = Wm;
     p.num_tiles = (p.total_q + kTileM - 1) / kTileM;
-    p.bias = bias; p.mask = mask; p.out = out;
+    p.bias = bias; p.mask = mask; p.out = out; p.dbias = dbias;
     p.relu_out = flags & 1; p.round_out = (flags >> 1) & 1; p.mask_mode = (flags >> 2) & 3;
     if (p.mask_mode && !mask) return (int)cudaErrorInvalidValue;
     p.halo_rows = (kTileM + 2 * Wp + 2 + 7) / 8 * 8;               // whole 1024-byte swizzle atoms

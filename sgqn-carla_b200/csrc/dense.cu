@@ -241,11 +241,35 @@ extern "C" int sgqn_conv1_im2col(const float* obs, float* col, int B, int Hin, v
     return SGQN_CHECK_LAUNCH();
 }
 
-// tcgen05 variant: col[pix][96] (three 32-channel chunks), values rounded to TF32
+// tcgen05 variant: col[pix][96] (three 32-channel chunks), values rounded to TF32.  One CTA per output row (b, y):
+// the 27 input rows (9 channels x 3 ky) it needs are staged in shared memory with coalesced loads, scaled and
+// rounded once, and the 41 x 96 output row is written as one contiguous 15.7 KB run -- the kernel is bound by
+// that write (82.6 MB at B=128), not by the stride-2 gather.
+__global__ void __launch_bounds__(256) conv1_im2col96_rows_kernel(const float* __restrict__ obs, float4* __restrict__ col, int Hin, int crop) {
+    __shared__ float s[27][84];
+    const int y = blockIdx.x % 41, b = blockIdx.x / 41;
+    for (int i = threadIdx.x; i < 27 * 84; i += 256) {
+        int r = i / 84, c = i - r * 84, ci = r / 3, ky = r - ci * 3;
+        float v = __fdiv_rn(__ldg(obs + ((size_t)(b * 9 + ci) * Hin + (2 * y + ky + crop)) * Hin + c + crop), 255.0f);
+        uint32_t t; asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(v));
+        s[r][c] = __uint_as_float(t);
+    }
+    __syncthreads();
+    float4* dst = col + (size_t)(b * 1681 + y * 41) * 24;
+    for (int i = threadIdx.x; i < 41 * 24; i += 256) {
+        int x = i / 24, c4 = i - x * 24;
+        float v[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            int c = c4 * 4 + e, r = c / 3, kx = c - r * 3;          // c = ci*9 + ky*3 + kx  =>  r = ci*3 + ky
+            v[e] = c < 81 ? s[r][2 * x + kx] : 0.f;
+        }
+        dst[i] = make_float4(v[0], v[1], v[2], v[3]);
+    }
+}
 extern "C" int sgqn_conv1_im2col96(const float* obs, float* col, int B, int Hin, void* stream) {
-    long long total = (long long)B * 1681 * 24;
-    if (total <= 0) return 0;
-    conv1_im2col_kernel<<<(unsigned)cdivll(total, 256), 256, 0, (cudaStream_t)stream>>>(obs, (float4*)col, Hin, (Hin - 84) / 2, total, 24, 1);
+    if (B <= 0) return 0;
+    conv1_im2col96_rows_kernel<<<(unsigned)(B * 41), 256, 0, (cudaStream_t)stream>>>(obs, (float4*)col, Hin, (Hin - 84) / 2);
     return SGQN_CHECK_LAUNCH();
 }
 

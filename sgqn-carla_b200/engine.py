@@ -68,18 +68,23 @@ class UpdateEngine:
         self.opt_aux = _Opt(dev, x1 - x0, getattr(args, "aux_lr", 3e-4), getattr(args, "aux_beta", 0.9))
         self.quantile = float(getattr(args, "sgqn_quantile", 0.5))
 
-        R = 2 * B                                       # rows of the critic slot: [clean | masked] or [obs | aug]
+        R = 2 * B                                       # rows of the critic heads: [clean | masked] or [obs | aug]
+        E = 3 * B                                       # encoder rows of the critic slot: [next_obs | obs | masked / aug]
         f32 = lambda *s: torch.zeros(*s, device=dev)
-        self.obs2 = f32(R, 9, 84, 84)                   # [obs ; masked_obs / overlay-augmented obs]
-        self.next_obs = f32(B, 9, 84, 84)
+        # One observation buffer so that encoder passes which share weights run as ONE batch: [next_obs ; obs] before
+        # the critic update (actor(next_obs) and critic(obs), sac.py:109,114) and [obs ; s_tilde] after it (attribution
+        # #2 / the actor update and the aux forward, sgsac.py:175-184) -- s_tilde overwrites the dead masked rows.
+        self.obs3 = f32(E, 9, 84, 84)
+        self.next_obs = self.obs3[:B]
+        self.obs2 = self.obs3[B:]                       # [obs ; masked_obs / overlay-augmented obs]
         self.action = f32(B, A); self.reward = f32(B, 1); self.not_done = f32(B, 1)
         # activations: NHWC, post-ReLU; layers 0..9 carry 2 spare zero rows per sample ([n][h+2][h][32], tcgen05 path)
-        self.actS = [f32(R * (h + 2) * h * 32) for h in ENC_H]  # critic slot
-        self.actT = [f32(B * (h + 2) * h * 32) for h in ENC_H]  # transient slot
+        self.actS = [f32(E * (h + 2) * h * 32) for h in ENC_H]  # critic slot (encoder rows = obs3 rows)
+        self.actT = [f32(B * (h + 2) * h * 32) for h in ENC_H]  # target-network / acting slot
         self.dbuf = [f32(R * 41 * 41 * 32), f32(R * 41 * 41 * 32)]
         # im2col matrices of the first conv (col[n*1681][84]) per slot: built once per observation batch by enc_fwd and
         # re-used by that slot's weight gradient; dcol is the attribution's data-gradient workspace
-        self.colS, self.colT, self.dcol = f32(R * 1681 * 96), f32(B * 1681 * 96), f32(B * 1681 * 84)
+        self.colS, self.colT, self.dcol = f32(E * 1681 * 96), f32(B * 1681 * 96), f32(B * 1681 * 84)
         self.w1p, self.w1p_t = f32(32 * 96), f32(32 * 96)          # TF32 operand copies of cnn.0 ([32][96]) / target
         # tcgen05 conv path (conv_tc.cu): TF32-rounded operand copies of the 32->32 conv weights (forward; flipped +
         # transposed for the data gradient; forward copy of the target net) and one zero-bordered (pad 2) gradient
@@ -109,7 +114,7 @@ class UpdateEngine:
         self.rng_counter = torch.zeros(1, dtype=torch.int64, device=dev)
         self.seed = int(getattr(args, "seed", 0))
         if algorithm == "sgsac":
-            self.s_tilde = f32(B, 9, 84, 84)
+            self.s_tilde = self.obs2[B:]                 # overlay-augmented obs (written after the critic update)
             self.dl = f32(B, FEAT); self.ddl = f32(B, FEAT)
             self.d1 = f32(B * 21 * 21 * 128); self.dd1 = f32(B * 21 * 21 * 128)
             self.d2 = f32(B * 42 * 42 * 64); self.dd2 = f32(B * 42 * 42 * 64)
@@ -169,7 +174,7 @@ class UpdateEngine:
                 hi, ho = ENC_H[l - 1], ENC_H[l]
                 last = l == 10                                  # the feature map that feeds the projection is compact
                 K.conv_tc(_ptr(acts[l - 1], row0 * (hi + 2) * hi * 32), _ptr(wf, (l - 1) * 9216), W(f"cnn.{l}.bias"), 0,
-                          _ptr(acts[l], row0 * (ho * ho if last else (ho + 2) * ho) * 32), n, hi + 2, hi, ho, ho, 0,
+                          _ptr(acts[l], row0 * (ho * ho if last else (ho + 2) * ho) * 32), 0, n, hi + 2, hi, ho, ho, 0,
                           ho if last else ho + 2, ho, 0, 0, 0, 0, 0 if last else 3, st)
             return
         K.conv1_fwd_col(col, W("cnn.0.weight"), W("cnn.0.bias"), _ptr(acts[0], row0 * 41 * 41 * 32), n, 1, st)
@@ -270,12 +275,14 @@ class UpdateEngine:
             d = _ptr(self.gpad[l])                                  # d(act_l): [n][ho+4][ho+2][32] == [n][hi+2][hi][32]
             if wgrad:
                 K.conv_wgrad_tc(a_in, d, self.G(f"cnn.{l}.weight"), n, hi + 2, hi, st)
-                K.colsum(d, 32, n * (hi + 2) * hi, 32, self.G(f"cnn.{l}.bias"), st)
+                if l == 10:                             # the other layers' bias gradients ride on the data-gradient epilogues
+                    K.colsum(d, 32, n * (hi + 2) * hi, 32, self.G("cnn.10.bias"), st)
+            db = self.G(f"cnn.{l - 1}.bias") if wgrad else 0    # sum of d(act_{l-1}) = bias gradient of layer l-1
             if l > 1:
-                K.conv_tc(d, _ptr(self.wd, (l - 1) * 9216), 0, a_in, _ptr(self.gpad[l - 1]), n, ho + 4, ho + 2, hi, hi, -2,
+                K.conv_tc(d, _ptr(self.wd, (l - 1) * 9216), 0, a_in, _ptr(self.gpad[l - 1]), db, n, ho + 4, ho + 2, hi, hi, -2,
                           hi + 4, hi + 2, 2, 0, hi + 2, hi, 2 | (mode << 2), st)
-            else:                                       # d(act_0) compact: consumed by the CUDA-core first-conv kernels
-                K.conv_tc(d, _ptr(self.wd), 0, a_in, _ptr(self.dbuf[0]), n, ho + 4, ho + 2, hi, hi, -2,
+            else:                                       # d(act_0) compact: consumed by the first-conv kernels
+                K.conv_tc(d, _ptr(self.wd), 0, a_in, _ptr(self.dbuf[0]), db, n, ho + 4, ho + 2, hi, hi, -2,
                           hi, hi, 0, 0, hi + 2, hi, 2 | (mode << 2), st)
         self._conv1_bwd(_ptr(self.dbuf[0]), n, acts, row0, wgrad, dobs)
 
@@ -285,24 +292,24 @@ class UpdateEngine:
         tc = self.precision == "tf32"
         col = _ptr(self.colS if acts is self.actS else self.colT, row0 * 1681 * (96 if tc else 84))
         if wgrad and tc:
-            K.gemm_wgrad_tcg(col, d, self.G("cnn.0.weight"), n, 41, 41, 96, 32, 0, 0, 1, 81, st)
-            K.colsum(d, 32, n * 1681, 32, self.G("cnn.0.bias"), st)
+            K.gemm_wgrad_tcg(col, d, self.G("cnn.0.weight"), n, 41, 41, 96, 32, 0, 0, 1, 81, st)   # (bias gradient: see enc_bwd)
         elif wgrad:
             K.conv1_wgrad_col(col, d, self.G("cnn.0.weight"), self.G("cnn.0.bias"), n, st)
         if dobs:
             K.conv1_dgrad_col(d, self.P("cnn.0.weight"), _ptr(self.dcol), dobs, n, st)
 
-    def attribution(self, acts, row0, ha, z, obs_grad):
+    def attribution(self, erow, ha, z, obs_grad):
         """compute_attribution (rl_utils.py:57-62): guided backprop of sum_b Q1[b] to the observation, re-using the
-        forward activations of critic(obs) (acts / z / ha / z1 / z2 rows [row0, row0+B))."""
+        forward activations of critic(obs): critic-slot encoder rows [erow, erow+B), head rows [0, B)."""
         B, L, st = self.B, self.lay, self.st
-        self.q_dgrad(_ptr(self.ones), 0, B, row0, 1, 2, _ptr(self.dhaT))
+        acts = self.actS
+        self.q_dgrad(_ptr(self.ones), 0, B, 0, 1, 2, _ptr(self.dhaT))
         K.ln_tanh_bwd(_ptr(self.dhaT), L.P + self.A, z, ha, L.P + self.A, self.P("critic_proj.1.weight"), _ptr(self.dzT),
                       0, 0, B, L.P, st)
         dfeat = _ptr(self.dbuf[1])
         K.linear_dgrad(_ptr(self.dzT), L.P, 0, self.P("critic_proj.0.weight"), 0, 0, 0, 0, dfeat, FEAT, 0, B, L.P, FEAT,
                        0, 0, 1, st)
-        self.enc_bwd(dfeat, B, acts, row0, 0, 2, False, dobs=obs_grad)
+        self.enc_bwd(dfeat, B, acts, erow, 0, 2, False, dobs=obs_grad)
 
     def adam(self, opt, rng, target=None, n_tau0=0, tau0=0.0, tau1=0.0):
         st = self.st
@@ -322,8 +329,8 @@ class UpdateEngine:
         B, A, L, st = self.B, self.A, self.lay, self.st
         a = self.args
         nx = _ptr(self.next_obs)
-        self.enc_fwd(nx, B, self.actT)
-        self.proj_fwd(_ptr(self.actT[10]), B, "actor_proj", _ptr(self.z_a), _ptr(self.h_a), L.P)
+        self.enc_fwd(_ptr(self.obs3), 2 * B, self.actS, 0)       # online encoder over [next_obs ; obs] in one batch
+        self.proj_fwd(_ptr(self.actS[10]), B, "actor_proj", _ptr(self.z_a), _ptr(self.h_a), L.P)
         self.actor_mlp_fwd(B)
         K.actor_head_fwd(_ptr(self.raw), _ptr(self.noise_next), float(a.actor_log_std_min), float(a.actor_log_std_max),
                          0, _ptr(self.haT, L.P), L.P + A, _ptr(self.next_log_pi), 0, B, A, st)
@@ -340,13 +347,14 @@ class UpdateEngine:
         K.linear_fwd(_ptr(self.az2), H, 0, self.P("actor_mlp.4.weight"), 0, self.P("actor_mlp.4.bias"), 0,
                      _ptr(self.raw), 2 * A, 0, n, 2 * A, H, 1, 1, 2, st)
 
-    def critic_fwd_rows(self, row0, n):
-        """critic(obs2[row0:row0+n], action) with activations kept in the critic slot."""
-        L, A, st = self.lay, self.A, self.st
+    def critic_fwd_rows(self, row0, n, encode=True):
+        """critic(obs2[row0:row0+n], action) with activations kept in the critic slot (encoder rows B + row0 ...)."""
+        L, A, st, B = self.lay, self.A, self.st, self.B
         P1 = L.P + A
-        self.enc_fwd(_ptr(self.obs2, row0 * 9 * 84 * 84), n, self.actS, row0)
+        if encode:
+            self.enc_fwd(_ptr(self.obs2, row0 * 9 * 84 * 84), n, self.actS, B + row0)
         K.set_cols(_ptr(self.haS, row0 * P1), P1, L.P, _ptr(self.action), A, n, A, st)
-        self.proj_fwd(_ptr(self.actS[10], row0 * FEAT), n, "critic_proj", _ptr(self.zS, row0 * L.P),
+        self.proj_fwd(_ptr(self.actS[10], (B + row0) * FEAT), n, "critic_proj", _ptr(self.zS, row0 * L.P),
                       _ptr(self.haS, row0 * P1), P1)
         self.q_fwd(_ptr(self.haS, row0 * P1), n, row0)
 
@@ -355,10 +363,10 @@ class UpdateEngine:
         B, A, L, st, a = self.B, self.A, self.lay, self.st, self.args
         P1 = L.P + A
         self.target_q_pass()
-        self.critic_fwd_rows(0, B)
+        self.critic_fwd_rows(0, B, encode=False)        # obs went through the encoder with next_obs
         R = B
         if mode == 1:
-            self.attribution(self.actS, 0, _ptr(self.haS), _ptr(self.zS), _ptr(self.obs_grad))
+            self.attribution(B, _ptr(self.haS), _ptr(self.zS), _ptr(self.obs_grad))
             K.minmax(_ptr(self.obs2), B * 9 * 84 * 84, _ptr(self.mm_scratch), _ptr(self.mm), st)
             if self.dist is not None:
                 self.dist.all_reduce_minmax(self.mm)
@@ -386,8 +394,8 @@ class UpdateEngine:
         self.q_wgrad(_ptr(self.haS), _ptr(self.dq), R, 0)
         dfeat = _ptr(self.dbuf[1])
         self.proj_bwd(_ptr(self.dhaS), P1, R, _ptr(self.zS), _ptr(self.haS), P1, "critic_proj", _ptr(self.dzS),
-                      feat_ptr=_ptr(self.actS[10]), dfeat=dfeat)
-        self.enc_bwd(dfeat, R, self.actS, 0, _ptr(self.obs2), 1, True)
+                      feat_ptr=_ptr(self.actS[10], B * FEAT), dfeat=dfeat)
+        self.enc_bwd(dfeat, R, self.actS, B, _ptr(self.obs2), 1, True)
         self.allreduce_grads((c0, c1))
 
     def critic_step(self, with_ema):
@@ -400,36 +408,47 @@ class UpdateEngine:
         if with_ema:
             self.prep_conv_weights(target=True)
 
-    def shared_obs_fwd(self):
-        """One encoder forward of obs with the updated critic weights, shared by attribution #2 (sgsac.py:175),
-        actor(obs, detach) and critic(obs, pi, detach) (sac.py:126-127)."""
-        B, A, L, st = self.B, self.A, self.lay, self.st
+    def shared_obs_fwd(self, with_aux=False):
+        """One encoder + projection forward with the updated critic weights of obs -- shared by attribution #2
+        (sgsac.py:175), actor(obs, detach) and critic(obs, pi, detach) (sac.py:126-127) -- and, batched with it when
+        the aux update follows, of the overlay-augmented s_tilde (sgsac.py:84-89; the actor update in between does not
+        touch these weights).  Re-uses the critic slot, whose contents are dead once the critic gradients are out:
+        encoder rows [B, 2B) / head rows [0, B) = obs, encoder rows [2B, 3B) / head rows [B, 2B) = s_tilde."""
+        B, A, L, st, a = self.B, self.A, self.lay, self.st, self.args
         P1 = L.P + A
-        self.enc_fwd(_ptr(self.obs2), B, self.actT)
-        K.set_cols(_ptr(self.haT), P1, L.P, _ptr(self.action), A, B, A, st)
-        self.proj_fwd(_ptr(self.actT[10]), B, "critic_proj", _ptr(self.zT), _ptr(self.haT), P1)
+        n = B
+        if with_aux:
+            al = float(getattr(a, "alpha_blending", 0.2))
+            K.overlay_u8(_ptr(self.obs2), _ptr(self.overlay_pool), _ptr(self.overlay_ids), float(np.float32(1 - al)),
+                         float(np.float32(al)), _ptr(self.s_tilde), B, 84 * 84, st)
+            n = 2 * B
+        self.enc_fwd(_ptr(self.obs2), n, self.actS, B)
+        K.set_cols(_ptr(self.haS), P1, L.P, _ptr(self.action), A, B, A, st)
+        if with_aux:
+            K.set_cols(_ptr(self.haS, B * P1), P1, L.P, _ptr(self.action), A, B, A, st)
+        self.proj_fwd(_ptr(self.actS[10], B * FEAT), n, "critic_proj", _ptr(self.zS), _ptr(self.haS), P1)
 
     def attribution2(self, want_mask):
         B, st = self.B, self.st
-        self.q_fwd(_ptr(self.haT), B, 0, 1)
-        self.attribution(self.actT, 0, _ptr(self.haT), _ptr(self.zT), _ptr(self.obs_grad))
+        self.q_fwd(_ptr(self.haS), B, 0, 1)
+        self.attribution(B, _ptr(self.haS), _ptr(self.zS), _ptr(self.obs_grad))
         if want_mask:
             K.attribution_mask(_ptr(self.obs_grad), 0, 0, 0, self.quantile, _ptr(self.mask), 0, B, 84 * 84, st)
 
     def update_actor_and_alpha(self):
-        """sac.py:125-151; expects shared_obs_fwd() state in the transient slot."""
+        """sac.py:125-151; expects shared_obs_fwd() state (critic slot, head rows [0,B))."""
         B, A, L, H, st, a = self.B, self.A, self.lay, self.H, self.st, self.args
         P1 = L.P + A
         lmin, lmax = float(a.actor_log_std_min), float(a.actor_log_std_max)
-        self.proj_fwd(_ptr(self.actT[10]), B, "actor_proj", _ptr(self.z_a), _ptr(self.h_a), L.P)
+        self.proj_fwd(_ptr(self.actS[10], B * FEAT), B, "actor_proj", _ptr(self.z_a), _ptr(self.h_a), L.P)
         self.actor_mlp_fwd(B)
-        K.actor_head_fwd(_ptr(self.raw), _ptr(self.noise_pi), lmin, lmax, 0, _ptr(self.haT, L.P), P1, _ptr(self.log_pi),
+        K.actor_head_fwd(_ptr(self.raw), _ptr(self.noise_pi), lmin, lmax, 0, _ptr(self.haS, L.P), P1, _ptr(self.log_pi),
                          0, B, A, st)
-        self.q_fwd(_ptr(self.haT), B, 0, 2)
+        self.q_fwd(_ptr(self.haS), B, 0, 2)
         K.actor_loss(_ptr(self.q), 2 * B, _ptr(self.log_pi), _ptr(self.log_alpha), self.target_entropy, _ptr(self.dq),
                      _ptr(self.logs, 1), _ptr(self.alpha_grad), B, self.Bg, st)
-        self.q_dgrad(_ptr(self.dq), 2 * B, B, 0, 2, 1, _ptr(self.dhaT))
-        K.actor_head_bwd(_ptr(self.raw), _ptr(self.noise_pi), _ptr(self.dhaT, L.P), P1, _ptr(self.log_alpha), lmin, lmax,
+        self.q_dgrad(_ptr(self.dq), 2 * B, B, 0, 2, 1, _ptr(self.dhaS))
+        K.actor_head_bwd(_ptr(self.raw), _ptr(self.noise_pi), _ptr(self.dhaS, L.P), P1, _ptr(self.log_alpha), lmin, lmax,
                          _ptr(self.draw), B, A, st)
         a0, a1 = L.ranges["actor"]
         K.zero(self._g + 4 * a0, 4 * (a1 - a0), st)
@@ -447,7 +466,7 @@ class UpdateEngine:
         K.linear_wgrad(_ptr(self.h_a), L.P, 0, _ptr(self.daz1), H, 0, self.G("actor_mlp.0.weight"), 0,
                        self.G("actor_mlp.0.bias"), 0, B, H, L.P, 0, 1, st)
         self.proj_bwd(_ptr(self.dh_a), L.P, B, _ptr(self.z_a), _ptr(self.h_a), L.P, "actor_proj", _ptr(self.dz_a),
-                      feat_ptr=_ptr(self.actT[10]), dfeat=0)
+                      feat_ptr=_ptr(self.actS[10], B * FEAT), dfeat=0)
         self.allreduce_grads((a0, a1))
         if self.dist is not None:
             self.dist.all_reduce_sum(self.alpha_grad)
@@ -456,30 +475,26 @@ class UpdateEngine:
                      float(a.alpha_lr), float(a.alpha_beta), 0.999, 1e-8, st)
 
     def update_aux(self):
-        """sgsac.py:82-102,163-167: overlay -> attribution predictor -> BCE vs mask of attribution #2."""
+        """sgsac.py:82-102,163-167: overlay -> attribution predictor -> BCE vs mask of attribution #2.  The overlay, the
+        encoder and the projection of s_tilde ran in shared_obs_fwd(with_aux=True): head rows [B, 2B)."""
         B, A, L, st, a = self.B, self.A, self.lay, self.st, self.args
         P1 = L.P + A
-        al = float(getattr(a, "alpha_blending", 0.2))
-        K.overlay_u8(_ptr(self.obs2), _ptr(self.overlay_pool), _ptr(self.overlay_ids), float(np.float32(1 - al)),
-                     float(np.float32(al)), _ptr(self.s_tilde), B, 84 * 84, st)
-        self.enc_fwd(_ptr(self.s_tilde), B, self.actT)
-        K.set_cols(_ptr(self.haT), P1, L.P, _ptr(self.action), A, B, A, st)
-        self.proj_fwd(_ptr(self.actT[10]), B, "critic_proj", _ptr(self.zT), _ptr(self.haT), P1)
+        ha, z = _ptr(self.haS, B * P1), _ptr(self.zS, B * L.P)
+        feat = _ptr(self.actS[10], 2 * B * FEAT)
         Wp, G = self.P, self.G
-        K.linear_fwd(_ptr(self.haT), P1, 0, Wp("dec.proj.weight"), 0, Wp("dec.proj.bias"), 0, _ptr(self.dl), FEAT, 0,
+        K.linear_fwd(ha, P1, 0, Wp("dec.proj.weight"), 0, Wp("dec.proj.bias"), 0, _ptr(self.dl), FEAT, 0,
                      B, FEAT, P1, 0, 1, 0, st)
         x0, x1 = L.ranges["aux"]
         if self.precision == "tf32":
             self._decoder_tc(B, st, Wp, G, x0, x1)
         else:
             self._decoder_simt(B, st, Wp, G, x0, x1)
-        K.linear_wgrad(_ptr(self.haT), P1, 0, _ptr(self.ddl), FEAT, 0, G("dec.proj.weight"), 0, G("dec.proj.bias"), 0,
+        K.linear_wgrad(ha, P1, 0, _ptr(self.ddl), FEAT, 0, G("dec.proj.weight"), 0, G("dec.proj.bias"), 0,
                        B, FEAT, P1, 0, 1, st)
         K.linear_dgrad(_ptr(self.ddl), FEAT, 0, Wp("dec.proj.weight"), 0, 0, 0, 0, _ptr(self.dhaT), P1, 0, B, FEAT, P1, 0, 2, 1, st)
         dfeat = _ptr(self.dbuf[1])
-        self.proj_bwd(_ptr(self.dhaT), P1, B, _ptr(self.zT), _ptr(self.haT), P1, "critic_proj", _ptr(self.dzT),
-                      feat_ptr=_ptr(self.actT[10]), dfeat=dfeat)
-        self.enc_bwd(dfeat, B, self.actT, 0, _ptr(self.s_tilde), 1, True)
+        self.proj_bwd(_ptr(self.dhaT), P1, B, z, ha, P1, "critic_proj", _ptr(self.dzT), feat_ptr=feat, dfeat=dfeat)
+        self.enc_bwd(dfeat, B, self.actS, 2 * B, _ptr(self.s_tilde), 1, True)
         self.allreduce_grads((x0, x1))
         self.adam(self.opt_aux, (x0, x1))
         self.prep_conv_weights()
@@ -544,7 +559,7 @@ class UpdateEngine:
         self.update_critic(1 if a.consistency else 0)
         self.critic_step(with_ema=do_target)
         if do_actor or do_aux:
-            self.shared_obs_fwd()
+            self.shared_obs_fwd(with_aux=do_aux)
         if do_aux:
             # attribution #2 with the updated critic feeds only update_aux's mask (sgsac.py:175-176,83); on steps
             # without an aux update the reference computes it and discards it (no side effects).

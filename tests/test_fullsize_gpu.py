@@ -31,7 +31,11 @@ def test_sgsac_full_batch_first_update(B):
         for (s, k), v in Lo.rows.items():
             rt = 3e-3 if k in ("train_critic/loss", "train_alpha/value", "train/aux_loss") else 2e-2
             np.testing.assert_allclose(vals[k], float(v), rtol=rt, atol=3e-3, err_msg=k)
-    # structure of the saliency products (rl_utils.py:76-82, sgsac.py:67-70), any size:
+    # structure of the saliency products (rl_utils.py:76-82, sgsac.py:67-70), any size.  Checked after an ODD step: on
+    # even steps the overlay-augmented s_tilde re-uses the masked rows once the critic gradients are out.
+    _supply(agent, idxs, rnd)
+    agent.update(rb, L, 3)
+    torch.cuda.synchronize()
     obs, masked = eng.obs2[:B], eng.obs2[B:]
     torch.testing.assert_close(obs.cpu(), rep.sample(idxs)[0])                      # gather is bit-exact
     m = eng.mask.reshape(B, 3, 84 * 84)
@@ -39,7 +43,6 @@ def test_sgsac_full_batch_first_update(B):
     assert int(kept.min()) >= 353 and int(kept.max()) <= 7056                      # Q=0.95 keeps >= 353 px / frame (more on ties)
     lo, hi = float(obs.min()), float(obs.max())
     fill = np.float32(lo) + (np.float32(hi) - np.float32(lo)) * np.float32(rnd["u"])
-    # `masked` was built from attribution #1's mask; eng.mask now holds attribution #2's -> check the value set instead
     is_obs = masked == obs
     is_fill = masked == float(fill)
     assert bool((is_obs | is_fill).all())

@@ -458,7 +458,7 @@ def test_conv_tc_forward(B, Hp):
     Ho = Hp - 2
     for flags in (0, 1, 3):
         y = torch.full((B, Ho + 2, Ho, 32), 7.0, device=DEV)          # output with 2 extra rows per sample, never written
-        K.conv_tc(P(xh), P(wf), P(b), 0, P(y), B, Hp + 2, Hp, Ho, Ho, 0, Ho + 2, Ho, 0, 0, 0, 0, flags, ST())
+        K.conv_tc(P(xh), P(wf), P(b), 0, P(y), 0, B, Hp + 2, Hp, Ho, Ho, 0, Ho + 2, Ho, 0, 0, 0, 0, flags, ST())
         torch.cuda.synchronize()
         r = ref.clone()
         if flags & 1:
@@ -489,9 +489,11 @@ def test_conv_tc_dgrad_and_wgrad(B, Hl, mode):
     assert torch.equal(dyp[:, 2:2 + Ho, :Ho].permute(0, 3, 1, 2), dy)
     out = torch.zeros(B, Hl + 4, Hl + 2, 32, device=DEV)
     acth = rows_pad(act, 2)                               # [B][Hl+2][Hl][32]
-    K.conv_tc(P(dyp), P(wd), 0, P(acth) if mode else 0, P(out), B, Ho + 4, Ho + 2, Hl, Hl, -2, Hl + 4, Hl + 2, 2, 0, Hl + 2, Hl,
+    dbs = torch.zeros(32, device=DEV)
+    K.conv_tc(P(dyp), P(wd), 0, P(acth) if mode else 0, P(out), P(dbs), B, Ho + 4, Ho + 2, Hl, Hl, -2, Hl + 4, Hl + 2, 2, 0, Hl + 2, Hl,
               (mode << 2), ST())
     torch.cuda.synchronize()
+    close(dbs, out.sum((0, 1, 2)), rtol=1e-4, what="fused bias gradient")
     ref = F.conv_transpose2d(dy.double(), tf32_round(w).double())
     if mode == 1:
         ref = ref * (act > 0)

@@ -66,9 +66,9 @@ def _relu_flips(eng, orc, tr, B):
             x = F.conv2d(F.relu(x), p[f"cnn.{l}.weight"], p[f"cnn.{l}.bias"])
         h = ENC_H[l]
         if eng.precision == "tf32" and l < 10:      # pitch-linear layout with 2 spare rows per sample
-            mine = eng.actS[l][:2 * B * (h + 2) * h * 32].reshape(2 * B, h + 2, h, 32)[:, :h].permute(0, 3, 1, 2).cpu()
+            mine = eng.actS[l].reshape(3 * B, h + 2, h, 32)[B:, :h].permute(0, 3, 1, 2).cpu()       # rows [next | obs | masked]
         else:
-            mine = eng.actS[l][:2 * B * h * h * 32].reshape(2 * B, h, h, 32).permute(0, 3, 1, 2).cpu()
+            mine = eng.actS[l][:3 * B * h * h * 32].reshape(3 * B, h, h, 32)[B:].permute(0, 3, 1, 2).cpu()
         if l < 10 and bool(((mine > 0) != (x > 0)).any()):
             flips.append(l)
     return flips
