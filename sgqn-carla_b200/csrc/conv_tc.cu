@@ -5,13 +5,21 @@
 // SWIZZLE_128B row.  Number the output positions in INPUT pitch coordinates, q = (b*Hp + y)*Wp + x; then for filter
 // tap (ky,kx) the A-operand row of output q is input row q + ky*Wp + kx -- for a tile of 128 consecutive q the A tile of
 // each tap is 128 CONSECUTIVE input rows, i.e. one plain 2-D TMA box {32 ch, 128 rows}.  Positions with x >= Wp-2 or
-// y >= Hp-2 are computed and dropped in the epilogue (5-17 % of the rows).  K loop: 9 taps x 4 UMMA_K(=8) steps,
-// D[128 x 32] accumulates in 32 TMEM columns; two accumulator buffers overlap the epilogue with the next tile.
+// y >= Hp-2 are computed and dropped in the epilogue (5-17 % of the rows).
+//
+// N = 32 output channels is a bad tcgen05 shape: a 128x32x8 TF32 MMA retires every ~83 cycles whatever N is (operand
+// fetch), so 9 taps x 4 k-steps cost ~3000 cycles per tile.  The kernel therefore widens N to 96 = (kx, cout): for
+// each ky ONE MMA chain multiplies the tile shifted by ky*Wp rows with the three kx taps' weights side by side,
+//     D_kx[r] = sum_ky A[q0 + r + ky*Wp] . W[ky][kx]          (12 MMAs of 128x96x8 instead of 36 of 128x32x8)
+// and the kx shift moves to the epilogue:  out[q0 + r] = D_0[r] + D_1[r+1] + D_2[r+2]  -- row offsets in the
+// shared-memory staging tile the epilogue goes through anyway to turn TMEM's row-per-thread layout into coalesced
+// stores.  A tile of 128 A rows yields 126 outputs.  Two 96-column accumulators in TMEM overlap the epilogue with the
+// next tile's MMAs.
 // The data-gradient is the same kernel on a zero-bordered (pad 2) gradient buffer with flipped / transposed weights
 // and a ReLU-mask (plain or guided, rl_utils.py:35-39) epilogue writing into the interior of the next padded buffer.
 //
 // Warp roles (320 threads): warp 0 = TMA producer (one lane), warp 1 = TMEM allocator + MMA issuer (one lane),
-// warps 2..9 = epilogue (TMEM -> registers -> bias / ReLU / mask / TF32 round -> global), two warps per TMEM lane quarter.
+// warps 2..9 = epilogue (TMEM -> shared staging -> kx shift + bias / ReLU / mask / TF32 round -> global).
 #include "tc_common.cuh"
 #include "../../include/sgqn_b200.h"
 
@@ -20,7 +28,13 @@ using namespace tc;
 namespace {
 
 constexpr int kMaxStages = 6;
-constexpr int kTileM = 128;
+constexpr int kTileM = 128;                    // A rows (TMEM lanes) per tile
+constexpr int kTileOut = 126;                  // outputs per tile: rows r with r + 2 < 128
+constexpr int kAccCols = 128;                  // TMEM column stride between the two accumulators (96 used)
+constexpr int kStgPitch = 400;                 // staging row: 96 floats + 16 B, so that 8 consecutive rows hit 8 different bank groups
+constexpr int kStgBytes = kTileM * kStgPitch;  // 50 KB
+constexpr int kEpiBytes = kStgBytes + 2048 + 128;   // staging tile, rowinfo[2][128], bias
+constexpr int kThreads = 320;                  // TMA warp, MMA warp, 8 epilogue warps
 constexpr int kWBytes = 9 * 32 * 128;          // 36 KB: 9 taps x [32 n][32 k] fp32
 constexpr int kSmemBudget = 200 * 1024;        // dynamic shared memory we ask for
 
@@ -28,7 +42,7 @@ struct TcParams {
     int total_q;            // B * Hr * Wp virtual output positions (input-pitch coordinates)
     int Hr, Wp;             // rows per sample and row pitch of the INPUT buffer
     int Hv, Wv;             // valid output extent: positions with y < Hv and x < Wv are written
-    int shift;              // A row of tap (ky,kx) for position q = q + ky*Wp + kx + shift
+    int shift;              // input row of tap (ky,kx) for position q = q + ky*Wp + kx + shift
     int Hq, Wq, oy, ox;     // output buffer: rows per sample, pitch, offset of output (0,0)
     int Hm, Wm;             // mask buffer: rows per sample, pitch (mask of output (y,x) at row y, col x)
     int num_tiles;
@@ -40,10 +54,10 @@ struct TcParams {
     int relu_out, round_out, mask_mode;
 };
 
-// kind::tf32, D fp32, A/B TF32 K-major, M = 128, N = 32 (cute::UMMA::InstrDescriptor)
-constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((32u >> 3) << 17) | ((128u >> 4) << 24);
+// kind::tf32, D fp32, A/B TF32 K-major, M = 128, N = 96 (cute::UMMA::InstrDescriptor)
+constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((96u >> 3) << 17) | ((128u >> 4) << 24);
 
-__global__ void __launch_bounds__(320, 1)
+__global__ void __launch_bounds__(kThreads, 1)
 conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, TcParams p) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -54,6 +68,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const uint32_t full0 = bars, empty0 = bars + 8 * kMaxStages, wbar = bars + 16 * kMaxStages;
     const uint32_t tfull0 = wbar + 8, tempty0 = tfull0 + 16;
     const uint32_t tmem_slot = tempty0 + 16;
+    const uint32_t stg_off = (bars - smem_u32(smem_raw)) + 256;   // byte offset of the epilogue staging area
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     if (warp == 0 && lane == 0) {
@@ -64,8 +79,9 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         for (int a = 0; a < 2; ++a) { mbar_init(tfull0 + 8 * a, 1); mbar_init(tempty0 + 8 * a, 256); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    if (warp == 2) reinterpret_cast<float*>(smem_raw + stg_off + kStgBytes + 2048)[lane] = p.bias ? __ldg(p.bias + lane) : 0.f;
     if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(64) : "memory");
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(256) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     tc_fence_before();
@@ -83,7 +99,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 // one halo tile per output tile: the 9 tap operands are row-shifted views of it (9x less L2->SM traffic)
                 mbar_wait(empty0 + 8 * stage, phase ^ 1u);
                 mbar_expect_tx(full0 + 8 * stage, p.stage_bytes);
-                tma_load_2d(&tmA, full0 + 8 * stage, a_sm + stage * p.stage_bytes, 0, tile * kTileM + p.shift);
+                tma_load_2d(&tmA, full0 + 8 * stage, a_sm + stage * p.stage_bytes, 0, tile * kTileOut + p.shift);
                 if (++stage == kStages) { stage = 0; phase ^= 1u; }
             }
         }
@@ -95,17 +111,18 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
                 mbar_wait(tempty0 + 8 * acc, acc_phase ^ 1u);
                 tc_fence_after();
-                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * 32);
+                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * kAccCols);
                 mbar_wait(full0 + 8 * stage, phase);
                 tc_fence_after();
-                for (int t = 0; t < 9; ++t) {
-                    // tap (ky,kx) = the halo tile shifted by ky*Wp + kx rows of 128 B; the 128B swizzle is a function of
-                    // the absolute shared-memory address, so a row-shifted start address reads what TMA wrote
-                    const uint64_t ad = make_desc_sw128(a_sm + stage * p.stage_bytes + ((t / 3) * p.Wp + (t % 3)) * 128);
-                    const uint64_t bd = make_desc_sw128(w_sm + t * 4096);
+                for (int ky = 0; ky < 3; ++ky) {
+                    // filter row ky = the halo tile shifted by ky*Wp rows of 128 B; the 128B swizzle is a function of
+                    // the absolute shared-memory address, so a row-shifted start address reads what TMA wrote.  B = the
+                    // three kx taps of this ky: 96 rows (kx, cout) x 32 cin, contiguous in the resident weights.
+                    const uint64_t ad = make_desc_sw128(a_sm + stage * p.stage_bytes + ky * p.Wp * 128);
+                    const uint64_t bd = make_desc_sw128(w_sm + ky * 3 * 4096);
 #pragma unroll
                     for (int k = 0; k < 4; ++k)          // advance 8 TF32 = 32 B inside the swizzle atom: +2 in the >>4 address field
-                        tc_mma_tf32(d_tmem, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), kIdesc, (t | k) != 0);
+                        tc_mma_tf32(d_tmem, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), kIdesc, (ky | k) != 0);
                 }
                 tc_commit(empty0 + 8 * stage);           // smem slot free once these MMAs retire
                 if (++stage == kStages) { stage = 0; phase ^= 1u; }
@@ -114,56 +131,99 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             }
         }
     } else {
-        // 8 epilogue warps: warp w works on TMEM lane quarter (w & 3) and on 16 of the 32 accumulator columns
+        // 8 epilogue warps, two phases per tile around a shared-memory staging tile (row pitch 400 B: conflict-free):
+        //  1. row-per-thread (the only way to read TMEM): warp w drains TMEM lane quarter (w & 3), 16 of the 32 channels
+        //     of D_0 | D_1 | D_2 -> stg[row][96]; the accumulator is released right after;
+        //  2. chunk-per-thread: thread t owns the 16-byte channel chunk t % 8 of rows t/8 + 32 j; it adds the three
+        //     kx-shifted partial sums  out[r] = D_0[r] + D_1[r+1] + D_2[r+2]  (plain row offsets in shared memory),
+        //     applies bias / ReLU / mask / TF32 rounding and stores -- 8 lanes cover one 128-byte pixel, so global
+        //     stores and mask loads are whole lines (a row-per-thread store touches 32 lines per instruction).
+        // Output / mask offsets of the tile's rows are computed once per row (rowinfo), one tile ahead, so that the
+        // mask loads of a tile are in flight while its accumulator is still being computed.
+        const int et = threadIdx.x - 64;                 // 0..255
         const int quarter = warp & 3;                    // TMEM lane quarter this warp may access
-        const int half = (warp - 2) >> 2;                // which 16 output channels
-        const int row = quarter * 32 + lane;
+        const int half = (warp - 2) >> 2;                // which 16 output channels (phase 1)
+        const int row = quarter * 32 + lane;             // phase-1 row
+        const int chunk = et & 7, rslot = et >> 3;       // phase-2 chunk / first row
         int acc = 0; uint32_t acc_phase = 0;
         const int HW = p.Hr * p.Wp;
-        float bias_r[16];
-#pragma unroll
-        for (int e = 0; e < 16; ++e) bias_r[e] = p.bias ? __ldg(p.bias + half * 16 + e) : 0.f;
-        float csum[16];
-#pragma unroll
-        for (int e = 0; e < 16; ++e) csum[e] = 0.f;
-        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-            // output coordinates first (independent of the accumulator), so the mask load is in flight during the wait
-            const int q = tile * kTileM + row;
-            const int b = q / HW; const int r2 = q - b * HW; const int y = r2 / p.Wp; const int x = r2 - y * p.Wp;
-            const bool valid = q < p.total_q && y < p.Hv && x < p.Wv;
-            float4 mk[4];
-            if (p.mask_mode && valid) {
-                const float4* mp = reinterpret_cast<const float4*>(p.mask + ((size_t)(b * p.Hm + y) * p.Wm + x) * 32 + half * 16);
-#pragma unroll
-                for (int c4 = 0; c4 < 4; ++c4) mk[c4] = __ldg(mp + c4);
+        uint8_t* stg = smem_raw + stg_off;
+        int2* rowinfo = reinterpret_cast<int2*>(smem_raw + stg_off + kStgBytes);          // [2][128]: {out, mask} offsets in float4
+        const float4 bias4 = reinterpret_cast<const float4*>(smem_raw + stg_off + kStgBytes + 2048)[chunk];
+        float csum[4] = {0.f, 0.f, 0.f, 0.f};
+        auto fill_rowinfo = [&](int tile, int par) {
+            if (half != 0) return;
+            int2 info = make_int2(-1, 0);
+            const int q = tile * kTileOut + row;
+            if (tile < p.num_tiles && row < kTileOut && q < p.total_q) {
+                const int b = q / HW; const int r2 = q - b * HW; const int y = r2 / p.Wp; const int x = r2 - y * p.Wp;
+                if (y < p.Hv && x < p.Wv)
+                    info = make_int2(((b * p.Hq + y + p.oy) * p.Wq + x + p.ox) * 8, ((b * p.Hm + y) * p.Wm + x) * 8);
             }
+            rowinfo[par * 128 + row] = info;
+        };
+        fill_rowinfo(blockIdx.x, 0);
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        int par = 0;
+        const float4* mask4 = reinterpret_cast<const float4*>(p.mask);
+        float4* out4 = reinterpret_cast<float4*>(p.out);
+        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, par ^= 1) {
+            // mask loads of this tile's four phase-2 items first: in flight during the accumulator wait
+            int2 info[4];
+            float4 mk[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int r = rslot + 32 * j;
+                info[j] = r < kTileOut ? rowinfo[par * 128 + r] : make_int2(-1, 0);
+                if (p.mask_mode && info[j].x >= 0) mk[j] = __ldg(mask4 + info[j].y + chunk);
+            }
+            fill_rowinfo(tile + gridDim.x, par ^ 1);
+            // ---- phase 1: TMEM -> staging
             mbar_wait(tfull0 + 8 * acc, acc_phase);
             tc_fence_after();
-            uint32_t v[16];
-            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * 32 + half * 16);
-            asm volatile(
-                "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-                "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-                : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-                  "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-                : "r"(taddr) : "memory");
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            tc_fence_before();
-            mbar_arrive(tempty0 + 8 * acc);              // accumulator drained: MMA warp may reuse it
-            if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
-            if (!valid) continue;
-            float* dst = p.out + ((size_t)(b * p.Hq + y + p.oy) * p.Wq + x + p.ox) * 32 + half * 16;
+            {
+                uint32_t v[48];
+                const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * kAccCols + half * 16);
+#define SGQN_TMEM_LD16(O, ADDR)                                                                                          \
+                asm volatile(                                                                                            \
+                    "tcgen05.ld.sync.aligned.32x32b.x16.b32 "                                                            \
+                    "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"                     \
+                    : "=r"(v[O + 0]), "=r"(v[O + 1]), "=r"(v[O + 2]), "=r"(v[O + 3]), "=r"(v[O + 4]), "=r"(v[O + 5]),    \
+                      "=r"(v[O + 6]), "=r"(v[O + 7]), "=r"(v[O + 8]), "=r"(v[O + 9]), "=r"(v[O + 10]), "=r"(v[O + 11]),  \
+                      "=r"(v[O + 12]), "=r"(v[O + 13]), "=r"(v[O + 14]), "=r"(v[O + 15])                                 \
+                    : "r"(ADDR) : "memory")
+                SGQN_TMEM_LD16(0, taddr);
+                SGQN_TMEM_LD16(16, taddr + 32u);
+                SGQN_TMEM_LD16(32, taddr + 64u);
+#undef SGQN_TMEM_LD16
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                tc_fence_before();
+                mbar_arrive(tempty0 + 8 * acc);          // accumulator drained: the MMA warp may reuse it
+                if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+                uint4* srow = reinterpret_cast<uint4*>(stg + row * kStgPitch + half * 64);
 #pragma unroll
-            for (int c4 = 0; c4 < 4; ++c4) {
-                float o[4];
+                for (int kx = 0; kx < 3; ++kx)
 #pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    float f = __uint_as_float(v[4 * c4 + e]) + bias_r[4 * c4 + e];
-                    if (p.relu_out) f = fmaxf(f, 0.f);
-                    o[e] = f;
+                    for (int c = 0; c < 4; ++c)
+                        srow[kx * 8 + c] = make_uint4(v[kx * 16 + 4 * c], v[kx * 16 + 4 * c + 1], v[kx * 16 + 4 * c + 2], v[kx * 16 + 4 * c + 3]);
+            }
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            // ---- phase 2: shifted sum, epilogue math, coalesced store
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                if (info[j].x < 0) continue;
+                const int r = rslot + 32 * j;
+                const float4 a0 = *reinterpret_cast<const float4*>(stg + r * kStgPitch + chunk * 16);
+                const float4 a1 = *reinterpret_cast<const float4*>(stg + (r + 1) * kStgPitch + 128 + chunk * 16);
+                const float4 a2 = *reinterpret_cast<const float4*>(stg + (r + 2) * kStgPitch + 256 + chunk * 16);
+                float o[4] = {a0.x + a1.x + a2.x + bias4.x, a0.y + a1.y + a2.y + bias4.y, a0.z + a1.z + a2.z + bias4.z,
+                              a0.w + a1.w + a2.w + bias4.w};
+                if (p.relu_out) {
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) o[e] = fmaxf(o[e], 0.f);
                 }
                 if (p.mask_mode) {
-                    const float mm[4] = {mk[c4].x, mk[c4].y, mk[c4].z, mk[c4].w};
+                    const float mm[4] = {mk[j].x, mk[j].y, mk[j].z, mk[j].w};
 #pragma unroll
                     for (int e = 0; e < 4; ++e) {
                         if (p.mask_mode == 2) o[e] = fmaxf(o[e], 0.f);
@@ -174,16 +234,19 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 #pragma unroll
                     for (int e = 0; e < 4; ++e) o[e] = round_tf32(o[e]);
                 }
-                reinterpret_cast<float4*>(dst)[c4] = make_float4(o[0], o[1], o[2], o[3]);
+                out4[info[j].x + chunk] = make_float4(o[0], o[1], o[2], o[3]);
 #pragma unroll
-                for (int e = 0; e < 4; ++e) csum[4 * c4 + e] += o[e];
+                for (int e = 0; e < 4; ++e) csum[e] += o[e];
             }
+            asm volatile("bar.sync 1, 256;" ::: "memory");       // staging tile and rowinfo[par] are free again
         }
-        if (p.dbias) {                                   // one warp reduction + 16 atomics per warp for the whole launch
+        if (p.dbias) {                                   // lanes with equal chunk hold the same channels: 2 shuffles + 4 atomics
 #pragma unroll
-            for (int e = 0; e < 16; ++e) {
-                float t = warp_sum(csum[e]);
-                if (lane == 0) atomicAdd(p.dbias + half * 16 + e, t);
+            for (int e = 0; e < 4; ++e) {
+                float t = csum[e];
+                t += __shfl_xor_sync(0xffffffffu, t, 8);
+                t += __shfl_xor_sync(0xffffffffu, t, 16);
+                if (lane < 8) atomicAdd(p.dbias + chunk * 4 + e, t);
             }
         }
     }
@@ -191,7 +254,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     __syncthreads();
     if (warp == 1) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(64) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256) : "memory");
     }
 }
 
@@ -220,14 +283,14 @@ extern "C" int sgqn_conv_tc(const float* x, const float* w, const float* bias, c
     TcParams p;
     p.total_q = B * Hr * Wp; p.Hr = Hr; p.Wp = Wp; p.Hv = Hv; p.Wv = Wv; p.shift = shift;
     p.Hq = Hq; p.Wq = Wq; p.oy = oy; p.ox = ox; p.Hm = Hm; p.Wm = Wm;
-    p.num_tiles = (p.total_q + kTileM - 1) / kTileM;
+    p.num_tiles = (p.total_q + kTileOut - 1) / kTileOut;
     p.bias = bias; p.mask = mask; p.out = out; p.dbias = dbias;
     p.relu_out = flags & 1; p.round_out = (flags >> 1) & 1; p.mask_mode = (flags >> 2) & 3;
     if (p.mask_mode && !mask) return (int)cudaErrorInvalidValue;
-    p.halo_rows = (kTileM + 2 * Wp + 2 + 7) / 8 * 8;               // whole 1024-byte swizzle atoms
+    p.halo_rows = (kTileM + 2 * Wp + 7) / 8 * 8;                   // whole 1024-byte swizzle atoms
     if (p.halo_rows > 256) return (int)cudaErrorInvalidValue;      // TMA box limit
     p.stage_bytes = p.halo_rows * 128;
-    p.stages = (kSmemBudget - kWBytes - 1024 - 256) / p.stage_bytes;
+    p.stages = (kSmemBudget - kWBytes - 1024 - 256 - kEpiBytes) / p.stage_bytes;
     if (p.stages > kMaxStages) p.stages = kMaxStages;
     if (p.stages < 2) return (int)cudaErrorInvalidValue;
     CUtensorMap tmA, tmW;
@@ -236,7 +299,7 @@ extern "C" int sgqn_conv_tc(const float* x, const float* w, const float* bias, c
     rc = make_map_2d(&tmW, w, 288, 32, 32, 32);
     if (rc) return rc;
     int grid = p.num_tiles < num_sms ? p.num_tiles : num_sms;
-    conv3x3_tc_kernel<<<grid, 320, kSmemBudget, (cudaStream_t)stream>>>(tmA, tmW, p);
+    conv3x3_tc_kernel<<<grid, kThreads, kSmemBudget, (cudaStream_t)stream>>>(tmA, tmW, p);
     return SGQN_CHECK_LAUNCH();
 }
 
@@ -298,7 +361,8 @@ constexpr int kWgTile = kWgRows * 128;                 // 8 KB
 constexpr int kWgStageBytes = 10 * kWgTile;            // 9 X tap tiles + 1 dY tile
 constexpr int kWgStages = 2;
 constexpr int kWgSmem = kWgStages * kWgStageBytes + 2 * kWgTile /*overrun of the 3rd accumulator's unused atoms*/ + 1024 + 256;
-constexpr uint32_t kIdescMN = kIdesc | (1u << 15) | (1u << 16);      // A and B MN-major
+// kind::tf32, D fp32, M = 128, N = 32, A and B MN-major
+constexpr uint32_t kIdescMN = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((32u >> 3) << 17) | ((128u >> 4) << 24);
 
 // MN-major TF32 operands only exist in the SWIZZLE_128B_BASE32B layout (cute::UMMA::Layout_MN_SW128_32B_Atom: rows of
 // 128 B = 32 channels, 32-byte chunks XOR-ed with row % 4, K atom = 4 rows = 512 B); TMA writes it with
