@@ -51,6 +51,17 @@ int sgqn_linear_dgrad(const float* dy, int lddy, long long dybs, const float* w,
 int sgqn_linear_wgrad(const float* x, int ldx, long long xbs, const float* dy, int lddy, long long dybs, float* dw,
                       long long dwbs, float* db, long long dbbs, int M, int N, int K, int relu_in, int batch, void* stream);
 int sgqn_colsum(const float* x, int ld, int M, int N, float* out, void* stream);
+/* The same three operations on tcgen05 with split-precision ("3xTF32") operands: x = tf32(x) + tf32(x - tf32(x)),
+ * A.B ~= As.Bb + Ab.Bs + Ab.Bb accumulated in fp32 -- fp32-grade accuracy (the reference's nn.Linear runs in fp32) at
+ * tensor-core speed.  Same arguments and semantics; every leading dimension / batch stride must be a multiple of 4
+ * floats and every base pointer 16-byte aligned (TMA), otherwise cudaErrorInvalidValue. */
+int sgqn_linear_fwd_tc(const float* x, int ldx, long long xbs, const float* w, long long wbs, const float* bias, long long bbs,
+                       float* y, int ldy, long long ybs, int M, int N, int K, int relu_in, int batch, int splitk, void* stream);
+int sgqn_linear_dgrad_tc(const float* dy, int lddy, long long dybs, const float* w, long long wbs, const float* zmask, int ldm,
+                         long long mbs, float* dx, int lddx, long long dxbs, int M, int N, int K, int mode, int accumulate,
+                         int batch, void* stream);
+int sgqn_linear_wgrad_tc(const float* x, int ldx, long long xbs, const float* dy, int lddy, long long dybs, float* dw,
+                         long long dwbs, float* db, long long dbbs, int M, int N, int K, int relu_in, int batch, void* stream);
 
 /* ---- 3x3 convolutions on NHWC fp32 (SharedCNN layers 2..11: modules.py:144-146, valid, stride 1; decoder
  *      convs: modules.py:319-326, pad 1, nearest x2 upsample of the input fused via up=2).

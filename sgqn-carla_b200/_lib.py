@@ -19,6 +19,9 @@ SIGNATURES = {
     "sgqn_linear_dgrad": [_p, _i, _ll, _p, _ll, _p, _i, _ll, _p, _i, _ll, _i, _i, _i, _i, _i, _i, _p],
     "sgqn_linear_wgrad": [_p, _i, _ll, _p, _i, _ll, _p, _ll, _p, _ll, _i, _i, _i, _i, _i, _p],
     "sgqn_colsum": [_p, _i, _i, _i, _p, _p],
+    "sgqn_linear_fwd_tc": [_p, _i, _ll, _p, _ll, _p, _ll, _p, _i, _ll, _i, _i, _i, _i, _i, _i, _p],
+    "sgqn_linear_dgrad_tc": [_p, _i, _ll, _p, _ll, _p, _i, _ll, _p, _i, _ll, _i, _i, _i, _i, _i, _i, _p],
+    "sgqn_linear_wgrad_tc": [_p, _i, _ll, _p, _i, _ll, _p, _ll, _p, _ll, _i, _i, _i, _i, _i, _p],
     "sgqn_conv_fwd": [_p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p],
     "sgqn_conv_dgrad": [_p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p],
     "sgqn_conv_wgrad": [_p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p],

@@ -94,6 +94,60 @@ def test_linear_wgrad(M, N, K_, relu):
     close(db, dy.sum(0), rtol=2e-4, what="linear_bgrad")
 
 
+# ------------------------------------------------------------------ dense layers on tcgen05 (3xTF32 split precision)
+def _err64(a, ref64):
+    """max |a - ref| relative to the output scale, both against an fp64 reference."""
+    return float((a.double() - ref64).abs().max() / (ref64.abs().max() + 1e-30))
+
+
+@pytest.mark.parametrize("M,N,K_,relu,split,batch", [(128, 100, 14112, 0, 2, 1), (256, 100, 14112, 0, 2, 1), (128, 1024, 1024, 1, 2, 2),
+                                                     (256, 1024, 1024, 1, 2, 2), (128, 1024, 100, 0, 0, 1), (77, 1024, 1024, 1, 0, 1),
+                                                     (1, 1024, 1024, 1, 2, 1)])
+def test_gemm_tc_fwd(M, N, K_, relu, split, batch):
+    """sgqn_linear_fwd_tc vs fp64 F.linear: within 1e-5 of the output scale (plain TF32 is ~1e-3, the fp32 CUDA-core kernel ~1e-6)."""
+    x, w, b = rnd(batch, M, K_, seed=1), rnd(batch, N, K_, seed=2, scale=0.05), rnd(batch, N, seed=3)
+    y = torch.full((batch, M, N), 7.0, device=DEV) if split != 1 else torch.zeros(batch, M, N, device=DEV)
+    y0 = torch.zeros(batch, M, N, device=DEV)
+    K.linear_fwd_tc(P(x), K_, M * K_, P(w), N * K_, P(b), N, P(y), N, M * N, M, N, K_, relu, batch, split, ST())
+    K.linear_fwd(P(x), K_, M * K_, P(w), N * K_, P(b), N, P(y0), N, M * N, M, N, K_, relu, batch, 2 if split else 0, ST())
+    xa = F.relu(x) if relu else x
+    ref = torch.einsum("bmk,bnk->bmn", xa.double(), w.double()) + b.double()[:, None, :]
+    e_tc, e_simt = _err64(y, ref), _err64(y0, ref)
+    # the tensor core adds into its fp32 accumulator with truncation, so a 1024-long chain inside one accumulator is ~1e-5;
+    # split-K shortens the chains (the partial sums meet through fp32 red.adds)
+    assert e_tc < max(4 * e_simt, 1e-5), (e_tc, e_simt)
+
+
+@pytest.mark.parametrize("M,N,K_,mode,acc,batch", [(128, 1024, 1024, 1, 2, 2), (256, 1024, 1024, 1, 2, 2), (128, 1024, 1024, 2, 0, 1),
+                                                   (200, 100, 14112, 0, 0, 1), (128, 1024, 100, 0, 2, 1), (128, 100, 14112, 0, 1, 1)])
+def test_gemm_tc_dgrad(M, N, K_, mode, acc, batch):
+    dy, w, z = rnd(batch, M, N, seed=1), rnd(batch, N, K_, seed=2, scale=0.05), rnd(batch, M, K_, seed=3)
+    init = rnd(batch, M, K_, seed=4) if acc == 1 else torch.full((batch, M, K_), 3.0, device=DEV)
+    dx = init.clone()
+    K.linear_dgrad_tc(P(dy), N, M * N, P(w), N * K_, P(z) if mode else 0, K_, M * K_, P(dx), K_, M * K_, M, N, K_, mode, acc, batch, ST())
+    ref = torch.einsum("bmn,bnk->bmk", dy.double(), w.double())
+    if mode == 1:
+        ref = ref * (z > 0)
+    if mode == 2:
+        ref = F.relu(ref) * (z > 0)
+    if acc == 1:
+        ref = ref + init.double()
+    assert _err64(dx, ref) < 2e-6, _err64(dx, ref)
+
+
+@pytest.mark.parametrize("M,N,K_,relu,batch", [(256, 1024, 1024, 1, 2), (128, 100, 14112, 0, 1), (256, 100, 14112, 0, 1), (128, 1024, 100, 0, 1),
+                                               (77, 1024, 1024, 1, 1)])
+def test_gemm_tc_wgrad(M, N, K_, relu, batch):
+    x, dy = rnd(batch, M, K_, seed=1), rnd(batch, M, N, seed=2)
+    dw0 = rnd(batch, N, K_, seed=5)
+    dw = dw0.clone(); db = torch.zeros(batch, N, device=DEV)
+    K.linear_wgrad_tc(P(x), K_, M * K_, P(dy), N, M * N, P(dw), N * K_, P(db), N, M, N, K_, relu, batch, ST())
+    xa = F.relu(x) if relu else x
+    ref = torch.einsum("bmn,bmk->bnk", dy.double(), xa.double()) + dw0.double()
+    assert _err64(dw, ref) < 2e-6, _err64(dw, ref)
+    close(db, dy.sum(1), rtol=2e-4, what="bias grad")
+
+
 # ------------------------------------------------------------------ convs (NHWC)
 CONVS = [  # B, Hs, Cin, Cout(real), Cout(stored), pad, up
     (3, 41, 32, 32, 32, 0, 1), (2, 23, 32, 32, 32, 0, 1), (2, 21, 32, 128, 128, 1, 1), (2, 21, 128, 64, 64, 1, 2),
