@@ -18,8 +18,8 @@
 // The data-gradient is the same kernel on a zero-bordered (pad 2) gradient buffer with flipped / transposed weights
 // and a ReLU-mask (plain or guided, rl_utils.py:35-39) epilogue writing into the interior of the next padded buffer.
 //
-// Warp roles (320 threads): warp 0 = TMA producer (one lane), warp 1 = TMEM allocator + MMA issuer (one lane),
-// warps 2..9 = epilogue (TMEM -> shared staging -> kx shift + bias / ReLU / mask / TF32 round -> global).
+// Warp roles (576 threads): warp 0 = TMA producer (one lane), warp 1 = TMEM allocator + MMA issuer (one lane),
+// warps 2..17 = epilogue (TMEM -> shared staging -> kx shift + bias / ReLU / mask / TF32 round -> global).
 #include "tc_common.cuh"
 #include "../../include/sgqn_b200.h"
 
@@ -34,7 +34,11 @@ constexpr int kAccCols = 128;                  // TMEM column stride between the
 constexpr int kStgPitch = 400;                 // staging row: 96 floats + 16 B, so that 8 consecutive rows hit 8 different bank groups
 constexpr int kStgBytes = kTileM * kStgPitch;  // 50 KB
 constexpr int kEpiBytes = kStgBytes + 2048 + 128;   // staging tile, rowinfo[2][128], bias
-constexpr int kThreads = 320;                  // TMA warp, MMA warp, 8 epilogue warps
+constexpr int kEpiWarps = 16;
+constexpr int kEpiThreads = kEpiWarps * 32;
+constexpr int kThreads = 64 + kEpiThreads;     // TMA warp, MMA warp, epilogue warps
+constexpr int kChPerThread = 128 / kEpiWarps;  // phase-1 channels per thread: 4 warps per TMEM quarter share its 32 channels
+constexpr int kItems = 1024 / kEpiThreads;     // phase-2 (row, 16-byte chunk) items per thread
 constexpr int kWBytes = 9 * 32 * 128;          // 36 KB: 9 taps x [32 n][32 k] fp32
 constexpr int kSmemBudget = 200 * 1024;        // dynamic shared memory we ask for
 
@@ -76,7 +80,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         asm volatile("prefetch.tensormap [%0];" ::"l"((unsigned long long)&tmW) : "memory");
         for (int s = 0; s < kMaxStages; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
         mbar_init(wbar, 1);
-        for (int a = 0; a < 2; ++a) { mbar_init(tfull0 + 8 * a, 1); mbar_init(tempty0 + 8 * a, 256); }
+        for (int a = 0; a < 2; ++a) { mbar_init(tfull0 + 8 * a, 1); mbar_init(tempty0 + 8 * a, kEpiThreads); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) reinterpret_cast<float*>(smem_raw + stg_off + kStgBytes + 2048)[lane] = p.bias ? __ldg(p.bias + lane) : 0.f;
@@ -131,18 +135,18 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             }
         }
     } else {
-        // 8 epilogue warps, two phases per tile around a shared-memory staging tile (row pitch 400 B: conflict-free):
-        //  1. row-per-thread (the only way to read TMEM): warp w drains TMEM lane quarter (w & 3), 16 of the 32 channels
+        // 16 epilogue warps, two phases per tile around a shared-memory staging tile (row pitch 400 B: conflict-free):
+        //  1. row-per-thread (the only way to read TMEM): warp w drains TMEM lane quarter (w & 3), 8 of the 32 channels
         //     of D_0 | D_1 | D_2 -> stg[row][96]; the accumulator is released right after;
-        //  2. chunk-per-thread: thread t owns the 16-byte channel chunk t % 8 of rows t/8 + 32 j; it adds the three
+        //  2. chunk-per-thread: thread t owns the 16-byte channel chunk t % 8 of rows t/8 + 64 j; it adds the three
         //     kx-shifted partial sums  out[r] = D_0[r] + D_1[r+1] + D_2[r+2]  (plain row offsets in shared memory),
         //     applies bias / ReLU / mask / TF32 rounding and stores -- 8 lanes cover one 128-byte pixel, so global
         //     stores and mask loads are whole lines (a row-per-thread store touches 32 lines per instruction).
         // Output / mask offsets of the tile's rows are computed once per row (rowinfo), one tile ahead, so that the
         // mask loads of a tile are in flight while its accumulator is still being computed.
-        const int et = threadIdx.x - 64;                 // 0..255
+        const int et = threadIdx.x - 64;
         const int quarter = warp & 3;                    // TMEM lane quarter this warp may access
-        const int half = (warp - 2) >> 2;                // which 16 output channels (phase 1)
+        const int half = (warp - 2) >> 2;                // which kChPerThread output channels (phase 1)
         const int row = quarter * 32 + lane;             // phase-1 row
         const int chunk = et & 7, rslot = et >> 3;       // phase-2 chunk / first row
         int acc = 0; uint32_t acc_phase = 0;
@@ -163,17 +167,17 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             rowinfo[par * 128 + row] = info;
         };
         fill_rowinfo(blockIdx.x, 0);
-        asm volatile("bar.sync 1, 256;" ::: "memory");
+        asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
         int par = 0;
         const float4* mask4 = reinterpret_cast<const float4*>(p.mask);
         float4* out4 = reinterpret_cast<float4*>(p.out);
         for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, par ^= 1) {
             // mask loads of this tile's four phase-2 items first: in flight during the accumulator wait
-            int2 info[4];
-            float4 mk[4];
+            int2 info[kItems];
+            float4 mk[kItems];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int r = rslot + 32 * j;
+            for (int j = 0; j < kItems; ++j) {
+                const int r = rslot + (kEpiThreads / 8) * j;
                 info[j] = r < kTileOut ? rowinfo[par * 128 + r] : make_int2(-1, 0);
                 if (p.mask_mode && info[j].x >= 0) mk[j] = __ldg(mask4 + info[j].y + chunk);
             }
@@ -182,37 +186,37 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             mbar_wait(tfull0 + 8 * acc, acc_phase);
             tc_fence_after();
             {
-                uint32_t v[48];
-                const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * kAccCols + half * 16);
-#define SGQN_TMEM_LD16(O, ADDR)                                                                                          \
+                uint32_t v[3 * kChPerThread];
+                const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * kAccCols + half * kChPerThread);
+                static_assert(kChPerThread == 8, "phase-1 TMEM loads are written for 8 channels per thread");
+#define SGQN_TMEM_LD8(O, ADDR)                                                                                            \
                 asm volatile(                                                                                            \
-                    "tcgen05.ld.sync.aligned.32x32b.x16.b32 "                                                            \
-                    "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"                     \
+                    "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"                      \
                     : "=r"(v[O + 0]), "=r"(v[O + 1]), "=r"(v[O + 2]), "=r"(v[O + 3]), "=r"(v[O + 4]), "=r"(v[O + 5]),    \
-                      "=r"(v[O + 6]), "=r"(v[O + 7]), "=r"(v[O + 8]), "=r"(v[O + 9]), "=r"(v[O + 10]), "=r"(v[O + 11]),  \
-                      "=r"(v[O + 12]), "=r"(v[O + 13]), "=r"(v[O + 14]), "=r"(v[O + 15])                                 \
+                      "=r"(v[O + 6]), "=r"(v[O + 7])                                                                     \
                     : "r"(ADDR) : "memory")
-                SGQN_TMEM_LD16(0, taddr);
-                SGQN_TMEM_LD16(16, taddr + 32u);
-                SGQN_TMEM_LD16(32, taddr + 64u);
-#undef SGQN_TMEM_LD16
+                SGQN_TMEM_LD8(0, taddr);
+                SGQN_TMEM_LD8(8, taddr + 32u);
+                SGQN_TMEM_LD8(16, taddr + 64u);
+#undef SGQN_TMEM_LD8
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
                 tc_fence_before();
                 mbar_arrive(tempty0 + 8 * acc);          // accumulator drained: the MMA warp may reuse it
                 if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
-                uint4* srow = reinterpret_cast<uint4*>(stg + row * kStgPitch + half * 64);
+                uint4* srow = reinterpret_cast<uint4*>(stg + row * kStgPitch + half * (kChPerThread * 4));
 #pragma unroll
                 for (int kx = 0; kx < 3; ++kx)
 #pragma unroll
-                    for (int c = 0; c < 4; ++c)
-                        srow[kx * 8 + c] = make_uint4(v[kx * 16 + 4 * c], v[kx * 16 + 4 * c + 1], v[kx * 16 + 4 * c + 2], v[kx * 16 + 4 * c + 3]);
+                    for (int c = 0; c < kChPerThread / 4; ++c)
+                        srow[kx * 8 + c] = make_uint4(v[kx * kChPerThread + 4 * c], v[kx * kChPerThread + 4 * c + 1],
+                                                      v[kx * kChPerThread + 4 * c + 2], v[kx * kChPerThread + 4 * c + 3]);
             }
-            asm volatile("bar.sync 1, 256;" ::: "memory");
+            asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
             // ---- phase 2: shifted sum, epilogue math, coalesced store
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
+            for (int j = 0; j < kItems; ++j) {
                 if (info[j].x < 0) continue;
-                const int r = rslot + 32 * j;
+                const int r = rslot + (kEpiThreads / 8) * j;
                 const float4 a0 = *reinterpret_cast<const float4*>(stg + r * kStgPitch + chunk * 16);
                 const float4 a1 = *reinterpret_cast<const float4*>(stg + (r + 1) * kStgPitch + 128 + chunk * 16);
                 const float4 a2 = *reinterpret_cast<const float4*>(stg + (r + 2) * kStgPitch + 256 + chunk * 16);
@@ -238,7 +242,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 #pragma unroll
                 for (int e = 0; e < 4; ++e) csum[e] += o[e];
             }
-            asm volatile("bar.sync 1, 256;" ::: "memory");       // staging tile and rowinfo[par] are free again
+            asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");       // staging tile and rowinfo[par] are free again
         }
         if (p.dbias) {                                   // lanes with equal chunk hold the same channels: 2 shuffles + 4 atomics
 #pragma unroll
@@ -346,27 +350,32 @@ extern "C" int sgqn_pad_copy(const float* src, float* dst, int B, int H, int W, 
 }
 
 // =====================================================================================================================
-// Weight gradient of the 32->32 convs on tcgen05:  dW[co][tap][ci] += sum_q dY[q][co] * X[q + (ky-2)*Wp + kx][ci].
+// Weight gradient of the 32->32 convs on tcgen05:  dW[co][ky][kx][ci] += sum_q dY[q][co] * X[q + (ky-2)*Wp + kx][ci].
 // X (post-ReLU activations of the previous layer) and dY (zero-bordered gradient of this layer's output) share one
-// pitch-linear geometry [B][Hr][Wp][32], so every tap's operand for a block of 64 consecutive q is again one 2-D TMA box.
-// GEMM view: D[M = (tap, ci)][N = co] with the reduction over pixels: both operands are "MN-major" (the pixel index runs
-// over the 128-byte rows of the SWIZZLE_128B tile, channels are contiguous), UMMA_K = 8 pixels = two 512-byte swizzle
-// atoms (SWIZZLE_128B_BASE32B, the only MN-major layout for TF32).  M = 128 packs 4 taps (4 atoms LBO = one tile apart); 9 taps = 3 accumulators of 32 TMEM columns (the third one
-// computes 3 unused row groups).  Each CTA reduces a contiguous range of pixel blocks in TMEM and adds its 9216 partial
-// sums to dW with red.global.add.f32 once at the end.
+// pitch-linear geometry [B][Hr][Wp][32].  Substituting q' = q + (ky-2)*Wp moves the ky shift onto dY:
+//         dW[co][ky][kx][ci] = sum_q' X[q' + kx][ci] * dY[q' + (2-ky)*Wp][co]
+// so ONE MMA chain per block of 128 consecutive q' produces all nine taps:  D[M = (kx, ci)][N = (2-ky, co)], reduction
+// over pixels.  Both operands are "MN-major" (the pixel index runs over the 128-byte rows of the tile, channels are
+// contiguous: SWIZZLE_128B_BASE32B, the only MN-major layout for TF32, UMMA_K = 8 pixels = two 512-byte atoms) and both
+// are HALO tiles loaded once per block: the four 32-row M atoms are the X tile shifted by kx = 0..3 rows (leading byte
+// offset 128 B; kx = 3 is computed and dropped), the three 32-column N atoms are the dY tile shifted by 0, Wp, 2Wp
+// rows (leading byte offset Wp*128 B).  Per 128 pixels the kernel moves 45 KB through shared memory (1.4x the
+// operands) and issues 16 MMAs of 128x96x8.  Each CTA reduces a contiguous range of pixel blocks in TMEM and adds its
+// 9216 partial sums to dW with red.global.add.f32 once at the end.
 namespace {
 
-constexpr int kWgRows = 64;
-constexpr int kWgTile = kWgRows * 128;                 // 8 KB
-constexpr int kWgStageBytes = 10 * kWgTile;            // 9 X tap tiles + 1 dY tile
-constexpr int kWgStages = 2;
-constexpr int kWgSmem = kWgStages * kWgStageBytes + 2 * kWgTile /*overrun of the 3rd accumulator's unused atoms*/ + 1024 + 256;
-// kind::tf32, D fp32, M = 128, N = 32, A and B MN-major
-constexpr uint32_t kIdescMN = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((32u >> 3) << 17) | ((128u >> 4) << 24);
+constexpr int kWgRows = 128;                           // pixels per k-block
+constexpr int kWgXRows = kWgRows + 8;                  // X halo: + kx <= 3, whole 8-row swizzle atoms
+constexpr int kWgXBytes = kWgXRows * 128;
+constexpr int kWgMaxStages = 4;
+constexpr int kWgSmemBudget = 200 * 1024;
+// kind::tf32, D fp32, M = 128, N = 96, A and B MN-major
+constexpr uint32_t kIdescMN = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((96u >> 3) << 17) | ((128u >> 4) << 24);
 
 // MN-major TF32 operands only exist in the SWIZZLE_128B_BASE32B layout (cute::UMMA::Layout_MN_SW128_32B_Atom: rows of
 // 128 B = 32 channels, 32-byte chunks XOR-ed with row % 4, K atom = 4 rows = 512 B); TMA writes it with
-// CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B.
+// CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B.  The swizzle is a function of the absolute shared-memory address, so atoms that
+// start at any multiple of 128 B (row-shifted views of one tile) read what TMA wrote.
 __device__ __forceinline__ uint64_t make_desc_mn_sw128(uint32_t saddr, uint32_t lbo_bytes) {
     uint64_t d = 0;
     d |= (uint64_t)((saddr >> 4) & 0x3FFF);
@@ -377,14 +386,14 @@ __device__ __forceinline__ uint64_t make_desc_mn_sw128(uint32_t saddr, uint32_t 
     return d;
 }
 
-struct WgParams { int total_q, Wp, kb_total, kb_per_cta; float* dw; };
+struct WgParams { int total_q, Wp, kb_total, kb_per_cta, drows, stage_bytes, stages; float* dw; };
 
 __global__ void __launch_bounds__(192, 1)
 conv3x3_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmD, WgParams p) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-    const uint32_t bars = base + kWgStages * kWgStageBytes + 2 * kWgTile;
-    const uint32_t full0 = bars, empty0 = bars + 8 * kWgStages, done_bar = bars + 16 * kWgStages, tmem_slot = done_bar + 8;
+    const uint32_t bars = base + p.stages * p.stage_bytes;
+    const uint32_t full0 = bars, empty0 = bars + 8 * kWgMaxStages, done_bar = bars + 16 * kWgMaxStages, tmem_slot = done_bar + 8;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int kb0 = blockIdx.x * p.kb_per_cta;
     const int kb1 = min(p.kb_total, kb0 + p.kb_per_cta);
@@ -392,7 +401,7 @@ conv3x3_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"((unsigned long long)&tmX) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"((unsigned long long)&tmD) : "memory");
-        for (int s = 0; s < kWgStages; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
+        for (int s = 0; s < kWgMaxStages; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
         mbar_init(done_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -411,43 +420,40 @@ conv3x3_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
             int stage = 0; uint32_t phase = 0;
             for (int kb = kb0; kb < kb1; ++kb) {
                 const int q0 = kb * kWgRows;
-                const uint32_t sb = base + stage * kWgStageBytes;
+                const uint32_t sb = base + stage * p.stage_bytes;
                 mbar_wait(empty0 + 8 * stage, phase ^ 1u);
-                mbar_expect_tx(full0 + 8 * stage, kWgStageBytes);
-                for (int t = 0; t < 9; ++t)
-                    tma_load_2d(&tmX, full0 + 8 * stage, sb + t * kWgTile, 0, q0 + (t / 3 - 2) * p.Wp + (t % 3));
-                tma_load_2d(&tmD, full0 + 8 * stage, sb + 9 * kWgTile, 0, q0);
-                if (++stage == kWgStages) { stage = 0; phase ^= 1u; }
+                mbar_expect_tx(full0 + 8 * stage, p.stage_bytes);
+                tma_load_2d(&tmX, full0 + 8 * stage, sb, 0, q0);                    // X rows q0 .. q0 + 135
+                tma_load_2d(&tmD, full0 + 8 * stage, sb + kWgXBytes, 0, q0);        // dY rows q0 .. q0 + 127 + 2 Wp
+                if (++stage == p.stages) { stage = 0; phase ^= 1u; }
             }
         }
     } else if (warp == 1) {
         if (lane == 0) {
             int stage = 0; uint32_t phase = 0;
+            const uint32_t lbo_d = (uint32_t)p.Wp * 128u;
             for (int kb = kb0; kb < kb1; ++kb) {
-                const uint32_t sb = base + stage * kWgStageBytes;
+                const uint32_t sb = base + stage * p.stage_bytes;
                 mbar_wait(full0 + 8 * stage, phase);
                 tc_fence_after();
-#pragma unroll 1
+#pragma unroll 4
                 for (int j = 0; j < kWgRows / 8; ++j) {
-                    const uint64_t bd = make_desc_mn_sw128(sb + 9 * kWgTile + j * 1024, kWgTile);
-#pragma unroll
-                    for (int g = 0; g < 3; ++g) {
-                        const uint64_t ad = make_desc_mn_sw128(sb + g * 4 * kWgTile + j * 1024, kWgTile);
-                        tc_mma_tf32(tmem_base + (uint32_t)(g * 32), ad, bd, kIdescMN, (kb != kb0 || j != 0) ? 1u : 0u);
-                    }
+                    const uint64_t ad = make_desc_mn_sw128(sb + j * 1024, 128);                 // atoms: kx = 0..3 row shifts
+                    const uint64_t bd = make_desc_mn_sw128(sb + kWgXBytes + j * 1024, lbo_d);   // atoms: 0, Wp, 2 Wp row shifts
+                    tc_mma_tf32(tmem_base, ad, bd, kIdescMN, (kb != kb0 || j != 0) ? 1u : 0u);
                 }
                 tc_commit(empty0 + 8 * stage);
-                if (++stage == kWgStages) { stage = 0; phase ^= 1u; }
+                if (++stage == p.stages) { stage = 0; phase ^= 1u; }
             }
             tc_commit(done_bar);
         }
     } else if (kb1 > kb0) {
-        const int quarter = warp & 3;
+        const int kx = warp & 3;                           // TMEM lane quarter = rows (kx, ci = lane)
         mbar_wait(done_bar, 0);
         tc_fence_after();
-        for (int g = 0; g < 3; ++g) {
+        for (int g = 0; g < 3; ++g) {                      // column group g = dY shifted by g*Wp rows = filter row ky = 2 - g
             uint32_t v[32];
-            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(g * 32);
+            const uint32_t taddr = tmem_base + ((uint32_t)(kx * 32) << 16) + (uint32_t)(g * 32);
             asm volatile(
                 "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
                 "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
@@ -458,9 +464,8 @@ conv3x3_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
                   "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
                 : "r"(taddr) : "memory");
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            const int tap = g * 4 + quarter;               // accumulator row m = (tap - 4g)*32 + ci, ci = lane
-            if (tap < 9) {
-                float* dst = p.dw + tap * 32 + lane;
+            if (kx < 3) {
+                float* dst = p.dw + ((2 - g) * 3 + kx) * 32 + lane;
 #pragma unroll
                 for (int co = 0; co < 32; ++co) atomicAdd(dst + co * 288, __uint_as_float(v[co]));
             }
@@ -482,7 +487,7 @@ extern "C" int sgqn_conv_wgrad_tc(const float* x, const float* dy, float* dw, in
     if (B <= 0) return 0;
     static int inited = 0, num_sms = 0;
     if (!inited) {
-        cudaError_t e = cudaFuncSetAttribute(conv3x3_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWgSmem);
+        cudaError_t e = cudaFuncSetAttribute(conv3x3_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWgSmemBudget);
         if (e != cudaSuccess) return (int)e;
         int dev = 0;
         cudaGetDevice(&dev);
@@ -491,15 +496,21 @@ extern "C" int sgqn_conv_wgrad_tc(const float* x, const float* dy, float* dw, in
     }
     WgParams p;
     p.total_q = B * Hr * Wp; p.Wp = Wp; p.dw = dw;
+    p.drows = (kWgRows + 2 * Wp + 7) / 8 * 8;                       // dY halo, whole swizzle atoms
+    if (p.drows > 256) return (int)cudaErrorInvalidValue;           // TMA box limit
+    p.stage_bytes = kWgXBytes + p.drows * 128;
+    p.stages = (kWgSmemBudget - 1024 - 256) / p.stage_bytes;
+    if (p.stages > kWgMaxStages) p.stages = kWgMaxStages;
+    if (p.stages < 2) return (int)cudaErrorInvalidValue;
     p.kb_total = (p.total_q + kWgRows - 1) / kWgRows;
     int grid = p.kb_total < num_sms ? p.kb_total : num_sms;
     p.kb_per_cta = (p.kb_total + grid - 1) / grid;
     grid = (p.kb_total + p.kb_per_cta - 1) / p.kb_per_cta;
     CUtensorMap tmX, tmD;
-    int rc = make_map_2d(&tmX, x, 32, (uint64_t)p.total_q, 32, kWgRows, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+    int rc = make_map_2d(&tmX, x, 32, (uint64_t)p.total_q, 32, kWgXRows, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
     if (rc) return rc;
-    rc = make_map_2d(&tmD, dy, 32, (uint64_t)p.total_q, 32, kWgRows, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+    rc = make_map_2d(&tmD, dy, 32, (uint64_t)p.total_q, 32, (uint32_t)p.drows, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
     if (rc) return rc;
-    conv3x3_wgrad_tc_kernel<<<grid, 192, kWgSmem, (cudaStream_t)stream>>>(tmX, tmD, p);
+    conv3x3_wgrad_tc_kernel<<<grid, 192, kWgSmemBudget, (cudaStream_t)stream>>>(tmX, tmD, p);
     return SGQN_CHECK_LAUNCH();
 }
