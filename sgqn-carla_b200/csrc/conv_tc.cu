@@ -34,11 +34,6 @@ constexpr int kAccCols = 128;                  // TMEM column stride between the
 constexpr int kStgPitch = 400;                 // staging row: 96 floats + 16 B, so that 8 consecutive rows hit 8 different bank groups
 constexpr int kStgBytes = kTileM * kStgPitch;  // 50 KB
 constexpr int kEpiBytes = kStgBytes + 2048 + 128;   // staging tile, rowinfo[2][128], bias
-constexpr int kEpiWarps = 16;
-constexpr int kEpiThreads = kEpiWarps * 32;
-constexpr int kThreads = 64 + kEpiThreads;     // TMA warp, MMA warp, epilogue warps
-constexpr int kChPerThread = 128 / kEpiWarps;  // phase-1 channels per thread: 4 warps per TMEM quarter share its 32 channels
-constexpr int kItems = 1024 / kEpiThreads;     // phase-2 (row, 16-byte chunk) items per thread
 constexpr int kWBytes = 9 * 32 * 128;          // 36 KB: 9 taps x [32 n][32 k] fp32
 constexpr int kSmemBudget = 200 * 1024;        // dynamic shared memory we ask for
 
@@ -61,8 +56,13 @@ struct TcParams {
 // kind::tf32, D fp32, A/B TF32 K-major, M = 128, N = 96 (cute::UMMA::InstrDescriptor)
 constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((96u >> 3) << 17) | ((128u >> 4) << 24);
 
-__global__ void __launch_bounds__(kThreads, 1)
+// kEpiWarps = 16 for the forward (more rows in flight), 8 for the data gradient (its mask loads want fewer, fatter threads)
+template <int kEpiWarps>
+__global__ void __launch_bounds__(64 + kEpiWarps * 32, 1)
 conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, TcParams p) {
+    constexpr int kEpiThreads = kEpiWarps * 32;
+    constexpr int kChPerThread = 128 / kEpiWarps;  // phase-1 channels per thread: the warps of a TMEM quarter share its 32 channels
+    constexpr int kItems = 1024 / kEpiThreads;     // phase-2 (row, 16-byte chunk) items per thread
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const int kStages = p.stages;
@@ -188,16 +188,17 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             {
                 uint32_t v[3 * kChPerThread];
                 const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * kAccCols + half * kChPerThread);
-                static_assert(kChPerThread == 8, "phase-1 TMEM loads are written for 8 channels per thread");
+                static_assert(kChPerThread == 8 || kChPerThread == 16, "phase-1 TMEM loads: 8 or 16 channels per thread");
 #define SGQN_TMEM_LD8(O, ADDR)                                                                                            \
                 asm volatile(                                                                                            \
                     "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"                      \
                     : "=r"(v[O + 0]), "=r"(v[O + 1]), "=r"(v[O + 2]), "=r"(v[O + 3]), "=r"(v[O + 4]), "=r"(v[O + 5]),    \
                       "=r"(v[O + 6]), "=r"(v[O + 7])                                                                     \
                     : "r"(ADDR) : "memory")
-                SGQN_TMEM_LD8(0, taddr);
-                SGQN_TMEM_LD8(8, taddr + 32u);
-                SGQN_TMEM_LD8(16, taddr + 64u);
+#pragma unroll
+                for (int kx = 0; kx < 3; ++kx)
+#pragma unroll
+                    for (int h = 0; h < kChPerThread / 8; ++h) SGQN_TMEM_LD8(kx * kChPerThread + 8 * h, taddr + (uint32_t)(32 * kx + 8 * h));
 #undef SGQN_TMEM_LD8
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
                 tc_fence_before();
@@ -277,7 +278,9 @@ extern "C" int sgqn_conv_tc(const float* x, const float* w, const float* bias, c
     static int smem_set = 0;
     static int num_sms = 0;
     if (!smem_set) {
-        cudaError_t e = cudaFuncSetAttribute(conv3x3_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget);
+        cudaError_t e = cudaFuncSetAttribute(conv3x3_tc_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget);
+        if (e != cudaSuccess) return (int)e;
+        e = cudaFuncSetAttribute(conv3x3_tc_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget);
         if (e != cudaSuccess) return (int)e;
         int dev = 0;
         cudaGetDevice(&dev);
@@ -303,7 +306,8 @@ extern "C" int sgqn_conv_tc(const float* x, const float* w, const float* bias, c
     rc = make_map_2d(&tmW, w, 288, 32, 32, 32);
     if (rc) return rc;
     int grid = p.num_tiles < num_sms ? p.num_tiles : num_sms;
-    conv3x3_tc_kernel<<<grid, kThreads, kSmemBudget, (cudaStream_t)stream>>>(tmA, tmW, p);
+    if (p.mask_mode) conv3x3_tc_kernel<8><<<grid, 64 + 8 * 32, kSmemBudget, (cudaStream_t)stream>>>(tmA, tmW, p);
+    else conv3x3_tc_kernel<16><<<grid, 64 + 16 * 32, kSmemBudget, (cudaStream_t)stream>>>(tmA, tmW, p);
     return SGQN_CHECK_LAUNCH();
 }
 
