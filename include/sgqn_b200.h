@@ -83,7 +83,9 @@ int sgqn_conv1_dgrad(const float* dy, const float* w, float* dobs, int B, int Ci
  *      arithmetic is paid once per observation batch, forward / weight gradient / data gradient become plain GEMMs */
 int sgqn_conv1_im2col(const float* obs, float* col, int B, int Hin, void* stream);
 int sgqn_conv1_im2col96(const float* obs, float* col, int B, int Hin, void* stream);   /* col[.][96], TF32-rounded (tcgen05 path) */
-int sgqn_conv1_weights_prep(const float* w, float* wp /* [32][96] */, void* stream);
+int sgqn_conv1_weights_prep(const float* w, float* wp /* [32][96] */, float* wd /* optional transpose [96][32] */, void* stream);
+/* observation gradient dobs[B][9][84][84] gathered from dcol[B*1681][pitch] = d(act_0) * W (col index ci*9+ky*3+kx), / 255 */
+int sgqn_conv1_col2im(const float* dcol, int pitch, float* dobs, int B, void* stream);
 int sgqn_conv1_fwd_col(const float* col, const float* w, const float* bias, float* y, int B, int flags, void* stream);
 int sgqn_conv1_wgrad_col(const float* col, const float* dy, float* dw, float* db, int B, void* stream);
 int sgqn_conv1_dgrad_col(const float* dy, const float* w, float* dcol, float* dobs, int B, void* stream);

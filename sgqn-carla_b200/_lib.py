@@ -40,7 +40,8 @@ SIGNATURES = {
     "sgqn_conv_tcg_taps": [_p, _p, _p, _p, _p] + [_i] * 16 + [_p],
     "sgqn_gemm_wgrad_tcg": [_p, _p, _p] + [_i] * 9 + [_p],
     "sgqn_conv1_im2col96": [_p, _p, _i, _i, _p],
-    "sgqn_conv1_weights_prep": [_p, _p, _p],
+    "sgqn_conv1_weights_prep": [_p, _p, _p, _p],
+    "sgqn_conv1_col2im": [_p, _i, _p, _i, _p],
     "sgqn_conv_weights_prep_g": [_p, _p, _p, _i, _i, _i, _p],
     "sgqn_conv_wgrad_tcg": [_p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p],
     "sgqn_pool2_bwd": [_p, _p, _p, _i, _i, _i, _i, _p],

@@ -39,7 +39,7 @@ __global__ void __launch_bounds__(320, 1)
 conv3x3_tcg_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, GParams p) {
     constexpr int kWBytes = N * 128;
     constexpr uint32_t kIdescN = idesc_tf32(N, false, false);
-    constexpr int kTmemCols = 2 * N < 32 ? 32 : 2 * N;               // 64 / 128 / 256: powers of two
+    constexpr int kTmemCols = 2 * N <= 64 ? 64 : (2 * N <= 128 ? 128 : 256);      // power of two >= two accumulators
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t a_sm = base;
@@ -238,7 +238,7 @@ extern "C" int sgqn_conv_tcg_taps(const float* x, const float* wop, const float*
                                   int Wp, int Cin, int Cout, int Hv, int Wv, int shift, int Hq, int Wq, int oy, int ox, int Hm,
                                   int Wm, int flags, int ntaps, void* stream) {
     if (B <= 0) return 0;
-    if ((Cin & 31) || (Cout != 32 && Cout != 64 && Cout != 128)) return (int)cudaErrorInvalidValue;
+    if ((Cin & 31) || (Cout != 32 && Cout != 64 && Cout != 96 && Cout != 128)) return (int)cudaErrorInvalidValue;
     GParams p;
     p.total_q = B * Hr * Wp; p.Hr = Hr; p.Wp = Wp; p.Hv = Hv; p.Wv = Wv; p.shift = shift;
     p.Hq = Hq; p.Wq = Wq; p.oy = oy; p.ox = ox; p.Hm = Hm; p.Wm = Wm;
@@ -268,6 +268,7 @@ extern "C" int sgqn_conv_tcg_taps(const float* x, const float* wop, const float*
     cudaStream_t st = (cudaStream_t)stream;
     if (Cout == 32) return launch_tcg<32>(tmA, tmW, p, smem, st);
     if (Cout == 64) return launch_tcg<64>(tmA, tmW, p, smem, st);
+    if (Cout == 96) return launch_tcg<96>(tmA, tmW, p, smem, st);
     return launch_tcg<128>(tmA, tmW, p, smem, st);
 }
 

@@ -274,16 +274,18 @@ extern "C" int sgqn_conv1_im2col96(const float* obs, float* col, int B, int Hin,
 }
 
 // TF32 operand copy of the first conv's weights for the per-position GEMM: wp[32][96] = rna(w[32][81]), zero padded
-__global__ void conv1_weights_prep_kernel(const float* __restrict__ w, float* __restrict__ wp) {
+// ... and, optionally, its transpose wd[96][32] = the operand of the data gradient dcol[pix][96] = d(act_0)[pix][32] * W
+__global__ void conv1_weights_prep_kernel(const float* __restrict__ w, float* __restrict__ wp, float* __restrict__ wd) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= 32 * 96) return;
     int co = i / 96, c = i - co * 96;
     float v = c < 81 ? w[co * 81 + c] : 0.f;
     uint32_t r; asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
     wp[i] = __uint_as_float(r);
+    if (wd) wd[c * 32 + co] = __uint_as_float(r);
 }
-extern "C" int sgqn_conv1_weights_prep(const float* w, float* wp, void* stream) {
-    conv1_weights_prep_kernel<<<12, 256, 0, (cudaStream_t)stream>>>(w, wp);
+extern "C" int sgqn_conv1_weights_prep(const float* w, float* wp, float* wd, void* stream) {
+    conv1_weights_prep_kernel<<<12, 256, 0, (cudaStream_t)stream>>>(w, wp, wd);
     return SGQN_CHECK_LAUNCH();
 }
 
@@ -323,6 +325,57 @@ __global__ void conv1_col2im_kernel(const float* __restrict__ dcol, float* __res
         }
     }
     dobs[i] = __fdiv_rn(s, 255.0f);
+}
+
+// The same gather with the two dcol rows an output row pair needs staged in shared memory: CTA (b, y) reads dcol rows
+// y and y-1 (coalesced, 15.7 KB each at pitch 96) and writes observation rows Y = 2y (taps ky = 0 from row y, ky = 2 from
+// row y-1) and Y = 2y+1 (ky = 1 from row y), all 9 channels.  Pixel pitch 97 floats in shared memory: consecutive x hit
+// consecutive banks.
+__global__ void __launch_bounds__(256) conv1_col2im_rows_kernel(const float* __restrict__ dcol, int pitch, float* __restrict__ dobs) {
+    __shared__ float s[2][41 * 97];
+    const int y = blockIdx.x % 42, b = blockIdx.x / 42;
+    for (int r = 0; r < 2; ++r) {
+        const int yy = y - r;
+        const bool ok = yy >= 0 && yy < 41;
+        const float4* src = reinterpret_cast<const float4*>(dcol + ((size_t)(b * 41 + (ok ? yy : 0)) * 41) * pitch);
+        const int p4 = pitch / 4;
+        for (int i = threadIdx.x; i < 41 * 21; i += 256) {          // 84 of the columns are enough (81 real)
+            int x = i / 21, c4 = i - x * 21;
+            float4 v = ok ? __ldg(src + x * p4 + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+            float* d = &s[r][x * 97 + c4 * 4];
+            d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 2 * 9 * 84; i += 256) {
+        const int X = i % 84; int t = i / 84; const int ci = t % 9; const int yo = t / 9;
+        const int Y = 2 * y + yo;
+        if (Y >= 84) continue;
+        float acc = 0.f;
+        // column taps: X even -> kx = 0 (x = X/2), kx = 2 (x = X/2 - 1); X odd -> kx = 1 (x = (X-1)/2)
+        const int x0 = X >> 1;
+        if (yo == 1) {                                   // ky = 1, row y
+            if (X & 1) { if (x0 < 41) acc += s[0][x0 * 97 + ci * 9 + 3 + 1]; }
+            else {
+                if (x0 < 41) acc += s[0][x0 * 97 + ci * 9 + 3 + 0];
+                if (x0 >= 1) acc += s[0][(x0 - 1) * 97 + ci * 9 + 3 + 2];
+            }
+        } else {                                         // ky = 0 from row y, ky = 2 from row y-1
+            if (X & 1) { if (x0 < 41) acc += s[0][x0 * 97 + ci * 9 + 1] + s[1][x0 * 97 + ci * 9 + 6 + 1]; }
+            else {
+                if (x0 < 41) acc += s[0][x0 * 97 + ci * 9 + 0] + s[1][x0 * 97 + ci * 9 + 6 + 0];
+                if (x0 >= 1) acc += s[0][(x0 - 1) * 97 + ci * 9 + 2] + s[1][(x0 - 1) * 97 + ci * 9 + 6 + 2];
+            }
+        }
+        dobs[((size_t)(b * 9 + ci) * 84 + Y) * 84 + X] = __fdiv_rn(acc, 255.0f);
+    }
+}
+// dobs[B][9][84][84] from dcol[B*1681][pitch] (pitch a multiple of 4, >= 84)
+extern "C" int sgqn_conv1_col2im(const float* dcol, int pitch, float* dobs, int B, void* stream) {
+    if (B <= 0) return 0;
+    if ((pitch & 3) || pitch < 84) return (int)cudaErrorInvalidValue;
+    conv1_col2im_rows_kernel<<<(unsigned)(B * 42), 256, 0, (cudaStream_t)stream>>>(dcol, pitch, dobs);
+    return SGQN_CHECK_LAUNCH();
 }
 
 extern "C" int sgqn_conv1_dgrad_col(const float* dy, const float* w, float* dcol, float* dobs, int B, void* stream) {

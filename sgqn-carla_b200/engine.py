@@ -88,8 +88,9 @@ class UpdateEngine:
         self.dbuf = [f32(R * 41 * 41 * 32), f32(R * 41 * 41 * 32)]
         # im2col matrices of the first conv (col[n*1681][84]) per slot: built once per observation batch by enc_fwd and
         # re-used by that slot's weight gradient; dcol is the attribution's data-gradient workspace
-        self.colS, self.colT, self.dcol = f32(E * 1681 * 96), f32(B * 1681 * 96), f32(B * 1681 * 84)
+        self.colS, self.colT, self.dcol = f32(E * 1681 * 96), f32(B * 1681 * 96), f32(B * 1681 * 96)
         self.w1p, self.w1p_t = f32(32 * 96), f32(32 * 96)          # TF32 operand copies of cnn.0 ([32][96]) / target
+        self.w1d = f32(96 * 32)                                    # ... transposed ([96][32]): data-gradient operand
         # tcgen05 conv path (conv_tc.cu): TF32-rounded operand copies of the 32->32 conv weights (forward; flipped +
         # transposed for the data gradient; forward copy of the target net) and one zero-bordered (pad 2) gradient
         # buffer per layer -- borders are written once here (zeros) and never again.
@@ -209,10 +210,10 @@ class UpdateEngine:
         ls = L.off("cnn.2.weight") - L.off("cnn.1.weight")
         if target:
             K.conv_weights_prep(self.T("cnn.1.weight"), ls, _ptr(self.wf_t), _ptr(self.wd_t), 10, self.st)
-            K.conv1_weights_prep(self.T("cnn.0.weight"), _ptr(self.w1p_t), self.st)
+            K.conv1_weights_prep(self.T("cnn.0.weight"), _ptr(self.w1p_t), 0, self.st)
         else:
             K.conv_weights_prep(self.P("cnn.1.weight"), ls, _ptr(self.wf), _ptr(self.wd), 10, self.st)
-            K.conv1_weights_prep(self.P("cnn.0.weight"), _ptr(self.w1p), self.st)
+            K.conv1_weights_prep(self.P("cnn.0.weight"), _ptr(self.w1p), _ptr(self.w1d), self.st)
 
     def proj_fwd(self, feat_ptr, n, pre, z, h, ldh, target=False):
         """RLProjection (modules.py:102-113): Linear(14112->100) (split-K) -> LayerNorm -> tanh, h row stride ldh."""
@@ -308,7 +309,10 @@ class UpdateEngine:
             K.gemm_wgrad_tcg(col, d, self.G("cnn.0.weight"), n, 41, 41, 96, 32, 0, 0, 1, 81, st)   # (bias gradient: see enc_bwd)
         elif wgrad:
             K.conv1_wgrad_col(col, d, self.G("cnn.0.weight"), self.G("cnn.0.bias"), n, st)
-        if dobs:
+        if dobs and tc:                                   # dcol[pix][96] = d(act_0)[pix][32] W on tcgen05, then the gather
+            K.conv_tcg_taps(d, _ptr(self.w1d), 0, 0, _ptr(self.dcol), n, 41, 41, 32, 96, 41, 41, 0, 41, 41, 0, 0, 0, 0, 0, 1, st)
+            K.conv1_col2im(_ptr(self.dcol), 96, dobs, n, st)
+        elif dobs:
             K.conv1_dgrad_col(d, self.P("cnn.0.weight"), _ptr(self.dcol), dobs, n, st)
 
     def attribution(self, erow, ha, z, obs_grad):

@@ -604,6 +604,20 @@ def test_conv1_via_im2col_matches_direct_kernels():
     K.conv1_dgrad(P(dy), P(w), P(d0), B, 9, 32, ST())
     K.conv1_dgrad_col(P(dy), P(w), P(dcol), P(d1), B, ST())
     close(d1, d0, rtol=1e-5, what="conv1 dgrad via col")
+    # tcgen05 variant: dcol[pix][96] = tf32(dy)[pix][32] * tf32(W) through the per-position GEMM, then the staged gather
+    wp = torch.zeros(32 * 96, device=DEV); wd = torch.zeros(96 * 32, device=DEV)
+    K.conv1_weights_prep(P(w), P(wp), P(wd), ST())
+    dyr = tf32_round(dy)
+    dcol96 = torch.zeros(B * 1681, 96, device=DEV); d2 = torch.ones(B, 9, 84, 84, device=DEV); d3 = torch.zeros(B, 9, 84, 84, device=DEV)
+    K.conv_tcg_taps(P(dyr), P(wd), 0, 0, P(dcol96), B, 41, 41, 32, 96, 41, 41, 0, 41, 41, 0, 0, 0, 0, 0, 1, ST())
+    K.conv1_col2im(P(dcol96), 96, P(d2), B, ST())
+    wr = tf32_round(w.reshape(32, 81)).reshape(w.shape)
+    K.conv1_dgrad(P(dyr), P(wr), P(d3), B, 9, 32, ST())
+    close(d2, d3, rtol=2e-5, what="conv1 dgrad on tcgen05")
+    # the staged gather alone against the element-wise one (same terms, different summation order)
+    d4 = torch.ones(B, 9, 84, 84, device=DEV)
+    K.conv1_col2im(P(dcol), 84, P(d4), B, ST())
+    close(d4, d1, rtol=1e-6, what="staged col2im")
 
 
 # ------------------------------------------------------------------ generalised tcgen05 convs (decoder shapes)
@@ -699,7 +713,7 @@ def test_conv1_tcgen05_path_matches_cuda_core_path():
     K.conv1_im2col(P(obs), P(col), B, 84, ST()); K.conv1_im2col96(P(obs), P(col96), B, 84, ST())
     assert torch.equal(col96[:, :81], tf32_round(col[:, :81])) and float(col96[:, 81:].abs().max()) == 0.0
     wp = torch.zeros(32 * 96, device=DEV)
-    K.conv1_weights_prep(P(w), P(wp), ST())
+    K.conv1_weights_prep(P(w), P(wp), 0, ST())
     assert torch.equal(wp.reshape(32, 96)[:, :81], tf32_round(w.reshape(32, 81)))
     y0 = torch.zeros(B, 43, 41, 32, device=DEV); y1 = torch.zeros(B, 43, 41, 32, device=DEV)
     K.conv1_fwd_col(P(col), P(w), P(b), P(y0), B, 7, ST())
