@@ -37,7 +37,7 @@ POOL_N = 2048               # overlay frames (43 MB)
 # algorithmic FLOPs per sample (minimal / de-duplicated schedule), FLOP = 2*MAC
 GFLOP_ODD, GFLOP_EVEN = 1.671, 3.712
 # dram__bytes_read.sum + dram__bytes_write.sum per launch, from the committed `ncu --set full` captures under profiles/
-NCU_TRAFFIC = {"conv_tc_fwd_l1": 28961024 + 49920}
+NCU_TRAFFIC = {"conv_tc_fwd_l1": 28954368 + 29440}
 WORKLOAD = ("SGSAC full update loop (critic + attribution mask consistency + actor/alpha + target EMA + overlay aux), "
             "batch 128 per GPU, 9x84x84 uint8 stacks, A=2, sgqn_quantile=0.95, reference init, steps alternate odd/even")
 
@@ -188,7 +188,7 @@ def profile_kernels(agent, rb, nsteps=4):
             cin, cout = (args[7], args[8])
             key = f"{n}[{cin}->{cout}]"
         t = e0.elapsed_time(e1)
-        fl = 0.0
+        fl, by = 0.0, 0.0
         if n == "conv_fwd":
             B, Hs, Ws, Cin, Cout, pad, up = args[4], args[5], args[6], args[7], args[8], args[9], args[10]
             Ho = Hs * up + 2 * pad - 2
@@ -198,8 +198,11 @@ def profile_kernels(agent, rb, nsteps=4):
             Ho = Hl + 2 * pad - 2
             fl = 2.0 * B * Ho * Ho * 9 * Cin * (9 if Cout == 16 else Cout)
         elif n == "conv_tc":
-            B, Hv = args[6], args[9]
+            B, Hv, masked = args[6], args[9], (args[-2] >> 2) & 3
             fl = 2.0 * B * Hv * Hv * 9 * 32 * 32
+            # algorithmic bytes: every input pixel read once, every output pixel written once, 128 B each;
+            # the data gradient also reads the 128-byte ReLU mask (the layer's input activation) of every output pixel
+            by = 128.0 * B * ((Hv + 2) * (Hv + 2) + Hv * Hv * (2 if masked else 1))
             key = "conv_tc[32->32 " + ("dgrad" if args[11] else "fwd") + "]"
         elif n == "conv_tcg_taps":
             B, Cin, Cout, Hv = args[5], args[8], args[9], args[10]
@@ -220,11 +223,14 @@ def profile_kernels(agent, rb, nsteps=4):
             B, Hs, Ws, Cin, Cout, pad, up = args[4], args[5], args[6], args[7], args[8], args[9], args[10]
             Ho = Hs * up + 2 * pad - 2
             fl = 2.0 * B * Ho * Ho * 9 * Cin * (9 if Cout == 16 else Cout)
-        tot, cnt, flops = fam.get(key, (0.0, 0, 0.0))
-        fam[key] = (tot + t, cnt + 1, flops + fl)
-        if n == "conv_tc" and args[11] == 0 and args[7] == 43:      # largest forward layer (41x41 -> 39x39), see NCU_TRAFFIC
-            t0, c0 = fam.get("_conv_tc_fwd_l1", (0.0, 0, 0.0))[:2]
-            fam["_conv_tc_fwd_l1"] = (t0 + t, c0 + 1, fl)
+        tot, cnt, flops, nbytes = fam.get(key, (0.0, 0, 0.0, 0.0))
+        fam[key] = (tot + t, cnt + 1, flops + fl, nbytes + by)
+        if n == "conv_tc":                                          # the kernel behind both conv_tc families
+            t0, c0, f0, b0 = fam.get("_conv3x3_tc_kernel", (0.0, 0, 0.0, 0.0))
+            fam["_conv3x3_tc_kernel"] = (t0 + t, c0 + 1, f0 + fl, b0 + by)
+            if args[11] == 0 and args[7] == 43 and args[6] == PER_GPU_BATCH:   # forward, 41x41 -> 39x39, B = 128: see NCU_TRAFFIC
+                t0, c0 = fam.get("_conv_tc_fwd_l1", (0.0, 0, 0.0, 0.0))[:2]
+                fam["_conv_tc_fwd_l1"] = (t0 + t, c0 + 1, fl, by)
     return fam, nsteps
 
 
@@ -294,25 +300,29 @@ def run_b200(a):
     roof, fam_rows = None, None
     fam, nst = profile_kernels(agent, rb, 4)          # every rank runs it (the updates contain collectives)
     if rank == 0:
-        tot = sum(v[0] for v in fam.values())
-        fam_rows = sorted(((k, v[0] / nst, v[1] // nst, v[2] / nst) for k, v in fam.items()), key=lambda r: -r[1])
+        tot = sum(v[0] for k, v in fam.items() if not k.startswith("_"))
+        fam_rows = sorted(((k, v[0] / nst, v[1] // nst, v[2] / nst) for k, v in fam.items() if not k.startswith("_")), key=lambda r: -r[1])
         hbm, tf_burst, tf_sus, how = peaks()
-        l1 = fam.pop("_conv_tc_fwd_l1", None)
-        fam_rows = [r for r in fam_rows if not r[0].startswith("_")]
-        top = next(r for r in fam_rows if r[3] > 0)
-        achieved = top[3] / (top[1] * 1e-3) / 1e12
-        peak = tf_sus / 2.0                                  # TF32 dense = bf16 / 2 (derived from measured bf16, sustained)
-        roof = {"bound": "tensor", "kernel": top[0], "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                "frac": achieved / peak, "traffic": None, "share_of_step": top[1] / (tot / nst),
-                "peak_source": f"bf16 sustained {tf_sus} TF/s ({how}) / 2 = TF32 dense, derived",
-                "launches_per_step": top[2], "ms_per_step_in_kernel": top[1]}
-        if l1 is not None and top[0].startswith("conv_tc"):
-            # per-launch view of the family's largest launch: algorithmic FLOPs / its own CUDA-event time, and the DRAM
-            # traffic ncu measured for exactly this launch (profiles/prof_r1_convtc_fwd.md)
+        kt = fam["_conv3x3_tc_kernel"]                       # (ms, launches, flops, algorithmic bytes) over nst updates
+        l1 = fam.get("_conv_tc_fwd_l1")
+        # conv3x3_tc_kernel (SharedCNN 32->32 layers, forward + data gradient) is the step's dominant kernel.  72 (fwd) /
+        # 48 (dgrad) FLOP per algorithmic byte is below the B200 ridge (TF32 692 TF/s / 6.5 TB/s = 106 FLOP/B): HBM-bound.
+        achieved = kt[3] / (kt[0] * 1e-3) / 1e9
+        roof = {"bound": "hbm", "kernel": "conv3x3_tc_kernel (conv_tc fwd + dgrad launches)", "achieved": achieved, "peak": hbm,
+                "unit": "GB/s", "frac": achieved / hbm, "traffic": None, "share_of_step": kt[0] / tot,
+                "peak_source": f"HBM copy bandwidth {hbm} GB/s ({how})",
+                "launches_per_step": kt[1] / nst, "ms_per_step_in_kernel": kt[0] / nst,
+                "algorithmic_bytes_per_launch": kt[3] / kt[1], "avg_launch_us": kt[0] / kt[1] * 1e3,
+                "timing": "CUDA events around every launch of the kernel in an eager (graph-free) pass over 4 updates",
+                "tensor_view": {"achieved_tflops": kt[2] / (kt[0] * 1e-3) / 1e12, "peak_tflops": tf_sus / 2.0,
+                                "peak_source": f"bf16 sustained {tf_sus} TF/s ({how}) / 2 = TF32 dense, derived"}}
+        if l1 is not None:
+            # one specific launch, so that `traffic` (ncu --set full, profiles/prof_r1_convtc_v2.md) and the live time refer to
+            # the same work: forward 41x41 -> 39x39 at B = 128
             us = l1[0] / l1[1] * 1e3
-            roof.update({"launch": "conv3x3_tc_kernel forward, layer 41x41->39x39, B=128 (largest launch of the family)",
-                         "launch_us": us, "launch_achieved": l1[2] / (us * 1e-6) / 1e12, "launch_frac": l1[2] / (us * 1e-6) / 1e12 / peak,
-                         "traffic": NCU_TRAFFIC["conv_tc_fwd_l1"], "algorithmic_bytes": 128 * (43 * 41 + 41 * 39) * 128})
+            roof.update({"traffic": NCU_TRAFFIC["conv_tc_fwd_l1"],
+                         "traffic_launch": {"what": "forward layer 41x41->39x39, B=128", "algorithmic_bytes": l1[3], "live_us": us,
+                                            "achieved_gbs": l1[3] / (us * 1e-6) / 1e9, "ncu_us_cold_cache": 19.2}})
     if world > 1:
         barrier()
 
