@@ -168,6 +168,8 @@ def profile_kernels(agent, rb, nsteps=4):
         setattr(api, n, wrap)
     graphs = agent.use_cuda_graphs
     agent.use_cuda_graphs = False                     # per-call timing needs the eager path
+    overlap = agent.engine.overlap
+    agent.engine.overlap = False                      # ... and every kernel on the stream the events are recorded on
     try:
         L = NullLog()
         for s in range(1, nsteps + 1):
@@ -175,6 +177,7 @@ def profile_kernels(agent, rb, nsteps=4):
         torch.cuda.synchronize()
     finally:
         agent.use_cuda_graphs = graphs
+        agent.engine.overlap = overlap
         for n, fn in saved.items():
             setattr(api, n, fn)
     dump = os.environ.get("SGQN_PROFILE_CALLS")

@@ -46,9 +46,14 @@ class UpdateEngine:
         # trunks and the 14112 <-> 100 projections) run on tcgen05 with split-precision ("3xTF32") operands in the product
         # mode; the (P + A = 102)-wide layers, the 1-/2A-wide output layers and precision="fp32" use the CUDA-core GEMM
         self.tc_dense = precision == "tf32"
+        # (self.overlap / self.side) Independent kernels run on a side stream so that one kernel's prologue (TMEM allocation,
+        # weight / first-tile loads) overlaps the other's last tiles: the weight gradient of layer l beside the data-gradient
+        # chain, the target encoder beside the online one.  Fork / join with events; in a CUDA graph: parallel branches.
         if not torch.cuda.is_available():
             raise RuntimeError("sgqn-carla_b200 needs a CUDA device (B200, sm_100a); there is no CPU path")
         self.dev = torch.device(device)
+        self.overlap = precision == "tf32"
+        self.side = torch.cuda.Stream(device=self.dev) if self.overlap else None
         self.args, self.A, self.B = args, int(action_dim), int(batch_size)
         self.Bg = int(global_batch) if global_batch else self.B
         self.dist = dist
@@ -283,14 +288,20 @@ class UpdateEngine:
             self._conv1_bwd(d, n, acts, row0, wgrad, dobs)
             return
         K.pad_copy(dfeat, _ptr(self.gpad[10]), n, 21, 21, 32, 25, 23, 2, 0, 1, st)
+        side = self.side if (wgrad and self.overlap) else None
+        main = torch.cuda.current_stream()
         for l in range(10, 0, -1):
             hi, ho = ENC_H[l - 1], ENC_H[l]
             a_in = _ptr(acts[l - 1], row0 * (hi + 2) * hi * 32)     # [n][hi+2][hi][32], post-ReLU
             d = _ptr(self.gpad[l])                                  # d(act_l): [n][ho+4][ho+2][32] == [n][hi+2][hi][32]
             if wgrad:
-                K.conv_wgrad_tc(a_in, d, self.G(f"cnn.{l}.weight"), n, hi + 2, hi, st)
+                ws = st
+                if side is not None:                    # d(act_l) is complete on the main stream: fork
+                    ev = torch.cuda.Event(); ev.record(main); side.wait_event(ev)
+                    ws = side.cuda_stream
+                K.conv_wgrad_tc(a_in, d, self.G(f"cnn.{l}.weight"), n, hi + 2, hi, ws)
                 if l == 10:                             # the other layers' bias gradients ride on the data-gradient epilogues
-                    K.colsum(d, 32, n * (hi + 2) * hi, 32, self.G("cnn.10.bias"), st)
+                    K.colsum(d, 32, n * (hi + 2) * hi, 32, self.G("cnn.10.bias"), ws)
             db = self.G(f"cnn.{l - 1}.bias") if wgrad else 0    # sum of d(act_{l-1}) = bias gradient of layer l-1
             if l > 1:
                 K.conv_tc(d, _ptr(self.wd, (l - 1) * 9216), 0, a_in, _ptr(self.gpad[l - 1]), db, n, ho + 4, ho + 2, hi, hi, -2,
@@ -299,6 +310,8 @@ class UpdateEngine:
                 K.conv_tc(d, _ptr(self.wd), 0, a_in, _ptr(self.dbuf[0]), db, n, ho + 4, ho + 2, hi, hi, -2,
                           hi, hi, 0, 0, hi + 2, hi, 2 | (mode << 2), st)
         self._conv1_bwd(_ptr(self.dbuf[0]), n, acts, row0, wgrad, dobs)
+        if side is not None:                            # join: the gradient buffers are reused by the next backward
+            ev = torch.cuda.Event(); ev.record(side); main.wait_event(ev)
 
     def _conv1_bwd(self, d, n, acts, row0, wgrad, dobs):
         """Backward of the first conv from d = d(act_0) (compact [n][41][41][32]) through the slot's im2col matrix."""
@@ -346,12 +359,22 @@ class UpdateEngine:
         B, A, L, st = self.B, self.A, self.lay, self.st
         a = self.args
         nx = _ptr(self.next_obs)
+        ev_t = None
+        if self.overlap:                                # target encoder (B rows) beside the online one (2B rows)
+            main = torch.cuda.current_stream()
+            ev = torch.cuda.Event(); ev.record(main); self.side.wait_event(ev)
+            with torch.cuda.stream(self.side):
+                self.enc_fwd(nx, B, self.actT, target=True)
+                ev_t = torch.cuda.Event(); ev_t.record(self.side)
         self.enc_fwd(_ptr(self.obs3), 2 * B, self.actS, 0)       # online encoder over [next_obs ; obs] in one batch
         self.proj_fwd(_ptr(self.actS[10]), B, "actor_proj", _ptr(self.z_a), _ptr(self.h_a), L.P)
         self.actor_mlp_fwd(B)
         K.actor_head_fwd(_ptr(self.raw), _ptr(self.noise_next), float(a.actor_log_std_min), float(a.actor_log_std_max),
                          0, _ptr(self.haT, L.P), L.P + A, _ptr(self.next_log_pi), 0, B, A, st)
-        self.enc_fwd(nx, B, self.actT, target=True)
+        if ev_t is not None:
+            torch.cuda.current_stream().wait_event(ev_t)
+        else:
+            self.enc_fwd(nx, B, self.actT, target=True)
         self.proj_fwd(_ptr(self.actT[10]), B, "critic_proj", _ptr(self.zT), _ptr(self.haT), L.P + A, target=True)
         self.q_fwd(_ptr(self.haT), B, 0, 2, target=True)
 
