@@ -54,6 +54,7 @@ class UpdateEngine:
         self.dev = torch.device(device)
         self.overlap = precision == "tf32"
         self.side = torch.cuda.Stream(device=self.dev) if self.overlap else None
+        self.side2 = torch.cuda.Stream(device=self.dev) if self.overlap else None
         self.args, self.A, self.B = args, int(action_dim), int(batch_size)
         self.Bg = int(global_batch) if global_batch else self.B
         self.dist = dist
@@ -604,10 +605,21 @@ class UpdateEngine:
             # attribution #2 with the updated critic feeds only update_aux's mask (sgsac.py:175-176,83); on steps
             # without an aux update the reference computes it and discards it (no side effects).
             self.attribution2(want_mask=True)
-        if do_actor:
-            self.update_actor_and_alpha()
-        if do_aux:
+        if do_actor and do_aux and self.overlap and self.dist is None:
+            # the actor / alpha update (~40 small launches on the heads) is independent of the aux update (encoder + decoder
+            # heavy): disjoint parameter / gradient ranges and head rows -> run it beside the aux update
+            main = torch.cuda.current_stream()
+            ev = torch.cuda.Event(); ev.record(main); self.side2.wait_event(ev)
+            with torch.cuda.stream(self.side2):
+                self.update_actor_and_alpha()
+                ev2 = torch.cuda.Event(); ev2.record(self.side2)
             self.update_aux()
+            main.wait_event(ev2)
+        else:
+            if do_actor:
+                self.update_actor_and_alpha()
+            if do_aux:
+                self.update_aux()
         self._finish_logs()
 
     def update_sac(self, step, mode=0):
