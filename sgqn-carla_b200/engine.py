@@ -171,6 +171,18 @@ class UpdateEngine:
     def lin_wgrad(self, *a):
         (K.linear_wgrad_tc if self.tc_dense else K.linear_wgrad)(*a)
 
+    def _fork(self):
+        """Stream for work that only depends on what the current stream has enqueued so far (the side stream once it has
+        waited for that point), or the current stream itself when overlap is off."""
+        if not self.overlap:
+            return self.st
+        ev = torch.cuda.Event(); ev.record(torch.cuda.current_stream()); self.side.wait_event(ev)
+        return self.side.cuda_stream
+
+    def _join(self):
+        if self.overlap:
+            ev = torch.cuda.Event(); ev.record(self.side); torch.cuda.current_stream().wait_event(ev)
+
     # ------------------------------------------------------------------ building blocks
     def enc_fwd(self, x_ptr, n, acts, row0=0, target=False, hin=84):
         """SharedCNN forward (modules.py:132-152): x (n,9,hin,hin) fp32 NCHW -> acts[0..10] rows [row0, row0+n)."""
@@ -253,8 +265,9 @@ class UpdateEngine:
         K.zero(dha, 4 * n * P1, st)
         K.linear_dgrad(dz1, H, R * H, self.P("Q1.0.weight"), qs, 0, 0, 0, dha, P1, 0, n, H, P1, 0, 1, nheads, st)
 
-    def q_wgrad(self, ha, dq, n, row0):
-        L, H, R, st = self.lay, self.H, 2 * self.B, self.st
+    def q_wgrad(self, ha, dq, n, row0, st=None):
+        L, H, R = self.lay, self.H, 2 * self.B
+        st = st if st is not None else self.st
         P1, qs = L.P + self.A, L.q_stride
         z1, z2 = _ptr(self.z1, row0 * H), _ptr(self.z2, row0 * H)
         dz1, dz2 = _ptr(self.dz1, row0 * H), _ptr(self.dz2, row0 * H)
@@ -266,9 +279,9 @@ class UpdateEngine:
         st, P = self.st, self.lay.P
         K.ln_tanh_bwd(dh, lddh, z, h, ldh, self.P(f"{pre}.1.weight"), dz,
                       self.G(f"{pre}.1.weight") if wgrad else 0, self.G(f"{pre}.1.bias") if wgrad else 0, n, P, st)
-        if wgrad:
+        if wgrad:                                         # beside the data gradient when one follows (joined by enc_bwd)
             self.lin_wgrad(feat_ptr, FEAT, 0, dz, P, 0, self.G(f"{pre}.0.weight"), 0, self.G(f"{pre}.0.bias"), 0,
-                           n, P, FEAT, 0, 1, st)
+                           n, P, FEAT, 0, 1, self._fork() if dfeat else st)
         if dfeat:
             self.lin_dgrad(dz, P, 0, self.P(f"{pre}.0.weight"), 0, 0, 0, 0, dfeat, FEAT, 0, n, P, FEAT, 0, 0, 1, st)
 
@@ -432,7 +445,7 @@ class UpdateEngine:
         c0, c1 = L.ranges["critic"]
         K.zero(self._g + 4 * c0, 4 * (c1 - c0), st)
         self.q_dgrad(_ptr(self.dq), 2 * B, R, 0, 2, 1, _ptr(self.dhaS))
-        self.q_wgrad(_ptr(self.haS), _ptr(self.dq), R, 0)
+        self.q_wgrad(_ptr(self.haS), _ptr(self.dq), R, 0, st=self._fork())     # joined at the end of enc_bwd
         dfeat = _ptr(self.dbuf[1])
         self.proj_bwd(_ptr(self.dhaS), P1, R, _ptr(self.zS), _ptr(self.haS), P1, "critic_proj", _ptr(self.dzS),
                       feat_ptr=_ptr(self.actS[10], B * FEAT), dfeat=dfeat)
@@ -575,20 +588,24 @@ class UpdateEngine:
         K.bce(_ptr(self.lg), _ptr(self.mask), _ptr(self.logs, 4), _ptr(self.dlg), B, 84, 84, 86, 86, 1, 0, DEC_C3, self.Bg, 1, st)
         K.zero(self._g + 4 * x0, 4 * (x1 - x0), st)
         # conv3 backward
-        K.conv_wgrad_tcg(_ptr(self.xin3), _ptr(self.dlg), G("dec.conv3.weight"), B, 86, 86, 64, DEC_C3, -1, -1, st)
-        K.colsum(_ptr(self.dlg), DEC_C3, B * 86 * 86, DEC_C3, G("dec.conv3.bias"), st)
+        ws = self._fork()                                     # weight / bias gradients beside the data-gradient chain
+        K.conv_wgrad_tcg(_ptr(self.xin3), _ptr(self.dlg), G("dec.conv3.weight"), B, 86, 86, 64, DEC_C3, -1, -1, ws)
+        K.colsum(_ptr(self.dlg), DEC_C3, B * 86 * 86, DEC_C3, G("dec.conv3.bias"), ws)
         K.conv_tcg(_ptr(self.dlg), _ptr(wd[2]), 0, 0, _ptr(self.dup3), B, 86, 86, DEC_C3, 64, 84, 84, -1, 84, 84, 0, 0, 0, 0, 0, st)
         K.pool2_bwd(_ptr(self.dup3), _ptr(self.xin3), _ptr(self.dd2g), B, 42, 42, 64, st)
         # conv2 backward
-        K.conv_wgrad_tcg(_ptr(self.xin2), _ptr(self.dd2g), G("dec.conv2.weight"), B, 44, 44, 128, 64, -1, -1, st)
-        K.colsum(_ptr(self.dd2g), 64, B * 44 * 44, 64, G("dec.conv2.bias"), st)
+        ws = self._fork()
+        K.conv_wgrad_tcg(_ptr(self.xin2), _ptr(self.dd2g), G("dec.conv2.weight"), B, 44, 44, 128, 64, -1, -1, ws)
+        K.colsum(_ptr(self.dd2g), 64, B * 44 * 44, 64, G("dec.conv2.bias"), ws)
         K.conv_tcg(_ptr(self.dd2g), _ptr(wd[1]), 0, 0, _ptr(self.dup2), B, 44, 44, 64, 128, 42, 42, -1, 42, 42, 0, 0, 0, 0, 0, st)
         K.pool2_bwd(_ptr(self.dup2), _ptr(self.xin2), _ptr(self.dd1g), B, 21, 21, 128, st)
         # conv1 backward (ReLU mask of the projection output)
-        K.conv_wgrad_tcg(_ptr(self.xin1), _ptr(self.dd1g), G("dec.conv1.weight"), B, 23, 23, 32, 128, -1, -1, st)
-        K.colsum(_ptr(self.dd1g), 128, B * 23 * 23, 128, G("dec.conv1.bias"), st)
+        ws = self._fork()
+        K.conv_wgrad_tcg(_ptr(self.xin1), _ptr(self.dd1g), G("dec.conv1.weight"), B, 23, 23, 32, 128, -1, -1, ws)
+        K.colsum(_ptr(self.dd1g), 128, B * 23 * 23, 128, G("dec.conv1.bias"), ws)
         K.conv_tcg(_ptr(self.dd1g), _ptr(wd[0]), 0, _ptr(self.dl), _ptr(self.ddl), B, 23, 23, 128, 32, 21, 21, -1, 21, 21, 0, 0,
                    21, 21, 1 << 2, st)
+        self._join()
 
     def update_sgsac(self, step):
         """sgsac.py:169-185 after the sample (obs2[:B], next_obs, action, reward, not_done and the step's randomness
