@@ -148,6 +148,9 @@ int sgqn_critic_loss(const float* q, long long qs, const float* tq1, const float
                      float wb, float* target_q, float* dq, float* loss, int B, int Bg, void* stream);
 int sgqn_actor_loss(const float* q, long long qs, const float* log_pi, const double* log_alpha, float target_entropy, float* dq,
                     float* out3, double* alpha_grad, int B, int Bg, void* stream);
+/* BCE-with-logits of the 9 real channels against the attribution mask (sgsac.py:163-167); logits / dlogits are NHWC with
+ * Cs >= 9 stored channels.  Channels 9..11 of dlogits are written as zero; with Cs >= 12 the padding channels >= 12 are not
+ * touched (keep them zero). */
 int sgqn_bce(const float* logits, const uint8_t* mask, float* loss, float* dlogits, int B, int H, int W, int Hq, int Wq, int oy,
              int ox, int Cs, int Bg, int round_out, void* stream);
 

@@ -253,11 +253,54 @@ bce_kernel(const float* __restrict__ logits, const uint8_t* __restrict__ mask, f
     if (threadIdx.x == 0) atomicAdd(loss, tot * inv_n);
 }
 
+// Vectorised variant for Cs % 4 == 0, Cs >= 12: three lanes per pixel, one float4 chunk (channels 4k..4k+3) each, so the
+// 9 real channels are read and written as 48 contiguous bytes per pixel.  Channels >= 12 of dlogits are NOT written: the
+// caller keeps them zero (they are zero from allocation on and nothing else writes the buffer).
+__global__ void __launch_bounds__(256)
+bce_vec_kernel(const float* __restrict__ logits, const uint8_t* __restrict__ mask, float* __restrict__ loss,
+               float* __restrict__ dlogits, int H, int W, int Hq, int Wq, int oy, int ox, int Cs, long long nitems, float inv_n,
+               int round_out) {
+    __shared__ float sh[33];
+    float acc = 0.f;
+    const int HW = H * W;
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < nitems; t += (long long)gridDim.x * blockDim.x) {
+        const long long p = t / 3; const int k = (int)(t - p * 3);
+        int b = (int)(p / HW), i = (int)(p - (long long)b * HW);
+        int y = i / W, xx = i - y * W;
+        size_t o = (((size_t)b * Hq + y + oy) * Wq + xx + ox) * Cs + 4 * k;
+        const float4 xv = __ldg(reinterpret_cast<const float4*>(logits + o));
+        const float x[4] = {xv.x, xv.y, xv.z, xv.w};
+        float g[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int c = 4 * k + e;
+            g[e] = 0.f;
+            if (c < 9) {
+                float yv = (float)mask[((size_t)b * 3 + c / 3) * HW + i];
+                float v = x[e];
+                acc += fmaxf(v, 0.f) - v * yv + log1pf(expf(-fabsf(v)));
+                float gg = (1.f / (1.f + expf(-v)) - yv) * inv_n;
+                if (round_out) { uint32_t r; asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(gg)); gg = __uint_as_float(r); }
+                g[e] = gg;
+            }
+        }
+        *reinterpret_cast<float4*>(dlogits + o) = make_float4(g[0], g[1], g[2], g[3]);
+    }
+    float tot = block_sum(acc, sh);
+    if (threadIdx.x == 0) atomicAdd(loss, tot * inv_n);
+}
+
 extern "C" int sgqn_bce(const float* logits, const uint8_t* mask, float* loss, float* dlogits, int B, int H, int W, int Hq, int Wq,
                         int oy, int ox, int Cs, int Bg, int round_out, void* stream) {
     long long npix = (long long)B * H * W;
     if (npix <= 0) return 0;
     float inv_n = 1.0f / ((float)Bg * 9.0f * (float)(H * W));
+    if (Cs >= 12 && (Cs & 3) == 0 && (((size_t)logits | (size_t)dlogits) & 15) == 0) {
+        long long nitems = npix * 3;
+        int grid = (int)(cdivll(nitems, 256) < 4736 ? cdivll(nitems, 256) : 4736);
+        bce_vec_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(logits, mask, loss, dlogits, H, W, Hq, Wq, oy, ox, Cs, nitems, inv_n, round_out);
+        return SGQN_CHECK_LAUNCH();
+    }
     int grid = (int)(cdivll(npix, 256) < 1184 ? cdivll(npix, 256) : 1184);
     bce_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(logits, mask, loss, dlogits, H, W, Hq, Wq, oy, ox, Cs, npix, inv_n, round_out);
     return SGQN_CHECK_LAUNCH();

@@ -310,6 +310,7 @@ def test_bce():
     ref = F.binary_cross_entropy_with_logits(x, y)
     ref.backward()
     loss = torch.zeros(1, device=DEV); d = torch.ones(B, HW, Cs, device=DEV)
+    d[:, :, 12:] = 0            # padding channels >= 12 are the caller's to keep zero (the kernel writes channels 0..11 only)
     K.bce(P(lg), P(mask), P(loss), P(d), B, 84, 84, 84, 84, 0, 0, Cs, B, 0, ST())
     close(loss, ref.detach().reshape(1), what="bce loss")
     close(d[:, :, :9].permute(0, 2, 1), x.grad, rtol=2e-4, what="bce grad")
