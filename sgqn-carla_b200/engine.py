@@ -489,7 +489,7 @@ class UpdateEngine:
         if want_mask:
             K.attribution_mask(_ptr(self.obs_grad), 0, 0, 0, self.quantile, _ptr(self.mask), 0, B, 84 * 84, st)
 
-    def update_actor_and_alpha(self):
+    def update_actor_and_alpha(self, finish=True):
         """sac.py:125-151; expects shared_obs_fwd() state (critic slot, head rows [0,B))."""
         B, A, L, H, st, a = self.B, self.A, self.lay, self.H, self.st, self.args
         P1 = L.P + A
@@ -521,6 +521,14 @@ class UpdateEngine:
                        self.G("actor_mlp.0.bias"), 0, B, H, L.P, 0, 1, st)
         self.proj_bwd(_ptr(self.dh_a), L.P, B, _ptr(self.z_a), _ptr(self.h_a), L.P, "actor_proj", _ptr(self.dz_a),
                       feat_ptr=_ptr(self.actS[10], B * FEAT), dfeat=0)
+        if finish:
+            self.actor_finish()
+
+    def actor_finish(self):
+        """Gradient exchange + optimiser steps of the actor / alpha update (separate so that, when the backward ran on the
+        second stream, every collective is still issued from the main stream in one fixed order on all ranks)."""
+        a, st = self.args, self.st
+        a0, a1 = self.lay.ranges["actor"]
         self.allreduce_grads((a0, a1))
         if self.dist is not None:
             self.dist.all_reduce_sum(self.alpha_grad)
@@ -622,16 +630,17 @@ class UpdateEngine:
             # attribution #2 with the updated critic feeds only update_aux's mask (sgsac.py:175-176,83); on steps
             # without an aux update the reference computes it and discards it (no side effects).
             self.attribution2(want_mask=True)
-        if do_actor and do_aux and self.overlap and self.dist is None:
+        if do_actor and do_aux and self.overlap:
             # the actor / alpha update (~40 small launches on the heads) is independent of the aux update (encoder + decoder
             # heavy): disjoint parameter / gradient ranges and head rows -> run it beside the aux update
             main = torch.cuda.current_stream()
             ev = torch.cuda.Event(); ev.record(main); self.side2.wait_event(ev)
             with torch.cuda.stream(self.side2):
-                self.update_actor_and_alpha()
+                self.update_actor_and_alpha(finish=False)
                 ev2 = torch.cuda.Event(); ev2.record(self.side2)
             self.update_aux()
             main.wait_event(ev2)
+            self.actor_finish()
         else:
             if do_actor:
                 self.update_actor_and_alpha()
