@@ -145,6 +145,7 @@ class UpdateEngine:
             self.places = f32(B, 3, 84 * 84)
         self.debug_masked_obs = None
         self.overlay_pool = None       # uint8 (N,3,84*84) device pool for the 'carla' overlay
+        self._obs_col_valid = False
         self._p = self.params.data_ptr(); self._g = self.grads.data_ptr(); self._t = self.target.data_ptr()
         self._c0 = c0
 
@@ -184,8 +185,10 @@ class UpdateEngine:
             ev = torch.cuda.Event(); ev.record(self.side); torch.cuda.current_stream().wait_event(ev)
 
     # ------------------------------------------------------------------ building blocks
-    def enc_fwd(self, x_ptr, n, acts, row0=0, target=False, hin=84):
-        """SharedCNN forward (modules.py:132-152): x (n,9,hin,hin) fp32 NCHW -> acts[0..10] rows [row0, row0+n)."""
+    def enc_fwd(self, x_ptr, n, acts, row0=0, target=False, hin=84, col_ready=0):
+        """SharedCNN forward (modules.py:132-152): x (n,9,hin,hin) fp32 NCHW -> acts[0..10] rows [row0, row0+n).
+        col_ready: the first `col_ready` rows' im2col matrix is still valid in the slot (same observations as the previous
+        pass over these rows; the matrix does not depend on the weights)."""
         W = self.T if target else self.P
         wf = self.wf_t if target else self.wf
         st = self.st
@@ -194,7 +197,8 @@ class UpdateEngine:
         tc = self.precision == "tf32"
         col = _ptr(self.colS if acts is self.actS else self.colT, row0 * 1681 * (96 if tc else 84))
         if tc:
-            K.conv1_im2col96(x_ptr, col, n, hin, st)
+            if n > col_ready:
+                K.conv1_im2col96(x_ptr + col_ready * 9 * hin * hin * 4, col + col_ready * 1681 * 96 * 4, n - col_ready, hin, st)
         else:
             K.conv1_im2col(x_ptr, col, n, hin, st)
         if tc:
@@ -417,6 +421,7 @@ class UpdateEngine:
         B, A, L, st, a = self.B, self.A, self.lay, self.st, self.args
         P1 = L.P + A
         self.target_q_pass()
+        self._obs_col_valid = True                      # colS rows [B, 2B) = im2col(obs2[:B]) until obs2[:B] changes
         self.critic_fwd_rows(0, B, encode=False)        # obs went through the encoder with next_obs
         R = B
         if mode == 1:
@@ -476,7 +481,9 @@ class UpdateEngine:
             K.overlay_u8(_ptr(self.obs2), _ptr(self.overlay_pool), _ptr(self.overlay_ids), float(np.float32(1 - al)),
                          float(np.float32(al)), _ptr(self.s_tilde), B, 84 * 84, st)
             n = 2 * B
-        self.enc_fwd(_ptr(self.obs2), n, self.actS, B)
+        # rows [B, 2B) of the slot's im2col matrix still hold im2col(obs) from the critic pass when update_critic ran first
+        self.enc_fwd(_ptr(self.obs2), n, self.actS, B, col_ready=B if self._obs_col_valid else 0)
+        self._obs_col_valid = False
         K.set_cols(_ptr(self.haS), P1, L.P, _ptr(self.action), A, B, A, st)
         if with_aux:
             K.set_cols(_ptr(self.haS, B * P1), P1, L.P, _ptr(self.action), A, B, A, st)
@@ -661,6 +668,7 @@ class UpdateEngine:
         self._finish_logs()
 
     def _finish_logs(self):
+        self._obs_col_valid = False                     # the next caller may bring new observations
         if self.dist is not None:
             self.dist.all_reduce_logs(self.logs)
 
