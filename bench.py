@@ -340,6 +340,20 @@ def run_b200(a):
     h2d = 2 * B * 9 * 84 * 84 + B * 8 * 2 + 8                 # sampled uint8 stacks pulled from pinned host memory (+ nothing else: actions etc. live on device)
     d2h = 8 * 4
 
+    # ---- acting latency: host uint8 stack -> action on the host, one CUDA graph launch per call
+    act = None
+    if rank == 0:
+        ob = frames[:3].reshape(9, 84, 84)
+        for fn_name in ("select_action", "sample_action"):
+            fn = getattr(agent2, fn_name)
+            for _ in range(5):
+                fn(ob)
+            ts = []
+            for _ in range(200):
+                t0 = time.perf_counter(); fn(ob); ts.append(time.perf_counter() - t0)
+            act = dict(act or {}, **{fn_name + "_us": float(np.median(ts) * 1e6)})
+        act["how"] = "median host wall time of 200 calls, uint8 (9,84,84) host array in -> float32 (A,) host array out"
+
     if rank != 0:
         _finish(world)
         return
@@ -360,7 +374,7 @@ def run_b200(a):
         "e2e": {"value": e2e_v, "unit": "updates/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "how": "agent.update(replay_buffer, L, step) with the replay frame ring in pinned HOST memory (gather kernel pulls the "
                        "sampled stacks host->device every step) and the loss vector copied device->host every step"},
-        "gpu_launches": launches, "clocks": sampler.summary(), "roofline": roof, "cpu_baseline": cpu,
+        "act_latency": act, "gpu_launches": launches, "clocks": sampler.summary(), "roofline": roof, "cpu_baseline": cpu,
         "algorithmic_gflop_per_update": gflop, "achieved_tflops_whole_step": gflop * ups / 1e3,
         "kernel_families_ms_per_step": [[r[0], round(r[1], 4), r[2]] for r in (fam_rows or [])[:12]],
         "losses_last_step": last,

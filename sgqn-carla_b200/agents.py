@@ -103,6 +103,7 @@ class SAC(object):
         # (the NCCL all-reduces of the sharded configuration are captured too; SGQN_DIST_GRAPHS=0 keeps that case eager)
         self.use_cuda_graphs = dist is None or os.environ.get("SGQN_DIST_GRAPHS", "1") == "1"
         self._graphs, self._eager_runs, self._graph_rb, self._graph_nodes = {}, {}, None, {}
+        self._act = {}                  # (H, sample) -> staging buffers + captured batch-1 actor graph
         self.train()
 
     # ---- parameters
@@ -129,6 +130,55 @@ class SAC(object):
         out["log_alpha"] = eng.log_alpha.clone().reshape(())
         return out
 
+    # ---- checkpoints: reference-keyed module state_dicts (what train.py:206-219 saves one file each)
+    #      + what the reference never saves: the optimisers' moments / step counts, log_alpha, the device RNG counter
+    def _modules(self):
+        mods = {"actor": self.actor, "critic": self.critic, "critic_target": self.critic_target}
+        if hasattr(self, "attribution_predictor"):
+            mods["attribution_predictor"] = self.attribution_predictor
+        return mods
+
+    def _optims(self):
+        eng = self.engine
+        return {"critic": eng.opt_critic, "actor": eng.opt_actor, "aux": eng.opt_aux}
+
+    def checkpoint(self):
+        eng = self.engine
+        ck = {"format": "sgqn_b200/1", "algorithm": self.algorithm, "layout": [eng.lay.total, eng.A, eng.H],
+              "modules": {k: OrderedDict((n, t.detach().cpu().clone()) for n, t in m.state_dict().items())
+                          for k, m in self._modules().items()},
+              "log_alpha": eng.log_alpha.cpu().clone(),
+              "optim": {k: {"m": o.m.cpu().clone(), "v": o.v.cpu().clone(), "step": o.step.cpu().clone()}
+                        for k, o in self._optims().items()},
+              "alpha_optim": {"state": eng.alpha_st.cpu().clone(), "step": eng.alpha_step.cpu().clone()},
+              "rng_counter": eng.rng_counter.cpu().clone(), "seed": int(eng.seed)}
+        return ck
+
+    def load_checkpoint_dict(self, ck, strict=True):
+        eng = self.engine
+        if ck.get("format") != "sgqn_b200/1":
+            raise ValueError("not a sgqn_b200 checkpoint (for reference checkpoints use agent.actor.load_state_dict(...) etc.)")
+        if list(ck["layout"]) != [eng.lay.total, eng.A, eng.H]:
+            raise ValueError(f"checkpoint layout {ck['layout']} != agent layout {[eng.lay.total, eng.A, eng.H]}")
+        for k, m in self._modules().items():
+            if k in ck["modules"]:
+                m.load_state_dict(ck["modules"][k], strict=strict)
+            elif strict:
+                raise KeyError(k)
+        eng.log_alpha.copy_(ck["log_alpha"])
+        for k, o in self._optims().items():
+            st = ck["optim"][k]
+            o.m.copy_(st["m"]); o.v.copy_(st["v"]); o.step.copy_(st["step"])
+        eng.alpha_st.copy_(ck["alpha_optim"]["state"]); eng.alpha_step.copy_(ck["alpha_optim"]["step"])
+        eng.rng_counter.copy_(ck["rng_counter"]); eng.seed = int(ck["seed"])
+        self._graphs.clear(); self._eager_runs.clear()       # the seed is baked into the captured graphs
+
+    def save_checkpoint(self, path):
+        torch.save(self.checkpoint(), path)
+
+    def load_checkpoint(self, path, strict=True):
+        self.load_checkpoint_dict(torch.load(path, map_location="cpu", weights_only=False), strict=strict)
+
     def train(self, training=True):
         self.training = training
         self.actor.train(training)
@@ -150,11 +200,67 @@ class SAC(object):
         _obs = np.asarray(obs)
         return torch.as_tensor(_obs, dtype=torch.float32).to(self.engine.dev).unsqueeze(0)
 
+    def _act_fast(self, obs, sample):
+        """Batch-1 actor as ONE CUDA graph launch: the uint8 stack goes host -> pinned staging -> device
+        (63.5 KB instead of the reference's 254 KB fp32 pageable copy, sac.py:86-93), uint8 -> fp32 conversion, encoder,
+        projection, MLP, head and the device -> pinned-host copy of the action are nodes of the same graph; the host does
+        one memcpy into the staging buffer, one cudaGraphLaunch and one stream synchronise per environment step."""
+        arr = np.asarray(obs)
+        if arr.dtype != np.uint8 or arr.ndim != 3 or arr.shape[0] != 9 or arr.shape[1] != arr.shape[2] or arr.shape[1] % 4:
+            return None
+        H = int(arr.shape[1])
+        eng, A = self.engine, self.action_shape[0]
+        slot = self._act.get((H, sample))
+        if slot is None:
+            dev = eng.dev
+            slot = dict(stage=torch.zeros(9, H, H, dtype=torch.uint8).pin_memory(),
+                        frames=torch.zeros(9, H, H, dtype=torch.uint8, device=dev),
+                        fidx=torch.tensor([0, 1, 2, 0, 1, 2], dtype=torch.int32, device=dev),
+                        idx=torch.zeros(1, dtype=torch.int64, device=dev),
+                        obs=torch.zeros(2, 9, H, H, device=dev), noise=torch.zeros(1, A, device=dev),
+                        out=torch.zeros(A).pin_memory(), graph=None, runs=0)
+            slot["stage_np"] = slot["stage"].numpy()
+            slot["out_np"] = slot["out"].numpy()
+            self._act[(H, sample)] = slot
+
+        def body():
+            slot["frames"].copy_(slot["stage"], non_blocking=True)
+            K.replay_gather(_ptr(slot["frames"]), _ptr(slot["fidx"]), _ptr(slot["idx"]), 0, _ptr(slot["obs"]), _ptr(slot["obs"][1]),
+                            1, H, H, 0, 4, eng.st)
+            if sample:
+                slot["noise"].normal_()
+            res = eng.act(slot["obs"][:1], H, sample=sample, noise=slot["noise"] if sample else None)
+            slot["out"].copy_(res, non_blocking=True)
+
+        np.copyto(slot["stage_np"], arr)
+        if slot["graph"] is None and slot["runs"] >= 1 and self.use_cuda_graphs:
+            g = torch.cuda.CUDAGraph()
+            c0 = _lib.launch_count
+            with torch.cuda.graph(g):
+                body()
+            slot["graph"], slot["nodes"] = g, _lib.launch_count - c0
+            _lib.launch_count = c0
+        if slot["graph"] is not None:
+            slot["graph"].replay()
+            _lib.launch_count += slot["nodes"]
+        else:
+            slot["runs"] += 1
+            body()
+        torch.cuda.current_stream().synchronize()
+        return slot["out_np"].copy()
+
     def select_action(self, obs):
+        a = self._act_fast(obs, sample=False)
+        if a is not None:
+            return a
         x = self._obs_to_input(obs)
         return self.engine.act(x, x.shape[-1], sample=False).cpu().numpy().flatten()
 
     def sample_action(self, obs, noise=None):
+        if noise is None:
+            a = self._act_fast(obs, sample=True)
+            if a is not None:
+                return a
         x = self._obs_to_input(obs)
         if noise is not None:
             noise = torch.as_tensor(noise, dtype=torch.float32).to(self.engine.dev).reshape(1, -1)

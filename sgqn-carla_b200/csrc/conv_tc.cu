@@ -83,7 +83,6 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         for (int a = 0; a < 2; ++a) { mbar_init(tfull0 + 8 * a, 1); mbar_init(tempty0 + 8 * a, kEpiThreads); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 2) reinterpret_cast<float*>(smem_raw + stg_off + kStgBytes + 2048)[lane] = p.bias ? __ldg(p.bias + lane) : 0.f;
     if (warp == 1) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(256) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -93,6 +92,9 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     tc_fence_after();
     uint32_t tmem_base;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+    // everything above overlapped the previous kernel's last tiles (PDL, common.cuh); global memory from here on
+    pdl_wait();
+    pdl_launch();
 
     if (warp == 0) {
         if (lane == 0) {
@@ -153,7 +155,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         const int HW = p.Hr * p.Wp;
         uint8_t* stg = smem_raw + stg_off;
         int2* rowinfo = reinterpret_cast<int2*>(smem_raw + stg_off + kStgBytes);          // [2][128]: {out, mask} offsets in float4
-        const float4 bias4 = reinterpret_cast<const float4*>(smem_raw + stg_off + kStgBytes + 2048)[chunk];
+        const float4 bias4 = p.bias ? __ldg(reinterpret_cast<const float4*>(p.bias) + chunk) : make_float4(0.f, 0.f, 0.f, 0.f);
         float csum[4] = {0.f, 0.f, 0.f, 0.f};
         auto fill_rowinfo = [&](int tile, int par) {
             if (half != 0) return;
@@ -306,9 +308,8 @@ extern "C" int sgqn_conv_tc(const float* x, const float* w, const float* bias, c
     rc = make_map_2d(&tmW, w, 288, 32, 32, 32);
     if (rc) return rc;
     int grid = p.num_tiles < num_sms ? p.num_tiles : num_sms;
-    if (p.mask_mode) conv3x3_tc_kernel<8><<<grid, 64 + 8 * 32, kSmemBudget, (cudaStream_t)stream>>>(tmA, tmW, p);
-    else conv3x3_tc_kernel<16><<<grid, 64 + 16 * 32, kSmemBudget, (cudaStream_t)stream>>>(tmA, tmW, p);
-    return SGQN_CHECK_LAUNCH();
+    if (p.mask_mode) return launch_pdl(conv3x3_tc_kernel<8>, dim3(grid), dim3(64 + 8 * 32), kSmemBudget, stream, tmA, tmW, p);
+    return launch_pdl(conv3x3_tc_kernel<16>, dim3(grid), dim3(64 + 16 * 32), kSmemBudget, stream, tmA, tmW, p);
 }
 
 // TF32-rounded operand copies of the 32->32 conv weights, refreshed after every optimiser step that touches them:
@@ -418,6 +419,8 @@ conv3x3_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
     tc_fence_after();
     uint32_t tmem_base;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+    pdl_wait();
+    pdl_launch();
 
     if (warp == 0) {
         if (lane == 0) {
@@ -515,6 +518,5 @@ extern "C" int sgqn_conv_wgrad_tc(const float* x, const float* dy, float* dw, in
     if (rc) return rc;
     rc = make_map_2d(&tmD, dy, 32, (uint64_t)p.total_q, 32, (uint32_t)p.drows, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
     if (rc) return rc;
-    conv3x3_wgrad_tc_kernel<<<grid, 192, kWgSmemBudget, (cudaStream_t)stream>>>(tmX, tmD, p);
-    return SGQN_CHECK_LAUNCH();
+    return launch_pdl(conv3x3_wgrad_tc_kernel, dim3(grid), dim3(192), kWgSmemBudget, stream, tmX, tmD, p);
 }

@@ -109,6 +109,72 @@ def test_select_and_sample_action():
     assert agent.select_action(x).shape == (2,) and agent.select_action(x).dtype == np.float32
 
 
+def test_checkpoint_roundtrip_resumes(tmp_path):
+    """modules (reference keys) + optimiser moments / steps + log_alpha + device RNG counter survive a
+    save / load into a differently initialised agent, and training resumes on the same trajectory."""
+    import sgqn_carla_b200 as S
+    agent, rb, orc, rep, args = _mk(B=8)
+    L = _L()
+    for step in (2, 3, 4):
+        agent.update(rb, L, step)
+    path = str(tmp_path / "ck.pt")
+    agent.save_checkpoint(path)
+    ck = agent.checkpoint()
+    for step in (5, 6):
+        agent.update(rb, L, step)
+    want = agent.get_parameters()
+    other = S.make_agent((9, 84, 84), (2,), args)           # fresh init, different parameters
+    other.set_overlay_pool(torch.as_tensor(np.random.RandomState(7).randint(0, 256, size=(16, 3, 84, 84), dtype=np.uint8)))
+    assert not torch.equal(other.get_parameters()["cnn.1.weight"], ck["modules"]["critic"]["encoder.shared_cnn.layers.4.weight"].to("cuda"))
+    other.load_checkpoint(path)
+    ck2 = other.checkpoint()
+
+    def same(a, b, path="ck"):
+        if isinstance(a, dict):
+            assert a.keys() == b.keys(), path
+            for k in a:
+                same(a[k], b[k], f"{path}.{k}")
+        elif torch.is_tensor(a):
+            assert torch.equal(a, b), path
+        else:
+            assert a == b, path
+    same(ck, ck2)
+    assert int(ck["optim"]["critic"]["step"]) == 3 and int(ck["optim"]["aux"]["step"]) == 2
+    L2 = _L()
+    for step in (5, 6):
+        other.update(rb, L2, step)
+    got = other.get_parameters()
+    for n in want:      # atomics reorder the fp32 gradient sums and Adam turns a rounding-level gradient difference of a
+        d = (got[n].double() - want[n].double()).abs()        # near-zero-gradient element into a fraction of lr per step
+        assert float(d.max()) <= 2.1 * (1e-3 + 3e-4) * 2, (n, float(d.max()))        # (sign of a ~0 gradient: +-lr per step)
+        assert float(d.mean()) <= 0.1 * 1e-3 * 2, (n, float(d.mean()))
+    for key, v in L2.rows.items():
+        np.testing.assert_allclose(float(v), float(L.rows[key]), rtol=5e-2, atol=1e-3)
+    with pytest.raises(ValueError):
+        other.load_checkpoint_dict({"format": "something else"})
+
+
+def test_graphed_batch1_actor_equals_eager():
+    """select_action / sample_action replayed as one CUDA graph (pinned uint8 upload inside) give what the
+    eager kernels give; float input takes the reference's fp32 route; device noise differs from call to call."""
+    agent, rb, orc, rep, args = _mk(B=4)
+    xs = [rep.sample(np.array([i]))[0][0].numpy().astype(np.uint8) for i in (1, 2, 3)]
+    agent.use_cuda_graphs = False
+    eager = [agent.select_action(x) for x in xs]
+    agent.use_cuda_graphs = True
+    agent._act.clear()
+    for rep_i in range(3):                               # call 1 eager, call 2 captures, later calls replay
+        for x, e in zip(xs, eager):
+            np.testing.assert_array_equal(agent.select_action(x), e)
+    assert agent._act[(84, False)]["graph"] is not None
+    np.testing.assert_allclose(agent.select_action(xs[0].astype(np.float32)), eager[0], rtol=1e-5, atol=1e-6)
+    for x, e in zip(xs, eager):
+        np.testing.assert_allclose(e, orc.select_action(x), rtol=1e-3, atol=1e-5)
+    draws = np.stack([agent.sample_action(xs[0]) for _ in range(6)])
+    assert draws.shape == (6, 2) and np.all(np.isfinite(draws)) and np.all(np.abs(draws) <= 1.0)
+    assert len({tuple(np.round(d, 6)) for d in draws}) == 6
+
+
 @pytest.mark.parametrize("dense,quantile,precision", [(0.05, 0.95, "fp32"), (0.05, 0.5, "fp32"), (None, 0.95, "fp32"),
                                                       (0.05, 0.95, "tf32"), (None, 0.95, "tf32")])
 def test_sgsac_critic_stage(dense, quantile, precision):
