@@ -119,6 +119,14 @@ int sgqn_conv_weights_prep_g(const float* w, float* wf, float* wd, int Cout, int
 int sgqn_conv_wgrad_tcg(const float* x, const float* dy, float* dw, int B, int Hr, int Wp, int Cin, int Cout, int ta, int tb,
                         void* stream);
 int sgqn_pool2_bwd(const float* dup, const float* src, float* dst, int B, int H, int W, int C, void* stream);
+/* Sub-pixel ("phase") form of conv3x3(pad 1) after F.upsample(x, 2) (modules.py:333-337 then :324-326): a 3x3 pad-1 conv at LOW
+ * resolution with 4*Cg output channels -- phase p = 2a+b, channels [p*Cg, p*Cg+Cout_real) = output pixel (2y+a, 2x+b) -- run
+ * through sgqn_conv_tcg / sgqn_conv_wgrad_tcg; the upsampled tensor is never materialised.  prep: w [>=Cout_real][9][Cin] ->
+ * wf [4Cg][9][Cin] (forward operand), wd [Cin][9][4Cg] (data-gradient operand), bphi [4Cg]; fold: the chain rule back to the
+ * reference's dW [Cout_real][9][Cin] / db (+=). */
+int sgqn_conv_weights_prep_phase(const float* w, const float* bias, float* wf, float* wd, float* bphi, int Cin, int Cout_real,
+                                 int Cg, void* stream);
+int sgqn_conv_phase_fold(const float* dwphi, const float* dbphi, float* dw, float* db, int Cin, int Cout_real, int Cg, void* stream);
 /* backward of F.upsample(x, 2) followed by ReLU mask of the pre-upsample activation (modules.py:333-337) */
 int sgqn_upsample2_bwd(const float* dup, const float* act, float* dx, int B, int Hs, int Ws, int C, void* stream);
 
@@ -153,6 +161,9 @@ int sgqn_actor_loss(const float* q, long long qs, const float* log_pi, const dou
  * touched (keep them zero). */
 int sgqn_bce(const float* logits, const uint8_t* mask, float* loss, float* dlogits, int B, int H, int W, int Hq, int Wq, int oy,
              int ox, int Cs, int Bg, int round_out, void* stream);
+/* the same on the phase layout of the logits: [B][Hq][Wq][4][16] at H/2 x W/2 pixels (see sgqn_conv_weights_prep_phase) */
+int sgqn_bce_phase(const float* logits, const uint8_t* mask, float* loss, float* dlogits, int B, int H, int W, int Hq, int Wq,
+                   int oy, int ox, int Bg, int round_out, void* stream);
 
 /* ---- optimiser: torch.optim.Adam (sac.py:60-68, sgsac.py:35-39) over a flat range, soft target update
  *      (utils.py:31-33, sac.py:153-158) fused when target != NULL */

@@ -44,6 +44,9 @@ SIGNATURES = {
     "sgqn_conv1_col2im": [_p, _i, _p, _i, _p],
     "sgqn_conv_weights_prep_g": [_p, _p, _p, _i, _i, _i, _p],
     "sgqn_conv_wgrad_tcg": [_p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p],
+    "sgqn_conv_weights_prep_phase": [_p, _p, _p, _p, _p, _i, _i, _i, _p],
+    "sgqn_conv_phase_fold": [_p, _p, _p, _p, _i, _i, _i, _p],
+    "sgqn_bce_phase": [_p, _p, _p, _p] + [_i] * 9 + [_p],
     "sgqn_pool2_bwd": [_p, _p, _p, _i, _i, _i, _i, _p],
     "sgqn_upsample2_bwd": [_p, _p, _p, _i, _i, _i, _i, _p],
     "sgqn_minmax": [_p, _ll, _p, _p, _p],

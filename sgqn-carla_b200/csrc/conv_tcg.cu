@@ -290,6 +290,70 @@ extern "C" int sgqn_conv_weights_prep_g(const float* w, float* wf, float* wd, in
     return SGQN_CHECK_LAUNCH();
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Sub-pixel ("phase") form of  conv3x3(pad 1) o nearest-x2-upsample  (modules.py:327-337: F.upsample then the next conv).
+// Output pixel (2y+a, 2x+b) of the conv over the upsampled image only ever sees the 3x3 LOW-resolution neighbourhood of
+// (y,x): upsampled rows 2y+a-1 .. 2y+a+1 are low-res rows {y-1, y, y} (a = 0) or {y, y, y+1} (a = 1), same for columns.  So
+//     Y[2y+a][2x+b][co] = sum_{dy,dx in -1..1} Wphi[(a,b,co)][dy][dx][:] . X[y+dy][x+dx][:]
+// with Wphi[(a,b,co)][dy][dx] = sum of the W[co][ky][kx] whose (ky,kx) land on (dy,dx): a plain 3x3 pad-1 conv at LOW
+// resolution with 4*Cg output channels (phase p = 2a+b owns channels [p*Cg, p*Cg + Cout_real)), whose output is the
+// space-to-depth view of Y.  The upsampled tensor (4x the bytes, read by forward, weight gradient and written by the data
+// gradient) is never materialised, the MMA N grows 4x (32 -> 64 for conv3: a 128x32x8 TF32 MMA costs as much as 128x64x8)
+// and the data gradient lands directly on the low-res tensor (the 2x2 sum-pool of the upsample backward is the sum over
+// phases inside the GEMM).  The zero ring of the upsampled image is the zero ring of the low-res one (row -1 <-> row -1,
+// row 2H <-> row H).
+__device__ __forceinline__ int phase_tap(int a, int k) { return a == 0 ? (k == 0 ? -1 : 0) : (k == 2 ? 1 : 0); }
+
+// w: [>= Cout_real][9][Cin] fp32 (reference taps); wf: [4*Cg][9][Cin] = rna(Wphi) (forward operand), wd: [Cin][9 flipped][4*Cg]
+// (data-gradient operand), bphi: [4*Cg] = bias replicated per phase (0 in the padding channels).
+__global__ void conv_weights_prep_phase_kernel(const float* __restrict__ w, const float* __restrict__ bias, float* __restrict__ wf,
+                                               float* __restrict__ wd, float* __restrict__ bphi, int Cin, int Cout_real, int Cg) {
+    const int Np = 4 * Cg;
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= Np * 9 * Cin) return;
+    int row = i / (9 * Cin), r = i - row * 9 * Cin, t = r / Cin, ci = r - t * Cin;
+    int ph = row / Cg, co = row - ph * Cg, a = ph >> 1, b = ph & 1, dy = t / 3 - 1, dx = t % 3 - 1;
+    float v = 0.f;
+    if (co < Cout_real)
+        for (int ky = 0; ky < 3; ++ky)
+            for (int kx = 0; kx < 3; ++kx)
+                if (phase_tap(a, ky) == dy && phase_tap(b, kx) == dx) v += w[((size_t)co * 9 + ky * 3 + kx) * Cin + ci];
+    v = round_tf32(v);
+    wf[i] = v;
+    wd[((size_t)ci * 9 + (8 - t)) * Np + row] = v;
+    if (i < Np) bphi[i] = (i % Cg) < Cout_real ? bias[i % Cg] : 0.f;
+}
+extern "C" int sgqn_conv_weights_prep_phase(const float* w, const float* bias, float* wf, float* wd, float* bphi, int Cin,
+                                            int Cout_real, int Cg, void* stream) {
+    int n = 4 * Cg * 9 * Cin;
+    if (n <= 0 || Cout_real > Cg) return (int)cudaErrorInvalidValue;
+    conv_weights_prep_phase_kernel<<<cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>(w, bias, wf, wd, bphi, Cin, Cout_real, Cg);
+    return SGQN_CHECK_LAUNCH();
+}
+
+// Chain rule of the map above: dW[co][ky][kx][ci] += sum_{a,b} dWphi[(a,b,co)][tap(a,ky)][tap(b,kx)][ci];
+// db[co] += sum_p dbphi[p*Cg + co].  Single writer per element (plain +=).
+__global__ void conv_phase_fold_kernel(const float* __restrict__ dwphi, const float* __restrict__ dbphi, float* __restrict__ dw,
+                                       float* __restrict__ db, int Cin, int Cout_real, int Cg) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= Cout_real * 9 * Cin) return;
+    int co = i / (9 * Cin), r = i - co * 9 * Cin, t = r / Cin, ci = r - t * Cin, ky = t / 3, kx = t % 3;
+    float s = 0.f;
+    for (int ph = 0; ph < 4; ++ph) {
+        int tp = (phase_tap(ph >> 1, ky) + 1) * 3 + phase_tap(ph & 1, kx) + 1;
+        s += dwphi[((size_t)(ph * Cg + co) * 9 + tp) * Cin + ci];
+    }
+    dw[i] += s;
+    if (i < Cout_real && db) db[i] += (dbphi[i] + dbphi[Cg + i]) + (dbphi[2 * Cg + i] + dbphi[3 * Cg + i]);
+}
+extern "C" int sgqn_conv_phase_fold(const float* dwphi, const float* dbphi, float* dw, float* db, int Cin, int Cout_real, int Cg,
+                                    void* stream) {
+    int n = Cout_real * 9 * Cin;
+    if (n <= 0 || Cout_real > Cg) return (int)cudaErrorInvalidValue;
+    conv_phase_fold_kernel<<<cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>(dwphi, dbphi, dw, db, Cin, Cout_real, Cg);
+    return SGQN_CHECK_LAUNCH();
+}
+
 // =====================================================================================================================
 // Generalised weight gradient:  dW[co][ky*3+kx][c*32+ci] += sum_q dY[q][co] * X[q + (ky+ta)*Wp + kx + tb][c*32+ci]
 // X: [rows][Cin = 32*KC], dY: [rows][N = 32*NA], both pitch-linear over the same position index q.

@@ -290,6 +290,54 @@ bce_vec_kernel(const float* __restrict__ logits, const uint8_t* __restrict__ mas
     if (threadIdx.x == 0) atomicAdd(loss, tot * inv_n);
 }
 
+// The same loss on the sub-pixel ("phase") layout of the logits (conv_tcg.cu, conv_weights_prep_phase): buffers are
+// [B][Hq][Wq][4 phases][16] at LOW resolution (H/2 x W/2 pixels, pixel (y,x) at row y+oy, col x+ox); phase p = 2a+b,
+// channel c < 9 of low-res pixel (y,x) is logit c of output pixel (2y+a, 2x+b).  One 16-byte chunk per work item, 12 of the
+// 16 chunks of a pixel (channels 12..15 of each phase are padding: never read, never written, zero in dlogits).
+__global__ void __launch_bounds__(256)
+bce_phase_kernel(const float* __restrict__ logits, const uint8_t* __restrict__ mask, float* __restrict__ loss,
+                 float* __restrict__ dlogits, int H, int W, int Hq, int Wq, int oy, int ox, long long nitems, float inv_n, int round_out) {
+    __shared__ float sh[33];
+    float acc = 0.f;
+    const int Hl = H >> 1, Wl = W >> 1, HW = H * W;
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < nitems; t += (long long)gridDim.x * blockDim.x) {
+        const int k = (int)(t % 3); long long u = t / 3; const int ph = (int)(u & 3); u >>= 2;
+        const int xl = (int)(u % Wl); u /= Wl; const int yl = (int)(u % Hl); const int b = (int)(u / Hl);
+        const int i = (2 * yl + (ph >> 1)) * W + 2 * xl + (ph & 1);
+        const size_t o = (((size_t)b * Hq + yl + oy) * Wq + xl + ox) * 64 + 16 * ph + 4 * k;
+        const float4 xv = __ldg(reinterpret_cast<const float4*>(logits + o));
+        const float x[4] = {xv.x, xv.y, xv.z, xv.w};
+        float g[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int c = 4 * k + e;
+            g[e] = 0.f;
+            if (c < 9) {
+                float yv = (float)mask[((size_t)b * 3 + c / 3) * HW + i];
+                float v = x[e];
+                acc += fmaxf(v, 0.f) - v * yv + log1pf(expf(-fabsf(v)));
+                float gg = (1.f / (1.f + expf(-v)) - yv) * inv_n;
+                if (round_out) { uint32_t r; asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(gg)); gg = __uint_as_float(r); }
+                g[e] = gg;
+            }
+        }
+        *reinterpret_cast<float4*>(dlogits + o) = make_float4(g[0], g[1], g[2], g[3]);
+    }
+    float tot = block_sum(acc, sh);
+    if (threadIdx.x == 0) atomicAdd(loss, tot * inv_n);
+}
+
+extern "C" int sgqn_bce_phase(const float* logits, const uint8_t* mask, float* loss, float* dlogits, int B, int H, int W, int Hq,
+                              int Wq, int oy, int ox, int Bg, int round_out, void* stream) {
+    if ((H | W) & 1) return (int)cudaErrorInvalidValue;
+    long long nitems = (long long)B * (H / 2) * (W / 2) * 12;
+    if (nitems <= 0) return 0;
+    float inv_n = 1.0f / ((float)Bg * 9.0f * (float)(H * W));
+    int grid = (int)(cdivll(nitems, 256) < 4736 ? cdivll(nitems, 256) : 4736);
+    bce_phase_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(logits, mask, loss, dlogits, H, W, Hq, Wq, oy, ox, nitems, inv_n, round_out);
+    return SGQN_CHECK_LAUNCH();
+}
+
 extern "C" int sgqn_bce(const float* logits, const uint8_t* mask, float* loss, float* dlogits, int B, int H, int W, int Hq, int Wq,
                         int oy, int ox, int Cs, int Bg, int round_out, void* stream) {
     long long npix = (long long)B * H * W;

@@ -129,18 +129,25 @@ class UpdateEngine:
             self.dl = f32(B, FEAT); self.ddl = f32(B, FEAT)
             self.d1 = f32(B * 21 * 21 * 128); self.dd1 = f32(B * 21 * 21 * 128)
             self.d2 = f32(B * 42 * 42 * 64); self.dd2 = f32(B * 42 * 42 * 64)
-            self.lg = f32(B * 86 * 86 * DEC_C3); self.dlg = f32(B * 86 * 86 * DEC_C3)
-            self.dup3 = f32(B * 84 * 84 * 64); self.dup2 = f32(B * 42 * 42 * 128)
+            self.dup2 = f32(B * 42 * 42 * 128)
+            if precision != "tf32":
+                self.lg = f32(B * 86 * 86 * DEC_C3); self.dlg = f32(B * 86 * 86 * DEC_C3)
+                self.dup3 = f32(B * 84 * 84 * 64)
             if precision == "tf32":
                 # tcgen05 decoder: zero-bordered pitch-linear buffers [B][H+2][W+2][C], image at rows [1,H+1), cols [0,W)
                 # (borders are zero from this allocation on; kernels only ever write the interior)
                 self.xin1 = f32(B * 23 * 23 * 32)        # relu(proj output)
                 self.xin2 = f32(B * 44 * 44 * 128)       # up2(relu(conv1))
-                self.xin3 = f32(B * 86 * 86 * 64)        # up2(relu(conv2))
+                # conv3 runs in its sub-pixel form on relu(conv2) at 42x42 (conv_tcg.cu, sgqn_conv_weights_prep_phase): the
+                # 84x84x64 upsampled tensor (242 MB at B = 128) and its gradient are never materialised
+                self.xin3 = f32(B * 44 * 44 * 64)        # relu(conv2), zero-bordered
+                self.lgp = f32(B * 44 * 44 * 64); self.dlgp = f32(B * 44 * 44 * 64)   # logits / d logits, [4 phases][16]
+                self.w3f, self.w3d, self.b3p = f32(64 * 9 * 64), f32(64 * 9 * 64), f32(64)
+                self.dw3p, self.db3p = f32(64 * 9 * 64), f32(64)
                 self.dd2g = f32(B * 44 * 44 * 64)        # d conv2 output
                 self.dd1g = f32(B * 23 * 23 * 128)       # d conv1 output
-                self.dwf = [f32(128 * 9 * 32), f32(64 * 9 * 128), f32(DEC_C3 * 9 * 64)]     # TF32 operand copies (forward)
-                self.dwd = [f32(128 * 9 * 32), f32(64 * 9 * 128), f32(DEC_C3 * 9 * 64)]     # ... (data gradient)
+                self.dwf = [f32(128 * 9 * 32), f32(64 * 9 * 128)]     # TF32 operand copies (forward) of conv1 / conv2
+                self.dwd = [f32(128 * 9 * 32), f32(64 * 9 * 128)]     # ... (data gradient)
         if algorithm == "svea":
             self.places = f32(B, 3, 84 * 84)
         self.debug_masked_obs = None
@@ -222,9 +229,10 @@ class UpdateEngine:
     def prep_dec_weights(self):
         if self.algorithm != "sgsac" or self.precision != "tf32":
             return
-        for i, (name, co, ci, cr) in enumerate((("dec.conv1.weight", 128, 32, 128), ("dec.conv2.weight", 64, 128, 64),
-                                                ("dec.conv3.weight", DEC_C3, 64, 9))):
+        for i, (name, co, ci, cr) in enumerate((("dec.conv1.weight", 128, 32, 128), ("dec.conv2.weight", 64, 128, 64))):
             K.conv_weights_prep_g(self.P(name), _ptr(self.dwf[i]), _ptr(self.dwd[i]), co, ci, cr, self.st)
+        K.conv_weights_prep_phase(self.P("dec.conv3.weight"), self.P("dec.conv3.bias"), _ptr(self.w3f), _ptr(self.w3d),
+                                  _ptr(self.b3p), 64, 9, 16, self.st)
 
     def prep_conv_weights(self, target=False):
         """Refresh the TF32 operand copies after the 32->32 conv weights changed (optimiser step / EMA / load)."""
@@ -596,18 +604,22 @@ class UpdateEngine:
         K.conv_tcg(_ptr(self.xin1), _ptr(wf[0]), Wp("dec.conv1.bias"), 0, _ptr(self.xin2), B, 23, 23, 32, 128, 21, 21, -1,
                    44, 44, 1, 0, 0, 0, RU, st)
         K.conv_tcg(_ptr(self.xin2), _ptr(wf[1]), Wp("dec.conv2.bias"), 0, _ptr(self.xin3), B, 44, 44, 128, 64, 42, 42, -1,
-                   86, 86, 1, 0, 0, 0, RU, st)
-        K.conv_tcg(_ptr(self.xin3), _ptr(wf[2]), Wp("dec.conv3.bias"), 0, _ptr(self.lg), B, 86, 86, 64, DEC_C3, 84, 84, -1,
-                   86, 86, 1, 0, 0, 0, 0, st)
+                   44, 44, 1, 0, 0, 0, 1 | 2, st)             # relu(conv2) at 42x42: conv3 consumes it in sub-pixel form
+        K.conv_tcg(_ptr(self.xin3), _ptr(self.w3f), _ptr(self.b3p), 0, _ptr(self.lgp), B, 44, 44, 64, 64, 42, 42, -1,
+                   44, 44, 1, 0, 0, 0, 0, st)
         K.zero(_ptr(self.logs, 4), 4, st)
-        K.bce(_ptr(self.lg), _ptr(self.mask), _ptr(self.logs, 4), _ptr(self.dlg), B, 84, 84, 86, 86, 1, 0, DEC_C3, self.Bg, 1, st)
+        K.bce_phase(_ptr(self.lgp), _ptr(self.mask), _ptr(self.logs, 4), _ptr(self.dlgp), B, 84, 84, 44, 44, 1, 0, self.Bg, 1, st)
         K.zero(self._g + 4 * x0, 4 * (x1 - x0), st)
-        # conv3 backward
+        # conv3 backward, all at 42x42: phase weight gradient folded back onto the 3x3 taps; the data gradient lands on
+        # relu(conv2) directly (sum over phases = the 2x2 sum-pool of the upsample backward) with its ReLU mask fused
         ws = self._fork()                                     # weight / bias gradients beside the data-gradient chain
-        K.conv_wgrad_tcg(_ptr(self.xin3), _ptr(self.dlg), G("dec.conv3.weight"), B, 86, 86, 64, DEC_C3, -1, -1, ws)
-        K.colsum(_ptr(self.dlg), DEC_C3, B * 86 * 86, DEC_C3, G("dec.conv3.bias"), ws)
-        K.conv_tcg(_ptr(self.dlg), _ptr(wd[2]), 0, 0, _ptr(self.dup3), B, 86, 86, DEC_C3, 64, 84, 84, -1, 84, 84, 0, 0, 0, 0, 0, st)
-        K.pool2_bwd(_ptr(self.dup3), _ptr(self.xin3), _ptr(self.dd2g), B, 42, 42, 64, st)
+        K.zero(_ptr(self.dw3p), 4 * self.dw3p.numel(), ws)
+        K.zero(_ptr(self.db3p), 4 * 64, ws)
+        K.conv_wgrad_tcg(_ptr(self.xin3), _ptr(self.dlgp), _ptr(self.dw3p), B, 44, 44, 64, 64, -1, -1, ws)
+        K.colsum(_ptr(self.dlgp), 64, B * 44 * 44, 64, _ptr(self.db3p), ws)
+        K.conv_phase_fold(_ptr(self.dw3p), _ptr(self.db3p), G("dec.conv3.weight"), G("dec.conv3.bias"), 64, 9, 16, ws)
+        K.conv_tcg(_ptr(self.dlgp), _ptr(self.w3d), 0, _ptr(self.xin3, 44 * 64), _ptr(self.dd2g), B, 44, 44, 64, 64, 42, 42, -1,
+                   44, 44, 1, 0, 44, 44, (1 << 2) | 2, st)
         # conv2 backward
         ws = self._fork()
         K.conv_wgrad_tcg(_ptr(self.xin2), _ptr(self.dd2g), G("dec.conv2.weight"), B, 44, 44, 128, 64, -1, -1, ws)

@@ -690,6 +690,78 @@ def test_conv_tcg_forward_dgrad_wgrad(B, H, Cin, Co, Cs):
     close(dw.reshape(Cs, 3, 3, Cin).permute(0, 3, 1, 2)[:Co], wr.grad.float(), rtol=3e-5, what="conv_wgrad_tcg")
 
 
+@pytest.mark.parametrize("B,Hl,Cin,Co,Cg", [(2, 42, 64, 9, 16), (3, 10, 64, 9, 16), (1, 21, 32, 5, 8)])
+def test_phase_conv_equals_conv_after_upsample(B, Hl, Cin, Co, Cg):
+    """conv3x3(pad 1) o F.upsample(x, 2) in its sub-pixel form (sgqn_conv_weights_prep_phase + sgqn_conv_tcg at low
+    resolution + sgqn_conv_phase_fold) against torch on the materialised upsampled tensor: forward logits, masked data
+    gradient w.r.t. the low-res activation, folded weight / bias gradients."""
+    Np, H = 4 * Cg, 2 * Hl
+    if Np not in (32, 64, 128):
+        pytest.skip("conv_tcg N")
+    x = tf32_round(F.relu(rnd(B, Cin, Hl, Hl, seed=1)))
+    w = rnd(Co, Cin, 3, 3, seed=2, scale=0.05); b = rnd(Co, seed=3)
+    wst = torch.zeros(Co + 3, Cin, 3, 3, device=DEV); wst[:Co] = w                 # stored with padding rows
+    wk_ = wk(wst).contiguous()
+    wf = torch.zeros(Np * 9 * Cin, device=DEV); wd = torch.zeros(Np * 9 * Cin, device=DEV); bp = torch.zeros(Np, device=DEV)
+    K.conv_weights_prep_phase(P(wk_), P(b), P(wf), P(wd), P(bp), Cin, Co, Cg, ST())
+    xin = bordered(x, Hl + 2, Hl + 2, 1, 0)
+    yp = torch.zeros(B, Hl + 2, Hl + 2, Np, device=DEV)
+    K.conv_tcg(P(xin), P(wf), P(bp), 0, P(yp), B, Hl + 2, Hl + 2, Cin, Np, Hl, Hl, -1, Hl + 2, Hl + 2, 1, 0, 0, 0, 0, ST())
+    torch.cuda.synchronize()
+    xr = x.double().requires_grad_(True); wr = w.double().requires_grad_(True); br = b.double().requires_grad_(True)
+    ref = F.conv2d(F.interpolate(xr, scale_factor=2), wr, br, padding=1)            # (B,Co,H,H)
+    # depth-to-space of our output: phase p = 2a+b, channels [p*Cg, p*Cg+Co) -> pixel (2y+a, 2x+b)
+    got = yp[:, 1:Hl + 1, :Hl].reshape(B, Hl, Hl, 2, 2, Cg)[..., :Co].permute(0, 5, 1, 3, 2, 4).reshape(B, Co, H, H)
+    close(got, ref.detach().float(), rtol=2e-3, atol=2e-3 * float(ref.abs().max()), what="phase conv fwd")   # TF32 of summed taps
+    assert float(yp[:, 1:Hl + 1, :Hl].reshape(B, Hl, Hl, 4, Cg)[..., Co:].abs().max()) == 0.0
+    # backward
+    dy = tf32_round(rnd(B, Co, H, H, seed=4))
+    ref.backward(dy.double())
+    dyp = torch.zeros(B, Hl + 2, Hl + 2, 4, Cg, device=DEV)
+    dyp[:, 1:Hl + 1, :Hl, :, :Co] = dy.reshape(B, Co, Hl, 2, Hl, 2).permute(0, 2, 4, 3, 5, 1).reshape(B, Hl, Hl, 4, Co)
+    dx = torch.zeros(B, Hl + 2, Hl + 2, Cin, device=DEV)
+    K.conv_tcg(P(dyp), P(wd), 0, P(xin, (Hl + 2) * Cin), P(dx), B, Hl + 2, Hl + 2, Np, Cin, Hl, Hl, -1, Hl + 2, Hl + 2, 1, 0,
+               Hl + 2, Hl + 2, (1 << 2) | 2, ST())
+    torch.cuda.synchronize()
+    refd = (xr.grad * (x > 0)).float()
+    close(dx[:, 1:Hl + 1, :Hl].permute(0, 3, 1, 2), refd, rtol=2e-3, atol=2e-3 * float(refd.abs().max()), what="phase conv dgrad")
+    bz = dx.clone(); bz[:, 1:Hl + 1, :Hl] = 0
+    assert float(bz.abs().max()) == 0.0
+    dwp = torch.zeros(Np * 9 * Cin, device=DEV); dbp = torch.zeros(Np, device=DEV)
+    K.conv_wgrad_tcg(P(xin), P(dyp), P(dwp), B, Hl + 2, Hl + 2, Cin, Np, -1, -1, ST())
+    K.colsum(P(dyp), Np, B * (Hl + 2) * (Hl + 2), Np, P(dbp), ST())
+    dw = torch.zeros((Co + 3) * 9 * Cin, device=DEV); db = torch.zeros(Co + 3, device=DEV)
+    K.conv_phase_fold(P(dwp), P(dbp), P(dw), P(db), Cin, Co, Cg, ST())
+    torch.cuda.synchronize()
+    close(dw.reshape(Co + 3, 3, 3, Cin).permute(0, 3, 1, 2)[:Co], wr.grad.float(), rtol=1e-4, atol=1e-4 * float(wr.grad.abs().max()),
+          what="phase conv wgrad (folded)")
+    close(db[:Co], br.grad.float(), rtol=1e-4, what="phase conv bias grad")
+    assert float(dw.reshape(Co + 3, -1)[Co:].abs().max()) == 0.0
+
+
+def test_bce_phase_equals_bce():
+    B, H = 3, 84
+    Hl = H // 2
+    lg = rnd(B, 9, H, H, seed=1, scale=2.0)
+    mask = (rnd(B, 3, H * H, seed=2) > 0.8).to(torch.uint8)
+    x = lg.clone().requires_grad_(True)
+    y = mask.float().reshape(B, 3, H, H).repeat_interleave(3, dim=1)
+    ref = F.binary_cross_entropy_with_logits(x, y)
+    ref.backward()
+    lgp = torch.zeros(B, Hl + 2, Hl + 2, 4, 16, device=DEV)
+    lgp[:, 1:Hl + 1, :Hl, :, :9] = lg.reshape(B, 9, Hl, 2, Hl, 2).permute(0, 2, 4, 3, 5, 1).reshape(B, Hl, Hl, 4, 9)
+    lgp[..., 12:] = 7.0                                            # padding channels must be ignored
+    loss = torch.zeros(1, device=DEV); d = torch.zeros_like(lgp)
+    K.bce_phase(P(lgp), P(mask), P(loss), P(d), B, H, H, Hl + 2, Hl + 2, 1, 0, B, 0, ST())
+    torch.cuda.synchronize()
+    close(loss, ref.detach().reshape(1), what="bce_phase loss")
+    got = d[:, 1:Hl + 1, :Hl, :, :9].reshape(B, Hl, Hl, 2, 2, 9).permute(0, 5, 1, 3, 2, 4).reshape(B, 9, H, H)
+    close(got, x.grad, rtol=2e-4, what="bce_phase grad")
+    assert float(d[..., 9:].abs().max()) == 0.0
+    bz = d.clone(); bz[:, 1:Hl + 1, :Hl] = 0
+    assert float(bz.abs().max()) == 0.0
+
+
 def test_pool2_bwd():
     B, H, C = 2, 21, 128
     dup = rnd(B, 2 * H, 2 * H, C, seed=1)
