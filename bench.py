@@ -207,10 +207,12 @@ def profile_kernels(agent, rb, nsteps=4):
             # the data gradient also reads the 128-byte ReLU mask (the layer's input activation) of every output pixel
             by = 128.0 * B * ((Hv + 2) * (Hv + 2) + Hv * Hv * (2 if masked else 1))
             key = "conv_tc[32->32 " + ("dgrad" if args[11] else "fwd") + "]"
+        elif n == "conv1_fused_tc":
+            fl = 2.0 * args[5] * 1681 * 81 * 32
         elif n == "conv_tcg_taps":
             B, Cin, Cout, Hv = args[5], args[8], args[9], args[10]
-            fl = 2.0 * B * Hv * Hv * 81 * Cout
-            key = "conv1_tcg[fwd]"
+            fl = 2.0 * B * Hv * Hv * 81 * 32
+            key = "conv1_tcg[dgrad]"
         elif n == "conv_tcg":
             B, Cin, Cout, Hv = args[5], args[8], args[9], args[10]
             fl = 2.0 * B * Hv * Hv * 9 * Cin * Cout

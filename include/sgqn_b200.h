@@ -115,6 +115,11 @@ int sgqn_conv_tcg_taps(const float* x, const float* wop, const float* bias, cons
                        int ntaps /* 9: 3x3 conv, 1: per-position GEMM (the first conv on its im2col matrix) */, void* stream);
 int sgqn_gemm_wgrad_tcg(const float* x, const float* dy, float* dw, int B, int Hr, int Wp, int Cin, int Cout, int ta, int tb,
                         int ntaps, int kvalid, void* stream);
+/* NormalizeImg + first conv (stride 2) + ReLU as one tcgen05 kernel whose im2col tile is built in shared memory (modules.py:86-93,
+ * 143-144): obs (B,9,Hin,Hin) fp32 0..255 -> out [B][43][41][32] pitch-linear, TF32-rounded.  w1p from sgqn_conv1_weights_prep.
+ * col (optional, for the weight gradient): the im2col matrix [B*1681][96] of the samples >= col_row0, written by TMA. */
+int sgqn_conv1_fused_tc(const float* obs, const float* w1p, const float* bias, float* out, float* col, int B, int Hin, int col_row0,
+                        void* stream);
 int sgqn_conv_weights_prep_g(const float* w, float* wf, float* wd, int Cout, int Cin, int Cout_real, void* stream);
 int sgqn_conv_wgrad_tcg(const float* x, const float* dy, float* dw, int B, int Hr, int Wp, int Cin, int Cout, int ta, int tb,
                         void* stream);

@@ -44,7 +44,7 @@ def aux_and_actor():
     eng.actor_finish()
 
 def crit_fwd_part():
-    eng.target_q_pass(); eng._obs_col_valid = True; eng.critic_fwd_rows(0, B, encode=False)
+    eng.target_q_pass(); eng.critic_fwd_rows(0, B, encode=False)
 
 phases = [("sample", sample), ("target_q_pass+critic_fwd(obs)", crit_fwd_part),
           ("update_critic (whole)", lambda: eng.update_critic(1)),

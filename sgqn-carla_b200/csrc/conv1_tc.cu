@@ -1,0 +1,231 @@
+// First encoder conv (NormalizeImg + Conv2d(9, 32, 3, stride 2), modules.py:86-93,143) + the ReLU that follows it, as ONE
+// tcgen05 kernel: the im2col matrix is built in shared memory, never in HBM.
+//
+// Per-position GEMM out[pix][32] = A[pix][96] * W[32][96]^T with A[pix][c*9 + ky*3 + kx] = tf32(obs[b][c][2y+ky][2x+kx] / 255)
+// (81 real columns).  TMA cannot express the stride-2 window gather over an NCHW fp32 image, so the A tile of 128 output
+// pixels is produced by eight producer warps (two groups of four alternate tiles): thread r of a group gathers the 81
+// values of pixel r straight from the observation (27 float2 + 27 float loads, consecutive lanes = consecutive 8-byte
+// words), scales / rounds them and writes its row as 24 16-byte units in the SWIZZLE_128B K-major layout the UMMA
+// descriptor expects (unit u of row r at ((u ^ (r & 7)) << 4): every quarter-warp store covers all 32 banks),
+// fence.proxy.async, mbarrier arrive.  One thread issues the 12 MMAs (3 chunks x 4 k-steps of 128x32x8, TF32) per tile into
+// one of two TMEM accumulators; four epilogue warps add bias, apply ReLU, round to TF32 (the next layer's operand format)
+// and store the pitch-linear activation [n][43][41][32].
+// The materialised version moved 384 B per output pixel through HBM twice (im2col write + GEMM read: 165 MB each way at
+// 256 samples, 120 us); this one reads the observation once (65 MB) and writes the activation (58 MB).
+// The weight gradient of the layer still wants A as a matrix: when `col` is given, the finished shared-memory tile is
+// ALSO copied out by TMA (cp.async.bulk.tensor store, no thread instructions) for the tiles at or after `col_row0`.
+#include "tc_common.cuh"
+#include "../../include/sgqn_b200.h"
+
+using namespace tc;
+
+namespace {
+
+constexpr int kStages = 4;                        // A stages; producer group g owns stages g and g + 2
+constexpr int kChunkBytes = 128 * 128;            // [128 rows][32 floats]
+constexpr int kABytes = 3 * kChunkBytes;          // 48 KB
+constexpr int kWBytes = 3 * 32 * 128;             // 12 KB: three [32 co][32 k] chunks
+constexpr int kSmem = kStages * kABytes + kWBytes + 1024 + 256;
+constexpr int kThreads = 32 * 13;                 // warp 0 MMA, warps 1-4 epilogue, warps 5-12 producers
+constexpr int kPix = 41 * 41;
+
+struct C1Params {
+    const float* obs; const float* bias; float* out;
+    int n_pix, Hin, crop, num_tiles, col_first_tile, write_col;
+};
+
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* tm, uint32_t src, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                 ::"l"((unsigned long long)tm), "r"(src), "r"(c0), "r"(c1) : "memory");
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+conv1_fused_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmCol, C1Params p) {
+    constexpr uint32_t kIdesc = idesc_tf32(32, false, false);
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t a_sm = base;
+    const uint32_t w_sm = a_sm + kStages * kABytes;
+    const uint32_t bars = w_sm + kWBytes;
+    const uint32_t full0 = bars, empty0 = full0 + 8 * kStages, wbar = empty0 + 8 * kStages;
+    const uint32_t tfull0 = wbar + 8, tempty0 = tfull0 + 16, tmem_slot = tempty0 + 16;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"((unsigned long long)&tmW) : "memory");
+        if (p.write_col) asm volatile("prefetch.tensormap [%0];" ::"l"((unsigned long long)&tmCol) : "memory");
+        for (int s = 0; s < kStages; ++s) { mbar_init(full0 + 8 * s, 128); mbar_init(empty0 + 8 * s, 1); }
+        mbar_init(wbar, 1);
+        for (int a = 0; a < 2; ++a) { mbar_init(tfull0 + 8 * a, 1); mbar_init(tempty0 + 8 * a, 128); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(64) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    uint32_t tmem_base;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+    pdl_wait();
+    pdl_launch();
+
+    if (warp == 0) {
+        if (lane == 0) {
+            mbar_expect_tx(wbar, kWBytes);
+            for (int c = 0; c < 3; ++c) tma_load_2d(&tmW, wbar, w_sm + c * 4096, c * 32, 0);
+            mbar_wait(wbar, 0);
+            tc_fence_after();
+            int i = 0;
+            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++i) {
+                const int stage = i & (kStages - 1), acc = i & 1;
+                mbar_wait(tempty0 + 8 * acc, ((uint32_t)(i >> 1) & 1u) ^ 1u);
+                mbar_wait(full0 + 8 * stage, (uint32_t)(i / kStages) & 1u);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * 32);
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    const uint64_t ad = make_desc_sw128(a_sm + stage * kABytes + c * kChunkBytes);
+                    const uint64_t bd = make_desc_sw128(w_sm + c * 4096);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        tc_mma_tf32(d_tmem, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), kIdesc, (c | k) != 0);
+                }
+                tc_commit(empty0 + 8 * stage);
+                tc_commit(tfull0 + 8 * acc);
+            }
+        }
+    } else if (warp <= 4) {
+        // ---- epilogue: TMEM lane quarter (warp & 3) -> bias, ReLU, TF32 round -> out[((b*43 + y)*41 + x)*32 ...]
+        const int quarter = warp & 3;
+        const int row = quarter * 32 + lane;
+        float bv[32];
+#pragma unroll
+        for (int c = 0; c < 32; ++c) bv[c] = __ldg(p.bias + c);
+        int i = 0;
+        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++i) {
+            const int acc = i & 1;
+            const int q = tile * 128 + row;
+            mbar_wait(tfull0 + 8 * acc, (uint32_t)(i >> 1) & 1u);
+            tc_fence_after();
+            uint32_t v[32];
+            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * 32);
+            asm volatile(
+                "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                  "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+                  "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+                  "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                : "r"(taddr) : "memory");
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            tc_fence_before();
+            mbar_arrive(tempty0 + 8 * acc);
+            if (q >= p.n_pix) continue;
+            const int b = q / kPix, rem = q - b * kPix, y = rem / 41, x = rem - y * 41;
+            float4* dst = reinterpret_cast<float4*>(p.out + ((size_t)(b * 43 + y) * 41 + x) * 32);
+#pragma unroll
+            for (int c4 = 0; c4 < 8; ++c4) {
+                float o[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) o[e] = round_tf32(fmaxf(__uint_as_float(v[4 * c4 + e]) + bv[4 * c4 + e], 0.f));
+                dst[c4] = make_float4(o[0], o[1], o[2], o[3]);
+            }
+        }
+    } else {
+        // ---- producers: group g = tiles i with i % 2 == g; thread r builds row r of the A tile
+        const int g = (warp - 5) >> 2;
+        const int r = ((warp - 5) & 3) * 32 + lane;
+        const bool elected = r == 0;
+        const int Hin = p.Hin;
+        const size_t plane = (size_t)Hin * Hin;
+        int i = g;
+        for (int tile = blockIdx.x + g * gridDim.x; tile < p.num_tiles; tile += 2 * gridDim.x, i += 2) {
+            const int stage = i & (kStages - 1);
+            const uint32_t srow = a_sm + stage * kABytes + r * 128;
+            mbar_wait(empty0 + 8 * stage, ((uint32_t)(i / kStages) & 1u) ^ 1u);
+            if (p.write_col) {                       // the TMA store that read this stage two group-tiles ago must be done
+                if (elected) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                asm volatile("bar.sync %0, 128;" ::"r"(2 + g) : "memory");
+            }
+            const int q = tile * 128 + r;
+            if (q < p.n_pix) {
+                const int b = q / kPix, rem = q - b * kPix, y = rem / 41, x = rem - y * 41;
+                const float* src = p.obs + (size_t)b * 9 * plane + (size_t)(2 * y + p.crop) * Hin + 2 * x + p.crop;
+                float a[96];
+#pragma unroll
+                for (int c = 0; c < 9; ++c)
+#pragma unroll
+                    for (int ky = 0; ky < 3; ++ky) {
+                        const float* pr = src + c * plane + ky * Hin;
+                        const float2 v01 = __ldg(reinterpret_cast<const float2*>(pr));
+                        const float v2 = __ldg(pr + 2);
+                        a[c * 9 + ky * 3 + 0] = v01.x; a[c * 9 + ky * 3 + 1] = v01.y; a[c * 9 + ky * 3 + 2] = v2;
+                    }
+#pragma unroll
+                for (int k = 0; k < 81; ++k) a[k] = round_tf32(__fdiv_rn(a[k], 255.0f));
+#pragma unroll
+                for (int k = 81; k < 96; ++k) a[k] = 0.f;
+#pragma unroll
+                for (int u = 0; u < 24; ++u) {
+                    const uint32_t addr = srow + (u >> 3) * kChunkBytes + (((u & 7) ^ (r & 7)) << 4);
+                    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a[4 * u]), "f"(a[4 * u + 1]),
+                                 "f"(a[4 * u + 2]), "f"(a[4 * u + 3]) : "memory");
+                }
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            mbar_arrive(full0 + 8 * stage);
+            if (p.write_col) {
+                asm volatile("bar.sync %0, 128;" ::"r"(2 + g) : "memory");     // every row written and fenced
+                if (elected) {
+                    if (tile >= p.col_first_tile)
+                        for (int c = 0; c < 3; ++c) tma_store_2d(&tmCol, a_sm + stage * kABytes + c * kChunkBytes, c * 32, tile * 128);
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                }
+            }
+        }
+        if (p.write_col && elected) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(64) : "memory");
+    }
+}
+
+}  // namespace
+
+// obs: (B, 9, Hin, Hin) fp32 NCHW with values 0..255 (Hin = 84, or 100 = centre crop, modules.py:70-83); w1p: TF32 operand
+// copy [32][96] of the conv weight (sgqn_conv1_weights_prep); out: relu(conv1(obs / 255)) rounded to TF32, pitch-linear
+// [B][43][41][32] (rows 41, 42 of every sample are never written).  col (optional): im2col matrix [B*1681][96] for the
+// weight gradient, written for the 128-pixel tiles that contain samples >= col_row0 (earlier rows of col: unspecified).
+extern "C" int sgqn_conv1_fused_tc(const float* obs, const float* w1p, const float* bias, float* out, float* col, int B, int Hin,
+                                   int col_row0, void* stream) {
+    if (B <= 0) return 0;
+    if (Hin < 84 || ((Hin - 84) & 3) || !bias) return (int)cudaErrorInvalidValue;
+    static int inited = 0, num_sms = 0;
+    if (!inited) {
+        cudaError_t e = cudaFuncSetAttribute(conv1_fused_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
+        if (e != cudaSuccess) return (int)e;
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+        inited = 1;
+    }
+    C1Params p;
+    p.obs = obs; p.bias = bias; p.out = out;
+    p.n_pix = B * kPix; p.Hin = Hin; p.crop = (Hin - 84) / 2;
+    p.num_tiles = (p.n_pix + 127) / 128;
+    p.write_col = col != nullptr && col_row0 < B;
+    p.col_first_tile = p.write_col ? (col_row0 * kPix) / 128 : p.num_tiles;
+    CUtensorMap tmW, tmCol;
+    int rc = make_map_2d(&tmW, w1p, 96, 32, 32, 32);
+    if (rc) return rc;
+    rc = make_map_2d(&tmCol, p.write_col ? col : w1p, 96, p.write_col ? (uint64_t)p.n_pix : 32, 32, p.write_col ? 128 : 32);
+    if (rc) return rc;
+    int grid = p.num_tiles < num_sms ? p.num_tiles : num_sms;
+    return launch_pdl(conv1_fused_tc_kernel, dim3(grid), dim3(kThreads), kSmem, stream, tmW, tmCol, p);
+}

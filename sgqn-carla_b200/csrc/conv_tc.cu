@@ -247,13 +247,24 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             }
             asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");       // staging tile and rowinfo[par] are free again
         }
-        if (p.dbias) {                                   // lanes with equal chunk hold the same channels: 2 shuffles + 4 atomics
+        if (p.dbias) {
+            // lanes with equal chunk hold the same channels: 2 shuffles, then across the warps through the (now free) staging
+            // tile, then ONE atomic per channel per CTA (per-lane atomics from every warp of every CTA onto the same 32
+            // addresses serialised in L2 and cost ~10 us per launch)
+            float* red = reinterpret_cast<float*>(stg);
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
                 float t = csum[e];
                 t += __shfl_xor_sync(0xffffffffu, t, 8);
                 t += __shfl_xor_sync(0xffffffffu, t, 16);
-                if (lane < 8) atomicAdd(p.dbias + chunk * 4 + e, t);
+                if (lane < 8) red[(warp - 2) * 32 + chunk * 4 + e] = t;
+            }
+            asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
+            if (et < 32) {
+                float t = 0.f;
+#pragma unroll
+                for (int w = 0; w < kEpiWarps; ++w) t += red[w * 32 + et];
+                atomicAdd(p.dbias + et, t);
             }
         }
     }

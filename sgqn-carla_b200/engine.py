@@ -152,7 +152,6 @@ class UpdateEngine:
             self.places = f32(B, 3, 84 * 84)
         self.debug_masked_obs = None
         self.overlay_pool = None       # uint8 (N,3,84*84) device pool for the 'carla' overlay
-        self._obs_col_valid = False
         self._p = self.params.data_ptr(); self._g = self.grads.data_ptr(); self._t = self.target.data_ptr()
         self._c0 = c0
 
@@ -192,10 +191,10 @@ class UpdateEngine:
             ev = torch.cuda.Event(); ev.record(self.side); torch.cuda.current_stream().wait_event(ev)
 
     # ------------------------------------------------------------------ building blocks
-    def enc_fwd(self, x_ptr, n, acts, row0=0, target=False, hin=84, col_ready=0):
+    def enc_fwd(self, x_ptr, n, acts, row0=0, target=False, hin=84, col_from=None):
         """SharedCNN forward (modules.py:132-152): x (n,9,hin,hin) fp32 NCHW -> acts[0..10] rows [row0, row0+n).
-        col_ready: the first `col_ready` rows' im2col matrix is still valid in the slot (same observations as the previous
-        pass over these rows; the matrix does not depend on the weights)."""
+        col_from (tf32 path): the first conv also leaves the im2col matrix of the samples >= col_from in the slot's col
+        buffer for the weight gradient of a backward pass over these rows (None: no backward follows)."""
         W = self.T if target else self.P
         wf = self.wf_t if target else self.wf
         st = self.st
@@ -204,15 +203,10 @@ class UpdateEngine:
         tc = self.precision == "tf32"
         col = _ptr(self.colS if acts is self.actS else self.colT, row0 * 1681 * (96 if tc else 84))
         if tc:
-            if n > col_ready:
-                K.conv1_im2col96(x_ptr + col_ready * 9 * hin * hin * 4, col + col_ready * 1681 * 96 * 4, n - col_ready, hin, st)
-        else:
-            K.conv1_im2col(x_ptr, col, n, hin, st)
-        if tc:
             # pitch-linear layout [n][h+2][h][32]: the 2 spare rows per sample stay zero (never written) so that the
             # weight-gradient kernel can pair activations and the zero-bordered output gradient row by row
-            K.conv_tcg_taps(col, _ptr(self.w1p_t if target else self.w1p), W("cnn.0.bias"), 0, _ptr(acts[0], row0 * 43 * 41 * 32),
-                            n, 41, 41, 96, 32, 41, 41, 0, 43, 41, 0, 0, 0, 0, 3, 1, st)
+            K.conv1_fused_tc(x_ptr, _ptr(self.w1p_t if target else self.w1p), W("cnn.0.bias"), _ptr(acts[0], row0 * 43 * 41 * 32),
+                             col if col_from is not None else 0, n, hin, col_from if col_from is not None else n, st)
             for l in range(1, 11):
                 hi, ho = ENC_H[l - 1], ENC_H[l]
                 last = l == 10                                  # the feature map that feeds the projection is compact
@@ -220,6 +214,7 @@ class UpdateEngine:
                           _ptr(acts[l], row0 * (ho * ho if last else (ho + 2) * ho) * 32), 0, n, hi + 2, hi, ho, ho, 0,
                           ho if last else ho + 2, ho, 0, 0, 0, 0, 0 if last else 3, st)
             return
+        K.conv1_im2col(x_ptr, col, n, hin, st)
         K.conv1_fwd_col(col, W("cnn.0.weight"), W("cnn.0.bias"), _ptr(acts[0], row0 * 41 * 41 * 32), n, 1, st)
         for l in range(1, 11):                                  # fp32 CUDA-core path, compact [n][h][h][32] layout
             hi, ho = ENC_H[l - 1], ENC_H[l]
@@ -392,7 +387,8 @@ class UpdateEngine:
             with torch.cuda.stream(self.side):
                 self.enc_fwd(nx, B, self.actT, target=True)
                 ev_t = torch.cuda.Event(); ev_t.record(self.side)
-        self.enc_fwd(_ptr(self.obs3), 2 * B, self.actS, 0)       # online encoder over [next_obs ; obs] in one batch
+        self.enc_fwd(_ptr(self.obs3), 2 * B, self.actS, 0, col_from=B)   # online encoder over [next_obs ; obs] in one batch (the obs half is
+                                                                         # differentiated by the critic backward)
         self.proj_fwd(_ptr(self.actS[10]), B, "actor_proj", _ptr(self.z_a), _ptr(self.h_a), L.P)
         self.actor_mlp_fwd(B)
         K.actor_head_fwd(_ptr(self.raw), _ptr(self.noise_next), float(a.actor_log_std_min), float(a.actor_log_std_max),
@@ -418,7 +414,7 @@ class UpdateEngine:
         L, A, st, B = self.lay, self.A, self.st, self.B
         P1 = L.P + A
         if encode:
-            self.enc_fwd(_ptr(self.obs2, row0 * 9 * 84 * 84), n, self.actS, B + row0)
+            self.enc_fwd(_ptr(self.obs2, row0 * 9 * 84 * 84), n, self.actS, B + row0, col_from=0)
         K.set_cols(_ptr(self.haS, row0 * P1), P1, L.P, _ptr(self.action), A, n, A, st)
         self.proj_fwd(_ptr(self.actS[10], (B + row0) * FEAT), n, "critic_proj", _ptr(self.zS, row0 * L.P),
                       _ptr(self.haS, row0 * P1), P1)
@@ -429,7 +425,6 @@ class UpdateEngine:
         B, A, L, st, a = self.B, self.A, self.lay, self.st, self.args
         P1 = L.P + A
         self.target_q_pass()
-        self._obs_col_valid = True                      # colS rows [B, 2B) = im2col(obs2[:B]) until obs2[:B] changes
         self.critic_fwd_rows(0, B, encode=False)        # obs went through the encoder with next_obs
         R = B
         if mode == 1:
@@ -489,9 +484,8 @@ class UpdateEngine:
             K.overlay_u8(_ptr(self.obs2), _ptr(self.overlay_pool), _ptr(self.overlay_ids), float(np.float32(1 - al)),
                          float(np.float32(al)), _ptr(self.s_tilde), B, 84 * 84, st)
             n = 2 * B
-        # rows [B, 2B) of the slot's im2col matrix still hold im2col(obs) from the critic pass when update_critic ran first
-        self.enc_fwd(_ptr(self.obs2), n, self.actS, B, col_ready=B if self._obs_col_valid else 0)
-        self._obs_col_valid = False
+        # only the s_tilde half gets a backward pass (the aux update); obs feeds attribution #2 / the detached actor update
+        self.enc_fwd(_ptr(self.obs2), n, self.actS, B, col_from=B if with_aux else None)
         K.set_cols(_ptr(self.haS), P1, L.P, _ptr(self.action), A, B, A, st)
         if with_aux:
             K.set_cols(_ptr(self.haS, B * P1), P1, L.P, _ptr(self.action), A, B, A, st)
@@ -680,7 +674,6 @@ class UpdateEngine:
         self._finish_logs()
 
     def _finish_logs(self):
-        self._obs_col_valid = False                     # the next caller may bring new observations
         if self.dist is not None:
             self.dist.all_reduce_logs(self.logs)
 

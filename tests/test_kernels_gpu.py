@@ -800,3 +800,37 @@ def test_conv1_tcgen05_path_matches_cuda_core_path():
     K.gemm_wgrad_tcg(P(col96), P(dy), P(dw1), B, 41, 41, 96, 32, 0, 0, 1, 81, ST())
     torch.cuda.synchronize()
     close(dw1, dw0, rtol=2e-3, what="conv1 tcgen05 wgrad")
+
+
+@pytest.mark.parametrize("B,Hin,col_row0", [(5, 84, 0), (7, 84, 3), (3, 100, 0), (130, 84, 130), (1, 84, 0)])
+def test_conv1_fused_matches_im2col_path(B, Hin, col_row0):
+    """First conv with the im2col tile built in shared memory (sgqn_conv1_fused_tc) against the materialised-im2col
+    tcgen05 path it replaces (same operands, same K order) and against torch; the optional TMA-stored im2col matrix is
+    bit-exact for the requested samples."""
+    g = torch.Generator().manual_seed(5)
+    obs = torch.randint(0, 256, (B, 9, Hin, Hin), generator=g).float().to(DEV)
+    obs[0] = obs[0] * 0.37 + 1.3                                   # non-integer pixels too (masked / overlaid observations)
+    w = rnd(32, 9, 3, 3, seed=2, scale=0.2); b = rnd(32, seed=3)
+    wp = torch.zeros(32 * 96, device=DEV)
+    K.conv1_weights_prep(P(w), P(wp), 0, ST())
+    col96 = torch.zeros(B * 1681, 96, device=DEV)
+    K.conv1_im2col96(P(obs), P(col96), B, Hin, ST())
+    y1 = torch.zeros(B, 43, 41, 32, device=DEV)
+    K.conv_tcg_taps(P(col96), P(wp), P(b), 0, P(y1), B, 41, 41, 96, 32, 41, 41, 0, 43, 41, 0, 0, 0, 0, 3, 1, ST())
+    y2 = torch.zeros(B, 43, 41, 32, device=DEV)
+    colf = torch.full((B * 1681, 96), -7.0, device=DEV)
+    want_col = col_row0 < B
+    K.conv1_fused_tc(P(obs), P(wp), P(b), P(y2), P(colf) if want_col else 0, B, Hin, col_row0, ST())
+    torch.cuda.synchronize()
+    assert torch.equal(y2, y1)
+    assert float(y2[:, 41:].abs().max()) == 0.0
+    c = (Hin - 84) // 2
+    x = obs[:, :, c:c + 84, c:c + 84]
+    ref = tf32_round(F.relu(F.conv2d(tf32_round(x / 255.0).double(), tf32_round(w).double(), b.double(), stride=2)).float())
+    close(y2[:, :41].permute(0, 3, 1, 2), ref, rtol=2e-3, atol=1e-5, what="conv1 fused vs torch")
+    if want_col:
+        assert torch.equal(colf[col_row0 * 1681:], col96[col_row0 * 1681:])
+        first_tile_row = (col_row0 * 1681) // 128 * 128
+        assert float((colf[:first_tile_row] + 7.0).abs().max()) == 0.0 if first_tile_row else True
+    else:
+        assert float((colf + 7.0).abs().max()) == 0.0
