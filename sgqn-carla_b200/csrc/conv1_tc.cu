@@ -3,9 +3,10 @@
 //
 // Per-position GEMM out[pix][32] = A[pix][96] * W[32][96]^T with A[pix][c*9 + ky*3 + kx] = tf32(obs[b][c][2y+ky][2x+kx] / 255)
 // (81 real columns).  TMA cannot express the stride-2 window gather over an NCHW fp32 image, so the A tile of 128 output
-// pixels is produced by eight producer warps (two groups of four alternate tiles): thread r of a group gathers the 81
-// values of pixel r straight from the observation (27 float2 + 27 float loads, consecutive lanes = consecutive 8-byte
-// words), scales / rounds them and writes its row as 24 16-byte units in the SWIZZLE_128B K-major layout the UMMA
+// pixels is produced by sixteen producer warps (two groups of eight alternate tiles; the producers are latency-bound, so
+// what matters is loads in flight): two threads per pixel gather its 81 values straight from the observation (k < 48 /
+// k >= 48; one float2 + one float load per (channel, ky), consecutive lanes = consecutive 8-byte words), scale / round
+// them and write their half of the row as 12 16-byte units in the SWIZZLE_128B K-major layout the UMMA
 // descriptor expects (unit u of row r at ((u ^ (r & 7)) << 4): every quarter-warp store covers all 32 banks),
 // fence.proxy.async, mbarrier arrive.  One thread issues the 12 MMAs (3 chunks x 4 k-steps of 128x32x8, TF32) per tile into
 // one of two TMEM accumulators; four epilogue warps add bias, apply ReLU, round to TF32 (the next layer's operand format)
@@ -25,36 +26,82 @@ constexpr int kStages = 4;                        // A stages; producer group g 
 constexpr int kChunkBytes = 128 * 128;            // [128 rows][32 floats]
 constexpr int kABytes = 3 * kChunkBytes;          // 48 KB
 constexpr int kWBytes = 3 * 32 * 128;             // 12 KB: three [32 co][32 k] chunks
-constexpr int kSmem = kStages * kABytes + kWBytes + 1024 + 256;
-constexpr int kThreads = 32 * 13;                 // warp 0 MMA, warps 1-4 epilogue, warps 5-12 producers
+constexpr int kSmem = kStages * kABytes + kWBytes + kChunkBytes + 1024 + 256;
+constexpr int kThreads = 32 * 21;                 // warp 0 MMA, warps 1-4 epilogue, warps 5-20 producers
 constexpr int kPix = 41 * 41;
+constexpr int kTilesPerSample = (kPix + 127) / 128;    // 14: tiles never straddle two samples (the last one of a sample has 17 rows)
 
 struct C1Params {
     const float* obs; const float* bias; float* out;
-    int n_pix, Hin, crop, num_tiles, col_first_tile, write_col;
+    int n_pix, Hin, crop, num_tiles, col_first_tile, write_col, B;
 };
 
-__device__ __forceinline__ void tma_store_2d(const CUtensorMap* tm, uint32_t src, int c0, int c1) {
-    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
-                 ::"l"((unsigned long long)tm), "r"(src), "r"(c0), "r"(c1) : "memory");
+// cvt.rna.tf32.f32 for finite inputs (round to nearest, ties away from zero, on the 13 dropped bits) with two integer
+// instructions instead of the conversion pipe (16 lanes / clk / SM: 113 conversions per pixel kept it half busy)
+__device__ __forceinline__ float rna_tf32(float v) { return __uint_as_float((__float_as_uint(v) + 0x1000u) & 0xFFFFE000u); }
+
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* tm, uint32_t src, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+                 ::"l"((unsigned long long)tm), "r"(src), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+
+// One producer thread's share of an A row: (channel, ky) pairs [PAIR0, PAIR0 + NPAIR) = k in [3 PAIR0, 3 (PAIR0 + NPAIR)),
+// zero padded to 48 values, stored as the 12 swizzled 16-byte units starting at unit UNIT0.
+template <int PAIR0, int NPAIR, int UNIT0>
+__device__ __forceinline__ void build_half_row(const float* __restrict__ src, size_t plane, int Hin, uint32_t srow, int r,
+                                               bool own_third) {
+    float a[48];
+#pragma unroll
+    for (int j = 0; j < NPAIR; ++j) {
+        const int c = (PAIR0 + j) / 3, ky = (PAIR0 + j) % 3;
+        const float* pr = src + c * plane + ky * Hin;
+        // pixel x needs columns 2x, 2x+1, 2x+2: the third is the next lane's first (the next pixel of the same output row);
+        // only the last lane / the last pixel of a row loads it itself -- halves the L1 requests of the gather
+        const float2 v01 = __ldg(reinterpret_cast<const float2*>(pr));
+        float v2 = __shfl_down_sync(0xffffffffu, v01.x, 1);
+        if (own_third) v2 = __ldg(pr + 2);
+        a[3 * j] = v01.x; a[3 * j + 1] = v01.y; a[3 * j + 2] = v2;
+    }
+    // x / 255 correctly rounded without the division subroutine (~40 instructions, it made the producers the bottleneck):
+    // q = x * rcp, r = x - 255 q exactly (FMA), q + r * rcp rounds to RN(x / 255) (Markstein; rcp = RN(1/255), 255's
+    // significand is not all ones; no overflow / underflow for pixel-range inputs)
+    const float rcp = 1.0f / 255.0f;
+#pragma unroll
+    for (int k = 0; k < 3 * NPAIR; ++k) {
+        const float q0 = a[k] * rcp;
+        const float rem = __fmaf_rn(-q0, 255.0f, a[k]);
+        a[k] = rna_tf32(__fmaf_rn(rem, rcp, q0));
+    }
+#pragma unroll
+    for (int k = 3 * NPAIR; k < 48; ++k) a[k] = 0.f;
+#pragma unroll
+    for (int j = 0; j < 12; ++j) {
+        const int u = UNIT0 + j;
+        const uint32_t addr = srow + (u >> 3) * kChunkBytes + (((u & 7) ^ (r & 7)) << 4);
+        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a[4 * j]), "f"(a[4 * j + 1]), "f"(a[4 * j + 2]),
+                     "f"(a[4 * j + 3]) : "memory");
+    }
 }
 
 __global__ void __launch_bounds__(kThreads, 1)
-conv1_fused_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmCol, C1Params p) {
+conv1_fused_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmCol,
+                      const __grid_constant__ CUtensorMap tmOut, C1Params p) {
     constexpr uint32_t kIdesc = idesc_tf32(32, false, false);
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t a_sm = base;
     const uint32_t w_sm = a_sm + kStages * kABytes;
-    const uint32_t bars = w_sm + kWBytes;
+    const uint32_t stg_sm = w_sm + kWBytes;                       // epilogue staging tile [128][32] (1024-byte aligned)
+    const uint32_t bars = stg_sm + kChunkBytes;
     const uint32_t full0 = bars, empty0 = full0 + 8 * kStages, wbar = empty0 + 8 * kStages;
     const uint32_t tfull0 = wbar + 8, tempty0 = tfull0 + 16, tmem_slot = tempty0 + 16;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"((unsigned long long)&tmW) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"((unsigned long long)&tmOut) : "memory");
         if (p.write_col) asm volatile("prefetch.tensormap [%0];" ::"l"((unsigned long long)&tmCol) : "memory");
-        for (int s = 0; s < kStages; ++s) { mbar_init(full0 + 8 * s, 128); mbar_init(empty0 + 8 * s, 1); }
+        for (int s = 0; s < kStages; ++s) { mbar_init(full0 + 8 * s, 256); mbar_init(empty0 + 8 * s, 1); }
         mbar_init(wbar, 1);
         for (int a = 0; a < 2; ++a) { mbar_init(tfull0 + 8 * a, 1); mbar_init(tempty0 + 8 * a, 128); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -100,13 +147,13 @@ conv1_fused_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_cons
         // ---- epilogue: TMEM lane quarter (warp & 3) -> bias, ReLU, TF32 round -> out[((b*43 + y)*41 + x)*32 ...]
         const int quarter = warp & 3;
         const int row = quarter * 32 + lane;
+        const bool e_elected = threadIdx.x == 32;
         float bv[32];
 #pragma unroll
         for (int c = 0; c < 32; ++c) bv[c] = __ldg(p.bias + c);
         int i = 0;
         for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++i) {
             const int acc = i & 1;
-            const int q = tile * 128 + row;
             mbar_wait(tfull0 + 8 * acc, (uint32_t)(i >> 1) & 1u);
             tc_fence_after();
             uint32_t v[32];
@@ -123,22 +170,36 @@ conv1_fused_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_cons
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
             tc_fence_before();
             mbar_arrive(tempty0 + 8 * acc);
-            if (q >= p.n_pix) continue;
-            const int b = q / kPix, rem = q - b * kPix, y = rem / 41, x = rem - y * 41;
-            float4* dst = reinterpret_cast<float4*>(p.out + ((size_t)(b * 43 + y) * 41 + x) * 32);
+            float o[32];
+#pragma unroll
+            for (int c = 0; c < 32; ++c) o[c] = rna_tf32(fmaxf(__uint_as_float(v[c]) + bv[c], 0.f));
+            // row-per-thread global stores touch 32 lines per instruction (3.4 M half-sector writes at 256 samples, a
+            // quarter of the kernel): stage the tile in the swizzled layout and let TMA write whole rows.  The output
+            // tensor is seen as [B][1681][32] with a sample stride of 43*41 rows; the last tile of a sample is clipped by
+            // the tensor bounds.
+            if (e_elected) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            asm volatile("bar.sync 4, 128;" ::: "memory");
 #pragma unroll
             for (int c4 = 0; c4 < 8; ++c4) {
-                float o[4];
-#pragma unroll
-                for (int e = 0; e < 4; ++e) o[e] = round_tf32(fmaxf(__uint_as_float(v[4 * c4 + e]) + bv[4 * c4 + e], 0.f));
-                dst[c4] = make_float4(o[0], o[1], o[2], o[3]);
+                const uint32_t addr = stg_sm + row * 128 + ((c4 ^ (row & 7)) << 4);
+                asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(o[4 * c4]), "f"(o[4 * c4 + 1]), "f"(o[4 * c4 + 2]),
+                             "f"(o[4 * c4 + 3]) : "memory");
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            asm volatile("bar.sync 4, 128;" ::: "memory");
+            if (e_elected) {
+                const int b0 = tile / kTilesPerSample, p0 = (tile - b0 * kTilesPerSample) * 128;
+                tma_store_3d(&tmOut, stg_sm, 0, p0, b0);
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
             }
         }
+        if (e_elected) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     } else {
-        // ---- producers: group g = tiles i with i % 2 == g; thread r builds row r of the A tile
-        const int g = (warp - 5) >> 2;
-        const int r = ((warp - 5) & 3) * 32 + lane;
-        const bool elected = r == 0;
+        // ---- producers: group g = tiles i with i % 2 == g; threads (r, half) build the two halves of row r of the A tile
+        const int g = (warp - 5) >> 3;
+        const int pt = ((warp - 5) & 7) * 32 + lane;
+        const int r = pt & 127, half = pt >> 7;
+        const bool elected = pt == 0;
         const int Hin = p.Hin;
         const size_t plane = (size_t)Hin * Hin;
         int i = g;
@@ -148,40 +209,24 @@ conv1_fused_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_cons
             mbar_wait(empty0 + 8 * stage, ((uint32_t)(i / kStages) & 1u) ^ 1u);
             if (p.write_col) {                       // the TMA store that read this stage two group-tiles ago must be done
                 if (elected) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-                asm volatile("bar.sync %0, 128;" ::"r"(2 + g) : "memory");
+                asm volatile("bar.sync %0, 256;" ::"r"(2 + g) : "memory");
             }
-            const int q = tile * 128 + r;
-            if (q < p.n_pix) {
-                const int b = q / kPix, rem = q - b * kPix, y = rem / 41, x = rem - y * 41;
+            const int b = tile / kTilesPerSample, p0 = (tile - b * kTilesPerSample) * 128;
+            {
+                const int rem = min(p0 + r, kPix - 1);           // rows past the sample's end repeat its last pixel (never stored)
+                const int y = rem / 41, x = rem - y * 41;
                 const float* src = p.obs + (size_t)b * 9 * plane + (size_t)(2 * y + p.crop) * Hin + 2 * x + p.crop;
-                float a[96];
-#pragma unroll
-                for (int c = 0; c < 9; ++c)
-#pragma unroll
-                    for (int ky = 0; ky < 3; ++ky) {
-                        const float* pr = src + c * plane + ky * Hin;
-                        const float2 v01 = __ldg(reinterpret_cast<const float2*>(pr));
-                        const float v2 = __ldg(pr + 2);
-                        a[c * 9 + ky * 3 + 0] = v01.x; a[c * 9 + ky * 3 + 1] = v01.y; a[c * 9 + ky * 3 + 2] = v2;
-                    }
-#pragma unroll
-                for (int k = 0; k < 81; ++k) a[k] = round_tf32(__fdiv_rn(a[k], 255.0f));
-#pragma unroll
-                for (int k = 81; k < 96; ++k) a[k] = 0.f;
-#pragma unroll
-                for (int u = 0; u < 24; ++u) {
-                    const uint32_t addr = srow + (u >> 3) * kChunkBytes + (((u & 7) ^ (r & 7)) << 4);
-                    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a[4 * u]), "f"(a[4 * u + 1]),
-                                 "f"(a[4 * u + 2]), "f"(a[4 * u + 3]) : "memory");
-                }
+                const bool own_third = lane == 31 || x == 40;
+                if (half == 0) build_half_row<0, 16, 0>(src, plane, Hin, srow, r, own_third);
+                else build_half_row<16, 11, 12>(src, plane, Hin, srow, r, own_third);
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             mbar_arrive(full0 + 8 * stage);
             if (p.write_col) {
-                asm volatile("bar.sync %0, 128;" ::"r"(2 + g) : "memory");     // every row written and fenced
+                asm volatile("bar.sync %0, 256;" ::"r"(2 + g) : "memory");     // every row written and fenced
                 if (elected) {
                     if (tile >= p.col_first_tile)
-                        for (int c = 0; c < 3; ++c) tma_store_2d(&tmCol, a_sm + stage * kABytes + c * kChunkBytes, c * 32, tile * 128);
+                        for (int c = 0; c < 3; ++c) tma_store_3d(&tmCol, a_sm + stage * kABytes + c * kChunkBytes, c * 32, p0, b);
                     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                 }
             }
@@ -201,7 +246,7 @@ conv1_fused_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_cons
 // obs: (B, 9, Hin, Hin) fp32 NCHW with values 0..255 (Hin = 84, or 100 = centre crop, modules.py:70-83); w1p: TF32 operand
 // copy [32][96] of the conv weight (sgqn_conv1_weights_prep); out: relu(conv1(obs / 255)) rounded to TF32, pitch-linear
 // [B][43][41][32] (rows 41, 42 of every sample are never written).  col (optional): im2col matrix [B*1681][96] for the
-// weight gradient, written for the 128-pixel tiles that contain samples >= col_row0 (earlier rows of col: unspecified).
+// weight gradient, written for the samples >= col_row0 (earlier rows of col are not touched).
 extern "C" int sgqn_conv1_fused_tc(const float* obs, const float* w1p, const float* bias, float* out, float* col, int B, int Hin,
                                    int col_row0, void* stream) {
     if (B <= 0) return 0;
@@ -218,14 +263,28 @@ extern "C" int sgqn_conv1_fused_tc(const float* obs, const float* w1p, const flo
     C1Params p;
     p.obs = obs; p.bias = bias; p.out = out;
     p.n_pix = B * kPix; p.Hin = Hin; p.crop = (Hin - 84) / 2;
-    p.num_tiles = (p.n_pix + 127) / 128;
+    p.num_tiles = B * kTilesPerSample;
     p.write_col = col != nullptr && col_row0 < B;
-    p.col_first_tile = p.write_col ? (col_row0 * kPix) / 128 : p.num_tiles;
-    CUtensorMap tmW, tmCol;
+    p.B = B;
+    p.col_first_tile = p.write_col ? col_row0 * kTilesPerSample : p.num_tiles;
+    CUtensorMap tmW, tmCol, tmOut;
     int rc = make_map_2d(&tmW, w1p, 96, 32, 32, 32);
     if (rc) return rc;
-    rc = make_map_2d(&tmCol, p.write_col ? col : w1p, 96, p.write_col ? (uint64_t)p.n_pix : 32, 32, p.write_col ? 128 : 32);
+    EncodeTiledFn enc = get_encode_fn();
+    if (!enc) return (int)cudaErrorNotSupported;
+    auto map3 = [&](CUtensorMap* tm, const float* ptr, int cols, uint64_t sample_stride_bytes) -> int {      // [B][1681][cols], box {32, 128, 1}
+        cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)kPix, (cuuint64_t)B};
+        cuuint64_t strides[2] = {(cuuint64_t)cols * 4, sample_stride_bytes};
+        cuuint32_t box[3] = {32, 128, 1};
+        cuuint32_t estr[3] = {1, 1, 1};
+        CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        return r == CUDA_SUCCESS ? 0 : 900 + (int)r;
+    };
+    rc = map3(&tmOut, out, 32, (uint64_t)43 * 41 * 128);
+    if (rc) return rc;
+    rc = map3(&tmCol, p.write_col ? col : out, p.write_col ? 96 : 32, p.write_col ? (uint64_t)kPix * 384 : (uint64_t)43 * 41 * 128);
     if (rc) return rc;
     int grid = p.num_tiles < num_sms ? p.num_tiles : num_sms;
-    return launch_pdl(conv1_fused_tc_kernel, dim3(grid), dim3(kThreads), kSmem, stream, tmW, tmCol, p);
+    return launch_pdl(conv1_fused_tc_kernel, dim3(grid), dim3(kThreads), kSmem, stream, tmW, tmCol, tmOut, p);
 }
