@@ -123,6 +123,8 @@ int sgqn_conv1_fused_tc(const float* obs, const float* w1p, const float* bias, f
 int sgqn_conv_weights_prep_g(const float* w, float* wf, float* wd, int Cout, int Cin, int Cout_real, void* stream);
 int sgqn_conv_wgrad_tcg(const float* x, const float* dy, float* dw, int B, int Hr, int Wp, int Cin, int Cout, int ta, int tb,
                         void* stream);
+int sgqn_conv_wgrad_tcg_ld(const float* x, const float* dy, int ldy, float* dw, int B, int Hr, int Wp, int Cin, int Cout, int ta,
+                           int tb, void* stream);   /* dy = a Cout-column block of rows that are ldy floats apart */
 int sgqn_pool2_bwd(const float* dup, const float* src, float* dst, int B, int H, int W, int C, void* stream);
 /* Sub-pixel ("phase") form of conv3x3(pad 1) after F.upsample(x, 2) (modules.py:333-337 then :324-326): a 3x3 pad-1 conv at LOW
  * resolution with 4*Cg output channels -- phase p = 2a+b, channels [p*Cg, p*Cg+Cout_real) = output pixel (2y+a, 2x+b) -- run

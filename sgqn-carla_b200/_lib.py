@@ -48,6 +48,7 @@ SIGNATURES = {
     "sgqn_conv_weights_prep_phase": [_p, _p, _p, _p, _p, _i, _i, _i, _p],
     "sgqn_conv_phase_fold": [_p, _p, _p, _p, _i, _i, _i, _p],
     "sgqn_bce_phase": [_p, _p, _p, _p] + [_i] * 9 + [_p],
+    "sgqn_conv_wgrad_tcg_ld": [_p, _p, _i, _p, _i, _i, _i, _i, _i, _i, _i, _p],
     "sgqn_pool2_bwd": [_p, _p, _p, _i, _i, _i, _i, _p],
     "sgqn_upsample2_bwd": [_p, _p, _p, _i, _i, _i, _i, _p],
     "sgqn_minmax": [_p, _ll, _p, _p, _p],

@@ -32,6 +32,7 @@ struct GParams {
     const float* mask;
     float* out;
     int relu_out, round_out, mask_mode, upsample;
+    int shuffle;            // 0 none, 1 depth-to-space (phase channels -> 2x2 pixels), 2 space-to-depth (pixel -> phase channels)
 };
 
 template <int N>
@@ -39,7 +40,7 @@ __global__ void __launch_bounds__(320, 1)
 conv3x3_tcg_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, GParams p) {
     constexpr int kWBytes = N * 128;
     constexpr uint32_t kIdescN = idesc_tf32(N, false, false);
-    constexpr int kTmemCols = 2 * N <= 64 ? 64 : (2 * N <= 128 ? 128 : 256);      // power of two >= two accumulators
+    constexpr int kTmemCols = 2 * N <= 64 ? 64 : (2 * N <= 128 ? 128 : (2 * N <= 256 ? 256 : 512));   // power of two >= two accumulators
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t a_sm = base;
@@ -126,6 +127,64 @@ conv3x3_tcg_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             }
         }
     } else {
+        if constexpr (N > 128) {
+            // N = 256 (phase convs, 4 x 64 channels): 128 accumulator columns per thread, drained 32 at a time.  With
+            // depth-to-space (p.shuffle == 1) channel block ph = 2a + b' goes to pixel (2y+a, 2x+b') of a 64-channel output.
+            const int quarter = warp & 3;
+            const int half = (warp - 2) >> 2;
+            const int row = quarter * 32 + lane;
+            int acc = 0; uint32_t acc_phase = 0;
+            const int HW = p.Hr * p.Wp;
+            constexpr int NG = N / 4;                    // channels per phase
+            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+                const int q = tile * kTileM + row;
+                const int b = q / HW; const int r2 = q - b * HW; const int y = r2 / p.Wp; const int x = r2 - y * p.Wp;
+                const bool valid = q < p.total_q && y < p.Hv && x < p.Wv;
+                mbar_wait(tfull0 + 8 * acc, acc_phase);
+                tc_fence_after();
+#pragma unroll 1
+                for (int g = 0; g < N / 2 / 32; ++g) {
+                    const int c0 = half * (N / 2) + g * 32;
+                    uint32_t v[32];
+                    const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * N + c0);
+                    asm volatile(
+                        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+                          "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+                          "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                        : "r"(taddr) : "memory");
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                    if (!valid) continue;
+                    float* dst;
+                    if (p.shuffle == 1) {
+                        const int ph = c0 / NG, cc = c0 - ph * NG;
+                        dst = p.out + ((size_t)(b * p.Hq + 2 * y + (ph >> 1) + p.oy) * p.Wq + 2 * x + (ph & 1) + p.ox) * NG + cc;
+                    } else {
+                        dst = p.out + ((size_t)(b * p.Hq + y + p.oy) * p.Wq + x + p.ox) * N + c0;
+                    }
+#pragma unroll
+                    for (int c4 = 0; c4 < 8; ++c4) {
+                        float o[4];
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            float bv;
+                            asm volatile("ld.shared.f32 %0, [%1];" : "=f"(bv) : "r"(bias_sm + 4 * (c0 + 4 * c4 + e)));
+                            float f = __uint_as_float(v[4 * c4 + e]) + bv;
+                            if (p.relu_out) f = fmaxf(f, 0.f);
+                            if (p.round_out) f = round_tf32(f);
+                            o[e] = f;
+                        }
+                        reinterpret_cast<float4*>(dst)[c4] = make_float4(o[0], o[1], o[2], o[3]);
+                    }
+                }
+                tc_fence_before();
+                mbar_arrive(tempty0 + 8 * acc);
+                if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+            }
+        } else {
         constexpr int CPW = N / 2;                       // accumulator columns per epilogue warp
         const int quarter = warp & 3;
         const int half = (warp - 2) >> 2;
@@ -160,6 +219,8 @@ conv3x3_tcg_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             const float* mk = p.mask_mode ? p.mask + ((size_t)(b * p.Hm + y) * p.Wm + x) * N + c0 : nullptr;
             float* dst0;
             if (p.upsample) dst0 = p.out + ((size_t)(b * p.Hq + 2 * y + p.oy) * p.Wq + 2 * x + p.ox) * N + c0;
+            else if (p.shuffle == 2)      // space-to-depth: pixel (y,x) -> low-res pixel (y/2, x/2), channel block 2(y&1) + (x&1) of 4N
+                dst0 = p.out + ((size_t)(b * p.Hq + (y >> 1) + p.oy) * p.Wq + (x >> 1) + p.ox) * (4 * N) + (2 * (y & 1) + (x & 1)) * N + c0;
             else dst0 = p.out + ((size_t)(b * p.Hq + y + p.oy) * p.Wq + x + p.ox) * N + c0;
 #pragma unroll
             for (int c4 = 0; c4 < CPW / 4; ++c4) {
@@ -194,6 +255,7 @@ conv3x3_tcg_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                 }
             }
         }
+            }
     }
     tc_fence_before();
     __syncthreads();
@@ -225,7 +287,9 @@ int launch_tcg(const CUtensorMap& tmA, const CUtensorMap& tmW, const GParams& p,
 // [Cin_orig][9 flipped][Cout_orig] (data gradient), made by sgqn_conv_weights_prep_g.  Output (b,y,x), y < Hv, x < Wv, is the
 // 3x3 window sum over input rows q + ky*Wp + kx + shift, q = (b*Hr + y)*Wp + x, and goes to
 // out[((b*Hq + y+oy)*Wq + x+ox)*Cout]; with flags bit4 it goes to the 2x2 block at (2y+oy, 2x+ox) (nearest upsample).
-// flags: bit0 ReLU, bit1 TF32 round, bits 2-3 mask mode against mask[((b*Hm + y)*Wm + x)*Cout], bit4 upsample.
+// flags: bit0 ReLU, bit1 TF32 round, bits 2-3 mask mode against mask[((b*Hm + y)*Wm + x)*Cout], bit4 upsample,
+// bits 5-6: 1 = depth-to-space (Cout = 256 = 4 phases x 64: phase 2a+b' of (y,x) -> pixel (2y+a+oy, 2x+b'+ox) of a 64-channel
+// buffer), 2 = space-to-depth (pixel (y,x) -> channel block 2(y&1)+(x&1) of low-res pixel (y/2+oy, x/2+ox) in a 4*Cout-channel buffer).
 extern "C" int sgqn_conv_tcg(const float* x, const float* wop, const float* bias, const float* mask, float* out, int B, int Hr,
                              int Wp, int Cin, int Cout, int Hv, int Wv, int shift, int Hq, int Wq, int oy, int ox, int Hm, int Wm,
                              int flags, void* stream) {
@@ -238,7 +302,7 @@ extern "C" int sgqn_conv_tcg_taps(const float* x, const float* wop, const float*
                                   int Wp, int Cin, int Cout, int Hv, int Wv, int shift, int Hq, int Wq, int oy, int ox, int Hm,
                                   int Wm, int flags, int ntaps, void* stream) {
     if (B <= 0) return 0;
-    if ((Cin & 31) || (Cout != 32 && Cout != 64 && Cout != 96 && Cout != 128)) return (int)cudaErrorInvalidValue;
+    if ((Cin & 31) || (Cout != 32 && Cout != 64 && Cout != 96 && Cout != 128 && Cout != 256)) return (int)cudaErrorInvalidValue;
     GParams p;
     p.total_q = B * Hr * Wp; p.Hr = Hr; p.Wp = Wp; p.Hv = Hv; p.Wv = Wv; p.shift = shift;
     p.Hq = Hq; p.Wq = Wq; p.oy = oy; p.ox = ox; p.Hm = Hm; p.Wm = Wm;
@@ -247,6 +311,9 @@ extern "C" int sgqn_conv_tcg_taps(const float* x, const float* wop, const float*
     if (ntaps != 1 && ntaps != 9) return (int)cudaErrorInvalidValue;
     p.bias = bias; p.mask = mask; p.out = out;
     p.relu_out = flags & 1; p.round_out = (flags >> 1) & 1; p.mask_mode = (flags >> 2) & 3; p.upsample = (flags >> 4) & 1;
+    p.shuffle = (flags >> 5) & 3;
+    if ((p.shuffle == 1) != (Cout == 256) || (Cout == 256 && (p.mask_mode || p.upsample)) || (p.shuffle == 2 && p.upsample) || p.shuffle == 3)
+        return (int)cudaErrorInvalidValue;      // N = 256 exists for the depth-to-space phase conv only
     if (p.mask_mode && !mask) return (int)cudaErrorInvalidValue;
     int halo = ntaps == 9 ? kTileM + 2 * Wp + 2 : kTileM;
     p.pieces = halo > 256 ? 2 : 1;
@@ -269,6 +336,7 @@ extern "C" int sgqn_conv_tcg_taps(const float* x, const float* wop, const float*
     if (Cout == 32) return launch_tcg<32>(tmA, tmW, p, smem, st);
     if (Cout == 64) return launch_tcg<64>(tmA, tmW, p, smem, st);
     if (Cout == 96) return launch_tcg<96>(tmA, tmW, p, smem, st);
+    if (Cout == 256) return launch_tcg<256>(tmA, tmW, p, smem, st);
     return launch_tcg<128>(tmA, tmW, p, smem, st);
 }
 
@@ -515,8 +583,21 @@ extern "C" int sgqn_conv_wgrad_tcg(const float* x, const float* dy, float* dw, i
 }
 
 // ntaps = 1: dw[Cout][kvalid] += dy^T[Cout][rows] * x[rows][:kvalid]  (weight gradient of a per-position GEMM; Wp/ta/tb unused)
+static int wgrad_tcg_impl(const float* x, const float* dy, int ldy, float* dw, int B, int Hr, int Wp, int Cin, int Cout, int ta,
+                          int tb, int ntaps, int kvalid, void* stream);
 extern "C" int sgqn_gemm_wgrad_tcg(const float* x, const float* dy, float* dw, int B, int Hr, int Wp, int Cin, int Cout, int ta,
                                    int tb, int ntaps, int kvalid, void* stream) {
+    return wgrad_tcg_impl(x, dy, Cout, dw, B, Hr, Wp, Cin, Cout, ta, tb, ntaps, kvalid, stream);
+}
+// The 3x3 weight gradient against a column block of a wider dy: dy rows are ldy floats apart, the Cout columns starting at
+// `dy` are used (dw[Cout][9][Cin] of that block).  The phase form of conv2 has 256 output channels = two blocks of 128.
+extern "C" int sgqn_conv_wgrad_tcg_ld(const float* x, const float* dy, int ldy, float* dw, int B, int Hr, int Wp, int Cin, int Cout,
+                                      int ta, int tb, void* stream) {
+    if (ldy < Cout || (ldy & 3)) return (int)cudaErrorInvalidValue;
+    return wgrad_tcg_impl(x, dy, ldy, dw, B, Hr, Wp, Cin, Cout, ta, tb, 9, 0, stream);
+}
+static int wgrad_tcg_impl(const float* x, const float* dy, int ldy, float* dw, int B, int Hr, int Wp, int Cin, int Cout, int ta,
+                          int tb, int ntaps, int kvalid, void* stream) {
     if (B <= 0) return 0;
     if (ntaps != 1 && ntaps != 9) return (int)cudaErrorInvalidValue;
     if ((Cin & 31) || (Cout != 32 && Cout != 64 && Cout != 128) || (Cin / 32) * Cout > 512) return (int)cudaErrorInvalidValue;
@@ -531,7 +612,7 @@ extern "C" int sgqn_gemm_wgrad_tcg(const float* x, const float* dy, float* dw, i
     CUtensorMap tmX, tmD;
     int rc = make_map_2d(&tmX, x, (uint64_t)Cin, (uint64_t)p.total_q, 32, kGwXRows, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
     if (rc) return rc;
-    rc = make_map_2d(&tmD, dy, (uint64_t)Cout, (uint64_t)p.total_q, 32, kGwRows, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+    rc = make_map_2d(&tmD, dy, (uint64_t)ldy, (uint64_t)p.total_q, 32, kGwRows, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
     if (rc) return rc;
     cudaStream_t st = (cudaStream_t)stream;
     if (Cout == 32) return launch_wgrad_tcg<32>(tmX, tmD, p, st);

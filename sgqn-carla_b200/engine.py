@@ -127,27 +127,28 @@ class UpdateEngine:
         if algorithm == "sgsac":
             self.s_tilde = self.obs2[B:]                 # overlay-augmented obs (written after the critic update)
             self.dl = f32(B, FEAT); self.ddl = f32(B, FEAT)
-            self.d1 = f32(B * 21 * 21 * 128); self.dd1 = f32(B * 21 * 21 * 128)
-            self.d2 = f32(B * 42 * 42 * 64); self.dd2 = f32(B * 42 * 42 * 64)
-            self.dup2 = f32(B * 42 * 42 * 128)
             if precision != "tf32":
+                self.d1 = f32(B * 21 * 21 * 128); self.dd1 = f32(B * 21 * 21 * 128)
+                self.d2 = f32(B * 42 * 42 * 64); self.dd2 = f32(B * 42 * 42 * 64)
+                self.dup2 = f32(B * 42 * 42 * 128)
                 self.lg = f32(B * 86 * 86 * DEC_C3); self.dlg = f32(B * 86 * 86 * DEC_C3)
                 self.dup3 = f32(B * 84 * 84 * 64)
             if precision == "tf32":
                 # tcgen05 decoder: zero-bordered pitch-linear buffers [B][H+2][W+2][C], image at rows [1,H+1), cols [0,W)
-                # (borders are zero from this allocation on; kernels only ever write the interior)
+                # (borders are zero from this allocation on; kernels only ever write the interior).  conv2 and conv3 run in
+                # their sub-pixel ("phase") form on the PRE-upsample activations (conv_tcg.cu, sgqn_conv_weights_prep_phase):
+                # the nearest-x2 upsampled tensors (127 MB + 242 MB at B = 128) and their gradients are never materialised.
                 self.xin1 = f32(B * 23 * 23 * 32)        # relu(proj output)
-                self.xin2 = f32(B * 44 * 44 * 128)       # up2(relu(conv1))
-                # conv3 runs in its sub-pixel form on relu(conv2) at 42x42 (conv_tcg.cu, sgqn_conv_weights_prep_phase): the
-                # 84x84x64 upsampled tensor (242 MB at B = 128) and its gradient are never materialised
-                self.xin3 = f32(B * 44 * 44 * 64)        # relu(conv2), zero-bordered
+                self.xin2 = f32(B * 23 * 23 * 128)       # relu(conv1)
+                self.xin3 = f32(B * 44 * 44 * 64)        # relu(conv2)
                 self.lgp = f32(B * 44 * 44 * 64); self.dlgp = f32(B * 44 * 44 * 64)   # logits / d logits, [4 phases][16]
-                self.w3f, self.w3d, self.b3p = f32(64 * 9 * 64), f32(64 * 9 * 64), f32(64)
-                self.dw3p, self.db3p = f32(64 * 9 * 64), f32(64)
-                self.dd2g = f32(B * 44 * 44 * 64)        # d conv2 output
+                self.dd2s = f32(B * 23 * 23 * 256)       # d conv2 output in space-to-depth form [4 phases][64]
                 self.dd1g = f32(B * 23 * 23 * 128)       # d conv1 output
-                self.dwf = [f32(128 * 9 * 32), f32(64 * 9 * 128)]     # TF32 operand copies (forward) of conv1 / conv2
-                self.dwd = [f32(128 * 9 * 32), f32(64 * 9 * 128)]     # ... (data gradient)
+                self.dwf, self.dwd = f32(128 * 9 * 32), f32(128 * 9 * 32)             # TF32 operand copies of conv1 (fwd / dgrad)
+                self.w2f, self.w2d, self.b2p = f32(256 * 9 * 128), f32(256 * 9 * 128), f32(256)
+                self.w3f, self.w3d, self.b3p = f32(64 * 9 * 64), f32(64 * 9 * 64), f32(64)
+                self.dw2p, self.db2p = f32(256 * 9 * 128), f32(256)
+                self.dw3p, self.db3p = f32(64 * 9 * 64), f32(64)
         if algorithm == "svea":
             self.places = f32(B, 3, 84 * 84)
         self.debug_masked_obs = None
@@ -224,8 +225,9 @@ class UpdateEngine:
     def prep_dec_weights(self):
         if self.algorithm != "sgsac" or self.precision != "tf32":
             return
-        for i, (name, co, ci, cr) in enumerate((("dec.conv1.weight", 128, 32, 128), ("dec.conv2.weight", 64, 128, 64))):
-            K.conv_weights_prep_g(self.P(name), _ptr(self.dwf[i]), _ptr(self.dwd[i]), co, ci, cr, self.st)
+        K.conv_weights_prep_g(self.P("dec.conv1.weight"), _ptr(self.dwf), _ptr(self.dwd), 128, 32, 128, self.st)
+        K.conv_weights_prep_phase(self.P("dec.conv2.weight"), self.P("dec.conv2.bias"), _ptr(self.w2f), _ptr(self.w2d),
+                                  _ptr(self.b2p), 128, 64, 64, self.st)
         K.conv_weights_prep_phase(self.P("dec.conv3.weight"), self.P("dec.conv3.bias"), _ptr(self.w3f), _ptr(self.w3d),
                                   _ptr(self.b3p), 64, 9, 16, self.st)
 
@@ -590,41 +592,48 @@ class UpdateEngine:
 
     def _decoder_tc(self, B, st, Wp, G, x0, x1):
         """The same on the generalised tcgen05 kernels (conv_tcg.cu).  Every conv reads a zero-bordered pitch-linear
-        buffer [B][H+2][W+2][C] (image at rows [1,H+1), cols [0,W)); conv1 / conv2 write ReLU + nearest-x2 upsample + TF32
-        rounding of their output straight into the next conv's input buffer (modules.py:327-337 fused into the producer)."""
-        wf, wd = self.dwf, self.dwd
-        RU = 1 | 2 | 16                                       # ReLU, TF32 round, 2x2 upsample scatter
+        buffer [B][H+2][W+2][C] (image at rows [1,H+1), cols [0,W)).  conv2 / conv3 -- the convs that follow F.upsample
+        (modules.py:327-337) -- run in sub-pixel form at the resolution of their PRE-upsample input: 4x the output
+        channels (one block per output phase), ReLU + TF32 rounding fused into the producer, depth-to-space in conv2's
+        epilogue, and the BCE / data gradients work on the phase layout."""
+        R = 1 | 2                                             # ReLU, TF32 round
         K.pad_copy(_ptr(self.dl), _ptr(self.xin1), B, 21, 21, 32, 23, 23, 1, 0, 3, st)
-        K.conv_tcg(_ptr(self.xin1), _ptr(wf[0]), Wp("dec.conv1.bias"), 0, _ptr(self.xin2), B, 23, 23, 32, 128, 21, 21, -1,
-                   44, 44, 1, 0, 0, 0, RU, st)
-        K.conv_tcg(_ptr(self.xin2), _ptr(wf[1]), Wp("dec.conv2.bias"), 0, _ptr(self.xin3), B, 44, 44, 128, 64, 42, 42, -1,
-                   44, 44, 1, 0, 0, 0, 1 | 2, st)             # relu(conv2) at 42x42: conv3 consumes it in sub-pixel form
+        K.conv_tcg(_ptr(self.xin1), _ptr(self.dwf), Wp("dec.conv1.bias"), 0, _ptr(self.xin2), B, 23, 23, 32, 128, 21, 21, -1,
+                   23, 23, 1, 0, 0, 0, R, st)                 # relu(conv1) at 21x21
+        K.conv_tcg(_ptr(self.xin2), _ptr(self.w2f), _ptr(self.b2p), 0, _ptr(self.xin3), B, 23, 23, 128, 256, 21, 21, -1,
+                   44, 44, 1, 0, 0, 0, R | (1 << 5), st)      # relu(conv2(up2(.))) at 42x42 (depth-to-space epilogue)
         K.conv_tcg(_ptr(self.xin3), _ptr(self.w3f), _ptr(self.b3p), 0, _ptr(self.lgp), B, 44, 44, 64, 64, 42, 42, -1,
-                   44, 44, 1, 0, 0, 0, 0, st)
+                   44, 44, 1, 0, 0, 0, 0, st)                 # conv3(up2(.)) logits, kept in phase layout
         K.zero(_ptr(self.logs, 4), 4, st)
         K.bce_phase(_ptr(self.lgp), _ptr(self.mask), _ptr(self.logs, 4), _ptr(self.dlgp), B, 84, 84, 44, 44, 1, 0, self.Bg, 1, st)
         K.zero(self._g + 4 * x0, 4 * (x1 - x0), st)
-        # conv3 backward, all at 42x42: phase weight gradient folded back onto the 3x3 taps; the data gradient lands on
-        # relu(conv2) directly (sum over phases = the 2x2 sum-pool of the upsample backward) with its ReLU mask fused
+        # conv3 backward at 42x42: phase weight gradient folded back onto the 3x3 taps; the data gradient lands on
+        # relu(conv2) directly (sum over phases = the 2x2 sum-pool of the upsample backward) with its ReLU mask fused, and
+        # is written in space-to-depth form = the phase layout of conv2's output gradient
         ws = self._fork()                                     # weight / bias gradients beside the data-gradient chain
         K.zero(_ptr(self.dw3p), 4 * self.dw3p.numel(), ws)
         K.zero(_ptr(self.db3p), 4 * 64, ws)
         K.conv_wgrad_tcg(_ptr(self.xin3), _ptr(self.dlgp), _ptr(self.dw3p), B, 44, 44, 64, 64, -1, -1, ws)
         K.colsum(_ptr(self.dlgp), 64, B * 44 * 44, 64, _ptr(self.db3p), ws)
         K.conv_phase_fold(_ptr(self.dw3p), _ptr(self.db3p), G("dec.conv3.weight"), G("dec.conv3.bias"), 64, 9, 16, ws)
-        K.conv_tcg(_ptr(self.dlgp), _ptr(self.w3d), 0, _ptr(self.xin3, 44 * 64), _ptr(self.dd2g), B, 44, 44, 64, 64, 42, 42, -1,
-                   44, 44, 1, 0, 44, 44, (1 << 2) | 2, st)
-        # conv2 backward
+        K.conv_tcg(_ptr(self.dlgp), _ptr(self.w3d), 0, _ptr(self.xin3, 44 * 64), _ptr(self.dd2s), B, 44, 44, 64, 64, 42, 42, -1,
+                   23, 23, 1, 0, 44, 44, (1 << 2) | 2 | (2 << 5), st)
+        # conv2 backward at 21x21 (256 phase channels: the weight gradient runs as two blocks of 128)
         ws = self._fork()
-        K.conv_wgrad_tcg(_ptr(self.xin2), _ptr(self.dd2g), G("dec.conv2.weight"), B, 44, 44, 128, 64, -1, -1, ws)
-        K.colsum(_ptr(self.dd2g), 64, B * 44 * 44, 64, G("dec.conv2.bias"), ws)
-        K.conv_tcg(_ptr(self.dd2g), _ptr(wd[1]), 0, 0, _ptr(self.dup2), B, 44, 44, 64, 128, 42, 42, -1, 42, 42, 0, 0, 0, 0, 0, st)
-        K.pool2_bwd(_ptr(self.dup2), _ptr(self.xin2), _ptr(self.dd1g), B, 21, 21, 128, st)
+        K.zero(_ptr(self.dw2p), 4 * self.dw2p.numel(), ws)
+        K.zero(_ptr(self.db2p), 4 * 256, ws)
+        for h in range(2):
+            K.conv_wgrad_tcg_ld(_ptr(self.xin2), _ptr(self.dd2s, 128 * h), 256, _ptr(self.dw2p, h * 128 * 9 * 128), B, 23, 23, 128, 128,
+                                -1, -1, ws)
+        K.colsum(_ptr(self.dd2s), 256, B * 23 * 23, 256, _ptr(self.db2p), ws)
+        K.conv_phase_fold(_ptr(self.dw2p), _ptr(self.db2p), G("dec.conv2.weight"), G("dec.conv2.bias"), 128, 64, 64, ws)
+        K.conv_tcg(_ptr(self.dd2s), _ptr(self.w2d), 0, _ptr(self.xin2, 23 * 128), _ptr(self.dd1g), B, 23, 23, 256, 128, 21, 21, -1,
+                   23, 23, 1, 0, 23, 23, (1 << 2) | 2, st)
         # conv1 backward (ReLU mask of the projection output)
         ws = self._fork()
         K.conv_wgrad_tcg(_ptr(self.xin1), _ptr(self.dd1g), G("dec.conv1.weight"), B, 23, 23, 32, 128, -1, -1, ws)
         K.colsum(_ptr(self.dd1g), 128, B * 23 * 23, 128, G("dec.conv1.bias"), ws)
-        K.conv_tcg(_ptr(self.dd1g), _ptr(wd[0]), 0, _ptr(self.dl), _ptr(self.ddl), B, 23, 23, 128, 32, 21, 21, -1, 21, 21, 0, 0,
+        K.conv_tcg(_ptr(self.dd1g), _ptr(self.dwd), 0, _ptr(self.dl), _ptr(self.ddl), B, 23, 23, 128, 32, 21, 21, -1, 21, 21, 0, 0,
                    21, 21, 1 << 2, st)
         self._join()
 

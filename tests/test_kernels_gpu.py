@@ -690,30 +690,44 @@ def test_conv_tcg_forward_dgrad_wgrad(B, H, Cin, Co, Cs):
     close(dw.reshape(Cs, 3, 3, Cin).permute(0, 3, 1, 2)[:Co], wr.grad.float(), rtol=3e-5, what="conv_wgrad_tcg")
 
 
-@pytest.mark.parametrize("B,Hl,Cin,Co,Cg", [(2, 42, 64, 9, 16), (3, 10, 64, 9, 16), (1, 21, 32, 5, 8)])
+@pytest.mark.parametrize("B,Hl,Cin,Co,Cg", [(2, 42, 64, 9, 16), (3, 10, 64, 9, 16), (1, 21, 32, 5, 8), (2, 21, 128, 64, 64), (1, 7, 128, 64, 64)])
 def test_phase_conv_equals_conv_after_upsample(B, Hl, Cin, Co, Cg):
     """conv3x3(pad 1) o F.upsample(x, 2) in its sub-pixel form (sgqn_conv_weights_prep_phase + sgqn_conv_tcg at low
-    resolution + sgqn_conv_phase_fold) against torch on the materialised upsampled tensor: forward logits, masked data
-    gradient w.r.t. the low-res activation, folded weight / bias gradients."""
+    resolution + sgqn_conv_phase_fold) against torch on the materialised upsampled tensor: forward (phase layout, or
+    depth-to-space epilogue for the 256-channel conv2 form), masked data gradient w.r.t. the low-res activation (also
+    written in space-to-depth form), folded weight / bias gradients."""
     Np, H = 4 * Cg, 2 * Hl
-    if Np not in (32, 64, 128):
-        pytest.skip("conv_tcg N")
     x = tf32_round(F.relu(rnd(B, Cin, Hl, Hl, seed=1)))
     w = rnd(Co, Cin, 3, 3, seed=2, scale=0.05); b = rnd(Co, seed=3)
-    wst = torch.zeros(Co + 3, Cin, 3, 3, device=DEV); wst[:Co] = w                 # stored with padding rows
+    pad_rows = 3 if Co < Cg else 0
+    wst = torch.zeros(Co + pad_rows, Cin, 3, 3, device=DEV); wst[:Co] = w         # stored with padding rows
     wk_ = wk(wst).contiguous()
     wf = torch.zeros(Np * 9 * Cin, device=DEV); wd = torch.zeros(Np * 9 * Cin, device=DEV); bp = torch.zeros(Np, device=DEV)
     K.conv_weights_prep_phase(P(wk_), P(b), P(wf), P(wd), P(bp), Cin, Co, Cg, ST())
     xin = bordered(x, Hl + 2, Hl + 2, 1, 0)
-    yp = torch.zeros(B, Hl + 2, Hl + 2, Np, device=DEV)
-    K.conv_tcg(P(xin), P(wf), P(bp), 0, P(yp), B, Hl + 2, Hl + 2, Cin, Np, Hl, Hl, -1, Hl + 2, Hl + 2, 1, 0, 0, 0, 0, ST())
-    torch.cuda.synchronize()
     xr = x.double().requires_grad_(True); wr = w.double().requires_grad_(True); br = b.double().requires_grad_(True)
     ref = F.conv2d(F.interpolate(xr, scale_factor=2), wr, br, padding=1)            # (B,Co,H,H)
-    # depth-to-space of our output: phase p = 2a+b, channels [p*Cg, p*Cg+Co) -> pixel (2y+a, 2x+b)
-    got = yp[:, 1:Hl + 1, :Hl].reshape(B, Hl, Hl, 2, 2, Cg)[..., :Co].permute(0, 5, 1, 3, 2, 4).reshape(B, Co, H, H)
-    close(got, ref.detach().float(), rtol=2e-3, atol=2e-3 * float(ref.abs().max()), what="phase conv fwd")   # TF32 of summed taps
-    assert float(yp[:, 1:Hl + 1, :Hl].reshape(B, Hl, Hl, 4, Cg)[..., Co:].abs().max()) == 0.0
+    tol = dict(rtol=2e-3, atol=2e-3 * float(ref.detach().abs().max()))               # TF32 of summed taps
+    if Np == 256:       # depth-to-space epilogue: phase p = 2a+b of low-res (y,x) -> pixel (2y+a, 2x+b) of a Cg-channel buffer
+        yd = torch.zeros(B, H + 2, H + 2, Cg, device=DEV)
+        K.conv_tcg(P(xin), P(wf), P(bp), 0, P(yd), B, Hl + 2, Hl + 2, Cin, Np, Hl, Hl, -1, H + 2, H + 2, 1, 0, 0, 0, 1 << 5, ST())
+        torch.cuda.synchronize()
+        close(yd[:, 1:H + 1, :H].permute(0, 3, 1, 2), ref.detach().float(), what="phase conv fwd (depth-to-space)", **tol)
+        bz = yd.clone(); bz[:, 1:H + 1, :H] = 0
+        assert float(bz.abs().max()) == 0.0
+        yr = torch.zeros(B, H + 2, H + 2, Cg, device=DEV)
+        K.conv_tcg(P(xin), P(wf), P(bp), 0, P(yr), B, Hl + 2, Hl + 2, Cin, Np, Hl, Hl, -1, H + 2, H + 2, 1, 0, 0, 0, 1 | 2 | (1 << 5), ST())
+        torch.cuda.synchronize()
+        assert torch.equal(yr, tf32_round(F.relu(yd)))
+    else:
+        yp = torch.zeros(B, Hl + 2, Hl + 2, Np, device=DEV)
+        K.conv_tcg(P(xin), P(wf), P(bp), 0, P(yp), B, Hl + 2, Hl + 2, Cin, Np, Hl, Hl, -1, Hl + 2, Hl + 2, 1, 0, 0, 0, 0, ST())
+        torch.cuda.synchronize()
+        # depth-to-space of our output: phase p = 2a+b, channels [p*Cg, p*Cg+Co) -> pixel (2y+a, 2x+b)
+        got = yp[:, 1:Hl + 1, :Hl].reshape(B, Hl, Hl, 2, 2, Cg)[..., :Co].permute(0, 5, 1, 3, 2, 4).reshape(B, Co, H, H)
+        close(got, ref.detach().float(), what="phase conv fwd", **tol)
+        if Co < Cg:
+            assert float(yp[:, 1:Hl + 1, :Hl].reshape(B, Hl, Hl, 4, Cg)[..., Co:].abs().max()) == 0.0
     # backward
     dy = tf32_round(rnd(B, Co, H, H, seed=4))
     ref.backward(dy.double())
@@ -727,16 +741,31 @@ def test_phase_conv_equals_conv_after_upsample(B, Hl, Cin, Co, Cg):
     close(dx[:, 1:Hl + 1, :Hl].permute(0, 3, 1, 2), refd, rtol=2e-3, atol=2e-3 * float(refd.abs().max()), what="phase conv dgrad")
     bz = dx.clone(); bz[:, 1:Hl + 1, :Hl] = 0
     assert float(bz.abs().max()) == 0.0
+    if Hl % 2 == 0 and Cin in (32, 64):     # the same gradient written in space-to-depth form (what the next phase conv's backward reads)
+        h2 = Hl // 2
+        dxs = torch.zeros(B, h2 + 2, h2 + 2, 4, Cin, device=DEV)
+        K.conv_tcg(P(dyp), P(wd), 0, P(xin, (Hl + 2) * Cin), P(dxs), B, Hl + 2, Hl + 2, Np, Cin, Hl, Hl, -1, h2 + 2, h2 + 2, 1, 0,
+                   Hl + 2, Hl + 2, (1 << 2) | 2 | (2 << 5), ST())
+        torch.cuda.synchronize()
+        want = dx[:, 1:Hl + 1, :Hl].reshape(B, h2, 2, h2, 2, Cin).permute(0, 1, 3, 2, 4, 5).reshape(B, h2, h2, 4, Cin)
+        assert torch.equal(dxs[:, 1:h2 + 1, :h2], want)
+        bz = dxs.clone(); bz[:, 1:h2 + 1, :h2] = 0
+        assert float(bz.abs().max()) == 0.0
     dwp = torch.zeros(Np * 9 * Cin, device=DEV); dbp = torch.zeros(Np, device=DEV)
-    K.conv_wgrad_tcg(P(xin), P(dyp), P(dwp), B, Hl + 2, Hl + 2, Cin, Np, -1, -1, ST())
+    if Np == 256:
+        for h in range(2):
+            K.conv_wgrad_tcg_ld(P(xin), P(dyp, 128 * h), 256, P(dwp, h * 128 * 9 * Cin), B, Hl + 2, Hl + 2, Cin, 128, -1, -1, ST())
+    else:
+        K.conv_wgrad_tcg(P(xin), P(dyp), P(dwp), B, Hl + 2, Hl + 2, Cin, Np, -1, -1, ST())
     K.colsum(P(dyp), Np, B * (Hl + 2) * (Hl + 2), Np, P(dbp), ST())
-    dw = torch.zeros((Co + 3) * 9 * Cin, device=DEV); db = torch.zeros(Co + 3, device=DEV)
+    dw = torch.zeros((Co + pad_rows) * 9 * Cin, device=DEV); db = torch.zeros(Co + pad_rows, device=DEV)
     K.conv_phase_fold(P(dwp), P(dbp), P(dw), P(db), Cin, Co, Cg, ST())
     torch.cuda.synchronize()
-    close(dw.reshape(Co + 3, 3, 3, Cin).permute(0, 3, 1, 2)[:Co], wr.grad.float(), rtol=1e-4, atol=1e-4 * float(wr.grad.abs().max()),
+    close(dw.reshape(Co + pad_rows, 3, 3, Cin).permute(0, 3, 1, 2)[:Co], wr.grad.float(), rtol=1e-4, atol=1e-4 * float(wr.grad.abs().max()),
           what="phase conv wgrad (folded)")
     close(db[:Co], br.grad.float(), rtol=1e-4, what="phase conv bias grad")
-    assert float(dw.reshape(Co + 3, -1)[Co:].abs().max()) == 0.0
+    if pad_rows:
+        assert float(dw.reshape(Co + pad_rows, -1)[Co:].abs().max()) == 0.0
 
 
 def test_bce_phase_equals_bce():
