@@ -374,8 +374,10 @@ def run_b200(a):
                    "value_definition": "global updates/s x (global_batch/128)",
                    "cuda_graphs": bool(agent.use_cuda_graphs), "conv_precision": agent.engine.precision},
         "e2e": {"value": e2e_v, "unit": "updates/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "how": "agent.update(replay_buffer, L, step) with the replay frame ring in pinned HOST memory (gather kernel pulls the "
-                       "sampled stacks host->device every step) and the loss vector copied device->host every step"},
+                "how": "agent.update(replay_buffer, L, step) with the replay frame ring in pinned HOST memory: every step the sampled "
+                       "uint8 frames of the NEXT batch cross PCIe into a device staging ring (zero-copy kernel on a side stream, under "
+                       "the current update), are converted / cropped on the device at the start of their step, and the step's loss "
+                       "vector is copied device->host"},
         "act_latency": act, "gpu_launches": launches, "clocks": sampler.summary(), "roofline": roof, "cpu_baseline": cpu,
         "algorithmic_gflop_per_update": gflop, "achieved_tflops_whole_step": gflop * ups / 1e3,
         "kernel_families_ms_per_step": [[r[0], round(r[1], 4), r[2]] for r in (fam_rows or [])[:12]],

@@ -30,6 +30,9 @@ int sgqn_abi_version(void);
  *      idxs: int64 [B]; offs: int32 [2][B][2] (row, col) offsets for obs / next_obs, or NULL. */
 int sgqn_replay_gather(const uint8_t* frames, const int32_t* fidx, const int64_t* idxs, const int32_t* offs, float* obs,
                        float* next_obs, int B, int Hs, int Ho, int mode, int pad, void* stream);
+/* raw copy of the six uint8 frames of every sampled transition into a device staging ring [B][6][fbytes] (prefetch of the next
+ * batch from a pinned-host frame ring; the staging ring is then read with fidx = arange(6B), idxs = arange(B)) */
+int sgqn_frames_copy(const uint8_t* frames, const int32_t* fidx, const int64_t* idxs, uint8_t* dst, int B, int fbytes, void* stream);
 int sgqn_take_rows(const float* src, const int64_t* idxs, float* dst, int B, int width, void* stream);
 /* random_crop / random_shift on a materialised fp32 batch; offs int32 [B][2] */
 int sgqn_crop_shift(const float* x, const int32_t* offs, float* y, int B, int C, int Hs, int Ho, int mode, int pad, void* stream);

@@ -12,6 +12,7 @@ _p, _i, _ll, _f, _d, _ull = C.c_void_p, C.c_int, C.c_longlong, C.c_float, C.c_do
 # name -> argtypes, exactly the prototypes of include/sgqn_b200.h
 SIGNATURES = {
     "sgqn_replay_gather": [_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p],
+    "sgqn_frames_copy": [_p, _p, _p, _p, _i, _i, _p],
     "sgqn_take_rows": [_p, _p, _p, _i, _i, _p],
     "sgqn_crop_shift": [_p, _p, _p, _i, _i, _i, _i, _i, _i, _p],
     "sgqn_zero": [_p, _ll, _p],

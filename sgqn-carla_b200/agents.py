@@ -104,6 +104,8 @@ class SAC(object):
         self.use_cuda_graphs = dist is None or os.environ.get("SGQN_DIST_GRAPHS", "1") == "1"
         self._graphs, self._eager_runs, self._graph_rb, self._graph_nodes = {}, {}, None, {}
         self._act = {}                  # (H, sample) -> staging buffers + captured batch-1 actor graph
+        self._pf = None                 # prefetch state of a host-resident (pinned) replay buffer
+        self.prefetch = os.environ.get("SGQN_PREFETCH", "1") == "1"
         self.train()
 
     # ---- parameters
@@ -273,12 +275,12 @@ class SAC(object):
         self._supplied = dict(idxs=idxs, noise_next=noise_next, noise_pi=noise_pi, u=u, overlay_ids=overlay_ids,
                               offs=offs, places=places)
 
-    def _draw(self, replay_buffer):
+    def _draw(self, replay_buffer, skip_idxs=False):
         eng, B = self.engine, self.batch_size
         pool_n = eng.overlay_pool.shape[0] if eng.overlay_pool is not None else 1
         off_n = 9 if self.sample_mode == "shift" else max(1, getattr(replay_buffer, "Hs", 84) - 84)
         n_valid = replay_buffer.n_valid if isinstance(replay_buffer, ReplayBuffer) else eng.rng_counter.to(torch.int32)
-        K.rng_step(eng.seed, _ptr(eng.rng_counter), _ptr(n_valid), _ptr(eng.idxs), _ptr(eng.overlay_ids), pool_n,
+        K.rng_step(eng.seed, _ptr(eng.rng_counter), _ptr(n_valid), 0 if skip_idxs else _ptr(eng.idxs), _ptr(eng.overlay_ids), pool_n,
                    _ptr(eng.offs), off_n, _ptr(eng.noise_next), _ptr(eng.noise_pi), _ptr(eng.u), B, eng.A, eng.st)
         s, self._supplied = self._supplied, None
         if s:
@@ -330,7 +332,56 @@ class SAC(object):
     def _step_kind(self, step):
         return (step % self.actor_update_freq == 0, step % self.critic_target_update_freq == 0)
 
+    # ---- host-resident replay (storage="pinned"): the NEXT update's batch crosses PCIe under the CURRENT update
+    def _prefetch_issue(self, rb, pf):
+        """Draw the next batch's indices and pull its frames (raw uint8) + action / reward / not_done rows into the
+        device staging buffers, on the current stream."""
+        eng, B = self.engine, self.batch_size
+        st = eng.st
+        K.rng_step(eng.seed ^ 0x5DEECE66D, _ptr(pf["counter"]), _ptr(rb.n_valid), _ptr(pf["idxs"]), 0, 1, 0, 1, 0, 0, 0, B, eng.A, st)
+        K.frames_copy(_ptr(rb.frames), _ptr(rb.fidx), _ptr(pf["idxs"]), _ptr(pf["frames"]), B, 3 * rb.Hs * rb.Hs, st)
+        K.take_rows(_ptr(rb.actions), _ptr(pf["idxs"]), _ptr(pf["action"]), B, eng.A, st)
+        K.take_rows(_ptr(rb.rewards), _ptr(pf["idxs"]), _ptr(pf["reward"]), B, 1, st)
+        K.take_rows(_ptr(rb.not_dones), _ptr(pf["idxs"]), _ptr(pf["not_done"]), B, 1, st)
+
+    def _run_update_prefetched(self, rb, step):
+        eng, B = self.engine, self.batch_size
+        pf = self._pf
+        if pf is None or pf["rb"] is not rb:
+            dev = eng.dev
+            pf = self._pf = dict(rb=rb, primed=False, frames=torch.zeros(B * 6, 3 * rb.Hs * rb.Hs, dtype=torch.uint8, device=dev),
+                                 fidx=torch.arange(6 * B, dtype=torch.int32, device=dev).reshape(B, 6),
+                                 arange=torch.arange(B, dtype=torch.int64, device=dev),
+                                 idxs=torch.zeros(B, dtype=torch.int64, device=dev),
+                                 counter=torch.zeros(1, dtype=torch.int64, device=dev),
+                                 action=torch.zeros(B, eng.A, device=dev), reward=torch.zeros(B, 1, device=dev),
+                                 not_done=torch.zeros(B, 1, device=dev), stream=torch.cuda.Stream(device=dev))
+        if not pf["primed"]:                              # first update with this buffer: fetch synchronously
+            self._prefetch_issue(rb, pf)
+            pf["primed"] = True
+        # consume the staged batch: uint8 -> fp32 (+ crop / shift) on the device
+        self._draw(rb, skip_idxs=True)
+        if self.sample_mode == "shift":
+            mode, offs = 1, eng.offs
+        else:
+            mode, offs = 0, (eng.offs if rb.Hs > 84 else None)
+        K.replay_gather(_ptr(pf["frames"]), _ptr(pf["fidx"]), _ptr(pf["arange"]), _ptr(offs) if offs is not None else 0,
+                        _ptr(eng.obs2[:B]), _ptr(eng.next_obs), B, rb.Hs, 84, mode, 4, eng.st)
+        eng.idxs.copy_(pf["idxs"]); eng.action.copy_(pf["action"]); eng.reward.copy_(pf["reward"]); eng.not_done.copy_(pf["not_done"])
+        # the staging buffers are free again: fetch the next batch beside this update
+        main = torch.cuda.current_stream()
+        ev = torch.cuda.Event(); ev.record(main); pf["stream"].wait_event(ev)
+        with torch.cuda.stream(pf["stream"]):
+            self._prefetch_issue(rb, pf)
+            ev2 = torch.cuda.Event(); ev2.record(pf["stream"])
+        self._engine_update(step)
+        main.wait_event(ev2)
+
     def _run_update(self, replay_buffer, step):
+        if (self.prefetch and self._supplied is None and isinstance(replay_buffer, ReplayBuffer)
+                and replay_buffer.storage == "pinned"):
+            self._run_update_prefetched(replay_buffer, step)
+            return
         self._draw(replay_buffer)
         self._sample_into_engine(replay_buffer)
         self._engine_update(step)

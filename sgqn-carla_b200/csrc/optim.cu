@@ -129,7 +129,7 @@ __global__ void rng_step_kernel(unsigned long long seed, unsigned long long* __r
     philox4x32_10((uint32_t)id, (uint32_t)ctr, (uint32_t)(ctr >> 32), 0x5367514eu, (uint32_t)seed, (uint32_t)(seed >> 32), r);
     if (id < B) {
         unsigned long long x = ((unsigned long long)r[0] << 32) | r[1];
-        idxs[id] = (int64_t)(x % (unsigned long long)max(*n_valid, 1));
+        if (idxs) idxs[id] = (int64_t)(x % (unsigned long long)max(*n_valid, 1));
     } else if (id < 2 * B) {
         if (overlay_ids) overlay_ids[id - B] = (int64_t)(r[0] % (uint32_t)max(pool_n, 1));
     } else if (id < 3 * B) {
@@ -143,10 +143,10 @@ __global__ void rng_step_kernel(unsigned long long seed, unsigned long long* __r
     } else if (id < 3 * B + nA) {
         int i = id - 3 * B;
         float rad = sqrtf(-2.0f * logf(u01(r[0]))), ang = 6.283185307179586f * u01(r[1]);
-        noise_next[i] = rad * cosf(ang);
+        if (noise_next) noise_next[i] = rad * cosf(ang);
         float rad2 = sqrtf(-2.0f * logf(u01(r[2]))), ang2 = 6.283185307179586f * u01(r[3]);
-        noise_pi[i] = rad2 * cosf(ang2);
-    } else {
+        if (noise_pi) noise_pi[i] = rad2 * cosf(ang2);
+    } else if (u) {
         *u = (float)(r[0] >> 8) * (1.0f / 16777216.0f);   // [0,1)
     }
 }

@@ -52,6 +52,38 @@ extern "C" int sgqn_replay_gather(const uint8_t* frames, const int32_t* fidx, co
     return SGQN_CHECK_LAUNCH();
 }
 
+// Prefetch of the NEXT update's batch from a host-resident (pinned, zero-copy) frame ring: the six frames of every sampled
+// transition are copied as raw bytes into a device staging ring [B][6][fbytes], which sgqn_replay_gather then reads with
+// fidx = arange(6B), idxs = arange(B).  Runs on a side stream under the current update, so the PCIe transfer of step t+1
+// (16 MB at B = 128) is off the critical path of step t.
+// Few, fat CTAs (grid-stride over the 6B frames, four 16-byte loads in flight per thread): enough outstanding PCIe reads to
+// saturate the link (~47 GB/s measured) while leaving the SMs' block slots to the update's kernels it runs beside.
+__global__ void __launch_bounds__(512)
+frames_copy_kernel(const uint4* __restrict__ frames, const int32_t* __restrict__ fidx, const int64_t* __restrict__ idxs,
+                   uint4* __restrict__ dst, int n16, int nframes) {
+    for (int f = blockIdx.x; f < nframes; f += gridDim.x) {
+        const int b = f / 6, j = f - b * 6;
+        const uint4* src = frames + (size_t)fidx[idxs[b] * 6 + j] * n16;
+        uint4* d = dst + (size_t)f * n16;
+        int i = threadIdx.x;
+        for (; i + 3 * 512 < n16; i += 4 * 512) {
+            const uint4 v0 = src[i], v1 = src[i + 512], v2 = src[i + 1024], v3 = src[i + 1536];
+            d[i] = v0; d[i + 512] = v1; d[i + 1024] = v2; d[i + 1536] = v3;
+        }
+        for (; i < n16; i += 512) d[i] = src[i];
+    }
+}
+extern "C" int sgqn_frames_copy(const uint8_t* frames, const int32_t* fidx, const int64_t* idxs, uint8_t* dst, int B, int fbytes,
+                                void* stream) {
+    if (B <= 0) return 0;
+    if ((fbytes & 15) || (((size_t)frames | (size_t)dst) & 15)) return (int)cudaErrorInvalidValue;
+    static int ctas = 0;
+    if (!ctas) { const char* e = getenv("SGQN_COPY_CTAS"); ctas = e ? atoi(e) : 16; if (ctas < 1) ctas = 1; }
+    int grid = 6 * B < ctas ? 6 * B : ctas;
+    frames_copy_kernel<<<grid, 512, 0, (cudaStream_t)stream>>>((const uint4*)frames, fidx, idxs, (uint4*)dst, fbytes / 16, 6 * B);
+    return SGQN_CHECK_LAUNCH();
+}
+
 // actions / rewards / not_dones rows of the sampled transitions
 __global__ void take_rows_kernel(const float* __restrict__ src, const int64_t* __restrict__ idxs, float* __restrict__ dst,
                                  int B, int width) {

@@ -154,6 +154,35 @@ def test_checkpoint_roundtrip_resumes(tmp_path):
         other.load_checkpoint_dict({"format": "something else"})
 
 
+@pytest.mark.parametrize("algorithm,size", [("sgsac", 84), ("rad", 100), ("drq", 84)])
+def test_host_resident_replay_prefetch(algorithm, size):
+    """storage="pinned": the next batch is staged on the device (raw uint8 frames + action / reward / not_done rows) under
+    the current update; what an update consumes must be exactly the gather of the indices it reports, eager and graphed."""
+    import sgqn_carla_b200 as S
+    B, A, cap = 8, 2, 48
+    agent, _, orc, rep, args = _mk(algorithm=algorithm, B=B, A=A, size=size, cap=cap)
+    rb = S.ReplayBuffer((9, size, size), (A,), cap, B, storage="pinned")
+    rb.load_ring(rep.frames, rep.actions, rep.rewards, rep.not_dones)
+    assert agent.prefetch
+    L = _L()
+    seen = []
+    for step in range(1, 8):
+        agent.update(rb, L, step)
+        torch.cuda.synchronize()
+        eng = agent.engine
+        idxs = eng.idxs.cpu().numpy()
+        assert idxs.min() >= 0 and idxs.max() < cap
+        seen.append(tuple(idxs))
+        offs = eng.offs.cpu().numpy() if (algorithm == "drq" or size > 84) else None
+        fn = rb.sample_drq if algorithm == "drq" else rb.sample
+        obs, a, r, nxt, nd = fn(idxs=idxs, offs=offs)
+        assert torch.equal(eng.obs2[:B], obs) and torch.equal(eng.next_obs, nxt)
+        assert torch.equal(eng.action, a) and torch.equal(eng.reward, r) and torch.equal(eng.not_done, nd)
+    assert len(set(seen)) == len(seen)                                  # a fresh batch every step
+    assert agent._graphs, "the prefetched update must be graph-captured too"
+    assert all(np.isfinite(float(v)) for v in L.rows.values())
+
+
 def test_graphed_batch1_actor_equals_eager():
     """select_action / sample_action replayed as one CUDA graph (pinned uint8 upload inside) give what the
     eager kernels give; float input takes the reference's fp32 route; device noise differs from call to call."""
