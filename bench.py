@@ -173,6 +173,10 @@ def profile_kernels(agent, rb, nsteps=4):
     try:
         L = NullLog()
         for s in range(1, nsteps + 1):
+            # park the stream behind a ~40 ms spin so that the host (python + ctypes + tensor-map encoding, ~10 us per call)
+            # has queued the whole update before the GPU starts on it: the event pairs then bracket device time only
+            torch.cuda.synchronize()
+            torch.cuda._sleep(int(0.04 * 1.9e9))
             agent.update(rb, L, s)
         torch.cuda.synchronize()
     finally:
@@ -318,7 +322,8 @@ def run_b200(a):
                 "peak_source": f"HBM copy bandwidth {hbm} GB/s ({how})",
                 "launches_per_step": kt[1] / nst, "ms_per_step_in_kernel": kt[0] / nst,
                 "algorithmic_bytes_per_launch": kt[3] / kt[1], "avg_launch_us": kt[0] / kt[1] * 1e3,
-                "timing": "CUDA events around every launch of the kernel in an eager (graph-free) pass over 4 updates",
+                "timing": "CUDA events around every launch of the kernel in an eager (graph-free, single-stream) pass over 4 updates, the "
+                          "stream parked behind a spin kernel while the host queues each update so the events bracket device time only",
                 "tensor_view": {"achieved_tflops": kt[2] / (kt[0] * 1e-3) / 1e12, "peak_tflops": tf_sus / 2.0,
                                 "peak_source": f"bf16 sustained {tf_sus} TF/s ({how}) / 2 = TF32 dense, derived"}}
         if l1 is not None:

@@ -123,6 +123,9 @@ int sgqn_gemm_wgrad_tcg(const float* x, const float* dy, float* dw, int B, int H
  * col (optional, for the weight gradient): the im2col matrix [B*1681][96] of the samples >= col_row0, written by TMA. */
 int sgqn_conv1_fused_tc(const float* obs, const float* w1p, const float* bias, float* out, float* col, int B, int Hin, int col_row0,
                         void* stream);
+/* ... and its data gradient to the observation (last step of compute_attribution, rl_utils.py:57-62): d(act_0) compact
+ * [B][41][41][32] x w1d [96][32] on tcgen05, gathered to dobs (B,9,84,84) through shared memory (no dcol matrix in HBM). */
+int sgqn_conv1_dgrad_fused_tc(const float* d, const float* w1d, float* dobs, int B, void* stream);
 int sgqn_conv_weights_prep_g(const float* w, float* wf, float* wd, int Cout, int Cin, int Cout_real, void* stream);
 int sgqn_conv_wgrad_tcg(const float* x, const float* dy, float* dw, int B, int Hr, int Wp, int Cin, int Cout, int ta, int tb,
                         void* stream);

@@ -44,6 +44,7 @@ SIGNATURES = {
     "sgqn_conv1_weights_prep": [_p, _p, _p, _p],
     "sgqn_conv1_col2im": [_p, _i, _p, _i, _p],
     "sgqn_conv1_fused_tc": [_p, _p, _p, _p, _p, _i, _i, _i, _p],
+    "sgqn_conv1_dgrad_fused_tc": [_p, _p, _p, _i, _p],
     "sgqn_conv_weights_prep_g": [_p, _p, _p, _i, _i, _i, _p],
     "sgqn_conv_wgrad_tcg": [_p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p],
     "sgqn_conv_weights_prep_phase": [_p, _p, _p, _p, _p, _i, _i, _i, _p],

@@ -288,3 +288,202 @@ extern "C" int sgqn_conv1_fused_tc(const float* obs, const float* w1p, const flo
     int grid = p.num_tiles < num_sms ? p.num_tiles : num_sms;
     return launch_pdl(conv1_fused_tc_kernel, dim3(grid), dim3(kThreads), kSmem, stream, tmW, tmCol, tmOut, p);
 }
+
+// =====================================================================================================================
+// Data gradient of the first conv to the observation (the last step of compute_attribution, rl_utils.py:35-39,57-62) as
+// ONE kernel: dcol[pix][96] = d(act_0)[pix][32] * W1 on tcgen05, gathered back to the NCHW observation gradient through
+// shared memory -- the 82.6 MB dcol matrix (B = 128) is never written to / re-read from HBM.
+//
+// Tile = output rows y0 = 2t, y0+1, y0+2 of one sample (123 pixels = one TMA box of d(act_0), rows past the sample's end are
+// zero-filled by TMA: their dcol rows are exact zeros).  Observation row Y collects ky = 1 from output row (Y-1)/2 (Y odd) or
+// ky = 0 from row Y/2 and ky = 2 from row Y/2 - 1 (Y even), so the tile owns Y = 2y0+1 .. 2y0+4 (and Y = 0 for t = 0): every
+// observation pixel is written exactly once, no atomics.  Same summation order and exact /255 as conv1_col2im_rows_kernel.
+namespace {
+
+constexpr int kDgStages = 3;
+constexpr int kDgABytes = 128 * 128;                 // d(act_0) tile: [128 px][32 ch]
+constexpr int kDgWBytes = 96 * 128;                  // W1d: [96 k][32 co]
+constexpr int kDgPitch = 97;                         // dcol staging pitch (floats): consecutive pixels hit consecutive banks
+constexpr int kDgStgBytes = 123 * kDgPitch * 4;
+constexpr int kDgSmem = kDgStages * kDgABytes + kDgWBytes + kDgStgBytes + 1024 + 256;
+constexpr int kDgTilesPerSample = 21;
+
+struct DgParams { float* dobs; int B, num_tiles; };
+
+__device__ __forceinline__ void tma_load_3d(const CUtensorMap* tm, uint32_t bar, uint32_t dst, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                 ::"r"(dst), "l"((unsigned long long)tm), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+
+__global__ void __launch_bounds__(320, 2)
+conv1_dgrad_fused_tc_kernel(const __grid_constant__ CUtensorMap tmD, const __grid_constant__ CUtensorMap tmW, DgParams p) {
+    constexpr uint32_t kIdesc = idesc_tf32(96, false, false);
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t a_sm = base;
+    const uint32_t w_sm = a_sm + kDgStages * kDgABytes;
+    const uint32_t stg_off = (w_sm + kDgWBytes) - smem_u32(smem_raw);
+    const uint32_t bars = w_sm + kDgWBytes + ((kDgStgBytes + 15) & ~15);
+    const uint32_t full0 = bars, empty0 = full0 + 8 * kDgStages, wbar = empty0 + 8 * kDgStages;
+    const uint32_t tfull0 = wbar + 8, tempty0 = tfull0 + 16, tmem_slot = tempty0 + 16;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"((unsigned long long)&tmD) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"((unsigned long long)&tmW) : "memory");
+        for (int s = 0; s < kDgStages; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
+        mbar_init(wbar, 1);
+        for (int a = 0; a < 2; ++a) { mbar_init(tfull0 + 8 * a, 1); mbar_init(tempty0 + 8 * a, 256); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(256) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    uint32_t tmem_base;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+    pdl_wait();
+    pdl_launch();
+
+    if (warp == 0) {
+        if (lane == 0) {
+            mbar_expect_tx(wbar, kDgWBytes);
+            tma_load_2d(&tmW, wbar, w_sm, 0, 0);
+            int i = 0;
+            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++i) {
+                const int stage = i % kDgStages;
+                const int b = tile / kDgTilesPerSample, t = tile - b * kDgTilesPerSample;
+                mbar_wait(empty0 + 8 * stage, ((uint32_t)(i / kDgStages) & 1u) ^ 1u);
+                mbar_expect_tx(full0 + 8 * stage, kDgABytes);
+                tma_load_3d(&tmD, full0 + 8 * stage, a_sm + stage * kDgABytes, 0, 2 * t * 41, b);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            mbar_wait(wbar, 0);
+            tc_fence_after();
+            int i = 0;
+            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++i) {
+                const int stage = i % kDgStages, acc = i & 1;
+                mbar_wait(tempty0 + 8 * acc, ((uint32_t)(i >> 1) & 1u) ^ 1u);
+                mbar_wait(full0 + 8 * stage, (uint32_t)(i / kDgStages) & 1u);
+                tc_fence_after();
+                const uint64_t ad = make_desc_sw128(a_sm + stage * kDgABytes);
+                const uint64_t bd = make_desc_sw128(w_sm);
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    tc_mma_tf32(tmem_base + (uint32_t)(acc * 128), ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), kIdesc, k != 0);
+                tc_commit(empty0 + 8 * stage);
+                tc_commit(tfull0 + 8 * acc);
+            }
+        }
+    } else {
+        const int et = threadIdx.x - 64;                 // 0..255
+        const int quarter = warp & 3, half = (warp - 2) >> 2;
+        const int row = quarter * 32 + lane;
+        float* stg = reinterpret_cast<float*>(smem_raw + stg_off);
+        int i = 0;
+        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++i) {
+            const int acc = i & 1;
+            const int b = tile / kDgTilesPerSample, t = tile - b * kDgTilesPerSample;
+            mbar_wait(tfull0 + 8 * acc, (uint32_t)(i >> 1) & 1u);
+            tc_fence_after();
+            // ---- drain: thread (row, half) moves 48 of the pixel's 96 dcol values to the staging tile
+#pragma unroll
+            for (int g = 0; g < 3; ++g) {
+                uint32_t v[16];
+                const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * 128 + half * 48 + g * 16);
+                asm volatile(
+                    "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+                    "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                    : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                      "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                    : "r"(taddr) : "memory");
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                if (row < 123) {
+#pragma unroll
+                    for (int e = 0; e < 16; ++e) stg[row * kDgPitch + half * 48 + g * 16 + e] = __uint_as_float(v[e]);
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(tempty0 + 8 * acc);
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            // ---- gather: observation rows Y = 2 y0 + 1 .. 2 y0 + 4 (and Y = 0 for the first tile), 9 channels, 84 columns
+            const int y0 = 2 * t;
+            const int Ylo = t == 0 ? 0 : 2 * y0 + 1, Yhi = min(2 * y0 + 4, 83);
+            const int nrows = Yhi - Ylo + 1;
+            for (int o = et; o < nrows * 9 * 84; o += 256) {
+                const int X = o % 84; int tt = o / 84; const int ci = tt % 9; const int Y = Ylo + tt / 9;
+                const int x0 = X >> 1;
+                float a = 0.f;
+                if (Y & 1) {                                 // ky = 1 from output row (Y-1)/2
+                    const float* s0 = stg + (((Y - 1) >> 1) - y0) * 41 * kDgPitch + ci * 9 + 3;
+                    if (X & 1) { if (x0 < 41) a += s0[x0 * kDgPitch + 1]; }
+                    else {
+                        if (x0 < 41) a += s0[x0 * kDgPitch + 0];
+                        if (x0 >= 1) a += s0[(x0 - 1) * kDgPitch + 2];
+                    }
+                } else {                                     // ky = 0 from row Y/2, ky = 2 from row Y/2 - 1 (zero above the image)
+                    const int r0 = (Y >> 1) - y0;
+                    const float* s0 = stg + r0 * 41 * kDgPitch + ci * 9;
+                    const float* s1 = s0 - 41 * kDgPitch + 6;
+                    const bool up = r0 >= 1;                 // r0 == 0 only for Y = 0 (t = 0): no row above
+                    if (X & 1) { if (x0 < 41) a += s0[x0 * kDgPitch + 1] + (up ? s1[x0 * kDgPitch + 1] : 0.f); }
+                    else {
+                        if (x0 < 41) a += s0[x0 * kDgPitch + 0] + (up ? s1[x0 * kDgPitch + 0] : 0.f);
+                        if (x0 >= 1) a += s0[(x0 - 1) * kDgPitch + 2] + (up ? s1[(x0 - 1) * kDgPitch + 2] : 0.f);
+                    }
+                }
+                const float rcp = 1.0f / 255.0f;             // exact a / 255 (see build_half_row)
+                const float q0 = a * rcp;
+                p.dobs[((size_t)(b * 9 + ci) * 84 + Y) * 84 + X] = __fmaf_rn(__fmaf_rn(-q0, 255.0f, a), rcp, q0);
+            }
+            asm volatile("bar.sync 1, 256;" ::: "memory");   // staging tile free again
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256) : "memory");
+    }
+}
+
+}  // namespace
+
+// d: d(act_0) compact [B][41][41][32] (TF32-rounded); w1d: [96][32] transposed TF32 operand copy of the conv weight
+// (sgqn_conv1_weights_prep); dobs: (B, 9, 84, 84) fp32 gradient w.r.t. the 0..255 observation (includes NormalizeImg's 1/255),
+// every element written (row / column 83 are structurally zero).
+extern "C" int sgqn_conv1_dgrad_fused_tc(const float* d, const float* w1d, float* dobs, int B, void* stream) {
+    if (B <= 0) return 0;
+    static int inited = 0, num_sms = 0;
+    if (!inited) {
+        cudaError_t e = cudaFuncSetAttribute(conv1_dgrad_fused_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kDgSmem);
+        if (e != cudaSuccess) return (int)e;
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+        inited = 1;
+    }
+    DgParams p;
+    p.dobs = dobs; p.B = B; p.num_tiles = B * kDgTilesPerSample;
+    CUtensorMap tmD, tmW;
+    EncodeTiledFn enc = get_encode_fn();
+    if (!enc) return (int)cudaErrorNotSupported;
+    {
+        cuuint64_t dims[3] = {32, (cuuint64_t)kPix, (cuuint64_t)B};
+        cuuint64_t strides[2] = {128, (cuuint64_t)kPix * 128};
+        cuuint32_t box[3] = {32, 128, 1};
+        cuuint32_t estr[3] = {1, 1, 1};
+        CUresult r = enc(&tmD, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)d, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return 900 + (int)r;
+    }
+    int rc = make_map_2d(&tmW, w1d, 32, 96, 32, 96);
+    if (rc) return rc;
+    int grid = p.num_tiles < 2 * num_sms ? p.num_tiles : 2 * num_sms;
+    return launch_pdl(conv1_dgrad_fused_tc_kernel, dim3(grid), dim3(320), kDgSmem, stream, tmD, tmW, p);
+}

@@ -94,7 +94,8 @@ class UpdateEngine:
         self.dbuf = [f32(R * 41 * 41 * 32), f32(R * 41 * 41 * 32)]
         # im2col matrices of the first conv (col[n*1681][84]) per slot: built once per observation batch by enc_fwd and
         # re-used by that slot's weight gradient; dcol is the attribution's data-gradient workspace
-        self.colS, self.colT, self.dcol = f32(E * 1681 * 96), f32(B * 1681 * 96), f32(B * 1681 * 96)
+        self.colS, self.colT = f32(E * 1681 * 96), f32(B * 1681 * 96)
+        self.dcol = f32(B * 1681 * 96) if precision != "tf32" else None
         self.w1p, self.w1p_t = f32(32 * 96), f32(32 * 96)          # TF32 operand copies of cnn.0 ([32][96]) / target
         self.w1d = f32(96 * 32)                                    # ... transposed ([96][32]): data-gradient operand
         # tcgen05 conv path (conv_tc.cu): TF32-rounded operand copies of the 32->32 conv weights (forward; flipped +
@@ -345,9 +346,8 @@ class UpdateEngine:
             K.gemm_wgrad_tcg(col, d, self.G("cnn.0.weight"), n, 41, 41, 96, 32, 0, 0, 1, 81, st)   # (bias gradient: see enc_bwd)
         elif wgrad:
             K.conv1_wgrad_col(col, d, self.G("cnn.0.weight"), self.G("cnn.0.bias"), n, st)
-        if dobs and tc:                                   # dcol[pix][96] = d(act_0)[pix][32] W on tcgen05, then the gather
-            K.conv_tcg_taps(d, _ptr(self.w1d), 0, 0, _ptr(self.dcol), n, 41, 41, 32, 96, 41, 41, 0, 41, 41, 0, 0, 0, 0, 0, 1, st)
-            K.conv1_col2im(_ptr(self.dcol), 96, dobs, n, st)
+        if dobs and tc:                                   # dcol = d(act_0) W on tcgen05 + the gather to NCHW, one kernel
+            K.conv1_dgrad_fused_tc(d, _ptr(self.w1d), dobs, n, st)
         elif dobs:
             K.conv1_dgrad_col(d, self.P("cnn.0.weight"), _ptr(self.dcol), dobs, n, st)
 

@@ -863,3 +863,24 @@ def test_conv1_fused_matches_im2col_path(B, Hin, col_row0):
             assert float((colf[:col_row0 * 1681] + 7.0).abs().max()) == 0.0
     else:
         assert float((colf + 7.0).abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("B", [1, 3, 130])
+def test_conv1_dgrad_fused_matches_materialised_path(B):
+    """Observation gradient of the first conv in one kernel (dcol stays in TMEM / shared memory) against the path it replaces
+    (per-position GEMM into a dcol matrix + col2im gather: same operands, same summation order -> bit-exact) and torch."""
+    d = tf32_round(rnd(B, 41, 41, 32, seed=1) * (rnd(B, 41, 41, 32, seed=2) > 0.3))
+    w = rnd(32, 9, 3, 3, seed=3, scale=0.2)
+    wp = torch.zeros(32 * 96, device=DEV); wd = torch.zeros(96 * 32, device=DEV)
+    K.conv1_weights_prep(P(w), P(wp), P(wd), ST())
+    dcol = torch.zeros(B * 1681, 96, device=DEV)
+    K.conv_tcg_taps(P(d), P(wd), 0, 0, P(dcol), B, 41, 41, 32, 96, 41, 41, 0, 41, 41, 0, 0, 0, 0, 0, 1, ST())
+    d0 = torch.full((B, 9, 84, 84), 5.0, device=DEV)
+    K.conv1_col2im(P(dcol), 96, P(d0), B, ST())
+    d1 = torch.full((B, 9, 84, 84), -3.0, device=DEV)
+    K.conv1_dgrad_fused_tc(P(d), P(wd), P(d1), B, ST())
+    torch.cuda.synchronize()
+    assert torch.equal(d1, d0)
+    ref = F.conv_transpose2d(d.permute(0, 3, 1, 2).double(), tf32_round(w).double(), stride=2, output_padding=1) / 255.0
+    close(d1, ref.float(), rtol=2e-3, atol=2e-3 * float(ref.abs().max()), what="conv1 dgrad fused vs torch")
+    assert float(d1[:, :, 83].abs().max()) == 0.0 and float(d1[:, :, :, 83].abs().max()) == 0.0
