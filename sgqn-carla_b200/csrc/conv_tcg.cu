@@ -504,6 +504,14 @@ conv3x3_wgrad_tcg_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_c
 #pragma unroll 1
                 for (int j = 0; j < kGwRows / 8; ++j) {
                     const uint64_t bd = make_desc_mn32(sb + p.kc * xtile + j * 1024, dtile);
+                    if (p.ntaps == 1) {
+                        // per-position GEMM: no row shifts, so the four 32-row M atoms are the channel chunks themselves (their
+                        // tiles are xtile bytes apart; a 4th atom past kc = 3 reads the dY tile: finite garbage in accumulator
+                        // rows nobody reads) -- one MMA per k-step instead of one per chunk with three quarters of M wasted
+                        const uint64_t ad = make_desc_mn32(sb + j * 1024, xtile);
+                        tc_mma_tf32(tmem_base, ad, bd, kIdescMN, (kb != kb0 || j != 0) ? 1u : 0u);
+                        continue;
+                    }
                     for (int c = 0; c < p.kc; ++c) {
                         const uint64_t ad = make_desc_mn32(sb + c * xtile + j * 1024, 128);    // atoms = row shifts kx = 0..3
                         tc_mma_tf32(tmem_base + (uint32_t)(c * N), ad, bd, kIdescMN, (kb != kb0 || j != 0) ? 1u : 0u);
@@ -518,7 +526,7 @@ conv3x3_wgrad_tcg_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_c
         const int kx = warp & 3;                          // TMEM lane quarter = accumulator rows of tap kx
         mbar_wait(done_bar, 0);
         tc_fence_after();
-        for (int c = 0; c < p.kc; ++c) {
+        for (int c = 0; c < (p.ntaps == 1 ? 1 : p.kc); ++c) {
 #pragma unroll 1
             for (int g = 0; g < N / 16; ++g) {
                 uint32_t v[16];
@@ -536,8 +544,8 @@ conv3x3_wgrad_tcg_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_c
 #pragma unroll
                         for (int e = 0; e < 16; ++e) atomicAdd(dst + (size_t)(g * 16 + e) * 9 * p.cin, __uint_as_float(v[e]));
                     }
-                } else if (kx == 0 && c * 32 + lane < p.kvalid) {      // per-position GEMM: dw[co][kvalid], only the unshifted atom
-                    float* dst = p.dw + c * 32 + lane;
+                } else if (kx < p.kc && kx * 32 + lane < p.kvalid) {   // per-position GEMM: dw[co][kvalid]; lane quarter = channel chunk
+                    float* dst = p.dw + kx * 32 + lane;
 #pragma unroll
                     for (int e = 0; e < 16; ++e) atomicAdd(dst + (size_t)(g * 16 + e) * p.kvalid, __uint_as_float(v[e]));
                 }
@@ -601,6 +609,7 @@ static int wgrad_tcg_impl(const float* x, const float* dy, int ldy, float* dw, i
     if (B <= 0) return 0;
     if (ntaps != 1 && ntaps != 9) return (int)cudaErrorInvalidValue;
     if ((Cin & 31) || (Cout != 32 && Cout != 64 && Cout != 128) || (Cin / 32) * Cout > 512) return (int)cudaErrorInvalidValue;
+    if (ntaps == 1 && Cin > 128) return (int)cudaErrorInvalidValue;      // the channel chunks are the four M atoms of one MMA
     GwParams p;
     p.total_q = B * Hr * Wp; p.Wp = ntaps == 9 ? Wp : 0; p.ta = ntaps == 9 ? ta : 0; p.tb = ntaps == 9 ? tb : 0;
     p.kc = Cin / 32; p.cin = Cin; p.na = Cout / 32; p.dw = dw; p.ntaps = ntaps; p.kvalid = kvalid;
