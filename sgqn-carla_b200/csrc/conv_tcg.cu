@@ -435,7 +435,7 @@ constexpr int kGwRows = 64;
 constexpr int kGwXRows = 72;
 constexpr int kGwStagesMax = 4;
 
-struct GwParams { int total_q, Wp, ta, tb, kc, cin, na, kb_total, kb_per_cta, stages, stage_bytes, ntaps, kvalid; float* dw; };
+struct GwParams { int total_q, Wp, ta, tb, kc, cin, na, kb_total, kb_per_cta, stages, stage_bytes, ntaps, kvalid, fuse, xrows; float* dw; };
 
 __device__ __forceinline__ uint64_t make_desc_mn32(uint32_t saddr, uint32_t lbo_bytes) {
     uint64_t d = 0;
@@ -459,8 +459,11 @@ conv3x3_wgrad_tcg_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_c
     const int ky = blockIdx.y;
     const int kb0 = blockIdx.x * p.kb_per_cta;
     const int kb1 = min(p.kb_total, kb0 + p.kb_per_cta);
-    const int tmem_cols = p.kc * N < 32 ? 32 : (p.kc * N <= 64 ? 64 : (p.kc * N <= 128 ? 128 : (p.kc * N <= 256 ? 256 : 512)));
-    const uint32_t xtile = kGwXRows * 128, dtile = kGwRows * 128;
+    // fuse: all three filter rows in one CTA -- ONE X halo tile (72 + 2 Wp rows) serves ky = 0..2 as row-shifted views and dY is
+    // loaded once instead of three times (the ky-split version was L2 -> SM bound: 3 x 34 KB per 64 pixels at Cin = N = 64)
+    const int nacc = (p.fuse ? 3 : 1) * p.kc * N;
+    const int tmem_cols = nacc < 32 ? 32 : (nacc <= 64 ? 64 : (nacc <= 128 ? 128 : (nacc <= 256 ? 256 : 512)));
+    const uint32_t xtile = (uint32_t)p.xrows * 128, dtile = kGwRows * 128;
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"((unsigned long long)&tmX) : "memory");
@@ -504,6 +507,14 @@ conv3x3_wgrad_tcg_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_c
 #pragma unroll 1
                 for (int j = 0; j < kGwRows / 8; ++j) {
                     const uint64_t bd = make_desc_mn32(sb + p.kc * xtile + j * 1024, dtile);
+                    if (p.fuse) {
+                        for (int f = 0; f < 3; ++f)
+                            for (int c = 0; c < p.kc; ++c) {
+                                const uint64_t ad = make_desc_mn32(sb + c * xtile + (uint32_t)(f * p.Wp) * 128u + j * 1024, 128);
+                                tc_mma_tf32(tmem_base + (uint32_t)((f * p.kc + c) * N), ad, bd, kIdescMN, (kb != kb0 || j != 0) ? 1u : 0u);
+                            }
+                        continue;
+                    }
                     if (p.ntaps == 1) {
                         // per-position GEMM: no row shifts, so the four 32-row M atoms are the channel chunks themselves (their
                         // tiles are xtile bytes apart; a 4th atom past kc = 3 reads the dY tile: finite garbage in accumulator
@@ -526,11 +537,13 @@ conv3x3_wgrad_tcg_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_c
         const int kx = warp & 3;                          // TMEM lane quarter = accumulator rows of tap kx
         mbar_wait(done_bar, 0);
         tc_fence_after();
+        for (int f = 0; f < (p.fuse ? 3 : 1); ++f) {
+        const int kyf = p.fuse ? f : ky;
         for (int c = 0; c < (p.ntaps == 1 ? 1 : p.kc); ++c) {
 #pragma unroll 1
             for (int g = 0; g < N / 16; ++g) {
                 uint32_t v[16];
-                const uint32_t taddr = tmem_base + ((uint32_t)(kx * 32) << 16) + (uint32_t)(c * N + g * 16);
+                const uint32_t taddr = tmem_base + ((uint32_t)(kx * 32) << 16) + (uint32_t)((f * p.kc + c) * N + g * 16);
                 asm volatile(
                     "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
                     "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
@@ -540,7 +553,7 @@ conv3x3_wgrad_tcg_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_c
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
                 if (p.ntaps == 9) {
                     if (kx < 3) {
-                        float* dst = p.dw + (size_t)(ky * 3 + kx) * p.cin + c * 32 + lane;
+                        float* dst = p.dw + (size_t)(kyf * 3 + kx) * p.cin + c * 32 + lane;
 #pragma unroll
                         for (int e = 0; e < 16; ++e) atomicAdd(dst + (size_t)(g * 16 + e) * 9 * p.cin, __uint_as_float(v[e]));
                     }
@@ -550,6 +563,7 @@ conv3x3_wgrad_tcg_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_c
                     for (int e = 0; e < 16; ++e) atomicAdd(dst + (size_t)(g * 16 + e) * p.kvalid, __uint_as_float(v[e]));
                 }
             }
+        }
         }
     }
     tc_fence_before();
@@ -571,7 +585,7 @@ int launch_wgrad_tcg(const CUtensorMap& tmX, const CUtensorMap& tmD, GwParams& p
         cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
         inited = 1;
     }
-    const int gy = p.ntaps == 9 ? 3 : 1;
+    const int gy = (p.ntaps == 9 && !p.fuse) ? 3 : 1;
     int gx = (num_sms + gy - 1) / gy;
     if (gx > p.kb_total) gx = p.kb_total;
     p.kb_per_cta = (p.kb_total + gx - 1) / gx;
@@ -614,12 +628,18 @@ static int wgrad_tcg_impl(const float* x, const float* dy, int ldy, float* dw, i
     p.total_q = B * Hr * Wp; p.Wp = ntaps == 9 ? Wp : 0; p.ta = ntaps == 9 ? ta : 0; p.tb = ntaps == 9 ? tb : 0;
     p.kc = Cin / 32; p.cin = Cin; p.na = Cout / 32; p.dw = dw; p.ntaps = ntaps; p.kvalid = kvalid;
     p.kb_total = (p.total_q + kGwRows - 1) / kGwRows;
-    p.stage_bytes = p.kc * kGwXRows * 128 + p.na * kGwRows * 128;
+    // all three filter rows in one CTA when their accumulators fit TMEM and two stages of the taller X halo tile fit shared memory
+    p.xrows = kGwXRows; p.fuse = 0;
+    if (ntaps == 9 && 3 * p.kc * Cout <= 512) {
+        int xr = (kGwXRows + 2 * Wp + 7) / 8 * 8;
+        if (xr <= 256 && 2 * (p.kc * xr * 128 + p.na * kGwRows * 128) <= kSmemBudget - 4096) { p.fuse = 1; p.xrows = xr; }
+    }
+    p.stage_bytes = p.kc * p.xrows * 128 + p.na * kGwRows * 128;
     p.stages = (kSmemBudget - 4096) / p.stage_bytes;
     if (p.stages > kGwStagesMax) p.stages = kGwStagesMax;
     if (p.stages < 2) return (int)cudaErrorInvalidValue;
     CUtensorMap tmX, tmD;
-    int rc = make_map_2d(&tmX, x, (uint64_t)Cin, (uint64_t)p.total_q, 32, kGwXRows, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+    int rc = make_map_2d(&tmX, x, (uint64_t)Cin, (uint64_t)p.total_q, 32, (uint32_t)p.xrows, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
     if (rc) return rc;
     rc = make_map_2d(&tmD, dy, (uint64_t)ldy, (uint64_t)p.total_q, 32, kGwRows, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
     if (rc) return rc;
