@@ -385,6 +385,11 @@ conv1_dgrad_fused_tc_kernel(const __grid_constant__ CUtensorMap tmD, const __gri
         const int quarter = warp & 3, half = (warp - 2) >> 2;
         const int row = quarter * 32 + lane;
         float* stg = reinterpret_cast<float*>(smem_raw + stg_off);
+        const int xg = et / 84, X = et - xg * 84;        // gather role: column X of observation rows dealt to group xg (xg == 3: idle)
+        const int x0 = X >> 1;
+        const bool xodd = X & 1, v0 = x0 < 41, v1 = x0 >= 1;
+        const int oA = x0 * kDgPitch + (xodd ? 1 : 0);   // X odd: tap kx = 1 of pixel x0; X even: tap kx = 0 of pixel x0 ...
+        const int oB = (x0 - 1) * kDgPitch + 2;          // ... and tap kx = 2 of pixel x0 - 1
         int i = 0;
         for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++i) {
             const int acc = i & 1;
@@ -415,31 +420,31 @@ conv1_dgrad_fused_tc_kernel(const __grid_constant__ CUtensorMap tmD, const __gri
             const int y0 = 2 * t;
             const int Ylo = t == 0 ? 0 : 2 * y0 + 1, Yhi = min(2 * y0 + 4, 83);
             const int nrows = Yhi - Ylo + 1;
-            for (int o = et; o < nrows * 9 * 84; o += 256) {
-                const int X = o % 84; int tt = o / 84; const int ci = tt % 9; const int Y = Ylo + tt / 9;
-                const int x0 = X >> 1;
-                float a = 0.f;
-                if (Y & 1) {                                 // ky = 1 from output row (Y-1)/2
-                    const float* s0 = stg + (((Y - 1) >> 1) - y0) * 41 * kDgPitch + ci * 9 + 3;
-                    if (X & 1) { if (x0 < 41) a += s0[x0 * kDgPitch + 1]; }
-                    else {
-                        if (x0 < 41) a += s0[x0 * kDgPitch + 0];
-                        if (x0 >= 1) a += s0[(x0 - 1) * kDgPitch + 2];
+            // three groups of 84 threads, one observation column X each (its tap offsets and bounds are loop invariants); the
+            // (row Y, channel) pairs are dealt round-robin to the groups and unrolled for independent shared-memory loads in
+            // flight -- a flat loop over the 3024 outputs with per-output index arithmetic was 80 % of the kernel
+            if (xg < 3) {
+                const int npairs = nrows * 9;
+#pragma unroll 4
+                for (int pr = xg; pr < npairs; pr += 3) {
+                    const int yi = pr / 9, ci = pr - yi * 9, Y = Ylo + yi;
+                    float a = 0.f;
+                    if (Y & 1) {                             // ky = 1 from output row (Y-1)/2
+                        const float* s0 = stg + (((Y - 1) >> 1) - y0) * 41 * kDgPitch + ci * 9 + 3;
+                        if (v0) a += s0[oA];
+                        if (!xodd && v1) a += s0[oB];
+                    } else {                                 // ky = 0 from row Y/2, ky = 2 from row Y/2 - 1 (zero above the image)
+                        const int r0 = (Y >> 1) - y0;
+                        const float* s0 = stg + r0 * 41 * kDgPitch + ci * 9;
+                        const float* s1 = s0 - 41 * kDgPitch + 6;
+                        const bool up = r0 >= 1;             // r0 == 0 only for Y = 0 (t = 0): no row above
+                        if (v0) a += s0[oA] + (up ? s1[oA] : 0.f);
+                        if (!xodd && v1) a += s0[oB] + (up ? s1[oB] : 0.f);
                     }
-                } else {                                     // ky = 0 from row Y/2, ky = 2 from row Y/2 - 1 (zero above the image)
-                    const int r0 = (Y >> 1) - y0;
-                    const float* s0 = stg + r0 * 41 * kDgPitch + ci * 9;
-                    const float* s1 = s0 - 41 * kDgPitch + 6;
-                    const bool up = r0 >= 1;                 // r0 == 0 only for Y = 0 (t = 0): no row above
-                    if (X & 1) { if (x0 < 41) a += s0[x0 * kDgPitch + 1] + (up ? s1[x0 * kDgPitch + 1] : 0.f); }
-                    else {
-                        if (x0 < 41) a += s0[x0 * kDgPitch + 0] + (up ? s1[x0 * kDgPitch + 0] : 0.f);
-                        if (x0 >= 1) a += s0[(x0 - 1) * kDgPitch + 2] + (up ? s1[(x0 - 1) * kDgPitch + 2] : 0.f);
-                    }
+                    const float rcp = 1.0f / 255.0f;         // exact a / 255 (see build_half_row)
+                    const float q0 = a * rcp;
+                    p.dobs[((size_t)(b * 9 + ci) * 84 + Y) * 84 + X] = __fmaf_rn(__fmaf_rn(-q0, 255.0f, a), rcp, q0);
                 }
-                const float rcp = 1.0f / 255.0f;             // exact a / 255 (see build_half_row)
-                const float q0 = a * rcp;
-                p.dobs[((size_t)(b * 9 + ci) * 84 + Y) * 84 + X] = __fmaf_rn(__fmaf_rn(-q0, 255.0f, a), rcp, q0);
             }
             asm volatile("bar.sync 1, 256;" ::: "memory");   // staging tile free again
         }
