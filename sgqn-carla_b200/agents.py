@@ -450,6 +450,11 @@ class SVEA(SAC):
     def set_places_pool(self, imgs):
         self.places_pool = torch.as_tensor(imgs, dtype=torch.float32).to(self.engine.dev)
 
+    def load_places_dir(self, data_dirs, n=4096, use_val=False, seed=0):
+        """Places365 as the reference reads it (augmentations.py:17-62), n transformed images drawn once into the device pool."""
+        from .datasets import load_places_pool
+        self.set_places_pool(load_places_pool(data_dirs, n, 84, use_val, seed))
+
     def _graphable(self):
         return False                    # the places batch is assembled with torch indexing per step
 
@@ -489,9 +494,9 @@ class SGSAC(SAC):
         self.engine.overlay_pool = t.to(self.engine.dev).reshape(t.shape[0], 3, -1).contiguous()
 
     def load_overlay_dir(self, path, limit=None):
-        import os
-        files = sorted(f for f in os.listdir(path) if f.endswith(".npy"))[:limit]
-        self.set_overlay_pool(np.stack([np.load(os.path.join(path, f)) for f in files]))
+        """`datasets/carla` of the reference (one uint8 (3,84,84) `.npy` per frame, utils.py:325-327), read once."""
+        from .datasets import load_carla_frames
+        self.set_overlay_pool(load_carla_frames(path, limit))
 
     def _log_cols(self, step):
         cols = super()._log_cols(step)

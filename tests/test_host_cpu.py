@@ -127,3 +127,38 @@ def test_default_args_against_reference_argparse():
     for k, v in mine.items():
         if k in ref:
             assert ref[k] == v, k
+
+
+def test_overlay_dataset_loaders(tmp_path):
+    """the reference's on-disk overlay formats (datasets/carla/*.npy, utils.py:325-327; Places365 ImageFolder,
+    augmentations.py:17-62) load into pools of the shapes / ranges the overlay kernels expect."""
+    import importlib
+    D = importlib.import_module("sgqn_carla_b200.datasets")
+    rs = np.random.RandomState(0)
+    carla = tmp_path / "carla"; carla.mkdir()
+    frames = rs.randint(0, 256, size=(5, 3, 84, 84), dtype=np.uint8)
+    for i, f in enumerate(frames):
+        np.save(carla / f"frame_{i:04d}.npy", f)
+    (carla / "notes.txt").write_text("ignored")
+    got = D.load_carla_frames(str(carla))
+    assert got.dtype == np.uint8 and got.shape == (5, 3, 84, 84) and np.array_equal(got, frames)
+    assert D.load_carla_frames(str(carla), limit=2).shape[0] == 2
+    np.save(carla / "zz_bad.npy", np.zeros((84, 84, 3), dtype=np.uint8))
+    with pytest.raises(ValueError):
+        D.load_carla_frames(str(carla))
+    with pytest.raises(FileNotFoundError):
+        D.load_carla_frames(str(tmp_path))
+    # Places365 layout: <dir>/places365_standard/train/<class>/*.png
+    from PIL import Image
+    root = tmp_path / "data"
+    for cls in ("a", "b"):
+        d = root / "places365_standard" / "train" / cls; d.mkdir(parents=True)
+        for i in range(3):
+            Image.fromarray(rs.randint(0, 256, size=(100, 120, 3), dtype=np.uint8)).save(d / f"{i}.png")
+    pool = D.load_places_pool([str(tmp_path / "missing"), str(root)], n=8, seed=1)
+    assert pool.shape == (8, 3, 84, 84) and pool.dtype == torch.float32
+    assert float(pool.min()) >= 0.0 and float(pool.max()) <= 1.0 and float(pool.std()) > 0.05
+    assert torch.equal(pool, D.load_places_pool(str(root), n=8, seed=1))                # reproducible
+    assert not torch.equal(pool, D.load_places_pool(str(root), n=8, seed=2))
+    with pytest.raises(FileNotFoundError):
+        D.load_places_pool([str(tmp_path / "missing")], n=2)
