@@ -105,7 +105,7 @@ class SAC(object):
         self._graphs, self._eager_runs, self._graph_rb, self._graph_nodes = {}, {}, None, {}
         self._act = {}                  # (H, sample) -> staging buffers + captured batch-1 actor graph
         self._pf = None                 # prefetch state of a host-resident (pinned) replay buffer
-        self.prefetch = os.environ.get("SGQN_PREFETCH", "1") == "1"
+        self._prefetch = os.environ.get("SGQN_PREFETCH", "1") == "1"
         self.train()
 
     # ---- parameters
@@ -331,6 +331,18 @@ class SAC(object):
 
     def _step_kind(self, step):
         return (step % self.actor_update_freq == 0, step % self.critic_target_update_freq == 0)
+
+    @property
+    def prefetch(self):
+        return self._prefetch
+
+    @prefetch.setter
+    def prefetch(self, on):
+        if bool(on) != self._prefetch:                    # the choice is baked into the captured update graphs
+            self._prefetch = bool(on)
+            self._graphs.clear(); self._eager_runs.clear()
+            if self._pf is not None:
+                self._pf["primed"] = False
 
     # ---- host-resident replay (storage="pinned"): the NEXT update's batch crosses PCIe under the CURRENT update
     def _prefetch_issue(self, rb, pf):
