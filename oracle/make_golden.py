@@ -123,3 +123,4 @@ if __name__ == "__main__":
     golden_update("sgsac", "sgsac_dense")
     golden_update("svea", "svea_dense", steps=(2, 3))
     golden_update("sac", "sac_dense", steps=(2, 3))
+    golden_update("drq", "drq_dense", steps=(2, 3))

@@ -109,7 +109,7 @@ def test_aug_golden():
     np.testing.assert_allclose(ov.numpy(), gold["overlay"], rtol=1e-6, atol=1e-4)
 
 
-@pytest.mark.parametrize("name", ["sgsac_dense", "svea_dense", "sac_dense"])
+@pytest.mark.parametrize("name", ["sgsac_dense", "svea_dense", "sac_dense", "drq_dense"])
 def test_update_golden(name):
     """Losses / updated-parameter digests of the reference.  Cross-host CPU conv kernels differ in
     summation order, so tolerance (fp32): losses rel 2e-4, parameter digests atol scaled by lr."""
@@ -136,7 +136,7 @@ def test_update_golden(name):
         idxs = rs.randint(0, 32, size=B)
         from oracle.pin_rnd import make_rnd
         rnd = make_rnd(rs, B, A, 16, with_places=(algorithm == "svea"))
-        if algorithm == "svea":
+        if algorithm in ("svea", "drq"):
             crop = [(rs.randint(0, 9, size=B), rs.randint(0, 9, size=B)) for _ in range(2)]
             batch = rep.sample_drq(idxs, (crop[0][0], crop[0][1], crop[1][0], crop[1][1]))
         else:
