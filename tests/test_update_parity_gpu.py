@@ -272,7 +272,7 @@ def test_sgsac_critic_stage(dense, quantile, precision):
 
 
 @pytest.mark.parametrize("algorithm,precision", [("sgsac", "fp32"), ("sac", "fp32"), ("svea", "fp32"), ("sgsac", "tf32"),
-                                                 ("svea", "tf32")])
+                                                 ("svea", "tf32"), ("drq", "fp32")])
 def test_full_updates_match_oracle(algorithm, precision):
     B, A = 8, 2
     tf = precision == "tf32"
@@ -288,7 +288,7 @@ def test_full_updates_match_oracle(algorithm, precision):
     for step in (2, 3, 4):
         idxs = rs.randint(0, 48, size=B); rnd = _rnd(rs, B, A, algorithm)
         offs = None
-        if algorithm == "svea":
+        if algorithm in ("svea", "drq"):                 # sample_drq: random_shift(pad 4) with host offsets in [0, 8]
             offs = rs.randint(0, 9, size=(2, B, 2))
             batch = rep.sample_drq(idxs, (offs[0, :, 0], offs[0, :, 1], offs[1, :, 0], offs[1, :, 1]))
         else:
