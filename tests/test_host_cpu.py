@@ -162,3 +162,26 @@ def test_overlay_dataset_loaders(tmp_path):
     assert not torch.equal(pool, D.load_places_pool(str(root), n=8, seed=2))
     with pytest.raises(FileNotFoundError):
         D.load_places_pool([str(tmp_path / "missing")], n=2)
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference`: rank 0 prints ONE JSON line with the contract's keys (the oracle port of the reference update on
+    the host cores); other ranks exit 0 without output."""
+    import json
+    import subprocess
+    import sys
+    env = dict(os.environ, RANK="1", WORLD_SIZE="2")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "2", "--warmup", "1"],
+                       capture_output=True, text=True, env=env, timeout=300)
+    assert r.returncode == 0 and r.stdout.strip() == ""
+    env = dict(os.environ, RANK="0", WORLD_SIZE="1")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "2", "--warmup", "1"],
+                       capture_output=True, text=True, env=env, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "updates/s" and d["higher_is_better"] is True and d["value"] > 0
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"] == {"value": d["value"], "unit": "updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert "workload" in d["config"] and d["metric"].startswith("SGSAC updates/sec")
