@@ -66,6 +66,29 @@ def test_oracle_equals_reference_live(algorithm, dense):
 
 
 @pytest.mark.ref
+def test_oracle_equals_reference_config1_batch128():
+    """BASELINE.json configs[0] (SURVEY.md 8d cfg 1): SGSAC, sgqn_quantile 0.95, batch 128, capacity 1000, overlay pool 256 -- one
+    even and one odd update of the UNMODIFIED reference against the oracle, bit-identical losses and parameters."""
+    from oracle import pin, ref_shim as R
+    B, A = 128, 2
+    agent, rb, orc, rep, args = pin.build_pair("sgsac", B=B, A=A, capacity=1000, pool_n=256)
+    rs = np.random.RandomState(3)
+    for step in (2, 3):
+        idxs = rs.randint(0, 1000, size=B)
+        rnd = pin.make_rnd(rs, B, A, 256)
+        ref_logs = pin.ref_step(agent, rb, idxs, rnd, step, "sgsac")
+        L = R.NullLogger()
+        orc.update_from_batch(rep.sample(idxs), rnd, L, step)
+        ol = {k: v for k, v, _ in L.rows}
+        assert set(ol) == set(ref_logs)
+        for k in ref_logs:
+            assert ol[k] == ref_logs[k], (step, k)
+        for n, t in pin.ref_params(agent).items():
+            o = orc.log_alpha if n == "log_alpha" else orc.p[n]
+            assert torch.equal(t, o), (step, n)
+
+
+@pytest.mark.ref
 def test_oracle_actions_equal_reference_live():
     from oracle import pin, ref_shim as R
     agent, rb, orc, rep, args = pin.build_pair("sgsac", B=2, dense_std=0.05)
