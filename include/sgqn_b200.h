@@ -145,10 +145,13 @@ int sgqn_upsample2_bwd(const float* dup, const float* act, float* dx, int B, int
 
 /* ---- saliency: compute_attribution_mask (rl_utils.py:76-82) fused with the mask application of
  *      update_critic (sgsac.py:67-70); mask uint8 [B][3][HW] (frame mask, the reference repeats it over the 3
- *      channels of a frame); masked_obs may be NULL (mask only).  minmax: 2 floats, u: 1 float (device). */
-int sgqn_minmax(const float* x, long long n, float* scratch /* >= 592 floats */, float* out2, void* stream);
+ *      channels of a frame); masked_obs may be NULL (mask only).  u: 1 float (device).
+ *      sgqn_minmax writes out4 = {min, max, -min, max}: the second pair is what ONE max-all-reduce turns into the global
+ *      batch's pair in the data-parallel configuration; sgqn_attribution_mask reads minmax[0..1] as {min, max}, or as
+ *      {-min, max} when minmax_neg != 0. */
+int sgqn_minmax(const float* x, long long n, float* scratch /* >= 592 floats */, float* out4, void* stream);
 int sgqn_attribution_mask(const float* grad, const float* obs, const float* minmax, const float* u, float quantile,
-                          uint8_t* mask, float* masked_obs, int B, int HW, void* stream);
+                          uint8_t* mask, float* masked_obs, int B, int HW, int minmax_neg, void* stream);
 /* random_overlay (augmentations.py:79-99): 'carla' pool of uint8 frames [N][3][HW] / float places batch [B][3][HW] */
 int sgqn_overlay_u8(const float* obs, const uint8_t* pool, const int64_t* ids, float one_minus_alpha, float alpha, float* out,
                     int B, int HW, void* stream);
@@ -162,8 +165,9 @@ int sgqn_ln_tanh_bwd(const float* dh, int lddh, const float* z, const float* h, 
 int sgqn_set_cols(float* dst, int ld, int col0, const float* src, int lds, int M, int n, void* stream);
 int sgqn_actor_head_fwd(const float* raw, const float* noise, float lmin, float lmax, float* mu_t, float* pi_t, int ldpi,
                         float* log_pi, float* log_std, int M, int A, void* stream);
+/* Bg: the global batch the actor-loss mean runs over (M = this shard's rows; Bg <= 0 means M) */
 int sgqn_actor_head_bwd(const float* raw, const float* noise, const float* dpi, int lddpi, const double* log_alpha, float lmin,
-                        float lmax, float* draw, int M, int A, void* stream);
+                        float lmax, float* draw, int M, int A, int Bg, void* stream);
 int sgqn_critic_loss(const float* q, long long qs, const float* tq1, const float* tq2, const float* next_log_pi,
                      const float* reward, const float* not_done, const double* log_alpha, float discount, int mode, float wa,
                      float wb, float* target_q, float* dq, float* loss, int B, int Bg, void* stream);
@@ -187,9 +191,11 @@ int sgqn_ema(const float* p, float* target, long long n, long long n_tau0, float
 int sgqn_alpha_adam(double* log_alpha, const double* grad, double* st, int* step, double lr, double b1, double b2, double eps,
                     void* stream);
 /* all random draws of one update (numpy idxs utils.py:127, python random sgsac.py:68 / augmentations.py:70, torch
- * randn_like modules.py:219, crop offsets augmentations.py:255-256) from one Philox launch */
+ * randn_like modules.py:219, crop offsets augmentations.py:255-256) from one Philox launch.  seed_u keys the fill scalar u
+ * alone: data-parallel ranks draw their own indices / noise (seed) but ONE u per global batch (sgsac.py:68-70) */
 int sgqn_rng_step(unsigned long long seed, unsigned long long* counter, const int* n_valid, int64_t* idxs, int64_t* overlay_ids,
-                  int pool_n, int32_t* offs, int off_n, float* noise_next, float* noise_pi, float* u, int B, int A, void* stream);
+                  int pool_n, int32_t* offs, int off_n, float* noise_next, float* noise_pi, float* u, int B, int A,
+                  unsigned long long seed_u, void* stream);
 
 #ifdef __cplusplus
 }

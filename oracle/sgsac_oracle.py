@@ -17,6 +17,17 @@ augmentations.py:229-233) -- the reference holds no tests for either, so those
 two are pinned only against our own restatement in ref_shim ("parity unpinned"
 by reference tests).
 
+TF32 mode (`tf32=True`): the reference runs its convolutions with cuDNN's
+`allow_tf32=True` default (SURVEY.md 8c "Oracle numerics"), i.e. every conv operand
+(activations, weights, output gradients) is rounded to a 10-bit mantissa before the
+multiply and products are accumulated in fp32.  The product path does the same on
+tcgen05 (`kind::tf32`), rounding to nearest-away (`cvt.rna.tf32.f32`) at the
+producer of every MMA operand.  `tf32=True` restates the convolutions with exactly
+those roundings (forward, data gradient and weight gradient; `nn.Linear` stays fp32
+as in the reference, matmul TF32 is off), so that this oracle and the product path
+differ by fp32 summation order only and can be held to rel 1e-3 end to end.
+`tf32=False` is the bit-exact CPU restatement that is pinned against the reference.
+
 All file:line citations are relative to /root/reference/src.
 """
 import math
@@ -202,6 +213,80 @@ def _relu(x, guided):
     return _GuidedReLU.apply(x) if guided else F.relu(x)
 
 
+def round_tf32(x):
+    """cvt.rna.tf32.f32 on finite fp32 values: round to nearest (ties away from zero) on the 13 dropped mantissa bits."""
+    bits = x.detach().contiguous().view(torch.int32)
+    return ((bits + 0x1000) & ~0x1FFF).view(torch.float32)
+
+
+class _TF32Conv(torch.autograd.Function):
+    """conv2d whose three contractions (forward, data gradient, weight gradient) take TF32-rounded operands and
+    accumulate in fp32 -- cuDNN allow_tf32 / tcgen05 kind::tf32 semantics.  The bias gradient is the sum of the
+    ROUNDED output gradient (the product path sums what it stores for the next MMA)."""
+
+    @staticmethod
+    def forward(ctx, x, w, b, stride, padding, acc):
+        xr, wr = round_tf32(x).to(acc), round_tf32(w).to(acc)
+        ctx.save_for_backward(xr, wr)
+        ctx.cfg = (stride, padding, b is not None, acc)
+        return F.conv2d(xr, wr, None if b is None else b.to(acc), stride=stride, padding=padding).float()
+
+    @staticmethod
+    def backward(ctx, g):
+        xr, wr = ctx.saved_tensors
+        stride, padding, has_b, acc = ctx.cfg
+        gr = round_tf32(g).to(acc)
+        gx = gw = gb = None
+        if ctx.needs_input_grad[0]:
+            gx = torch.nn.grad.conv2d_input(xr.shape, wr, gr, stride=stride, padding=padding).float()
+        if ctx.needs_input_grad[1]:
+            gw = torch.nn.grad.conv2d_weight(xr, wr.shape, gr, stride=stride, padding=padding).float()
+        if has_b and ctx.needs_input_grad[2]:
+            gb = gr.sum(dim=(0, 2, 3)).float()
+        return gx, gw, gb, None, None, None
+
+
+def conv2d(x, w, b, stride=1, padding=0, tf32=False):
+    """tf32: False = plain fp32 (the pinned restatement); True = TF32-rounded operands, fp32 accumulation (what cuDNN /
+    tcgen05 compute, up to summation order); "f64" = TF32-rounded operands with the products summed in fp64 and rounded
+    to fp32 once -- the summation-order-free centre that both an fp32-accumulating CPU run and the tensor-core run
+    scatter around (tests use it to calibrate how far ANY fp32-accumulating TF32 evaluation is from it)."""
+    if tf32:
+        return _TF32Conv.apply(x, w, b, stride, padding, torch.float64 if tf32 == "f64" else torch.float32)
+    return F.conv2d(x, w, b, stride=stride, padding=padding)
+
+
+def _phase_tap(a, k):
+    return (-1 if k == 0 else 0) if a == 0 else (1 if k == 2 else 0)
+
+
+def phase_weights(w):
+    """Sub-pixel form of conv3x3(pad 1) o nearest-x2-upsample (modules.py:327-337): the conv over the upsampled image
+    equals a 3x3 pad-1 conv at LOW resolution with 4x the output channels (phase p = 2a+b of low-res pixel (y,x) is
+    output pixel (2y+a, 2x+b)); W_phi[(a,b,co)][dy][dx] = sum of the taps (ky,kx) that land on low-res offset (dy,dx).
+    w (Cout,Cin,3,3) -> (4*Cout,Cin,3,3), differentiable (the chain rule folds dW_phi back onto the 3x3 taps)."""
+    out = []
+    for a in (0, 1):
+        for b in (0, 1):
+            taps = [[None] * 3 for _ in range(3)]
+            for ky in range(3):
+                for kx in range(3):
+                    dy, dx = _phase_tap(a, ky) + 1, _phase_tap(b, kx) + 1
+                    taps[dy][dx] = w[:, :, ky, kx] if taps[dy][dx] is None else taps[dy][dx] + w[:, :, ky, kx]
+            z = torch.zeros_like(w[:, :, 0, 0])
+            out.append(torch.stack([torch.stack([t if t is not None else z for t in row], -1) for row in taps], -2))
+    return torch.cat(out, 0)
+
+
+def conv_after_upsample(x, w, b, tf32=False):
+    """conv2d(F.interpolate(x, scale_factor=2), w, b, padding=1) evaluated in sub-pixel form: in TF32 mode the operand that
+    is rounded is W_phi (the fp32 sum of up to four taps), as on the product path (conv_tcg.cu)."""
+    co = w.size(0)
+    y = conv2d(x, phase_weights(w), b.repeat(4), padding=1, tf32=tf32)          # (B, 4*co, H, W), channel = (a, b, co)
+    B, _, H, W = y.shape
+    return y.view(B, 2, 2, co, H, W).permute(0, 3, 4, 1, 5, 2).reshape(B, co, 2 * H, 2 * W)
+
+
 def center_crop(x):
     """modules.py:70-83"""
     if x.size(2) == 84 and x.size(3) == 84:
@@ -210,13 +295,18 @@ def center_crop(x):
     return x[:, :, 8:-8, 8:-8]
 
 
-def cnn_forward(p, x, pre="cnn", guided=False, n_layers=11):
-    """modules.py:132-152 SharedCNN (+ HeadCNN with 0 layers = Flatten, :155-168)."""
+def cnn_forward(p, x, pre="cnn", guided=False, n_layers=11, tf32=False, keep=None):
+    """modules.py:132-152 SharedCNN (+ HeadCNN with 0 layers = Flatten, :155-168).  keep: optional list that receives
+    every layer's pre-activation (tests: ReLU sign patterns)."""
     x = center_crop(x) / 255.0
-    x = F.conv2d(x, p[f"{pre}.0.weight"], p[f"{pre}.0.bias"], stride=2)
+    x = conv2d(x, p[f"{pre}.0.weight"], p[f"{pre}.0.bias"], stride=2, tf32=tf32)
+    if keep is not None:
+        keep.append(x.detach())
     for i in range(1, n_layers):
         x = _relu(x, guided)
-        x = F.conv2d(x, p[f"{pre}.{i}.weight"], p[f"{pre}.{i}.bias"], stride=1)
+        x = conv2d(x, p[f"{pre}.{i}.weight"], p[f"{pre}.{i}.bias"], stride=1, tf32=tf32)
+        if keep is not None:
+            keep.append(x.detach())
     return x.reshape(x.size(0), -1)
 
 
@@ -233,10 +323,10 @@ def mlp3(p, x, pre, guided=False):
     return F.linear(x, p[f"{pre}.4.weight"], p[f"{pre}.4.bias"])
 
 
-def critic_forward(p, obs, action, detach=False, target=False, guided=False, only_q1=False):
+def critic_forward(p, obs, action, detach=False, target=False, guided=False, only_q1=False, tf32=False):
     """modules.py:252-261 Critic.forward (+ :171-184 Encoder.forward)."""
     t = "t_" if target else ""
-    feat = cnn_forward(p, obs, pre=t + "cnn", guided=guided)
+    feat = cnn_forward(p, obs, pre=t + "cnn", guided=guided, tf32=tf32)
     if detach:
         feat = feat.detach()
     h = projection(p, feat, t + "critic_proj")
@@ -247,9 +337,9 @@ def critic_forward(p, obs, action, detach=False, target=False, guided=False, onl
     return q1, mlp3(p, ha, t + "Q2", guided)
 
 
-def actor_forward(p, obs, args, noise=None, compute_pi=True, compute_log_pi=True, detach=False):
+def actor_forward(p, obs, args, noise=None, compute_pi=True, compute_log_pi=True, detach=False, tf32=False):
     """modules.py:201-232 Actor.forward with gaussian_logprob / squash (:20-33)."""
-    feat = cnn_forward(p, obs, pre="cnn")
+    feat = cnn_forward(p, obs, pre="cnn", tf32=tf32)
     if detach:
         feat = feat.detach()
     h = projection(p, feat, "actor_proj")
@@ -274,11 +364,16 @@ def actor_forward(p, obs, args, noise=None, compute_pi=True, compute_log_pi=True
     return mu, pi, log_pi, log_std
 
 
-def decoder_forward(p, h, action):
+def decoder_forward(p, h, action, tf32=False):
     """modules.py:315-341 AttributionDecoder (F.upsample default = nearest)."""
     x = torch.cat([h, action], dim=1)
     x = F.linear(x, p["dec.proj.weight"], p["dec.proj.bias"]).view(-1, 32, 21, 21)
     x = F.relu(x)
+    if tf32:
+        # relu and nearest upsample commute; the convs that follow an upsample run in sub-pixel form on the low-res tensor
+        x = F.relu(conv2d(x, p["dec.conv1.weight"], p["dec.conv1.bias"], padding=1, tf32=True))
+        x = F.relu(conv_after_upsample(x, p["dec.conv2.weight"], p["dec.conv2.bias"], tf32=True))
+        return conv_after_upsample(x, p["dec.conv3.weight"], p["dec.conv3.bias"], tf32=True)
     x = F.conv2d(x, p["dec.conv1.weight"], p["dec.conv1.bias"], padding=1)
     x = F.interpolate(x, scale_factor=2)
     x = F.relu(x)
@@ -288,21 +383,21 @@ def decoder_forward(p, h, action):
     return F.conv2d(x, p["dec.conv3.weight"], p["dec.conv3.bias"], padding=1)
 
 
-def attribution_predictor_forward(p, obs, action):
+def attribution_predictor_forward(p, obs, action, tf32=False):
     """modules.py:345-354: critic encoder (not detached) -> decoder."""
-    feat = cnn_forward(p, obs, pre="cnn")
-    return decoder_forward(p, projection(p, feat, "critic_proj"), action)
+    feat = cnn_forward(p, obs, pre="cnn", tf32=tf32)
+    return decoder_forward(p, projection(p, feat, "critic_proj"), action, tf32=tf32)
 
 
 # --------------------------------------------------------------------------
 # saliency (rl_utils.py:23-39,57-62,76-82)
 # --------------------------------------------------------------------------
-def compute_attribution(p, obs, action):
+def compute_attribution(p, obs, action, tf32=False):
     """Guided backprop of sum_b Q1[b] w.r.t. obs; Q1 only (ModelWrapper `[0]`, rl_utils.py:31-32)."""
     x = obs.detach().clone().requires_grad_(True)
     pd = {k: v.detach() for k, v in p.items()}
     with torch.enable_grad():
-        q1 = critic_forward(pd, x, action.detach(), guided=True, only_q1=True)
+        q1 = critic_forward(pd, x, action.detach(), guided=True, only_q1=True, tf32=tf32)
         (g,) = torch.autograd.grad(q1.sum(), x)
     return g
 
@@ -446,8 +541,9 @@ def synthetic_replay(capacity, action_dim=2, size=84, seed=0):
 class OracleSAC:
     """sac.py:21-169"""
 
-    def __init__(self, obs_shape, action_shape, args, params=None, dense_std=None, seed=0):
+    def __init__(self, obs_shape, action_shape, args, params=None, dense_std=None, seed=0, tf32=False):
         self.args = args
+        self.tf32 = tf32                # False | True | "f64": convolutions with TF32-rounded operands (see conv2d)
         self.A = int(action_shape[0])
         self.p = params if params is not None else init_params(
             obs_shape, self.A, args, torch.Generator().manual_seed(seed), dense_std)
@@ -482,13 +578,13 @@ class OracleSAC:
     def select_action(self, obs):
         x = torch.as_tensor(np.asarray(obs), dtype=torch.float32).unsqueeze(0)
         with torch.no_grad():
-            mu, _, _, _ = actor_forward(self.p, x, self.args, compute_pi=False, compute_log_pi=False)
+            mu, _, _, _ = actor_forward(self.p, x, self.args, compute_pi=False, compute_log_pi=False, tf32=self.tf32)
         return mu.numpy().flatten()
 
     def sample_action(self, obs, noise):
         x = torch.as_tensor(np.asarray(obs), dtype=torch.float32).unsqueeze(0)
         with torch.no_grad():
-            _, pi, _, _ = actor_forward(self.p, x, self.args, noise=noise, compute_log_pi=False)
+            _, pi, _, _ = actor_forward(self.p, x, self.args, noise=noise, compute_log_pi=False, tf32=self.tf32)
         return pi.numpy().flatten()
 
     # ---- pieces ----
@@ -501,15 +597,15 @@ class OracleSAC:
     def target_q(self, reward, next_obs, not_done, noise):
         """sac.py:108-112"""
         with torch.no_grad():
-            _, pa, log_pi, _ = actor_forward(self.p, next_obs, self.args, noise=noise)
-            tq1, tq2 = critic_forward(self.p, next_obs, pa, target=True)
+            _, pa, log_pi, _ = actor_forward(self.p, next_obs, self.args, noise=noise, tf32=self.tf32)
+            tq1, tq2 = critic_forward(self.p, next_obs, pa, target=True, tf32=self.tf32)
             tv = torch.min(tq1, tq2) - self.alpha.detach() * log_pi
             tq = reward + (not_done * self.args.discount * tv)
         self.trace.update(next_pi=pa, next_log_pi=log_pi, target_Q=tq, tQ1=tq1, tQ2=tq2)
         return tq
 
     def critic_loss(self, gp, obs, action, target_q, rnd):
-        q1, q2 = critic_forward(gp, obs, action)
+        q1, q2 = critic_forward(gp, obs, action, tf32=self.tf32)
         self.trace.update(Q1=q1.detach(), Q2=q2.detach())
         return F.mse_loss(q1, target_q) + F.mse_loss(q2, target_q)
 
@@ -529,8 +625,8 @@ class OracleSAC:
         """sac.py:125-151"""
         live = [n for n in self.actor_names if not n.startswith("cnn.")]     # detach=True
         gp = self._grad_params(live)
-        _, pi, log_pi, log_std = actor_forward(gp, obs, self.args, noise=rnd["noise_pi"], detach=True)
-        aq1, aq2 = critic_forward(gp, obs, pi, detach=True)
+        _, pi, log_pi, log_std = actor_forward(gp, obs, self.args, noise=rnd["noise_pi"], detach=True, tf32=self.tf32)
+        aq1, aq2 = critic_forward(gp, obs, pi, detach=True, tf32=self.tf32)
         actor_loss = (self.alpha.detach() * log_pi - torch.min(aq1, aq2)).mean()
         if L is not None:
             L.log("train_actor/loss", actor_loss, step)
@@ -602,8 +698,8 @@ class OracleSAC:
 class OracleSGSAC(OracleSAC):
     """sgsac.py:24-185"""
 
-    def __init__(self, obs_shape, action_shape, args, params=None, dense_std=None, seed=0, overlay_pool=None):
-        super().__init__(obs_shape, action_shape, args, params, dense_std, seed)
+    def __init__(self, obs_shape, action_shape, args, params=None, dense_std=None, seed=0, overlay_pool=None, tf32=False):
+        super().__init__(obs_shape, action_shape, args, params, dense_std, seed, tf32=tf32)
         self.aux_names = [n for n in self.p.keys() if _in_group(n, AUX_GROUP)]
         self.aux_opt = Adam(self.aux_names, args.aux_lr, args.aux_beta)
         self.quantile = args.sgqn_quantile
@@ -611,17 +707,22 @@ class OracleSGSAC(OracleSAC):
 
     def critic_loss(self, gp, obs, action, target_q, rnd):
         """sgsac.py:59-74"""
-        q1, q2 = critic_forward(gp, obs, action)
+        q1, q2 = critic_forward(gp, obs, action, tf32=self.tf32)
         loss = F.mse_loss(q1, target_q) + F.mse_loss(q2, target_q)
         self.trace.update(Q1=q1.detach(), Q2=q2.detach())
         if self.args.consistency:
-            obs_grad = compute_attribution(self.p, obs, action)
+            obs_grad = compute_attribution(self.p, obs, action, tf32=self.tf32)
             mask = compute_attribution_mask(obs_grad, self.quantile)
             masked_obs = obs * mask
             lo, hi = obs.view(-1).min(), obs.view(-1).max()
             fill = lo + (hi - lo) * rnd["u"]                                  # random.uniform(lo, hi)
             masked_obs[mask < 1] = fill
-            mq1, mq2 = critic_forward(gp, masked_obs, action)
+            self.trace.update(own_masked_obs=masked_obs)
+            if rnd.get("force_masked_obs") is not None:
+                # tests only: continue from a given masked observation (the mask is a discontinuous function of the
+                # attribution, so two evaluations that agree to rounding can differ in a few threshold pixels)
+                masked_obs = rnd["force_masked_obs"]
+            mq1, mq2 = critic_forward(gp, masked_obs, action, tf32=self.tf32)
             loss = loss + 0.5 * (F.mse_loss(q1, mq1) + F.mse_loss(q2, mq2))
             self.trace.update(obs_grad1=obs_grad, mask1=mask, masked_obs=masked_obs,
                               mQ1=mq1.detach(), mQ2=mq2.detach(), fill=fill)
@@ -633,7 +734,7 @@ class OracleSGSAC(OracleSAC):
         s_tilde = random_overlay_carla(obs.clone(), self.pool, rnd["overlay_ids"], self.args.alpha_blending)
         live = [n for n in self.aux_names if not n.startswith("fdec.")]
         gp = self._grad_params(live)
-        logits = attribution_predictor_forward(gp, s_tilde.detach(), action.detach())
+        logits = attribution_predictor_forward(gp, s_tilde.detach(), action.detach(), tf32=self.tf32)
         aux_loss = F.binary_cross_entropy_with_logits(logits, mask.float())
         grads = torch.autograd.grad(aux_loss, [gp[n] for n in live])
         g = dict(zip(live, grads))
@@ -648,7 +749,7 @@ class OracleSGSAC(OracleSAC):
         obs, action, reward, next_obs, not_done = batch
         self.trace = dict(obs=obs, next_obs=next_obs)
         self.update_critic(obs, action, reward, next_obs, not_done, rnd, L, step)
-        obs_grad = compute_attribution(self.p, obs, action)
+        obs_grad = compute_attribution(self.p, obs, action, tf32=self.tf32)
         mask = compute_attribution_mask(obs_grad, self.quantile)
         self.trace.update(obs_grad2=obs_grad, mask2=mask)
         if step % self.args.actor_update_freq == 0:
@@ -669,12 +770,12 @@ class OracleSVEA(OracleSAC):
         self.trace.update(obs_aug=aug)
         if a == b:
             o2 = torch.cat([obs, aug], 0); a2 = torch.cat([action, action], 0); t2 = torch.cat([target_q, target_q], 0)
-            q1, q2 = critic_forward(gp, o2, a2)
+            q1, q2 = critic_forward(gp, o2, a2, tf32=self.tf32)
             self.trace.update(Q1=q1.detach(), Q2=q2.detach())
             return (a + b) * (F.mse_loss(q1, t2) + F.mse_loss(q2, t2))
-        q1, q2 = critic_forward(gp, obs, action)
+        q1, q2 = critic_forward(gp, obs, action, tf32=self.tf32)
         loss = a * (F.mse_loss(q1, target_q) + F.mse_loss(q2, target_q))
-        q1a, q2a = critic_forward(gp, aug, action)
+        q1a, q2a = critic_forward(gp, aug, action, tf32=self.tf32)
         self.trace.update(Q1=q1.detach(), Q2=q2.detach())
         return loss + b * (F.mse_loss(q1a, target_q) + F.mse_loss(q2a, target_q))
 

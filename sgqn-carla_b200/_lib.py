@@ -5,7 +5,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libsgqn_b200.so")
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 _p, _i, _ll, _f, _d, _ull = C.c_void_p, C.c_int, C.c_longlong, C.c_float, C.c_double, C.c_ulonglong
 
@@ -54,14 +54,14 @@ SIGNATURES = {
     "sgqn_pool2_bwd": [_p, _p, _p, _i, _i, _i, _i, _p],
     "sgqn_upsample2_bwd": [_p, _p, _p, _i, _i, _i, _i, _p],
     "sgqn_minmax": [_p, _ll, _p, _p, _p],
-    "sgqn_attribution_mask": [_p, _p, _p, _p, _f, _p, _p, _i, _i, _p],
+    "sgqn_attribution_mask": [_p, _p, _p, _p, _f, _p, _p, _i, _i, _i, _p],
     "sgqn_overlay_u8": [_p, _p, _p, _f, _f, _p, _i, _i, _p],
     "sgqn_overlay_f32": [_p, _p, _f, _f, _p, _i, _i, _p],
     "sgqn_ln_tanh_fwd": [_p, _p, _p, _p, _i, _i, _i, _p],
     "sgqn_ln_tanh_bwd": [_p, _i, _p, _p, _i, _p, _p, _p, _p, _i, _i, _p],
     "sgqn_set_cols": [_p, _i, _i, _p, _i, _i, _i, _p],
     "sgqn_actor_head_fwd": [_p, _p, _f, _f, _p, _p, _i, _p, _p, _i, _i, _p],
-    "sgqn_actor_head_bwd": [_p, _p, _p, _i, _p, _f, _f, _p, _i, _i, _p],
+    "sgqn_actor_head_bwd": [_p, _p, _p, _i, _p, _f, _f, _p, _i, _i, _i, _p],
     "sgqn_critic_loss": [_p, _ll, _p, _p, _p, _p, _p, _p, _f, _i, _f, _f, _p, _p, _p, _i, _i, _p],
     "sgqn_actor_loss": [_p, _ll, _p, _p, _f, _p, _p, _p, _i, _i, _p],
     "sgqn_bce": [_p, _p, _p, _p] + [_i] * 10 + [_p],
@@ -69,7 +69,7 @@ SIGNATURES = {
     "sgqn_adam": [_p, _p, _p, _p, _ll, _p, _f, _f, _f, _f, _f, _p, _ll, _f, _f, _p],
     "sgqn_ema": [_p, _p, _ll, _ll, _f, _f, _p],
     "sgqn_alpha_adam": [_p, _p, _p, _p, _d, _d, _d, _d, _p],
-    "sgqn_rng_step": [_ull, _p, _p, _p, _p, _i, _p, _i, _p, _p, _p, _i, _i, _p],
+    "sgqn_rng_step": [_ull, _p, _p, _p, _p, _i, _p, _i, _p, _p, _p, _i, _i, _ull, _p],
 }
 
 _lib = None

@@ -122,6 +122,30 @@ class SAC(object):
         eng.prep_conv_weights(target=True)
         eng.prep_dec_weights()
 
+    def set_training_state(self, canonical, optim=None, alpha_optim=None):
+        """Overwrite the whole training state from reference-shaped tensors: parameters (`name`), target-network
+        parameters (`t_name`), `log_alpha`, and per optimiser ("critic" / "actor" / "aux") the Adam moments as
+        {name: tensor} dicts plus the step count -- what a `torch.optim.Adam.state_dict()` of the reference holds.
+        Tensors an optimiser has no state for (never received a gradient) get zero moments, as in torch."""
+        eng = self.engine
+        lay = eng.lay
+        self.set_parameters({k: v for k, v in canonical.items() if not k.startswith("t_")}, sync_target=False)
+        c0, c1 = lay.ranges["critic"]
+        crit = [n for n in lay.entries if c0 <= lay.off(n) < c1]
+        lay.pack({n: canonical["t_" + n] for n in crit if "t_" + n in canonical}, eng.target, names=crit, base=c0)
+        eng.prep_conv_weights(target=True)
+        for which, st in (optim or {}).items():
+            opt = self._optims()[which]
+            r0, r1 = lay.ranges[which]
+            names = [n for n in lay.entries if r0 <= lay.off(n) < r1]
+            opt.m.zero_(); opt.v.zero_()
+            lay.pack(st["m"], opt.m, names=names, base=r0)
+            lay.pack(st["v"], opt.v, names=names, base=r0)
+            opt.step.fill_(int(st["step"]))
+        if alpha_optim is not None:
+            eng.alpha_st.copy_(torch.tensor([float(alpha_optim["m"]), float(alpha_optim["v"])], dtype=torch.float64))
+            eng.alpha_step.fill_(int(alpha_optim["step"]))
+
     def get_parameters(self):
         eng = self.engine
         out = eng.lay.unpack(eng.params)
@@ -281,7 +305,8 @@ class SAC(object):
         off_n = 9 if self.sample_mode == "shift" else max(1, getattr(replay_buffer, "Hs", 84) - 84)
         n_valid = replay_buffer.n_valid if isinstance(replay_buffer, ReplayBuffer) else eng.rng_counter.to(torch.int32)
         K.rng_step(eng.seed, _ptr(eng.rng_counter), _ptr(n_valid), 0 if skip_idxs else _ptr(eng.idxs), _ptr(eng.overlay_ids), pool_n,
-                   _ptr(eng.offs), off_n, _ptr(eng.noise_next), _ptr(eng.noise_pi), _ptr(eng.u), B, eng.A, eng.st)
+                   _ptr(eng.offs), off_n, _ptr(eng.noise_next), _ptr(eng.noise_pi), _ptr(eng.u), B, eng.A,
+                   eng.seed_shared if eng.seed_shared is not None else eng.seed, eng.st)
         s, self._supplied = self._supplied, None
         if s:
             dev = eng.dev
@@ -319,8 +344,9 @@ class SAC(object):
         if L is None:
             return
         slot, serial = self._ring.push(self.engine.logs)
+        sync = self.engine.dist
         for key, col in cols:
-            v = LazyScalar([(self._ring, slot, serial, col, 1.0)])
+            v = LazyScalar([(self._ring, slot, serial, col, sync.log_scale(col) if sync is not None else 1.0)])
             L.log(key, v if self.defer_logs else float(v), step)
 
     def _log_cols(self, step):
@@ -350,7 +376,7 @@ class SAC(object):
         device staging buffers, on the current stream."""
         eng, B = self.engine, self.batch_size
         st = eng.st
-        K.rng_step(eng.seed ^ 0x5DEECE66D, _ptr(pf["counter"]), _ptr(rb.n_valid), _ptr(pf["idxs"]), 0, 1, 0, 1, 0, 0, 0, B, eng.A, st)
+        K.rng_step(eng.seed ^ 0x5DEECE66D, _ptr(pf["counter"]), _ptr(rb.n_valid), _ptr(pf["idxs"]), 0, 1, 0, 1, 0, 0, 0, B, eng.A, 0, st)
         K.frames_copy(_ptr(rb.frames), _ptr(rb.fidx), _ptr(pf["idxs"]), _ptr(pf["frames"]), B, 3 * rb.Hs * rb.Hs, st)
         K.take_rows(_ptr(rb.actions), _ptr(pf["idxs"]), _ptr(pf["action"]), B, eng.A, st)
         K.take_rows(_ptr(rb.rewards), _ptr(pf["idxs"]), _ptr(pf["reward"]), B, 1, st)
@@ -544,7 +570,7 @@ class SGSAC(SAC):
         eng, B = self.engine, obs_grad.shape[0]
         g = obs_grad.contiguous().float()
         mask = torch.empty(B, 3, 84 * 84, dtype=torch.uint8, device=eng.dev)
-        K.attribution_mask(_ptr(g), 0, 0, 0, float(self.quantile if quantile is None else quantile), _ptr(mask), 0, B, 84 * 84, eng.st)
+        K.attribution_mask(_ptr(g), 0, 0, 0, float(self.quantile if quantile is None else quantile), _ptr(mask), 0, B, 84 * 84, 0, eng.st)
         return mask.reshape(B, 3, 1, 84, 84).expand(B, 3, 3, 84, 84).reshape(B, 9, 84, 84).bool()
 
 

@@ -112,13 +112,14 @@ extern "C" int sgqn_actor_head_fwd(const float* raw, const float* noise, float l
     return SGQN_CHECK_LAUNCH();
 }
 
-// d raw given dL/d pi_t (from the Q heads) and dL/d log_pi = alpha / M  (sac.py:129-130)
+// d raw given dL/d pi_t (from the Q heads) and dL/d log_pi = alpha / Bg  (sac.py:129-130; Bg = the GLOBAL batch the
+// mean runs over: a data-parallel shard of M rows passes the global size, like the loss kernels, and gradients are summed)
 __global__ void actor_head_bwd_kernel(const float* __restrict__ raw, const float* __restrict__ noise,
                                       const float* __restrict__ dpi, int lddpi, const double* __restrict__ log_alpha, float lmin,
-                                      float lmax, float* __restrict__ draw, int M, int A) {
+                                      float lmax, float* __restrict__ draw, int M, int A, int Bg) {
     int r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= M) return;
-    float glp = (float)exp(*log_alpha) / (float)M;
+    float glp = (float)exp(*log_alpha) / (float)Bg;
     for (int a = 0; a < A; ++a) {
         float mu = raw[(size_t)r * 2 * A + a];
         float t = tanhf(raw[(size_t)r * 2 * A + A + a]);
@@ -136,9 +137,10 @@ __global__ void actor_head_bwd_kernel(const float* __restrict__ raw, const float
 }
 
 extern "C" int sgqn_actor_head_bwd(const float* raw, const float* noise, const float* dpi, int lddpi, const double* log_alpha,
-                                   float lmin, float lmax, float* draw, int M, int A, void* stream) {
+                                   float lmin, float lmax, float* draw, int M, int A, int Bg, void* stream) {
     if (M <= 0) return 0;
-    actor_head_bwd_kernel<<<cdiv(M, 128), 128, 0, (cudaStream_t)stream>>>(raw, noise, dpi, lddpi, log_alpha, lmin, lmax, draw, M, A);
+    actor_head_bwd_kernel<<<cdiv(M, 128), 128, 0, (cudaStream_t)stream>>>(raw, noise, dpi, lddpi, log_alpha, lmin, lmax, draw, M, A,
+                                                                          Bg > 0 ? Bg : M);
     return SGQN_CHECK_LAUNCH();
 }
 

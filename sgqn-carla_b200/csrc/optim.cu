@@ -119,7 +119,7 @@ __device__ __forceinline__ float u01(uint32_t x) { return ((float)(x >> 8) + 0.5
 __global__ void rng_step_kernel(unsigned long long seed, unsigned long long* __restrict__ counter, const int* __restrict__ n_valid,
                                 int64_t* __restrict__ idxs, int64_t* __restrict__ overlay_ids, int pool_n, int32_t* __restrict__ offs,
                                 int off_n, float* __restrict__ noise_next, float* __restrict__ noise_pi, float* __restrict__ u,
-                                int B, int A) {
+                                int B, int A, unsigned long long seed_u) {
     const int nA = B * A;
     const int total = 3 * B + nA + 1;
     int id = blockIdx.x * blockDim.x + threadIdx.x;
@@ -147,6 +147,8 @@ __global__ void rng_step_kernel(unsigned long long seed, unsigned long long* __r
         float rad2 = sqrtf(-2.0f * logf(u01(r[2]))), ang2 = 6.283185307179586f * u01(r[3]);
         if (noise_pi) noise_pi[i] = rad2 * cosf(ang2);
     } else if (u) {
+        // the fill scalar is ONE draw per global batch (sgsac.py:68-70): data-parallel ranks share seed_u and the counter
+        philox4x32_10((uint32_t)id, (uint32_t)ctr, (uint32_t)(ctr >> 32), 0x5367514eu, (uint32_t)seed_u, (uint32_t)(seed_u >> 32), r);
         *u = (float)(r[0] >> 8) * (1.0f / 16777216.0f);   // [0,1)
     }
 }
@@ -154,10 +156,10 @@ __global__ void rng_advance_kernel(unsigned long long* counter) { *counter += 1u
 
 extern "C" int sgqn_rng_step(unsigned long long seed, unsigned long long* counter, const int* n_valid, int64_t* idxs,
                              int64_t* overlay_ids, int pool_n, int32_t* offs, int off_n, float* noise_next, float* noise_pi,
-                             float* u, int B, int A, void* stream) {
+                             float* u, int B, int A, unsigned long long seed_u, void* stream) {
     int total = 3 * B + B * A + 1;
     rng_step_kernel<<<cdiv(total, 128), 128, 0, (cudaStream_t)stream>>>(seed, counter, n_valid, idxs, overlay_ids, pool_n, offs, off_n,
-                                                                     noise_next, noise_pi, u, B, A);
+                                                                     noise_next, noise_pi, u, B, A, seed_u);
     rng_advance_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(counter);
     return SGQN_CHECK_LAUNCH();
 }

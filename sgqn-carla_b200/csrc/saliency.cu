@@ -26,14 +26,15 @@ __global__ void minmax_final_kernel(const float* __restrict__ part, int nblk, fl
     float lo = INFINITY, hi = -INFINITY;
     for (int i = threadIdx.x; i < nblk; i += 32) { lo = fminf(lo, part[2 * i]); hi = fmaxf(hi, part[2 * i + 1]); }
     lo = warp_min(lo); hi = warp_max(hi);
-    if (threadIdx.x == 0) { out[0] = lo; out[1] = hi; }
+    // out[2..3] = {-min, max}: the form a single MAX all-reduce makes global (data-parallel shards, dist.py)
+    if (threadIdx.x == 0) { out[0] = lo; out[1] = hi; out[2] = -lo; out[3] = hi; }
 }
 
-extern "C" int sgqn_minmax(const float* x, long long n, float* scratch, float* out2, void* stream) {
+extern "C" int sgqn_minmax(const float* x, long long n, float* scratch, float* out4, void* stream) {
     if (n <= 0 || (n & 3)) return (int)cudaErrorInvalidValue;
     int nblk = 296;
     minmax_partial_kernel<<<nblk, 256, 0, (cudaStream_t)stream>>>((const float4*)x, n / 4, scratch);
-    minmax_final_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(scratch, nblk, out2);
+    minmax_final_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(scratch, nblk, out4);
     return SGQN_CHECK_LAUNCH();
 }
 
@@ -50,7 +51,7 @@ __device__ __forceinline__ float quantile_lerp(float x0, float x1, float w) {
 __global__ void __launch_bounds__(256)
 attribution_mask_kernel(const float* __restrict__ grad, const float* __restrict__ obs, const float* __restrict__ mm,
                         const float* __restrict__ u, float quantile, uint8_t* __restrict__ mask, float* __restrict__ masked,
-                        int HW) {
+                        int HW, int mm_neg) {
     extern __shared__ uint32_t keys[];
     __shared__ uint32_t hist[256];
     __shared__ uint32_t s_prefix, s_krem;
@@ -130,7 +131,10 @@ attribution_mask_kernel(const float* __restrict__ grad, const float* __restrict_
 
     // mask + fill: masked = mask ? obs : lo + (hi - lo) * u   (sgsac.py:67-70)
     float fill = 0.f;
-    if (masked) fill = __fadd_rn(mm[0], __fmul_rn(__fsub_rn(mm[1], mm[0]), u[0]));
+    if (masked) {
+        const float lo_v = mm_neg ? -mm[0] : mm[0];          // mm_neg: {-min, max} (the all-reduced exchange form of sgqn_minmax)
+        fill = __fadd_rn(lo_v, __fmul_rn(__fsub_rn(mm[1], lo_v), u[0]));
+    }
     uint8_t* mrow = mask + ((size_t)b * 3 + f) * HW;
     const float* o0 = obs + ((size_t)b * 9 + 3 * f) * HW;
     float* d0 = masked ? masked + ((size_t)b * 9 + 3 * f) * HW : nullptr;
@@ -146,7 +150,7 @@ attribution_mask_kernel(const float* __restrict__ grad, const float* __restrict_
 }
 
 extern "C" int sgqn_attribution_mask(const float* grad, const float* obs, const float* minmax, const float* u, float quantile,
-                                     uint8_t* mask, float* masked_obs, int B, int HW, void* stream) {
+                                     uint8_t* mask, float* masked_obs, int B, int HW, int minmax_neg, void* stream) {
     if (B <= 0) return 0;
     size_t smem = (size_t)HW * sizeof(uint32_t);
     if (smem > 200 * 1024) return (int)cudaErrorInvalidValue;
@@ -154,7 +158,7 @@ extern "C" int sgqn_attribution_mask(const float* grad, const float* obs, const 
         cudaError_t e = cudaFuncSetAttribute(attribution_mask_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return (int)e;
     }
-    attribution_mask_kernel<<<3 * B, 256, smem, (cudaStream_t)stream>>>(grad, obs, minmax, u, quantile, mask, masked_obs, HW);
+    attribution_mask_kernel<<<3 * B, 256, smem, (cudaStream_t)stream>>>(grad, obs, minmax, u, quantile, mask, masked_obs, HW, minmax_neg);
     return SGQN_CHECK_LAUNCH();
 }
 

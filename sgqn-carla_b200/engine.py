@@ -55,6 +55,9 @@ class UpdateEngine:
         self.overlap = precision == "tf32"
         self.side = torch.cuda.Stream(device=self.dev) if self.overlap else None
         self.side2 = torch.cuda.Stream(device=self.dev) if self.overlap else None
+        self.side3 = torch.cuda.Stream(device=self.dev) if self.overlap else None     # obs min / max (+ its exchange)
+        self.cstream = torch.cuda.Stream(device=self.dev) if (self.overlap and dist is not None) else None   # early gradient pieces
+        self._mm_ev, self._early_ev = None, None
         self.args, self.A, self.B = args, int(action_dim), int(batch_size)
         self.Bg = int(global_batch) if global_batch else self.B
         self.dist = dist
@@ -116,7 +119,7 @@ class UpdateEngine:
         self.ones = torch.ones(B, device=dev)
         self.obs_grad = f32(B, 9, 84, 84)
         self.mask = torch.zeros(B, 3, 84 * 84, dtype=torch.uint8, device=dev)
-        self.mm = f32(2); self.mm_scratch = f32(1024)
+        self.mm = f32(4); self.mm_scratch = f32(1024)      # {min, max, -min, max} of the obs batch (sgqn_minmax)
         self.logs = f32(8)          # critic_loss, actor_loss, alpha_loss, alpha, aux_loss
         # host-suppliable randomness of one step (SURVEY.md 5 'RNG')
         self.idxs = torch.zeros(B, dtype=torch.int64, device=dev)
@@ -125,6 +128,7 @@ class UpdateEngine:
         self.noise_next = f32(B, A); self.noise_pi = f32(B, A); self.u = f32(1)
         self.rng_counter = torch.zeros(1, dtype=torch.int64, device=dev)
         self.seed = int(getattr(args, "seed", 0))
+        self.seed_shared = None         # data-parallel ranks: a seed common to all ranks for the per-batch fill scalar u
         if algorithm == "sgsac":
             self.s_tilde = self.obs2[B:]                 # overlay-augmented obs (written after the critic update)
             self.dl = f32(B, FEAT); self.ddl = f32(B, FEAT)
@@ -372,9 +376,30 @@ class UpdateEngine:
                float(np.float32(1 - opt.b1)), opt.b2, float(np.float32(1 - opt.b2)), opt.eps,
                target if target else 0, n_tau0, tau0, tau1, st)
 
-    def allreduce_grads(self, rng):
+    def allreduce_grads(self, rng, group="main"):
         if self.dist is not None:
-            self.dist.all_reduce_sum(self.grads[rng[0]:rng[1]])
+            self.dist.all_reduce_sum(self.grads[rng[0]:rng[1]], group)
+
+    def _early_reduce(self, rng, after=None):
+        """Sharded configuration: sum-all-reduce grads[rng] as soon as the stream `after` (default: the current one) has
+        produced it, on the communication stream / the "early" communicator, beside the rest of the backward pass.  The
+        pieces of a bucket that are ready before its encoder backward starts (Q heads 9.2 MB, projection 5.6 MB, decoder
+        6.9 MB) overlap the data-gradient chain; only the conv range (0.38 MB) is left for the main stream."""
+        if self.dist is None:
+            return
+        if self.cstream is None:
+            self.dist.all_reduce_sum(self.grads[rng[0]:rng[1]], "early")
+            return
+        ev = torch.cuda.Event(); ev.record(after if after is not None else torch.cuda.current_stream())
+        self.cstream.wait_event(ev)
+        with torch.cuda.stream(self.cstream):
+            self.dist.all_reduce_sum(self.grads[rng[0]:rng[1]], "early")
+            self._early_ev = torch.cuda.Event(); self._early_ev.record(self.cstream)
+
+    def _early_join(self):
+        if self._early_ev is not None:
+            torch.cuda.current_stream().wait_event(self._early_ev)
+            self._early_ev = None
 
     # ------------------------------------------------------------------ the update
     def target_q_pass(self):
@@ -422,21 +447,47 @@ class UpdateEngine:
                       _ptr(self.haS, row0 * P1), P1)
         self.q_fwd(_ptr(self.haS, row0 * P1), n, row0)
 
+    def _obs_minmax_fork(self):
+        """Global min / max of the sampled obs batch (sgsac.py:68-69).  It depends on the batch only, so it -- and, in the
+        sharded configuration, its 2-float all-reduce -- is issued beside the target / critic forward passes (own stream,
+        own communicator) and joined just before the mask kernel needs it."""
+        B = self.B
+        if not self.overlap:
+            K.minmax(_ptr(self.obs2), B * 9 * 84 * 84, _ptr(self.mm_scratch), _ptr(self.mm), self.st)
+            if self.dist is not None:
+                self.dist.all_reduce_minmax(self.mm)
+            self._mm_ev = None
+            return
+        main = torch.cuda.current_stream()
+        ev = torch.cuda.Event(); ev.record(main); self.side3.wait_event(ev)
+        with torch.cuda.stream(self.side3):
+            K.minmax(_ptr(self.obs2), B * 9 * 84 * 84, _ptr(self.mm_scratch), _ptr(self.mm), self.st)
+            if self.dist is not None:
+                self.dist.all_reduce_minmax(self.mm)
+            self._mm_ev = torch.cuda.Event(); self._mm_ev.record(self.side3)
+
+    def _obs_minmax_join(self):
+        if self._mm_ev is not None:
+            torch.cuda.current_stream().wait_event(self._mm_ev)
+            self._mm_ev = None
+
     def update_critic(self, mode):
         """mode 0: SAC (sac.py:107-123); 1: SGSAC with consistency (sgsac.py:52-80); 2: SVEA (svea.py:19-52)."""
         B, A, L, st, a = self.B, self.A, self.lay, self.st, self.args
         P1 = L.P + A
+        if mode == 1:
+            self._obs_minmax_fork()
         self.target_q_pass()
         self.critic_fwd_rows(0, B, encode=False)        # obs went through the encoder with next_obs
         R = B
         if mode == 1:
             self.attribution(B, _ptr(self.haS), _ptr(self.zS), _ptr(self.obs_grad))
-            K.minmax(_ptr(self.obs2), B * 9 * 84 * 84, _ptr(self.mm_scratch), _ptr(self.mm), st)
-            if self.dist is not None:
-                self.dist.all_reduce_minmax(self.mm)
-            K.attribution_mask(_ptr(self.obs_grad), _ptr(self.obs2), _ptr(self.mm), _ptr(self.u), self.quantile,
-                               _ptr(self.mask), _ptr(self.obs2, B * 9 * 84 * 84), B, 84 * 84, st)
+            self._obs_minmax_join()
+            sharded = self.dist is not None             # then mm[2:4] = {-min, max} of the GLOBAL batch (sgsac.py:68-70)
+            K.attribution_mask(_ptr(self.obs_grad), _ptr(self.obs2), _ptr(self.mm, 2 if sharded else 0), _ptr(self.u), self.quantile,
+                               _ptr(self.mask), _ptr(self.obs2, B * 9 * 84 * 84), B, 84 * 84, 1 if sharded else 0, st)
             if self.debug_masked_obs is not None:           # parity tests: feed the oracle's masked obs forward
+                self.debug_own_masked_obs = self.obs2[B:].clone()
                 self.obs2[B:].copy_(self.debug_masked_obs)
                 self.debug_masked_obs = None
             self.critic_fwd_rows(B, B)
@@ -455,12 +506,16 @@ class UpdateEngine:
         c0, c1 = L.ranges["critic"]
         K.zero(self._g + 4 * c0, 4 * (c1 - c0), st)
         self.q_dgrad(_ptr(self.dq), 2 * B, R, 0, 2, 1, _ptr(self.dhaS))
+        wside = self.side if self.overlap else None
         self.q_wgrad(_ptr(self.haS), _ptr(self.dq), R, 0, st=self._fork())     # joined at the end of enc_bwd
+        self._early_reduce(L.ranges["critic_q"], after=wside)
         dfeat = _ptr(self.dbuf[1])
         self.proj_bwd(_ptr(self.dhaS), P1, R, _ptr(self.zS), _ptr(self.haS), P1, "critic_proj", _ptr(self.dzS),
                       feat_ptr=_ptr(self.actS[10], B * FEAT), dfeat=dfeat)
+        self._early_reduce(L.ranges["critic_proj"], after=wside)
         self.enc_bwd(dfeat, R, self.actS, B, _ptr(self.obs2), 1, True)
-        self.allreduce_grads((c0, c1))
+        self.allreduce_grads(L.ranges["cnn"])
+        self._early_join()
 
     def critic_step(self, with_ema):
         L, a = self.lay, self.args
@@ -498,7 +553,7 @@ class UpdateEngine:
         self.q_fwd(_ptr(self.haS), B, 0, 1)
         self.attribution(B, _ptr(self.haS), _ptr(self.zS), _ptr(self.obs_grad))
         if want_mask:
-            K.attribution_mask(_ptr(self.obs_grad), 0, 0, 0, self.quantile, _ptr(self.mask), 0, B, 84 * 84, st)
+            K.attribution_mask(_ptr(self.obs_grad), 0, 0, 0, self.quantile, _ptr(self.mask), 0, B, 84 * 84, 0, st)
 
     def update_actor_and_alpha(self, finish=True):
         """sac.py:125-151; expects shared_obs_fwd() state (critic slot, head rows [0,B))."""
@@ -514,7 +569,7 @@ class UpdateEngine:
                      _ptr(self.logs, 1), _ptr(self.alpha_grad), B, self.Bg, st)
         self.q_dgrad(_ptr(self.dq), 2 * B, B, 0, 2, 1, _ptr(self.dhaS))
         K.actor_head_bwd(_ptr(self.raw), _ptr(self.noise_pi), _ptr(self.dhaS, L.P), P1, _ptr(self.log_alpha), lmin, lmax,
-                         _ptr(self.draw), B, A, st)
+                         _ptr(self.draw), B, A, self.Bg, st)
         a0, a1 = L.ranges["actor"]
         K.zero(self._g + 4 * a0, 4 * (a1 - a0), st)
         # actor MLP backward
@@ -540,9 +595,9 @@ class UpdateEngine:
         second stream, every collective is still issued from the main stream in one fixed order on all ranks)."""
         a, st = self.args, self.st
         a0, a1 = self.lay.ranges["actor"]
-        self.allreduce_grads((a0, a1))
+        self.allreduce_grads((a0, a1), "actor")         # (own communicator: issued from the stream the actor update runs on)
         if self.dist is not None:
-            self.dist.all_reduce_sum(self.alpha_grad)
+            self.dist.all_reduce_sum(self.alpha_grad, "actor")
         self.adam(self.opt_actor, (a0, a1))
         K.alpha_adam(_ptr(self.log_alpha), _ptr(self.alpha_grad), _ptr(self.alpha_st), _ptr(self.alpha_step),
                      float(a.alpha_lr), float(a.alpha_beta), 0.999, 1e-8, st)
@@ -564,11 +619,14 @@ class UpdateEngine:
             self._decoder_simt(B, st, Wp, G, x0, x1)
         K.linear_wgrad(ha, P1, 0, _ptr(self.ddl), FEAT, 0, G("dec.proj.weight"), 0, G("dec.proj.bias"), 0,
                        B, FEAT, P1, 0, 1, st)
+        self._early_reduce(L.ranges["dec"])             # decoder gradients are complete: exchange them under the encoder backward
         K.linear_dgrad(_ptr(self.ddl), FEAT, 0, Wp("dec.proj.weight"), 0, 0, 0, 0, _ptr(self.dhaT), P1, 0, B, FEAT, P1, 0, 2, 1, st)
         dfeat = _ptr(self.dbuf[1])
         self.proj_bwd(_ptr(self.dhaT), P1, B, z, ha, P1, "critic_proj", _ptr(self.dzT), feat_ptr=feat, dfeat=dfeat)
+        self._early_reduce(L.ranges["critic_proj"], after=self.side if self.overlap else None)
         self.enc_bwd(dfeat, B, self.actS, 2 * B, _ptr(self.s_tilde), 1, True)
-        self.allreduce_grads((x0, x1))
+        self.allreduce_grads(L.ranges["cnn"])           # (fdec.* never receives a gradient: not exchanged)
+        self._early_join()
         self.adam(self.opt_aux, (x0, x1))
         self.prep_conv_weights()
         self.prep_dec_weights()
@@ -657,12 +715,11 @@ class UpdateEngine:
             # heavy): disjoint parameter / gradient ranges and head rows -> run it beside the aux update
             main = torch.cuda.current_stream()
             ev = torch.cuda.Event(); ev.record(main); self.side2.wait_event(ev)
-            with torch.cuda.stream(self.side2):
-                self.update_actor_and_alpha(finish=False)
+            with torch.cuda.stream(self.side2):         # incl. its gradient exchange ("actor" communicator) and optimiser steps
+                self.update_actor_and_alpha(finish=True)
                 ev2 = torch.cuda.Event(); ev2.record(self.side2)
             self.update_aux()
             main.wait_event(ev2)
-            self.actor_finish()
         else:
             if do_actor:
                 self.update_actor_and_alpha()

@@ -59,7 +59,9 @@ class ParamLayout:
         enc0 = off
         for i in range(num_layers):
             add(f"cnn.{i}.weight", (num_filters, in_ch if i == 0 else num_filters, 3, 3)); add(f"cnn.{i}.bias", (num_filters,))
+        self.ranges["cnn"] = (enc0, off)
         self._add_proj(add, "critic_proj")
+        self.ranges["critic_proj"] = (self.ranges["cnn"][1], off)
         self.ranges["critic"] = (start, off)
         self.ranges["critic_q"] = (start, enc0)
         dec0 = off

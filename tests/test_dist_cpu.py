@@ -20,12 +20,19 @@ WORKER = textwrap.dedent("""
     local = per_sample[r * 4:(r + 1) * 4].sum(0) / 8.0
     s.all_reduce_sum(local)
     assert torch.allclose(local, per_sample.mean(0), atol=1e-6)
-    mm = torch.tensor([3.0 + r, 200.0 - 10 * r])
+    lo, hi = 3.0 + r, 200.0 - 10 * r
+    mm = torch.tensor([lo, hi, -lo, hi])                          # what sgqn_minmax writes
     s.all_reduce_minmax(mm)
-    assert mm.tolist() == [3.0, 200.0], mm
+    assert mm.tolist() == [lo, hi, -3.0, 200.0], mm               # the second pair is global {-min, max}
     logs = torch.tensor([1.0 + r, 2.0, 3.0, 0.1, 4.0, 0, 0, 0])
     s.all_reduce_logs(logs)
-    assert abs(float(logs[0]) - 3.0) < 1e-6 and abs(float(logs[3]) - 0.1) < 1e-6
+    assert abs(float(logs[0]) * s.log_scale(0) - 3.0) < 1e-6 and abs(float(logs[3]) * s.log_scale(3) - 0.1) < 1e-6
+    # one communicator per issuing stream; each one reduces independently
+    for name in s.GROUPS:
+        t = torch.tensor([1.0 + r])
+        s.all_reduce_sum(t, name)
+        assert float(t) == 3.0, (name, t)
+    assert len({id(g) for g in s.groups.values()}) == len(s.GROUPS)
     dist.destroy_process_group()
     print("rank", r, "ok")
 """)

@@ -128,3 +128,91 @@ def test_sharded_batch_equals_full_batch_gradients():
     assert abs((l0 + l1) - lf) <= 1e-4 * abs(lf)
     rel = float((g0 + g1 - gf).norm() / gf.norm())
     assert rel <= 2e-3, rel
+
+
+class _FakeSync:
+    """In-process stand-in for dist.GradSync when the ranks of a sharded step are looped on one GPU: the min / max exchange
+    returns the known global pair, gradient sums are formed by the test."""
+
+    def __init__(self, lo, hi):
+        self.lo, self.hi, self.seen = lo, hi, []
+
+    world = 2
+
+    def all_reduce_sum(self, flat, group="main"):
+        pass
+
+    def all_reduce_minmax(self, mm, group="minmax"):
+        self.seen.append(mm[:2].clone())
+        mm[2], mm[3] = -self.lo, self.hi
+
+    def all_reduce_logs(self, logs, group="main"):
+        pass
+
+    def log_scale(self, col):
+        return 1.0
+
+
+@pytest.mark.parametrize("precision", ["fp32", "tf32"])
+def test_sgsac_sharded_equals_full_batch(precision):
+    """BASELINE config 4 semantics for SGSAC: two shards whose observations span DIFFERENT ranges, the fill
+    value built from the GLOBAL batch min / max (sgsac.py:68-70) and one shared u; every loss scaled by 1 / global batch.
+    Masked observations of the shards are bit-identical to the corresponding rows of the full-batch run; critic, actor
+    (incl. the alpha-weighted entropy term) and alpha gradients summed over the shards equal the full-batch gradients."""
+    import sgqn_carla_b200 as S
+    from oracle import sgsac_oracle as O
+    A, Bg = 2, 16
+    h = Bg // 2
+    args = S.default_args(algorithm="sgsac", batch_size=Bg, sgqn_quantile=0.95)
+    p0 = O.init_params((9, 84, 84), A, O.Args(**vars(args)), torch.Generator().manual_seed(5), dense_std=0.05)
+    rep = O.synthetic_replay(64, A, seed=2)
+    rep.frames[:36] = np.clip(rep.frames[:36], 20, 180)          # transitions 0..31 only see frames in [20, 180]
+    rs = np.random.RandomState(0)
+    idxs = np.concatenate([rs.randint(0, 32, size=h), rs.randint(36, 64, size=h)])     # shard 0: narrow range, shard 1: full range
+    rnd = _rnd(rs, Bg, A, "sgsac")
+    full_obs = torch.as_tensor(rep.stacks(idxs)[0]).float()
+    lo, hi = float(full_obs.min()), float(full_obs.max())
+    assert float(full_obs[:h].min()) > lo and float(full_obs[:h].max()) < hi
+
+    def run(batch, sl, sync):
+        a = S.default_args(algorithm="sgsac", batch_size=batch, sgqn_quantile=0.95)
+        ag = S.make_agent((9, 84, 84), (A,), a, precision=precision, global_batch=Bg, dist=sync)
+        ag.use_cuda_graphs = False
+        ag.set_parameters(p0)
+        rb = S.ReplayBuffer((9, 84, 84), (A,), 64, batch)
+        rb.load_ring(rep.frames, rep.actions, rep.rewards, rep.not_dones)
+        ag.supply(idxs=idxs[sl], noise_next=rnd["noise_next"][sl], noise_pi=rnd["noise_pi"][sl], u=rnd["u"])
+        ag._draw(rb); ag._sample_into_engine(rb)
+        eng = ag.engine
+        eng.update_critic(1)
+        torch.cuda.synchronize()
+        lay = eng.lay
+        c0, c1 = lay.ranges["critic"]
+        out = dict(masked=eng.obs2[batch:].clone(), mask=eng.mask.clone(), gc=eng.grads[c0:c1].clone(), lc=float(eng.logs[0]))
+        eng.shared_obs_fwd()
+        eng.update_actor_and_alpha(finish=False)
+        torch.cuda.synchronize()
+        a0, a1 = lay.ranges["actor"]
+        out.update(ga=eng.grads[a0:a1].clone(), la=float(eng.logs[1]), galpha=float(eng.alpha_grad))
+        return out
+
+    full = run(Bg, slice(0, Bg), None)
+    s0, s1 = _FakeSync(lo, hi), _FakeSync(lo, hi)
+    r0 = run(h, slice(0, h), s0)
+    r1 = run(h, slice(h, Bg), s1)
+    assert len(s0.seen) == 1 and s0.seen[0].tolist() != [lo, hi] and s1.seen[0].tolist() == [lo, hi]    # the exchange mattered
+    if precision == "fp32":          # same kernels, same per-sample arithmetic: the shards' rows are the full batch's rows
+        assert torch.equal(torch.cat([r0["mask"], r1["mask"]]), full["mask"])
+        assert torch.equal(torch.cat([r0["masked"], r1["masked"]]), full["masked"])
+    else:                            # tcgen05 tiles straddle samples differently at another batch size: rounding-level attributions
+        agree = (torch.cat([r0["mask"], r1["mask"]]) == full["mask"]).float().mean()
+        assert float(agree) >= 0.999
+        same = (torch.cat([r0["mask"], r1["mask"]]) == full["mask"]).reshape(Bg, 3, 1, 84 * 84).expand(Bg, 3, 3, 84 * 84).reshape(Bg, 9, 84, 84)
+        assert torch.equal(torch.cat([r0["masked"], r1["masked"]])[same], full["masked"][same])
+    tol = 2e-3 if precision == "fp32" else 5e-2
+    assert abs((r0["lc"] + r1["lc"]) - full["lc"]) <= 1e-3 * abs(full["lc"])
+    assert abs((r0["la"] + r1["la"]) - full["la"]) <= 1e-3 * abs(full["la"]) + 1e-4
+    assert abs((r0["galpha"] + r1["galpha"]) - full["galpha"]) <= 1e-4 * abs(full["galpha"]) + 1e-7
+    for k in ("gc", "ga"):
+        rel = float((r0[k] + r1[k] - full[k]).norm() / full[k].norm())
+        assert rel <= tol, (k, rel)

@@ -261,8 +261,14 @@ def test_actor_head_fwd_bwd(A):
     loss = (pi_r * dpi[:, :A]).sum() + (0.3 / M) * lp_r.sum()
     loss.backward()
     draw = torch.zeros(M, 2 * A, device=DEV)
-    K.actor_head_bwd(P(raw), P(noise), P(dpi), A + 3, P(log_alpha), -10.0, 2.0, P(draw), M, A, ST())
+    K.actor_head_bwd(P(raw), P(noise), P(dpi), A + 3, P(log_alpha), -10.0, 2.0, P(draw), M, A, M, ST())
     close(draw, rr.grad, rtol=5e-4, what="actor_head_bwd")
+    # a data-parallel shard: the entropy term is scaled by 1 / global batch (here 3 M), like the Q term that arrives in dpi
+    rr2 = raw.clone().requires_grad_(True)
+    _, pi2, lp2, _ = _actor_head_ref(rr2, noise, -10.0, 2.0)
+    ((pi2 * dpi[:, :A]).sum() + (0.3 / (3 * M)) * lp2.sum()).backward()
+    K.actor_head_bwd(P(raw), P(noise), P(dpi), A + 3, P(log_alpha), -10.0, 2.0, P(draw), M, A, 3 * M, ST())
+    close(draw, rr2.grad, rtol=5e-4, what="actor_head_bwd (global batch 3M)")
 
 
 @pytest.mark.parametrize("mode", [0, 1, 2])
@@ -318,12 +324,12 @@ def test_bce():
 
 
 # ------------------------------------------------------------------ saliency / augmentation / replay: bit-exact
-def _mask_gpu(grad, q, obs=None, mm=None, u=None):
+def _mask_gpu(grad, q, obs=None, mm=None, u=None, mm_neg=0):
     B = grad.shape[0]
     mask = torch.zeros(B, 3, 84 * 84, dtype=torch.uint8, device=DEV)
     masked = torch.zeros(B, 9, 84, 84, device=DEV) if obs is not None else None
     K.attribution_mask(P(grad), P(obs) if obs is not None else 0, P(mm) if mm is not None else 0, P(u) if u is not None else 0,
-                       float(q), P(mask), P(masked) if masked is not None else 0, B, 84 * 84, ST())
+                       float(q), P(mask), P(masked) if masked is not None else 0, B, 84 * 84, mm_neg, ST())
     full = mask.reshape(B, 3, 1, 84, 84).expand(B, 3, 3, 84, 84).reshape(B, 9, 84, 84).bool()
     return full, masked
 
@@ -348,12 +354,14 @@ def test_attribution_mask_vs_oracle_and_fill(q):
     grad[0, :3] = 0; grad[1, 3:6, :80] = 0; grad[2] = torch.round(grad[2] * 4000) / 4000
     obs = torch.randint(0, 256, (6, 9, 84, 84), generator=g).float()
     ref = O.compute_attribution_mask(grad, q)
-    mm = torch.zeros(2, device=DEV); scratch = torch.zeros(1024, device=DEV)
+    mm = torch.zeros(4, device=DEV); scratch = torch.zeros(1024, device=DEV)
     obs_d = obs.to(DEV)
     K.minmax(P(obs_d), obs.numel(), P(scratch), P(mm), ST())
-    assert mm.cpu().tolist() == [float(obs.min()), float(obs.max())]
+    assert mm.cpu().tolist() == [float(obs.min()), float(obs.max()), -float(obs.min()), float(obs.max())]
     u = torch.tensor([0.37], device=DEV)
     m, masked = _mask_gpu(grad.to(DEV), q, obs_d, mm, u)
+    m2, masked2 = _mask_gpu(grad.to(DEV), q, obs_d, mm[2:], u, mm_neg=1)        # the all-reduce exchange form {-min, max}
+    assert torch.equal(m2, m) and torch.equal(masked2, masked)
     assert torch.equal(m.cpu(), ref)
     fill = obs.min() + (obs.max() - obs.min()) * 0.37
     ref_masked = obs * ref
@@ -470,10 +478,16 @@ def test_rng_step_statistics():
     idxs = torch.zeros(B, dtype=torch.int64, device=DEV); ov = torch.zeros(B, dtype=torch.int64, device=DEV)
     offs = torch.zeros(2, B, 2, dtype=torch.int32, device=DEV)
     n1 = torch.zeros(B, A, device=DEV); n2 = torch.zeros(B, A, device=DEV); u = torch.zeros(1, device=DEV)
-    K.rng_step(7, P(ctr), P(nv), P(idxs), P(ov), 256, P(offs), 9, P(n1), P(n2), P(u), B, A, ST())
+    K.rng_step(7, P(ctr), P(nv), P(idxs), P(ov), 256, P(offs), 9, P(n1), P(n2), P(u), B, A, 7, ST())
     first = idxs.clone()
-    K.rng_step(7, P(ctr), P(nv), P(idxs), P(ov), 256, P(offs), 9, P(n1), P(n2), P(u), B, A, ST())
+    K.rng_step(7, P(ctr), P(nv), P(idxs), P(ov), 256, P(offs), 9, P(n1), P(n2), P(u), B, A, 7, ST())
     assert int(ctr) == 2 and not torch.equal(first, idxs)
+    # two data-parallel ranks: own seed (indices / noise differ), shared seed_u and counter (ONE fill scalar per global batch)
+    c0 = torch.zeros(1, dtype=torch.int64, device=DEV); c1 = torch.zeros(1, dtype=torch.int64, device=DEV)
+    i0, i1, u0, u1 = idxs.clone(), idxs.clone(), u.clone(), u.clone()
+    K.rng_step(100, P(c0), P(nv), P(i0), P(ov), 256, P(offs), 9, P(n1), P(n2), P(u0), B, A, 55, ST())
+    K.rng_step(101, P(c1), P(nv), P(i1), P(ov), 256, P(offs), 9, P(n1), P(n2), P(u1), B, A, 55, ST())
+    assert float(u0) == float(u1) and not torch.equal(i0, i1)
     assert 0 <= int(idxs.min()) and int(idxs.max()) < 1000 and int(ov.max()) < 256 and int(offs.max()) <= 8 and int(offs.min()) >= 0
     z = torch.cat([n1.flatten(), n2.flatten()])
     assert abs(float(z.mean())) < 0.15 and abs(float(z.std()) - 1.0) < 0.1 and 0.0 <= float(u) < 1.0

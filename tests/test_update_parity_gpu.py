@@ -26,7 +26,8 @@ def _mk(algorithm="sgsac", B=8, A=2, dense=0.05, quantile=0.95, seed=0, size=84,
     oargs = O.Args(**vars(args))
     p0 = O.init_params((9, 84, 84), A, oargs, torch.Generator().manual_seed(seed + 11), dense_std=dense)
     pool = torch.as_tensor(np.random.RandomState(seed + 7).randint(0, 256, size=(16, 3, 84, 84), dtype=np.uint8))
-    orc = O.make_oracle((9, 84, 84), (A,), oargs, params={k: v.clone() for k, v in p0.items()})
+    # the tf32 product path is checked against the oracle that rounds conv operands to TF32 where the tcgen05 kernels do
+    orc = O.make_oracle((9, 84, 84), (A,), oargs, params={k: v.clone() for k, v in p0.items()}, tf32=(precision == "tf32"))
     agent = S.make_agent((9, size, size), (A,), args, precision=precision)
     agent.set_parameters(p0)
     if algorithm == "sgsac":
@@ -53,25 +54,45 @@ def _relerr(a, b):
     return float((a - b).norm() / (b.norm() + 1e-30))
 
 
-def _relu_flips(eng, orc, tr, B):
-    """Encoder layers whose pre-activation sign pattern differs between the engine and the oracle."""
+def _relu_flips(eng, orc, tr, B, tf32=False):
+    """ReLU units whose sign differs between the engine and the oracle (evaluated in arithmetic `tf32`): the set of
+    encoder layers with a flip, and per Q head the hidden layers with one.  A pre-activation within rounding of 0 can
+    take the other sign in a different summation order; the gradient through that unit is then switched on / off -- a
+    discontinuity no tolerance on values covers."""
     import torch.nn.functional as F
+    from oracle import sgsac_oracle as O
     from sgqn_carla_b200.layout import ENC_H
     p = orc.p
     x = torch.cat([tr["obs"] if "obs" in tr else eng.obs2[:B].cpu(), tr["masked_obs"]], 0)
-    x = F.conv2d(x / 255.0, p["cnn.0.weight"], p["cnn.0.bias"], stride=2)
+    keep = []
+    feat = O.cnn_forward(p, x, tf32=tf32, keep=keep)
     flips = []
-    for l in range(11):
-        if l > 0:
-            x = F.conv2d(F.relu(x), p[f"cnn.{l}.weight"], p[f"cnn.{l}.bias"])
+    for l in range(10):
         h = ENC_H[l]
-        if eng.precision == "tf32" and l < 10:      # pitch-linear layout with 2 spare rows per sample
+        if eng.precision == "tf32":                     # pitch-linear layout with 2 spare rows per sample
             mine = eng.actS[l].reshape(3 * B, h + 2, h, 32)[B:, :h].permute(0, 3, 1, 2).cpu()       # rows [next | obs | masked]
         else:
             mine = eng.actS[l][:3 * B * h * h * 32].reshape(3 * B, h, h, 32)[B:].permute(0, 3, 1, 2).cpu()
-        if l < 10 and bool(((mine > 0) != (x > 0)).any()):
+        if bool(((mine > 0) != (keep[l] > 0)).any()):
             flips.append(l)
-    return flips
+    ha = torch.cat([O.projection(p, feat, "critic_proj"), torch.cat([eng.action.cpu()] * 2, 0)], 1)
+    head = {}
+    for hi, q in enumerate(("Q1", "Q2")):
+        z1 = F.linear(ha, p[f"{q}.0.weight"], p[f"{q}.0.bias"])
+        z2 = F.linear(F.relu(z1), p[f"{q}.2.weight"], p[f"{q}.2.bias"])
+        head[q] = [j for j, (mine, ref) in enumerate(((eng.z1[hi, :2 * B].cpu(), z1), (eng.z2[hi, :2 * B].cpu(), z2)))
+                   if bool(((mine > 0) != (ref > 0)).any())]
+    return flips, head
+
+
+def _flip_below(n, flips, head):
+    """True if the gradient of parameter tensor `n` passes through a ReLU layer with a flipped unit."""
+    if n.startswith("cnn."):
+        return any(f >= int(n.split(".")[1]) for f in flips) or bool(head["Q1"] or head["Q2"])
+    if n.startswith("critic_proj."):
+        return bool(head["Q1"] or head["Q2"])
+    q, j = n.split(".")[0], int(n.split(".")[1])
+    return any(f >= j // 2 for f in head[q])
 
 
 class _L:
@@ -204,16 +225,37 @@ def test_graphed_batch1_actor_equals_eager():
     assert len({tuple(np.round(d, 6)) for d in draws}) == 6
 
 
+def _oracle_critic_stage(orc, batch, rnd, tf32, force_masked=None):
+    """update_critic of the oracle up to the gradients, in the requested arithmetic (False | True | "f64")."""
+    keep = orc.tf32
+    orc.tf32, orc.trace = tf32, {}
+    r = dict(rnd, force_masked_obs=force_masked)
+    tq = orc.target_q(batch[2], batch[3], batch[4], rnd["noise_next"])
+    gp = orc._grad_params(orc.critic_names)
+    loss = orc.critic_loss(gp, batch[0], batch[1], tq, r)
+    grads = torch.autograd.grad(loss, [gp[n] for n in orc.critic_names])
+    tr = dict(orc.trace)
+    orc.tf32 = keep
+    return tr, loss.detach(), dict(zip(orc.critic_names, grads))
+
+
 @pytest.mark.parametrize("dense,quantile,precision", [(0.05, 0.95, "fp32"), (0.05, 0.5, "fp32"), (None, 0.95, "fp32"),
-                                                      (0.05, 0.95, "tf32"), (None, 0.95, "tf32")])
+                                                      (0.05, 0.95, "tf32"), (None, 0.95, "tf32"), (None, 0.5, "tf32")])
 def test_sgsac_critic_stage(dense, quantile, precision):
     """update_critic (sgsac.py:52-80) stage-wise: batch, target, Q, attribution, mask, masked obs, loss, gradients.
 
-    precision="fp32" (CUDA-core convs) carries the strict 1e-3 bars.  precision="tf32" is the product path (tcgen05
-    TF32 convs, like the reference's cuDNN allow_tf32=True default): 10-bit-mantissa operands through an 11-layer ReLU
-    chain give ~1e-3 on Q / loss and percent-level, direction-preserving differences on attributions and encoder
-    gradients (bars below), the same order the reference's own GPU run differs from its CPU run."""
-    from oracle import sgsac_oracle as O
+    precision="fp32" (CUDA-core convs) is compared with the plain fp32 oracle at rel 1e-3.
+
+    precision="tf32" is the product path (tcgen05 TF32 convs = the reference's cuDNN allow_tf32 default).  It is compared
+    with the oracle evaluated in the SAME arithmetic -- every conv operand rounded to TF32 where the kernels round, fp32
+    everywhere else (oracle/sgsac_oracle.py `tf32`) -- so the only difference left is the order of the fp32 sums.  The
+    centre of the comparison is the oracle with those products summed in fp64 ("f64": no summation order at all); the
+    bar for every quantity is  err(product, centre) <= 1e-3 + 2 * err(oracle with fp32 sums, centre):  rel 1e-3 wherever
+    TF32 arithmetic itself is reproducible to 1e-3 (losses, Q, and everything at the reference's initialisation), and
+    otherwise no further from the centre than torch's own fp32-accumulating evaluation of the same TF32 arithmetic is
+    (a dense random 11-layer ReLU net amplifies one flipped TF32 rounding to percent-level gradient differences in ANY
+    two evaluations that sum in different orders: measured spread of the oracle against itself 1.8e-2 on cnn.0.weight).
+    A second, looser assertion keeps the distance to the plain fp32 oracle (what the reference computes on a CPU)."""
     B, A = 8, 2
     tf = precision == "tf32"
     agent, rb, orc, rep, args = _mk(B=B, dense=dense, quantile=quantile, precision=precision)
@@ -221,94 +263,184 @@ def test_sgsac_critic_stage(dense, quantile, precision):
     rs = np.random.RandomState(2)
     idxs = rs.randint(0, 48, size=B); rnd = _rnd(rs, B, A, "sgsac")
     batch = rep.sample(idxs)
-    orc.trace = {}
-    tq = orc.target_q(batch[2], batch[3], batch[4], rnd["noise_next"])
-    gp = orc._grad_params(orc.critic_names)
-    loss = orc.critic_loss(gp, batch[0], batch[1], tq, rnd)
-    grads = torch.autograd.grad(loss, [gp[n] for n in orc.critic_names])
-    tr = orc.trace
+    if tf:
+        tr, loss, gref = _oracle_critic_stage(orc, batch, rnd, "f64")
+        tr32, loss32, g32 = _oracle_critic_stage(orc, batch, rnd, True, force_masked=tr["masked_obs"])
+        trf, lossf, gf = _oracle_critic_stage(orc, batch, rnd, False)
+    else:
+        tr, loss, gref = _oracle_critic_stage(orc, batch, rnd, False)
 
     _supply(agent, idxs, rnd)
     agent._draw(rb); agent._sample_into_engine(rb)
     assert torch.equal(eng.obs2[:B].cpu(), batch[0]) and torch.equal(eng.next_obs.cpu(), batch[3])
     assert torch.equal(eng.action.cpu(), batch[1]) and torch.equal(eng.reward.cpu(), batch[2])
+    if tf:
+        eng.debug_masked_obs = tr["masked_obs"].to(DEV)      # both continue from the centre's masked observation
     eng.update_critic(1)
     torch.cuda.synchronize()
-    qt = 3e-3 if tf else 1e-3
-    np.testing.assert_allclose(eng.target_q.cpu().numpy(), tr["target_Q"][:, 0].numpy(), rtol=qt, atol=qt * 0.1)
-    np.testing.assert_allclose(eng.q[0, :B].cpu().numpy(), tr["Q1"][:, 0].numpy(), rtol=qt, atol=qt * 0.1)
-    np.testing.assert_allclose(eng.q[1, :B].cpu().numpy(), tr["Q2"][:, 0].numpy(), rtol=qt, atol=qt * 0.1)
+    np.testing.assert_allclose(eng.target_q.cpu().numpy(), tr["target_Q"][:, 0].numpy(), rtol=1e-3, atol=1e-4)
+    np.testing.assert_allclose(eng.q[0, :B].cpu().numpy(), tr["Q1"][:, 0].numpy(), rtol=1e-3, atol=1e-4)
+    np.testing.assert_allclose(eng.q[1, :B].cpu().numpy(), tr["Q2"][:, 0].numpy(), rtol=1e-3, atol=1e-4)
     g_ref = tr["obs_grad1"]
+    mask = eng.mask.reshape(B, 3, 1, 84, 84).expand(B, 3, 3, 84, 84).reshape(B, 9, 84, 84).bool().cpu()
+    disagree = float((mask != tr["mask1"]).float().mean())
     if tf:
-        assert _relerr(eng.obs_grad, g_ref) <= 5e-2, ("attribution", _relerr(eng.obs_grad, g_ref))
+        spread = _relerr(tr32["obs_grad1"], g_ref)
+        e = _relerr(eng.obs_grad, g_ref)
+        # (guided backprop runs through every encoder ReLU and Q1's: a flipped unit there is a discontinuity, see _relu_flips)
+        fl, hd = _relu_flips(eng, orc, tr, B, tf32="f64")
+        assert e <= (5e-2 if (fl or hd["Q1"]) else 1e-3 + 2 * spread), ("attribution", e, spread, fl, hd)
+        assert _relerr(eng.obs_grad, trf["obs_grad1"]) <= 5e-2            # vs the plain fp32 oracle
+        m_spread = float((tr32["mask1"] != tr["mask1"]).float().mean())
+        assert disagree <= 1e-3 + 2 * m_spread, ("mask", disagree, m_spread)
+        mo = eng.debug_own_masked_obs.cpu()
+        own_ref = tr["own_masked_obs"]
     else:
         err = float((eng.obs_grad.cpu() - g_ref).abs().max())
         assert err <= 1e-3 * float(g_ref.abs().max()) + 1e-12, ("attribution", err, float(g_ref.abs().max()))
-    mask = eng.mask.reshape(B, 3, 1, 84, 84).expand(B, 3, 3, 84, 84).reshape(B, 9, 84, 84).bool().cpu()
-    agree = float((mask == tr["mask1"]).float().mean())
-    assert agree >= (0.998 if tf else 0.999), agree
+        assert disagree <= 1e-3, disagree
+        mo = eng.obs2[B:].cpu()
+        own_ref = tr["masked_obs"]
     same = (mask == tr["mask1"])
-    mo = eng.obs2[B:].cpu()
-    assert torch.allclose(mo[same], tr["masked_obs"][same], rtol=1e-6, atol=1e-4)
-    np.testing.assert_allclose(float(eng.logs[0]), float(loss.detach()), rtol=2e-3 if tf else 1e-3)
+    assert torch.allclose(mo[same], own_ref[same], rtol=1e-6, atol=1e-4)
+    np.testing.assert_allclose(float(eng.logs[0]), float(loss), rtol=1e-3)
     got = eng.lay.unpack(eng.grads)
     if tf:
-        for n, gr in zip(orc.critic_names, grads):
+        np.testing.assert_allclose(float(eng.logs[0]), float(lossf), rtol=2e-3)
+        flips, head = _relu_flips(eng, orc, tr, B, tf32="f64")
+        for n, gr in gref.items():
             if float(gr.norm()) < 1e-7:
                 continue
-            a, b = got[n].double().cpu().reshape(-1), gr.double().reshape(-1)
+            e, spread = _relerr(got[n], gr), _relerr(g32[n], gr)
+            tol = 1e-3 + 2 * spread
+            if _flip_below(n, flips, head):             # a flipped ReLU unit on the gradient's path (see _relu_flips)
+                tol = max(tol, 5e-2)
+            assert e <= tol, (n, e, spread, flips, head)
+            a, b = got[n].double().cpu().reshape(-1), gf[n].double().reshape(-1)     # vs the plain fp32 oracle
             cos = float((a @ b) / (a.norm() * b.norm() + 1e-300))
-            assert _relerr(got[n], gr) <= 0.1 and cos >= 0.995, (n, _relerr(got[n], gr), cos)
+            assert _relerr(got[n], gf[n]) <= 0.1 and cos >= 0.995, (n, _relerr(got[n], gf[n]), cos)
         return
     # ReLU patterns: a pre-activation within fp32 rounding of 0 can take the other sign in a different summation
     # order; its gradient is then switched on/off (a discontinuity no tolerance on values covers).  Gradients below
     # such a flip are compared loosely, everything else to 1e-3.
-    flips = _relu_flips(eng, orc, tr, B)
-    for n, gr in zip(orc.critic_names, grads):
+    flips, head = _relu_flips(eng, orc, tr, B)
+    for n, gr in gref.items():
         e = _relerr(got[n], gr)
-        layer = int(n.split(".")[1]) if n.startswith("cnn.") else 99
-        tol = 1e-3 if not any(f >= layer for f in flips) else 5e-2
-        assert e <= tol or float(gr.norm()) < 1e-7, (n, e, float(gr.norm()), flips)
+        tol = 5e-2 if _flip_below(n, flips, head) else 1e-3
+        assert e <= tol or float(gr.norm()) < 1e-7, (n, e, float(gr.norm()), flips, head)
 
 
-@pytest.mark.parametrize("algorithm,precision", [("sgsac", "fp32"), ("sac", "fp32"), ("svea", "fp32"), ("sgsac", "tf32"),
-                                                 ("svea", "tf32"), ("drq", "fp32")])
-def test_full_updates_match_oracle(algorithm, precision):
+def _batch_for(algorithm, rep, rs, B, lo=0, hi=9):
+    idxs = rs.randint(0, 48, size=B)
+    offs = None
+    if algorithm in ("svea", "drq"):                 # sample_drq: random_shift(pad 4) with host offsets in [0, 8]
+        offs = rs.randint(lo, hi, size=(2, B, 2))
+        batch = rep.sample_drq(idxs, (offs[0, :, 0], offs[0, :, 1], offs[1, :, 0], offs[1, :, 1]))
+    else:
+        batch = rep.sample(idxs)
+    return idxs, offs, batch
+
+
+def _force_state(agent, orc):
+    """Teacher forcing: the agent continues from exactly the oracle's parameters, targets and Adam states."""
+    opt = {"critic": orc.critic_opt, "actor": orc.actor_opt}
+    if hasattr(orc, "aux_opt"):
+        opt["aux"] = orc.aux_opt
+    st = {k: dict(m=o.m, v=o.v, step=max([o.t[n] for n in o.t] + [0])) for k, o in opt.items()}
+    ao = orc.alpha_opt
+    alpha = dict(m=ao.m.get("log_alpha", 0.0), v=ao.v.get("log_alpha", 0.0), step=ao.t.get("log_alpha", 0))
+    agent.set_training_state(dict(orc.p, log_alpha=orc.log_alpha), st, alpha)
+
+
+ALGO_CASES = [(a, p, d) for a in ("sgsac", "sac", "svea", "drq") for p, d in (("fp32", 0.05), ("tf32", None), ("tf32", 0.05))]
+
+
+@pytest.mark.parametrize("algorithm,precision,dense", ALGO_CASES)
+def test_teacher_forced_updates_match_oracle(algorithm, precision, dense):
+    """Four consecutive updates (even, odd, even, odd: critic / actor / alpha / target EMA / aux all exercised with non-trivial
+    Adam moments), each one started from EXACTLY the oracle's state (parameters, targets, Adam moments and step counts are
+    copied in before every update), so every update is held to the first-update bars instead of tracking a trajectory:
+    every logged loss to rel 1e-3 (+ an absolute floor for the losses that are small differences of O(1) numbers), the
+    updated parameters to the Adam-step bound with the per-element count check.  precision="tf32" is checked against the
+    TF32-rounding oracle, at the reference's initialisation and at the dense one."""
     B, A = 8, 2
     tf = precision == "tf32"
-    # fp32: dense N(0,0.05) weights (adversarial: every activation is live).  tf32: the reference's own initialisation
-    # (what training starts from); 10-bit-mantissa operands make a dense random 11-layer ReLU net drift by several %
-    # within a few Adam steps, which says nothing about the kernels.
-    agent, rb, orc, rep, args = _mk(algorithm=algorithm, B=B, precision=precision, dense=None if tf else 0.05)
-    if algorithm == "svea":
-        agent.set_places_pool(torch.rand(4, 3, 84, 84))
-    rs = np.random.RandomState(9)
+    agent, rb, orc, rep, args = _mk(algorithm=algorithm, B=B, precision=precision, dense=dense)
+    rs = np.random.RandomState(5)
     L, Lo = _L(), _L()
-    lr = 1e-3
-    for step in (2, 3, 4):
-        idxs = rs.randint(0, 48, size=B); rnd = _rnd(rs, B, A, algorithm)
-        offs = None
-        if algorithm in ("svea", "drq"):                 # sample_drq: random_shift(pad 4) with host offsets in [0, 8]
-            offs = rs.randint(0, 9, size=(2, B, 2))
-            batch = rep.sample_drq(idxs, (offs[0, :, 0], offs[0, :, 1], offs[1, :, 0], offs[1, :, 1]))
-        else:
-            batch = rep.sample(idxs)
+    for step in (2, 3, 4, 5):
+        idxs, offs, batch = _batch_for(algorithm, rep, rs, B)
+        rnd = _rnd(rs, B, A, algorithm)
+        _force_state(agent, orc)
+        before = {n: t.clone() for n, t in orc.p.items()}
         orc.update_from_batch(batch, rnd, Lo, step)
         _supply(agent, idxs, rnd, offs)
         agent.update(rb, L, step)
         torch.cuda.synchronize()
         keys = [k for (s, k) in Lo.rows if s == step]
         assert sorted(keys) == sorted(k for (s, k) in L.rows if s == step)
-        # first update: identical parameters -> rel 2e-3; later updates start from parameters that already differ by
-        # Adam's sign-sensitive steps (see below), so the losses are only required to track to 2 %.
-        rt = (5e-3 if tf else 2e-3) if step == 2 else (5e-2 if tf else 2e-2)
         for k in keys:
-            if tf and step == 2 and k != "train_critic/loss":
-                rt = 2e-2        # computed after this step's critic Adam update (sign-sensitive) on TF32 gradients
-            # alpha_loss = alpha*mean(-log_pi - target_entropy) is a small difference of O(1) numbers: absolute floor
-            np.testing.assert_allclose(float(L.rows[(step, k)]), float(Lo.rows[(step, k)]), rtol=rt,
-                                       atol=(3e-3 if step == 2 else 5e-2) if tf else 1e-4,
-                                       err_msg=f"{step} {k}")
+            # the critic loss is computed on identical parameters: rel 1e-3 everywhere.  The actor / alpha / aux losses are
+            # computed AFTER this update's critic Adam step, which moves every element by ~lr * sign(g) (from zero moments
+            # exactly that): where a gradient is ~0 its sign is rounding noise (floor: 2e-3 absolute).  On the dense
+            # adversarial initialisation (lr = 2 % of the weight scale, TF32 gradients reproducible to ~1e-2 only, see
+            # test_sgsac_critic_stage) those sign differences move the post-step losses by up to ~2 %.
+            # (there log_pi of a nearly saturated tanh policy is itself ill-conditioned: alpha_loss gets a 2e-2 floor)
+            loose = tf and dense and k != "train_critic/loss"
+            np.testing.assert_allclose(float(L.rows[(step, k)]), float(Lo.rows[(step, k)]), rtol=3e-2 if loose else 1e-3,
+                                       atol=1e-5 if k == "train_critic/loss" else (2e-2 if loose else 2e-3), err_msg=f"{step} {k}")
+        mine = agent.get_parameters()
+        for n, ref in orc.p.items():
+            if n not in mine:
+                continue
+            d = (mine[n].cpu().double() - ref.double()).abs()
+            moved = (ref.double() - before[n].double()).abs()
+            lr = 1e-3 + (3e-4 if n.startswith(("cnn.", "critic_proj.")) and algorithm == "sgsac" else 0.0)
+            # one update moves an element by <= ~lr (per optimiser that owns it); the two paths may differ by up to that
+            # where the gradient's sign is rounding noise, and must agree to a few % of a step everywhere else
+            assert float(d.max()) <= 2.1 * lr + 1e-6 * float(ref.abs().max()), (step, n, float(d.max()))
+            bad = int((d > 0.05 * lr).sum())
+            assert bad <= max(2, (0.10 if tf else 0.02) * d.numel()), (step, n, bad, d.numel())
+            assert float(d.mean()) <= ((0.1 if dense else 0.05) if tf else 0.01) * lr + 2 * 2.1 * lr / d.numel(), \
+                (step, n, float(d.mean()), float(moved.mean()))
+        assert abs(float(mine["log_alpha"]) - float(orc.log_alpha)) < 1e-6
+    # acting from identical (trained) parameters: sac.py:86-105
+    _force_state(agent, orc)
+    x = rep.stacks(np.array([7]))[0][0]
+    tol = dict(rtol=1e-3, atol=(2e-3 if dense else 2e-4) if tf else 1e-5)
+    np.testing.assert_allclose(agent.select_action(x), orc.select_action(x), **tol)
+    n = torch.full((1, A), -0.4)
+    np.testing.assert_allclose(agent.sample_action(x, noise=n), orc.sample_action(x, n), **tol)
+
+
+@pytest.mark.parametrize("algorithm,precision,dense", ALGO_CASES)
+def test_full_updates_match_oracle(algorithm, precision, dense):
+    """Free-running: three updates without re-synchronisation.  The first update is held to rel 1e-3; later updates start
+    from parameters that already differ by Adam's sign-sensitive steps, so they are only required to TRACK the oracle
+    (test_teacher_forced_updates_match_oracle holds every update to the strict bars)."""
+    B, A = 8, 2
+    tf = precision == "tf32"
+    agent, rb, orc, rep, args = _mk(algorithm=algorithm, B=B, precision=precision, dense=dense)
+    if algorithm == "svea":
+        agent.set_places_pool(torch.rand(4, 3, 84, 84))
+    rs = np.random.RandomState(9)
+    L, Lo = _L(), _L()
+    lr = 1e-3
+    for step in (2, 3, 4):
+        idxs, offs, batch = _batch_for(algorithm, rep, rs, B)
+        rnd = _rnd(rs, B, A, algorithm)
+        orc.update_from_batch(batch, rnd, Lo, step)
+        _supply(agent, idxs, rnd, offs)
+        agent.update(rb, L, step)
+        torch.cuda.synchronize()
+        keys = [k for (s, k) in Lo.rows if s == step]
+        assert sorted(keys) == sorted(k for (s, k) in L.rows if s == step)
+        for k in keys:
+            if step == 2:
+                rt, at = 1e-3, (1e-5 if k == "train_critic/loss" else 2e-3)
+            else:
+                rt, at = (5e-2, 5e-2) if tf else (2e-2, 1e-4)
+            np.testing.assert_allclose(float(L.rows[(step, k)]), float(Lo.rows[(step, k)]), rtol=rt, atol=at, err_msg=f"{step} {k}")
         mine = agent.get_parameters()
         nup = step - 1
         for n, ref in orc.p.items():
@@ -321,7 +453,7 @@ def test_full_updates_match_oracle(algorithm, precision):
             # (the shared conv weights take a critic step (lr 1e-3) AND an aux step (lr 3e-4) per even update)
             assert float(d.max()) <= 2.1 * (lr + 3e-4) * nup + 1e-6 * float(ref.abs().max()), (step, n, float(d.max()))
             bad = int((d > 0.05 * lr * nup).sum())
-            if not tf:       # TF32 gradients differ at the percent level on this dense random net -> only the mean is bounded
+            if not tf:
                 assert bad <= max(2, 0.10 * d.numel()), (step, n, bad, d.numel())
             assert float(d.mean()) <= (0.3 if tf else 0.03) * lr * nup, (step, n, float(d.mean()))
         assert abs(float(mine["log_alpha"]) - float(orc.log_alpha)) < (2e-5 if tf else 1e-7)      # alpha_lr = 1e-4 per step
@@ -330,7 +462,7 @@ def test_full_updates_match_oracle(algorithm, precision):
 def test_rad_crop_and_actions_at_100():
     """RAD config: 100x100 frames, sample() crops to 84 with host offsets; select_action centre-crops (modules.py:70-83)."""
     B, A = 4, 6
-    agent, rb, orc, rep, args = _mk(algorithm="rad", B=B, A=A, size=100)
+    agent, rb, orc, rep, args = _mk(algorithm="rad", B=B, A=A, size=100, dense=None)
     rs = np.random.RandomState(4)
     L, Lo = _L(), _L()
     for step in (2, 3):
@@ -341,10 +473,12 @@ def test_rad_crop_and_actions_at_100():
         _supply(agent, idxs, rnd, offs)
         agent.update(rb, L, step)
         for (s, k), v in Lo.rows.items():
-            if s == step:            # tf32 product path (see test_sgsac_critic_stage)
-                np.testing.assert_allclose(float(L.rows[(s, k)]), float(v), rtol=5e-3 if step == 2 else 5e-2, atol=3e-3)
+            if s == step:            # tf32 product path vs the TF32-rounding oracle, reference initialisation; free-running
+                np.testing.assert_allclose(float(L.rows[(s, k)]), float(v), rtol=1e-3 if step == 2 else 2e-2, atol=2e-3)
     x = rep.stacks(np.array([5]))[0][0]
-    np.testing.assert_allclose(agent.select_action(x), orc.select_action(x), rtol=1e-2, atol=3e-2)     # tf32, after 2 updates
+    # after 2 free-running updates (two sign-sensitive Adam steps of 1e-3 on weights of scale ~3e-2; the same check from
+    # identical parameters is part of test_teacher_forced_updates_match_oracle: 1e-3)
+    np.testing.assert_allclose(agent.select_action(x), orc.select_action(x), rtol=1e-2, atol=3e-2)
 
 
 def test_device_rng_update_runs_and_is_finite():
