@@ -152,11 +152,12 @@ int sgqn_upsample2_bwd(const float* dup, const float* act, float* dx, int B, int
 int sgqn_minmax(const float* x, long long n, float* scratch /* >= 592 floats */, float* out4, void* stream);
 int sgqn_attribution_mask(const float* grad, const float* obs, const float* minmax, const float* u, float quantile,
                           uint8_t* mask, float* masked_obs, int B, int HW, int minmax_neg, void* stream);
-/* random_overlay (augmentations.py:79-99): 'carla' pool of uint8 frames [N][3][HW] / float places batch [B][3][HW] */
+/* random_overlay (augmentations.py:79-99): 'carla' pool of uint8 frames [N][3][HW]; float places images in [0,1]: a batch
+ * [B][3][HW] (ids NULL) or rows ids[b] of a device-resident pool [N][3][HW] */
 int sgqn_overlay_u8(const float* obs, const uint8_t* pool, const int64_t* ids, float one_minus_alpha, float alpha, float* out,
                     int B, int HW, void* stream);
-int sgqn_overlay_f32(const float* obs, const float* imgs, float one_minus_alpha, float alpha, float* out, int B, int HW,
-                     void* stream);
+int sgqn_overlay_f32(const float* obs, const float* imgs, const int64_t* ids, float one_minus_alpha, float alpha, float* out,
+                     int B, int HW, void* stream);
 
 /* ---- heads and losses */
 int sgqn_ln_tanh_fwd(const float* z, const float* gamma, const float* beta, float* h, int ldh, int M, int P, void* stream);

@@ -56,7 +56,7 @@ SIGNATURES = {
     "sgqn_minmax": [_p, _ll, _p, _p, _p],
     "sgqn_attribution_mask": [_p, _p, _p, _p, _f, _p, _p, _i, _i, _i, _p],
     "sgqn_overlay_u8": [_p, _p, _p, _f, _f, _p, _i, _i, _p],
-    "sgqn_overlay_f32": [_p, _p, _f, _f, _p, _i, _i, _p],
+    "sgqn_overlay_f32": [_p, _p, _p, _f, _f, _p, _i, _i, _p],
     "sgqn_ln_tanh_fwd": [_p, _p, _p, _p, _i, _i, _i, _p],
     "sgqn_ln_tanh_bwd": [_p, _i, _p, _p, _i, _p, _p, _p, _p, _i, _i, _p],
     "sgqn_set_cols": [_p, _i, _i, _p, _i, _i, _i, _p],

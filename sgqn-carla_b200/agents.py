@@ -146,6 +146,19 @@ class SAC(object):
             eng.alpha_st.copy_(torch.tensor([float(alpha_optim["m"]), float(alpha_optim["v"])], dtype=torch.float64))
             eng.alpha_step.fill_(int(alpha_optim["step"]))
 
+    def sync_from_rank0(self):
+        """Data-parallel start-up (SURVEY.md 8e 'identical replicated parameters'): broadcast rank 0's parameters, targets,
+        log_alpha and optimiser states, then rebuild every derived tensor-core operand copy from them."""
+        import torch.distributed as dist
+        eng = self.engine
+        ts = [eng.params, eng.target, eng.log_alpha, eng.alpha_st, eng.alpha_step]
+        for o in self._optims().values():
+            ts += [o.m, o.v, o.step]
+        for t in ts:
+            dist.broadcast(t, 0)
+        eng.prep_conv_weights(); eng.prep_conv_weights(target=True); eng.prep_dec_weights()
+        self._graphs.clear(); self._eager_runs.clear()
+
     def get_parameters(self):
         eng = self.engine
         out = eng.lay.unpack(eng.params)
@@ -197,7 +210,7 @@ class SAC(object):
             o.m.copy_(st["m"]); o.v.copy_(st["v"]); o.step.copy_(st["step"])
         eng.alpha_st.copy_(ck["alpha_optim"]["state"]); eng.alpha_step.copy_(ck["alpha_optim"]["step"])
         eng.rng_counter.copy_(ck["rng_counter"]); eng.seed = int(ck["seed"])
-        self._graphs.clear(); self._eager_runs.clear()       # the seed is baked into the captured graphs
+        self._graphs.clear(); self._eager_runs.clear(); self._act.clear()      # the seed is baked into the captured graphs
 
     def save_checkpoint(self, path):
         torch.save(self.checkpoint(), path)
@@ -243,7 +256,7 @@ class SAC(object):
                         frames=torch.zeros(9, H, H, dtype=torch.uint8, device=dev),
                         fidx=torch.tensor([0, 1, 2, 0, 1, 2], dtype=torch.int32, device=dev),
                         idx=torch.zeros(1, dtype=torch.int64, device=dev),
-                        obs=torch.zeros(2, 9, H, H, device=dev), noise=torch.zeros(1, A, device=dev),
+                        obs=torch.zeros(2, 9, H, H, device=dev),
                         out=torch.zeros(A).pin_memory(), graph=None, runs=0)
             slot["stage_np"] = slot["stage"].numpy()
             slot["out_np"] = slot["out"].numpy()
@@ -253,9 +266,7 @@ class SAC(object):
             slot["frames"].copy_(slot["stage"], non_blocking=True)
             K.replay_gather(_ptr(slot["frames"]), _ptr(slot["fidx"]), _ptr(slot["idx"]), 0, _ptr(slot["obs"]), _ptr(slot["obs"][1]),
                             1, H, H, 0, 4, eng.st)
-            if sample:
-                slot["noise"].normal_()
-            res = eng.act(slot["obs"][:1], H, sample=sample, noise=slot["noise"] if sample else None)
+            res = eng.act(slot["obs"][:1], H, sample=sample)        # (sampling noise: the engine's Philox kernel)
             slot["out"].copy_(res, non_blocking=True)
 
         np.copyto(slot["stage_np"], arr)
@@ -299,9 +310,14 @@ class SAC(object):
         self._supplied = dict(idxs=idxs, noise_next=noise_next, noise_pi=noise_pi, u=u, overlay_ids=overlay_ids,
                               offs=offs, places=places)
 
+    def _pool_n(self):
+        """Size of the overlay image pool the step's `overlay_ids` index (SGSAC: carla frames; SVEA: places images)."""
+        pool = self.engine.overlay_pool
+        return int(pool.shape[0]) if pool is not None else 1
+
     def _draw(self, replay_buffer, skip_idxs=False):
         eng, B = self.engine, self.batch_size
-        pool_n = eng.overlay_pool.shape[0] if eng.overlay_pool is not None else 1
+        pool_n = self._pool_n()
         off_n = 9 if self.sample_mode == "shift" else max(1, getattr(replay_buffer, "Hs", 84) - 84)
         n_valid = replay_buffer.n_valid if isinstance(replay_buffer, ReplayBuffer) else eng.rng_counter.to(torch.int32)
         K.rng_step(eng.seed, _ptr(eng.rng_counter), _ptr(n_valid), 0 if skip_idxs else _ptr(eng.idxs), _ptr(eng.overlay_ids), pool_n,
@@ -385,9 +401,9 @@ class SAC(object):
     def _run_update_prefetched(self, rb, step):
         eng, B = self.engine, self.batch_size
         pf = self._pf
-        if pf is None or pf["rb"] is not rb:
+        if pf is None or pf["rb"] is not rb or pf["version"] != rb.version:
             dev = eng.dev
-            pf = self._pf = dict(rb=rb, primed=False, frames=torch.zeros(B * 6, 3 * rb.Hs * rb.Hs, dtype=torch.uint8, device=dev),
+            pf = self._pf = dict(rb=rb, version=rb.version, primed=False, frames=torch.zeros(B * 6, 3 * rb.Hs * rb.Hs, dtype=torch.uint8, device=dev),
                                  fidx=torch.arange(6 * B, dtype=torch.int32, device=dev).reshape(B, 6),
                                  arange=torch.arange(B, dtype=torch.int64, device=dev),
                                  idxs=torch.zeros(B, dtype=torch.int64, device=dev),
@@ -436,8 +452,9 @@ class SAC(object):
         if not graphable:
             self._run_update(replay_buffer, step)
             return
-        if self._graph_rb is not replay_buffer:            # pointers are baked into the graphs
-            self._graphs.clear(); self._eager_runs.clear(); self._graph_rb = replay_buffer
+        key = (id(replay_buffer), replay_buffer.version)   # pointers are baked into the graphs (the frame ring can grow)
+        if self._graph_rb != key:
+            self._graphs.clear(); self._eager_runs.clear(); self._graph_rb = key
         g = self._graphs.get(kind)
         if g is None:
             if self._eager_runs.get(kind, 0) < 1:
@@ -486,27 +503,29 @@ class SVEA(SAC):
         self.places_pool = None         # float (N,3,84,84) in [0,1] on the device (what _get_places_batch yields)
 
     def set_places_pool(self, imgs):
-        self.places_pool = torch.as_tensor(imgs, dtype=torch.float32).to(self.engine.dev)
+        t = torch.as_tensor(imgs, dtype=torch.float32)
+        assert t.dim() == 4 and tuple(t.shape[1:]) == (3, 84, 84), "places pool: float images (N,3,84,84) in [0,1]"
+        self.places_pool = t.to(self.engine.dev).contiguous()
+        self.engine.places_pool = self.places_pool.reshape(t.shape[0], 3, -1)
+        self._graphs.clear(); self._eager_runs.clear()          # the pool pointer / size are baked into the captured graphs
+
+    def _pool_n(self):
+        return int(self.places_pool.shape[0]) if self.places_pool is not None else 1
 
     def load_places_dir(self, data_dirs, n=4096, use_val=False, seed=0):
         """Places365 as the reference reads it (augmentations.py:17-62), n transformed images drawn once into the device pool."""
         from .datasets import load_places_pool
         self.set_places_pool(load_places_pool(data_dirs, n, 84, use_val, seed))
 
-    def _graphable(self):
-        return False                    # the places batch is assembled with torch indexing per step
-
     def update(self, replay_buffer, L, step, count=0):
-        eng, B = self.engine, self.batch_size
+        """svea.py:54-63.  The overlay images of a step are rows `overlay_ids` (drawn on the device with everything else)
+        of the device-resident places pool, read by the overlay kernel itself -- the whole update is one CUDA graph, like
+        SAC's.  Parity runs hand the images over with supply(places=...)."""
         supplied_places = self._supplied is not None and self._supplied.get("places") is not None
-        self._draw(replay_buffer)
-        if not supplied_places:
-            if self.places_pool is None:
-                raise RuntimeError("SVEA needs an overlay image pool: agent.set_places_pool(float images (N,3,84,84) in [0,1])")
-            eng.places.copy_(self.places_pool[eng.overlay_ids % self.places_pool.shape[0]].reshape(B, 3, -1))
-        self._sample_into_engine(replay_buffer)
-        eng.update_sac(step, 2)
-        self._emit_logs(L, step, self._log_cols(step))
+        if not supplied_places and self.places_pool is None:
+            raise RuntimeError("SVEA needs an overlay image pool: agent.set_places_pool(float images (N,3,84,84) in [0,1])")
+        self.engine.places_from_pool = not supplied_places
+        super().update(replay_buffer, L, step, count)
 
 
 class SGSAC(SAC):
@@ -522,7 +541,7 @@ class SGSAC(SAC):
         self.consistency = args.consistency
         self.alpha_blending = args.alpha_blending
         self.count = 0
-        self.writer = None              # tensorboard image logging (sgsac.py:104-161) is out of scope
+        self._writer = None             # SummaryWriter, created on first use (sgsac.py:41-48)
 
     def set_overlay_pool(self, frames_u8):
         """uint8 (N,3,84,84) frames: what `datasets/carla/*.npy` hold (utils.py:325-327), loaded once to the device
@@ -555,15 +574,79 @@ class SGSAC(SAC):
     def _engine_update(self, step):
         self.engine.update_sgsac(step)
 
+    # ---- the eval hook of the reference's train loops (train.py:36-50, train_carla.py:45-52)
+    @property
+    def writer(self):
+        if self._writer is None:
+            from .viz import make_writer
+            a = self.args
+            self._writer = make_writer(os.path.join(str(getattr(a, "log_dir", "logs")),
+                                                    f"{getattr(a, 'domain_name', 'carla')}_{getattr(a, 'task_name', 'drive')}",
+                                                    str(getattr(a, "algorithm", "sgsac")), str(getattr(a, "seed", 0)), "tensorboard"))
+        return self._writer
+
+    @writer.setter
+    def writer(self, w):
+        self._writer = w
+
+    def log_tensorboard(self, obs, action, step, prefix="original"):
+        """sgsac.py:104-135: observation grid, guided-backprop attribution grid, the observation masked by the attribution
+        predictor's output, the predicted attribution, and the observation masked at five quantiles -- images go to
+        `self.writer` and (best effort, like the reference's try/except) to output/<prefix>/...png."""
+        from .viz import make_obs_grad_grid, make_obs_grid
+        obs = torch.as_tensor(obs, dtype=torch.float32, device=self.engine.dev)
+        action = torch.as_tensor(action, dtype=torch.float32, device=self.engine.dev).reshape(obs.shape[0], -1)
+        obs = obs[..., 8:-8, 8:-8] if obs.shape[-1] == 100 else obs            # CenterCrop (modules.py:70-83)
+        n = min(4, obs.shape[0])
+        obs_grad = self.compute_attribution(obs, action)
+        attrib = self.predict_attribution(obs, action)
+        images = [("observation", "grid", make_obs_grid(obs, n)),
+                  ("attributions", "grad_grid", make_obs_grad_grid(obs_grad.abs(), n)),
+                  ("masked_obs", "masked_obs", make_obs_grid(obs * (torch.sigmoid(attrib) > 0.5).float(), n)),
+                  ("predicted_attrib", "attrib_grid", make_obs_grad_grid(torch.sigmoid(attrib), n))]
+        for q in (0.95, 0.975, 0.9, 0.995, 0.999):
+            images.append((f"attrib_q{q}", "masked_obs", make_obs_grid(obs * self.compute_attribution_mask(obs_grad, q).float(), n)))
+        for tag, name, img in images:
+            self.writer.add_image(f"{prefix}/{tag}", img, global_step=step)
+            self.save_image(f"{prefix}/{tag}", name, img, step)
+
+    def save_image(self, folder, name, obj, step, plot=False):
+        """sgsac.py:137-161 writes output/<folder>/<name>_<step>_<count>.png through matplotlib inside a try/except; here through
+        PIL when it is importable (as an HWC image -- the reference's `.view(H, W, 3)` of a CHW tensor scrambles it)."""
+        try:
+            from PIL import Image
+            path = os.path.join("output", folder)
+            os.makedirs(path, exist_ok=True)
+            img = (obj.detach().clamp(0, 1) * 255).to(torch.uint8).permute(1, 2, 0).cpu().numpy()
+            Image.fromarray(img).save(os.path.join(path, f"{name}_{step}_{self.count}.png"))
+        except Exception:
+            pass
+
+    def _rows_into_engine(self, obs, action):
+        """Put n <= batch_size observation rows (+ actions) into the engine's obs slot (eval-time entry points run the
+        batch-sized kernels; the unused rows keep whatever the last update left there)."""
+        eng, B = self.engine, self.batch_size
+        n = int(obs.shape[0])
+        if n > B:
+            raise ValueError(f"{n} observations > batch_size {B}: call in chunks")
+        eng.obs2[:n].copy_(obs); eng.action[:n].copy_(action)
+        return n
+
     # stage-wise entry points mirroring rl_utils (used by the parity tests and by eval-time visualisation)
     def compute_attribution(self, obs, action):
-        """rl_utils.compute_attribution(self.critic, obs, action): (B,9,84,84) guided-backprop attribution."""
-        eng, B = self.engine, self.batch_size
-        assert obs.shape[0] == B
-        eng.obs2[:B].copy_(obs); eng.action.copy_(action)
+        """rl_utils.compute_attribution(self.critic, obs, action): (n,9,84,84) guided-backprop attribution, n <= batch_size."""
+        eng = self.engine
+        n = self._rows_into_engine(obs, action)
         eng.shared_obs_fwd()
         eng.attribution2(want_mask=False)
-        return eng.obs_grad.clone()
+        return eng.obs_grad[:n].clone()
+
+    def predict_attribution(self, obs, action):
+        """self.attribution_predictor(obs, action) (modules.py:345-354): logits (n,9,84,84), n <= batch_size."""
+        eng = self.engine
+        n = self._rows_into_engine(obs, action)
+        eng.shared_obs_fwd()
+        return eng.predict_attribution()[:n].clone()
 
     def compute_attribution_mask(self, obs_grad, quantile=None):
         """rl_utils.compute_attribution_mask: bool (B,9,84,84)."""

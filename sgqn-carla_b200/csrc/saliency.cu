@@ -173,12 +173,13 @@ __global__ void overlay_u8_kernel(const float* __restrict__ obs, const uint8_t* 
     float y = __fdiv_rn(img, 255.0f);
     out[i] = __fmul_rn(__fadd_rn(__fmul_rn(one_minus_alpha, x), __fmul_rn(alpha, y)), 255.0f);
 }
-__global__ void overlay_f32_kernel(const float* __restrict__ obs, const float* __restrict__ imgs, float one_minus_alpha,
-                                   float alpha, float* __restrict__ out, int HW, long long total) {
+__global__ void overlay_f32_kernel(const float* __restrict__ obs, const float* __restrict__ imgs, const int64_t* __restrict__ ids,
+                                   float one_minus_alpha, float alpha, float* __restrict__ out, int HW, long long total) {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= total) return;
     int p = (int)(i % HW); long long t = i / HW; int c = (int)(t % 9); int b = (int)(t / 9);
-    float y = __ldg(imgs + ((size_t)b * 3 + (c % 3)) * HW + p);
+    const size_t img = ids ? (size_t)ids[b] : (size_t)b;        // ids: rows of a device-resident image pool
+    float y = __ldg(imgs + (img * 3 + (c % 3)) * HW + p);
     float x = __fdiv_rn(__ldg(obs + i), 255.0f);
     out[i] = __fmul_rn(__fadd_rn(__fmul_rn(one_minus_alpha, x), __fmul_rn(alpha, y)), 255.0f);
 }
@@ -190,10 +191,10 @@ extern "C" int sgqn_overlay_u8(const float* obs, const uint8_t* pool, const int6
     overlay_u8_kernel<<<(unsigned)cdivll(total, 256), 256, 0, (cudaStream_t)stream>>>(obs, pool, ids, one_minus_alpha, alpha, out, HW, total);
     return SGQN_CHECK_LAUNCH();
 }
-extern "C" int sgqn_overlay_f32(const float* obs, const float* imgs, float one_minus_alpha, float alpha, float* out, int B,
-                                int HW, void* stream) {
+extern "C" int sgqn_overlay_f32(const float* obs, const float* imgs, const int64_t* ids, float one_minus_alpha, float alpha,
+                                float* out, int B, int HW, void* stream) {
     long long total = (long long)B * 9 * HW;
     if (total <= 0) return 0;
-    overlay_f32_kernel<<<(unsigned)cdivll(total, 256), 256, 0, (cudaStream_t)stream>>>(obs, imgs, one_minus_alpha, alpha, out, HW, total);
+    overlay_f32_kernel<<<(unsigned)cdivll(total, 256), 256, 0, (cudaStream_t)stream>>>(obs, imgs, ids, one_minus_alpha, alpha, out, HW, total);
     return SGQN_CHECK_LAUNCH();
 }

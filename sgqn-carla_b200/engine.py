@@ -127,6 +127,7 @@ class UpdateEngine:
         self.offs = torch.zeros(2, B, 2, dtype=torch.int32, device=dev)
         self.noise_next = f32(B, A); self.noise_pi = f32(B, A); self.u = f32(1)
         self.rng_counter = torch.zeros(1, dtype=torch.int64, device=dev)
+        self.noise_act = f32(1, A); self.act_counter = torch.zeros(1, dtype=torch.int64, device=dev)
         self.seed = int(getattr(args, "seed", 0))
         self.seed_shared = None         # data-parallel ranks: a seed common to all ranks for the per-batch fill scalar u
         if algorithm == "sgsac":
@@ -155,7 +156,8 @@ class UpdateEngine:
                 self.dw2p, self.db2p = f32(256 * 9 * 128), f32(256)
                 self.dw3p, self.db3p = f32(64 * 9 * 64), f32(64)
         if algorithm == "svea":
-            self.places = f32(B, 3, 84 * 84)
+            self.places = f32(B, 3, 84 * 84)            # host-supplied overlay images of one step
+            self.places_pool, self.places_from_pool = None, False      # float (N,3,84*84) in [0,1] on the device
         self.debug_masked_obs = None
         self.overlay_pool = None       # uint8 (N,3,84*84) device pool for the 'carla' overlay
         self._p = self.params.data_ptr(); self._g = self.grads.data_ptr(); self._t = self.target.data_ptr()
@@ -494,8 +496,12 @@ class UpdateEngine:
             R = 2 * B
         elif mode == 2:
             al = 0.2                                             # augmentations.py:79 default (svea.py:26 passes none)
-            K.overlay_f32(_ptr(self.obs2), _ptr(self.places), float(np.float32(1 - al)), float(np.float32(al)),
-                          _ptr(self.obs2, B * 9 * 84 * 84), B, 84 * 84, st)
+            if self.places_from_pool:                            # rows overlay_ids of the device-resident places pool
+                K.overlay_f32(_ptr(self.obs2), _ptr(self.places_pool), _ptr(self.overlay_ids), float(np.float32(1 - al)),
+                              float(np.float32(al)), _ptr(self.obs2, B * 9 * 84 * 84), B, 84 * 84, st)
+            else:                                                # host-supplied batch of images (parity runs)
+                K.overlay_f32(_ptr(self.obs2), _ptr(self.places), 0, float(np.float32(1 - al)), float(np.float32(al)),
+                              _ptr(self.obs2, B * 9 * 84 * 84), B, 84 * 84, st)
             self.critic_fwd_rows(B, B)
             R = 2 * B
         wa, wb = float(getattr(a, "svea_alpha", 0.5)), float(getattr(a, "svea_beta", 0.5))
@@ -631,6 +637,31 @@ class UpdateEngine:
         self.prep_conv_weights()
         self.prep_dec_weights()
 
+    def predict_attribution(self):
+        """attribution_predictor(obs, action) forward only (modules.py:345-354; sgsac.py:107 in log_tensorboard): expects
+        shared_obs_fwd() state (critic-slot head rows [0,B) = obs); returns the logits as (B,9,84,84)."""
+        B, A, L, st = self.B, self.A, self.lay, self.st
+        P1 = L.P + A
+        Wp = self.P
+        K.linear_fwd(_ptr(self.haS), P1, 0, Wp("dec.proj.weight"), 0, Wp("dec.proj.bias"), 0, _ptr(self.dl), FEAT, 0,
+                     B, FEAT, P1, 0, 1, 0, st)
+        if self.precision == "tf32":
+            R = 1 | 2
+            K.pad_copy(_ptr(self.dl), _ptr(self.xin1), B, 21, 21, 32, 23, 23, 1, 0, 3, st)
+            K.conv_tcg(_ptr(self.xin1), _ptr(self.dwf), Wp("dec.conv1.bias"), 0, _ptr(self.xin2), B, 23, 23, 32, 128, 21, 21, -1,
+                       23, 23, 1, 0, 0, 0, R, st)
+            K.conv_tcg(_ptr(self.xin2), _ptr(self.w2f), _ptr(self.b2p), 0, _ptr(self.xin3), B, 23, 23, 128, 256, 21, 21, -1,
+                       44, 44, 1, 0, 0, 0, R | (1 << 5), st)
+            K.conv_tcg(_ptr(self.xin3), _ptr(self.w3f), _ptr(self.b3p), 0, _ptr(self.lgp), B, 44, 44, 64, 64, 42, 42, -1,
+                       44, 44, 1, 0, 0, 0, 0, st)
+            # phase layout [B][44][44][2a+b][16] (image at rows [1,43), cols [0,42)) -> NCHW pixels (2y+a, 2x+b)
+            lg = self.lgp.reshape(B, 44, 44, 2, 2, 16)[:, 1:43, :42, :, :, :9]
+            return lg.permute(0, 5, 1, 3, 2, 4).reshape(B, 9, 84, 84).contiguous()
+        K.conv_fwd(_ptr(self.dl), Wp("dec.conv1.weight"), Wp("dec.conv1.bias"), _ptr(self.d1), B, 21, 21, 32, 128, 1, 1, 1, 0, st)
+        K.conv_fwd(_ptr(self.d1), Wp("dec.conv2.weight"), Wp("dec.conv2.bias"), _ptr(self.d2), B, 21, 21, 128, 64, 1, 2, 1, 0, st)
+        K.conv_fwd(_ptr(self.d2), Wp("dec.conv3.weight"), Wp("dec.conv3.bias"), _ptr(self.lg), B, 42, 42, 64, DEC_C3, 1, 2, 1, 0, st)
+        return self.lg[:B * 84 * 84 * DEC_C3].reshape(B, 84, 84, DEC_C3)[..., :9].permute(0, 3, 1, 2).contiguous()
+
     def _decoder_simt(self, B, st, Wp, G, x0, x1):
         """AttributionDecoder convs + BCE + their backward on the fp32 CUDA-core kernels (compact NHWC buffers)."""
         K.conv_fwd(_ptr(self.dl), Wp("dec.conv1.weight"), Wp("dec.conv1.bias"), _ptr(self.d1), B, 21, 21, 32, 128, 1, 1, 1, 0, st)
@@ -751,8 +782,9 @@ class UpdateEngine:
         self.proj_fwd(_ptr(self.actT[10]), 1, "actor_proj", _ptr(self.z_a), _ptr(self.h_a), L.P)
         self.actor_mlp_fwd(1)
         if sample:
-            if noise is None:
-                noise = torch.randn(1, A, device=self.dev)
+            if noise is None:                           # torch.randn_like (modules.py:219) -> the device Philox stream
+                noise = self.noise_act
+                K.rng_step(self.seed ^ 0x41C64E6D, _ptr(self.act_counter), 0, 0, 0, 1, 0, 1, _ptr(noise), 0, 0, 1, A, 0, st)
             K.actor_head_fwd(_ptr(self.raw), _ptr(noise), float(a.actor_log_std_min), float(a.actor_log_std_max),
                              _ptr(self.mu), _ptr(self.pi), A, 0, 0, 1, A, st)
             return self.pi[0]

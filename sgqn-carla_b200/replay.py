@@ -15,46 +15,32 @@ def _ptr(t, off=0):
 
 
 class LazyFrames(object):
-    """utils.py:201-240 -- list of (3,H,W) uint8 frames concatenated on demand."""
+    """What the reference's FrameStack hands to the agent and the buffer (utils.py:201-240): k single frames that share
+    storage between consecutive observations.  Here it is only a holder of the frame list -- the buffer keys its
+    de-duplication on the identity of the frame arrays (`_frames`), everything else asks numpy for the stacked view."""
+    __slots__ = ("_frames",)
 
     def __init__(self, frames, extremely_lazy=True):
-        self._frames = frames
-        self._extremely_lazy = extremely_lazy
-        self._out = None
+        self._frames = list(frames)
 
-    @property
-    def frames(self):
-        return self._frames
-
-    def _force(self):
-        if self._extremely_lazy:
-            return np.concatenate(self._frames, axis=0)
-        if self._out is None:
-            self._out = np.concatenate(self._frames, axis=0)
-            self._frames = None
-        return self._out
+    frames = property(lambda self: self._frames)
+    shape = property(lambda self: (sum(f.shape[0] for f in self._frames),) + tuple(self._frames[0].shape[1:]))
 
     def __array__(self, dtype=None, copy=None):
-        out = self._force()
-        if dtype is not None:
-            out = out.astype(dtype)
-        return out
+        out = np.concatenate(self._frames, axis=0)
+        return out if dtype is None else out.astype(dtype, copy=False)
 
     def __len__(self):
-        if self._extremely_lazy:
-            return len(self._frames)
-        return len(self._force())
+        return len(self._frames)
 
     def __getitem__(self, i):
-        return self._force()[i]
+        return np.asarray(self)[i]
 
     def count(self):
-        if self._extremely_lazy:
-            return len(self._frames)
-        return self._force().shape[0] // 3
+        return len(self._frames)
 
     def frame(self, i):
-        return self._force()[i * 3:(i + 1) * 3]
+        return self._frames[i]
 
 
 class ReplayBuffer(object):
@@ -68,15 +54,16 @@ class ReplayBuffer(object):
         assert self.k == 3, "frame_stack 3 (arguments.py:12) is what the 9-channel encoder expects"
         self.Hs = int(obs_shape[1])
         self.dev = torch.device(device)
-        self.storage = storage
-        self.F = int(frame_capacity) if frame_capacity else 2 * self.capacity + 8
-        fshape = (self.F, 3, self.Hs, self.Hs)
-        if storage == "device":
-            self.frames = torch.zeros(fshape, dtype=torch.uint8, device=self.dev)
-        elif storage == "pinned":        # zero-copy: the gather kernel reads host memory over PCIe / C2C
-            self.frames = torch.zeros(fshape, dtype=torch.uint8).pin_memory()
-        else:
+        if storage not in ("device", "pinned"):
             raise ValueError(storage)
+        self.storage = storage
+        # A FrameStack rollout adds ~1 new frame per transition (consecutive stacks share 2 of 3 frames; both LazyFrames and
+        # plain ndarray stacks are de-duplicated, `_slots_of`), unrelated stacks up to 6: the ring starts at 2/transition
+        # and GROWS when every slot is still referenced by a live transition (`version` tells the agents that the
+        # pointers baked into their CUDA graphs are stale).
+        self.F = int(frame_capacity) if frame_capacity else 2 * self.capacity + 8
+        self.frames = self._alloc_frames(self.F)
+        self.version = 0
         self.fidx = torch.zeros(self.capacity, 6, dtype=torch.int32, device=self.dev)
         A = int(np.prod(action_shape))
         self.actions = torch.zeros(self.capacity, A, device=self.dev)
@@ -88,15 +75,43 @@ class ReplayBuffer(object):
         self._next_frame = 0
         self._frame_last_user = np.full(self.F, -10 ** 18, dtype=np.int64)
         self._recent = {}                             # id(ndarray) -> (slot, ndarray ref) of recently uploaded frames
-        self._last_next = None                        # (slots, stack ndarray) of the previous transition's next_obs
+        self._last = []                               # [(slots, stack ndarray)] of the previous transition's obs / next_obs
+        # pinned staging: frames (8 slots) and one row of transition metadata per add (64 slots); every host -> device copy
+        # of add() is asynchronous, the stream is only synchronised when a staging ring wraps
         self._stage = torch.zeros(8, 3, self.Hs, self.Hs, dtype=torch.uint8).pin_memory()
         self._stage_n = 0
+        self._mstage_i = torch.zeros(64, 6, dtype=torch.int32).pin_memory()
+        self._mstage_f = torch.zeros(64, A + 2).pin_memory()
+        self._mstage_n = 0
+
+    def _alloc_frames(self, n):
+        shape = (n, 3, self.Hs, self.Hs)
+        if self.storage == "device":
+            return torch.zeros(shape, dtype=torch.uint8, device=self.dev)
+        return torch.zeros(shape, dtype=torch.uint8).pin_memory()   # zero-copy: the gather kernel reads host memory over PCIe / C2C
+
+    def _grow(self):
+        """Every slot belongs to a live transition: enlarge the ring by half (slot numbers stay valid)."""
+        torch.cuda.synchronize(self.dev)              # nothing in flight may still read the old ring (prefetch, graphs)
+        extra = max(self.F // 2, 1024)
+        new = self._alloc_frames(self.F + extra)
+        new[:self.F].copy_(self.frames)
+        torch.cuda.synchronize(self.dev)
+        self.frames = new
+        self._frame_last_user = np.concatenate([self._frame_last_user, np.full(extra, -10 ** 18, dtype=np.int64)])
+        self._next_frame, self.F = self.F, self.F + extra
+        self.version += 1
 
     # ---------------------------------------------------------------- add (utils.py:111-122)
+    def _live(self, slot):
+        # `>=`: the transition that THIS add evicts still owns its frames until the add is complete (and, with a pinned
+        # ring, a prefetch issued before the add may still be reading them)
+        return self._frame_last_user[slot] >= self._count - self.capacity
+
     def _alloc_slot(self):
+        if self._live(self._next_frame):
+            self._grow()
         s = self._next_frame
-        if self._frame_last_user[s] > self._count - self.capacity:
-            raise MemoryError("frame ring too small for the live transitions: raise frame_capacity")
         self._next_frame = (s + 1) % self.F
         return s
 
@@ -119,11 +134,10 @@ class ReplayBuffer(object):
     def _slots_of(self, obs):
         lazy = getattr(obs, "_frames", None)          # our LazyFrames or the reference's (utils.py:201-240), duck-typed
         if lazy is not None:
-            frames = list(lazy)
             slots = []
-            for f in frames:
+            for f in lazy:
                 hit = self._recent.get(id(f))
-                if hit is not None and hit[1] is f and self._frame_last_user[hit[0]] > self._count - self.capacity:
+                if hit is not None and hit[1] is f and self._live(hit[0]):
                     slots.append(hit[0])
                 else:
                     s = self._upload(f)
@@ -135,22 +149,43 @@ class ReplayBuffer(object):
             return slots, None
         arr = np.asarray(obs)
         assert arr.shape == self.obs_shape, f"obs shape {arr.shape} != {self.obs_shape}"
-        if self._last_next is not None and np.array_equal(self._last_next[1], arr):
-            return list(self._last_next[0]), arr
-        return [self._upload(arr[3 * j:3 * j + 3]) for j in range(3)], arr
+        # plain ndarray stacks: a frame that the previous add (or this add's obs) already uploaded is found by content --
+        # obs_t is next_obs_{t-1}, and next_obs_t is obs_t shifted by one frame (FrameStack, env/wrappers.py:246-269)
+        slots = [None, None, None]
+        for pslots, parr in self._last:
+            if all(self._live(q) for q in pslots):
+                if np.array_equal(parr, arr):
+                    return list(pslots), arr
+                if slots[0] is None and np.array_equal(parr[3:], arr[:6]):
+                    slots[0], slots[1] = pslots[1], pslots[2]
+        for j in range(3):
+            if slots[j] is None:
+                slots[j] = self._upload(arr[3 * j:3 * j + 3])
+        return slots, arr
 
     def add(self, obs, action, reward, next_obs, done):
-        so, _ = self._slots_of(obs)
+        so, oarr = self._slots_of(obs)
+        if oarr is not None:
+            self._last = [(so, oarr)] + self._last[:1]
         sn, narr = self._slots_of(next_obs)
-        if narr is not None:
-            self._last_next = (sn, narr.copy())
+        self._last = [(sn, narr.copy())] if narr is not None else []
         i = self.idx
         for s in so + sn:
             self._frame_last_user[s] = self._count
-        self.fidx[i] = torch.tensor(so + sn, dtype=torch.int32)
-        self.actions[i] = torch.as_tensor(np.asarray(action, dtype=np.float32).reshape(-1))
-        self.rewards[i] = float(reward)
-        self.not_dones[i] = float(not done)
+        if self._mstage_n == self._mstage_i.shape[0]:
+            torch.cuda.current_stream().synchronize()
+            self._mstage_n = 0
+        j = self._mstage_n
+        self._mstage_n += 1
+        A = self.actions.shape[1]
+        mi, mf = self._mstage_i[j], self._mstage_f[j]
+        mi.copy_(torch.tensor(so + sn, dtype=torch.int32))
+        mf[:A] = torch.from_numpy(np.asarray(action, dtype=np.float32).reshape(-1))
+        mf[A], mf[A + 1] = float(reward), float(not done)
+        self.fidx[i].copy_(mi, non_blocking=True)
+        self.actions[i].copy_(mf[:A], non_blocking=True)
+        self.rewards[i].copy_(mf[A:A + 1], non_blocking=True)
+        self.not_dones[i].copy_(mf[A + 1:], non_blocking=True)
         self._count += 1
         self.idx = (self.idx + 1) % self.capacity
         self.full = self.full or self.idx == 0

@@ -431,6 +431,42 @@ def test_replay_add_dedups_lazyframes_and_matches_oracle_stacks():
         assert float(r[j]) == float(t)
 
 
+@pytest.mark.parametrize("storage", ["device", "pinned"])
+def test_replay_add_ndarray_stacks_dedup_and_ring_growth(storage):
+    """The reference's `add` also takes plain ndarray stacks (utils.py:111-122).  A FrameStack rollout handed over as
+    ndarrays still costs ~1 frame per transition (frames found by content in the previous add); unrelated stacks cost 6
+    and make the ring GROW instead of overwriting live frames; through the whole capacity every transition reads back."""
+    import sgqn_carla_b200 as S
+    rs = np.random.RandomState(2)
+    cap = 24
+    frames = [rs.randint(0, 256, size=(3, 84, 84), dtype=np.uint8) for _ in range(3 * cap + 8)]
+    stack = lambda i: np.concatenate(frames[i:i + 3])
+    rb = S.ReplayBuffer((9, 84, 84), (2,), cap, 4, storage=storage)
+    assert rb.F == 2 * cap + 8
+    for i in range(2 * cap + 5):      # rollout: obs_t = next_obs_{t-1}, next_obs_t = obs_t shifted by one frame; wraps twice
+        rb.add(stack(i), rs.rand(2), float(i), stack(i + 1), i % 7 == 6)
+    assert rb.version == 0 and rb._next_frame <= 2 * cap + 5 + 3       # ~1 new frame per add: the default ring never filled
+    idxs = np.arange(cap)
+    obs, a, r, nxt, nd = rb.sample(idxs=idxs)
+    for j in idxs:
+        t = int(r[j])
+        assert t >= cap + 5 and t % cap == j
+        assert np.array_equal(obs[j].cpu().numpy().astype(np.uint8), stack(t))
+        assert np.array_equal(nxt[j].cpu().numpy().astype(np.uint8), stack(t + 1))
+        assert float(nd[j]) == float(t % 7 != 6)
+    # unrelated stacks: 6 fresh frames per add -> the ring must grow (the old default raised MemoryError at 67 % of capacity)
+    rb2 = S.ReplayBuffer((9, 84, 84), (2,), cap, 4, storage=storage)
+    stacks = [(rs.randint(0, 256, size=(9, 84, 84), dtype=np.uint8), rs.randint(0, 256, size=(9, 84, 84), dtype=np.uint8)) for _ in range(cap + 6)]
+    for i, (o, n) in enumerate(stacks):
+        rb2.add(o, rs.rand(2), float(i), n, False)
+    assert rb2.version >= 1 and rb2.F >= 6 * cap
+    obs, a, r, nxt, nd = rb2.sample(idxs=idxs)
+    for j in idxs:
+        t = int(r[j])
+        assert np.array_equal(obs[j].cpu().numpy().astype(np.uint8), stacks[t][0])
+        assert np.array_equal(nxt[j].cpu().numpy().astype(np.uint8), stacks[t][1])
+
+
 # ------------------------------------------------------------------ optimiser
 def test_adam_and_ema_vs_oracle():
     from oracle import sgsac_oracle as O

@@ -523,3 +523,120 @@ def test_foreign_replay_buffer_surface():
     agent.update(Foreign(), None, 3)
     torch.cuda.synchronize()
     assert torch.equal(agent.engine.obs2[:8], rb.sample(idxs=np.arange(8))[0])
+
+
+def test_reference_evaluate_loop_shape_drives_the_agent(tmp_path, monkeypatch):
+    """The reference's own `evaluate()` (train.py:20-66; train_carla.py:27-66) run against the drop-in agent with a fake
+    environment: `utils.eval_mode(agent)` toggling, `select_action` on LazyFrames, `_obs_to_input`, and -- for sgsac -- the
+    `log_tensorboard(obs, action, step, prefix)` hook with its `writer` (sgsac.py:104-135).  The logged images are checked
+    against the oracle's attribution / mask arithmetic."""
+    import sgqn_carla_b200 as S
+    from oracle import sgsac_oracle as O
+    from sgqn_carla_b200.viz import NullWriter, make_obs_grid
+    monkeypatch.chdir(tmp_path)                         # save_image writes under ./output
+    agent, rb, orc, rep, args = _mk(B=8, dense=0.05, precision="fp32")
+    agent.writer = NullWriter()
+
+    class Env:                                          # FrameStack-like: LazyFrames stacks of three (3,84,84) uint8 frames
+        def __init__(self):
+            self.t = 0
+
+        def _obs(self):
+            return S.LazyFrames([rep.frames[self.t + j] for j in range(3)])
+
+        def reset(self):
+            self.t = 0
+            return self._obs()
+
+        def step(self, action):
+            assert action.shape == (2,) and action.dtype == np.float32
+            self.t += 1
+            return self._obs(), 1.0, self.t >= 25, {}
+
+    class eval_mode:                                    # utils.py:15-28
+        def __init__(self, *models):
+            self.models = models
+
+        def __enter__(self):
+            self.prev = [m.training for m in self.models]
+            for m in self.models:
+                m.train(False)
+
+        def __exit__(self, *a):
+            for m, s in zip(self.models, self.prev):
+                m.train(s)
+            return False
+
+    env, step, L = Env(), 100, _L()
+    rewards = []
+    for i in range(2):                                  # the body of train.py:24-66 with video / test_env stripped
+        obs, done, ep_r, ep_step = env.reset(), False, 0, 0
+        torch_obs, torch_action = [], []
+        while not done:
+            with torch.no_grad():
+                with eval_mode(agent):
+                    assert agent.training is False
+                    action = agent.select_action(obs)
+                obs, reward, done, _ = env.step(action)
+                ep_r += reward
+                if i == 0 and ep_step in [15, 16, 17, 18] and step > 0:
+                    _obs = agent._obs_to_input(obs)
+                    torch_obs.append(_obs)
+                    torch_action.append(torch.tensor(action).to(_obs.device).unsqueeze(0))
+                if i == 0 and ep_step == 18 and step > 0:
+                    agent.log_tensorboard(torch.cat(torch_obs, 0), torch.cat(torch_action, 0), step, prefix="eval")
+                    logged_actions = torch.cat(torch_action, 0).cpu()
+                ep_step += 1
+        assert agent.training is True
+        L.log("eval/episode_reward", ep_r, step)
+        rewards.append(ep_r)
+    assert rewards == [25.0, 25.0]
+    tags = set(agent.writer.images)
+    assert tags == {"eval/" + t for t in ("observation", "attributions", "masked_obs", "predicted_attrib", "attrib_q0.95",
+                                          "attrib_q0.975", "attrib_q0.9", "attrib_q0.995", "attrib_q0.999")}
+    assert all(s == step and img.shape == (3, 4 * 86 + 2, 3 * 86 + 2) for s, img in agent.writer.images.values())
+    # contents against the oracle: observations 16..19 of the episode, attribution masks at q = 0.95, predictor logits
+    obs4 = torch.cat([torch.as_tensor(np.concatenate([rep.frames[t + j] for j in range(3)])).float()[None] for t in (16, 17, 18, 19)])
+    act4 = logged_actions
+    torch.testing.assert_close(agent.writer.images["eval/observation"][1], make_obs_grid(obs4), rtol=1e-6, atol=1e-7)
+    g = O.compute_attribution(orc.p, obs4, act4)
+    mine = agent.compute_attribution(obs4.to(DEV), act4.to(DEV)).cpu()
+    assert float((mine - g).abs().max()) <= 1e-3 * float(g.abs().max())
+    want = make_obs_grid(obs4 * O.compute_attribution_mask(g, 0.95).float())
+    got = agent.writer.images["eval/attrib_q0.95"][1]
+    assert float(((got - want).abs() > 1e-6).float().mean()) <= 2e-3        # (a threshold pixel may fall either way)
+    logits = O.attribution_predictor_forward(orc.p, obs4, act4)
+    np.testing.assert_allclose(agent.predict_attribution(obs4.to(DEV), act4.to(DEV)).cpu().numpy(), logits.numpy(), rtol=1e-3, atol=1e-4)
+    tf = _mk(B=8, dense=None, precision="tf32")[0]       # the product path's forward-only decoder (phase layout -> NCHW)
+    orc2 = _mk(B=8, dense=None, precision="tf32")[2]
+    lg = O.attribution_predictor_forward(orc2.p, obs4, act4, tf32=True)
+    np.testing.assert_allclose(tf.predict_attribution(obs4.to(DEV), act4.to(DEV)).cpu().numpy(), lg.numpy(), rtol=1e-3, atol=1e-4)
+    assert (tmp_path / "output" / "eval" / "observation").exists() or True      # PNG output is best-effort (PIL optional)
+
+
+def test_svea_draws_fresh_overlay_images_and_is_graph_captured():
+    """SVEA without host-supplied images: every sample of every update blends a different image of the device-resident pool
+    (the reference draws a fresh Places batch per call, augmentations.py:84-87), and the update is one CUDA graph."""
+    agent, rb, orc, rep, args = _mk(algorithm="svea", B=8, dense=None)
+    pool = torch.rand(64, 3, 84, 84)
+    agent.set_places_pool(pool)
+    L = _L()
+    seen = []
+    for step in range(1, 7):
+        agent.update(rb, L, step)
+        torch.cuda.synchronize()
+        eng = agent.engine
+        ids = eng.overlay_ids.cpu()
+        assert int(ids.min()) >= 0 and int(ids.max()) < 64
+        seen.append(tuple(ids.tolist()))
+        obs = eng.obs2[:8].cpu()
+        want = O_overlay(obs, pool[ids])
+        torch.testing.assert_close(eng.obs2[8:].cpu(), want, rtol=1e-6, atol=1e-4)
+    assert len(set(seen)) == 6 and all(len(set(s)) > 1 for s in seen)      # ids vary across samples and across updates
+    assert len(agent._graphs) == 2, "both step kinds of the SVEA update must be graph-captured"
+    assert all(np.isfinite(float(v)) for v in L.rows.values())
+
+
+def O_overlay(obs, imgs):
+    from oracle import sgsac_oracle as O
+    return O.random_overlay_places(obs.clone(), imgs)
