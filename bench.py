@@ -26,7 +26,9 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-os.environ["NCCL_DEBUG"] = os.environ.get("SGQN_NCCL_DEBUG", "WARN")     # keep stdout to the one JSON line
+# NCCL's own log (communicator sizes, NVLS / ring choice) goes to stderr with everything else a library prints: stdout is
+# redirected to stderr while the benchmark runs (_StdoutToStderr) and carries exactly the one JSON line
+os.environ.setdefault("NCCL_DEBUG", os.environ.get("SGQN_NCCL_DEBUG", "INFO" if int(os.environ.get("WORLD_SIZE", "1")) > 1 else "WARN"))
 
 import numpy as np  # noqa: E402
 import torch  # noqa: E402
@@ -36,8 +38,6 @@ CAPACITY = 20000            # transitions; 20003 frames x 21 KB = 423 MB > 126 M
 POOL_N = 2048               # overlay frames (43 MB)
 # algorithmic FLOPs per sample (minimal / de-duplicated schedule), FLOP = 2*MAC
 GFLOP_ODD, GFLOP_EVEN = 1.671, 3.712
-# dram__bytes_read.sum + dram__bytes_write.sum per launch, from the committed `ncu --set full` captures under profiles/
-NCU_TRAFFIC = {"conv_tc_fwd_l1": 28954368 + 29440}
 WORKLOAD = ("SGSAC full update loop (critic + attribution mask consistency + actor/alpha + target EMA + overlay aux), "
             "batch 128 per GPU, 9x84x84 uint8 stacks, A=2, sgqn_quantile=0.95, reference init, steps alternate odd/even")
 
@@ -89,6 +89,16 @@ def synthetic(capacity, A=2, seed=0):
     rewards = rs.randn(capacity, 1).astype(np.float32)
     not_dones = np.ones((capacity, 1), dtype=np.float32)
     pool = rs.randint(0, 256, size=(POOL_N, 3, 84, 84), dtype=np.uint8)
+    return frames, actions, rewards, not_dones, pool
+
+
+def synthetic_sized(capacity, A, size, seed=0):
+    rs = np.random.RandomState(seed)
+    frames = rs.randint(0, 256, size=(capacity + 3, 3, size, size), dtype=np.uint8)
+    actions = rs.uniform(-1, 1, size=(capacity, A)).astype(np.float32)
+    rewards = rs.randn(capacity, 1).astype(np.float32)
+    not_dones = np.ones((capacity, 1), dtype=np.float32)
+    pool = rs.randint(0, 256, size=(512, 3, 84, 84), dtype=np.uint8)
     return frames, actions, rewards, not_dones, pool
 
 
@@ -237,10 +247,60 @@ def profile_kernels(agent, rb, nsteps=4):
         if n == "conv_tc":                                          # the kernel behind both conv_tc families
             t0, c0, f0, b0 = fam.get("_conv3x3_tc_kernel", (0.0, 0, 0.0, 0.0))
             fam["_conv3x3_tc_kernel"] = (t0 + t, c0 + 1, f0 + fl, b0 + by)
-            if args[11] == 0 and args[7] == 43 and args[6] == PER_GPU_BATCH:   # forward, 41x41 -> 39x39, B = 128: see NCU_TRAFFIC
+            if args[11] == 0 and args[7] == 43 and args[6] == 2 * PER_GPU_BATCH:   # forward, 41x41 -> 39x39, 256 samples: see ncu_traffic()
                 t0, c0 = fam.get("_conv_tc_fwd_l1", (0.0, 0, 0.0, 0.0))[:2]
                 fam["_conv_tc_fwd_l1"] = (t0 + t, c0 + 1, fl, by)
     return fam, nsteps
+
+
+def time_torch_eager_gpu(B, steps=6, warmup=3):
+    """The reference's arithmetic as PyTorch eager ON THE B200 (BASELINE.md 3 'second baseline'): the oracle port with its
+    tensors on cuda:0, cuDNN convs with allow_tf32=True and fp32 cuBLAS matmuls (the reference's defaults), CUDA-event timed.
+    Same synthetic inputs as config 1 / 2.  This is a baseline leg: none of the repo's kernels run here."""
+    from oracle import sgsac_oracle as O
+    from oracle.pin_rnd import make_rnd
+    dev = torch.device("cuda")
+    torch.backends.cudnn.allow_tf32 = True
+    torch.backends.cuda.matmul.allow_tf32 = False
+    args = O.Args(algorithm="sgsac", sgqn_quantile=0.95, batch_size=B)
+    rs = np.random.RandomState(0)
+    rep = O.synthetic_replay(1000, 2, seed=0)
+    orc = O.make_oracle((9, 84, 84), (2,), args, seed=0)
+    orc.p = type(orc.p)((k, v.to(dev)) for k, v in orc.p.items())
+    orc.pool = torch.as_tensor(rs.randint(0, 256, size=(256, 3, 84, 84), dtype=np.uint8)).to(dev)
+    L = NullLog()
+
+    def one(step):
+        batch = tuple(t.to(dev, non_blocking=True) for t in rep.sample(rs.randint(0, 1000, size=B)))
+        rnd = make_rnd(rs, B, 2, 256)
+        rnd = {k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in rnd.items()}
+        orc.update_from_batch(batch, rnd, L, step)
+
+    step = 1
+    for _ in range(warmup):
+        one(step); step += 1
+    torch.cuda.synchronize()
+    t0 = time.time()
+    for _ in range(steps):
+        one(step); step += 1
+    torch.cuda.synchronize()
+    dt = (time.time() - t0) / steps
+    return {"value": 1.0 / dt, "unit": "updates/s", "ms_per_step": dt * 1e3, "batch": B,
+            "what": "oracle port of SGSAC.update as PyTorch eager on cuda:0 (cuDNN conv allow_tf32=True, cuBLAS fp32 matmul, "
+                    "torch.sort-based quantile masks, per-tensor Adam), host-side sampling + H2D included, wall-clock over "
+                    f"{steps} updates ({steps // 2} even + {steps - steps // 2} odd) after {warmup} warm-up"}
+
+
+def ncu_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed summary of the
+    `ncu --set full` capture of THIS build (profiles/traffic_r2.json, written by profiles/summarize.py); None if absent."""
+    p = os.path.join(ROOT, "profiles", "traffic_r2.json")
+    if not os.path.exists(p):
+        return None
+    try:
+        return json.load(open(p))
+    except Exception:
+        return None
 
 
 def run_b200(a):
@@ -254,47 +314,67 @@ def run_b200(a):
     sync = None
     if world > 1:
         import datetime
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local), timeout=datetime.timedelta(seconds=120))
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local), timeout=datetime.timedelta(seconds=180))
         sync = GradSync()
-    B = PER_GPU_BATCH
-    Bg = B * world
-    args = S.default_args(algorithm="sgsac", batch_size=B, sgqn_quantile=0.95, seed=1 + rank)
-    frames, actions, rewards, not_dones, pool = synthetic(CAPACITY, 2, seed=rank)
-
-    def make(storage):
-        ag = S.make_agent((9, 84, 84), (2,), args, dist=sync, global_batch=Bg)
-        ag.engine.seed = 1234 + rank
-        if world > 1:                       # identical replicated parameters
-            dist.broadcast(ag.engine.params, 0); dist.broadcast(ag.engine.target, 0)
-        ag.set_overlay_pool(pool)
-        rb = S.ReplayBuffer((9, 84, 84), (2,), CAPACITY, B, storage=storage, frame_capacity=CAPACITY + 8)
-        rb.load_ring(frames, actions, rewards, not_dones)
-        return ag, rb
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(agent, rb, L, steps, warmup, s0=1):
+    def make(algorithm="sgsac", B=PER_GPU_BATCH, A=2, size=84, storage="device", Bg=None, capacity=CAPACITY, data=None):
+        """Agent + replay ring of one rank.  Bg = global batch (losses are means over it; None: single process)."""
+        args = S.default_args(algorithm=algorithm, batch_size=B, sgqn_quantile=0.95, seed=1 + rank)
+        ag = S.make_agent((9, size, size), (A,), args, dist=sync if Bg else None, global_batch=Bg)
+        ag.engine.seed, ag.engine.seed_shared = 1234 + rank, 1234      # own indices / noise per rank, ONE fill scalar per global batch
+        if Bg and world > 1:                # identical replicated parameters, targets, optimiser states (SURVEY.md 8e)
+            ag.sync_from_rank0()
+        frames, actions, rewards, not_dones, pool = data
+        if algorithm == "sgsac":
+            ag.set_overlay_pool(pool)
+        if algorithm == "svea":
+            ag.set_places_pool(torch.as_tensor(pool[:512]).float() / 255.0)
+        rb = S.ReplayBuffer((9, size, size), (A,), capacity, B, storage=storage, frame_capacity=capacity + 8)
+        rb.load_ring(frames, actions, rewards, not_dones)
+        return ag, rb
+
+    def timed(agent, rb, L, steps, warmup, s0=1, collective=True):
         step = s0
         for _ in range(warmup):
             agent.update(rb, L, step); step += 1
-        barrier()
+        barrier() if collective else torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         c0 = _lib.launch_count
         e0.record()
         for _ in range(steps):
             agent.update(rb, L, step); step += 1
         e1.record()
-        barrier()
+        barrier() if collective else torch.cuda.synchronize()
         ms = e0.elapsed_time(e1)
-        if world > 1:
+        if world > 1 and collective:
             t = torch.tensor([ms], device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MAX); ms = float(t)
         return ms, _lib.launch_count - c0
 
-    # ---- device-resident run (value)
-    agent, rb = make("device")
+    def roofline_of(fam, nst, batch):
+        """Roofline record of conv3x3_tc_kernel (the dominant kernel of every configuration) from a profile_kernels() pass."""
+        tot = sum(v[0] for k, v in fam.items() if not k.startswith("_"))
+        hbm, tf_burst, tf_sus, how = peaks()
+        kt = fam["_conv3x3_tc_kernel"]                       # (ms, launches, flops, algorithmic bytes) over nst updates
+        achieved = kt[3] / (kt[0] * 1e-3) / 1e9
+        return {"bound": "hbm", "kernel": "conv3x3_tc_kernel (conv_tc fwd + dgrad launches)", "achieved": achieved, "peak": hbm,
+                "unit": "GB/s", "frac": achieved / hbm, "traffic": None, "share_of_step": kt[0] / tot,
+                "peak_source": f"HBM copy bandwidth {hbm} GB/s ({how})",
+                "launches_per_step": kt[1] / nst, "ms_per_step_in_kernel": kt[0] / nst,
+                "algorithmic_bytes_per_launch": kt[3] / kt[1], "avg_launch_us": kt[0] / kt[1] * 1e3,
+                "tensor_view": {"achieved_tflops": kt[2] / (kt[0] * 1e-3) / 1e12, "peak_tflops": tf_sus / 2.0,
+                                "peak_source": f"bf16 sustained {tf_sus} TF/s ({how}) / 2 = TF32 dense, derived"}}
+
+    data84 = synthetic(CAPACITY, 2, seed=rank)
+    B = PER_GPU_BATCH
+    Bg = B * world
+
+    # ---- device-resident run (value): weak scaling, 128 samples per rank
+    agent, rb = make(Bg=Bg, data=data84)
     L = NullLog()
     sampler = ClockSampler(local)
     sampler.start()
@@ -311,34 +391,38 @@ def run_b200(a):
     if rank == 0:
         tot = sum(v[0] for k, v in fam.items() if not k.startswith("_"))
         fam_rows = sorted(((k, v[0] / nst, v[1] // nst, v[2] / nst) for k, v in fam.items() if not k.startswith("_")), key=lambda r: -r[1])
-        hbm, tf_burst, tf_sus, how = peaks()
-        kt = fam["_conv3x3_tc_kernel"]                       # (ms, launches, flops, algorithmic bytes) over nst updates
-        l1 = fam.get("_conv_tc_fwd_l1")
         # conv3x3_tc_kernel (SharedCNN 32->32 layers, forward + data gradient) is the step's dominant kernel.  72 (fwd) /
         # 48 (dgrad) FLOP per algorithmic byte is below the B200 ridge (TF32 692 TF/s / 6.5 TB/s = 106 FLOP/B): HBM-bound.
-        achieved = kt[3] / (kt[0] * 1e-3) / 1e9
-        roof = {"bound": "hbm", "kernel": "conv3x3_tc_kernel (conv_tc fwd + dgrad launches)", "achieved": achieved, "peak": hbm,
-                "unit": "GB/s", "frac": achieved / hbm, "traffic": None, "share_of_step": kt[0] / tot,
-                "peak_source": f"HBM copy bandwidth {hbm} GB/s ({how})",
-                "launches_per_step": kt[1] / nst, "ms_per_step_in_kernel": kt[0] / nst,
-                "algorithmic_bytes_per_launch": kt[3] / kt[1], "avg_launch_us": kt[0] / kt[1] * 1e3,
-                "timing": "CUDA events around every launch of the kernel in an eager (graph-free, single-stream) pass over 4 updates, the "
-                          "stream parked behind a spin kernel while the host queues each update so the events bracket device time only",
-                "tensor_view": {"achieved_tflops": kt[2] / (kt[0] * 1e-3) / 1e12, "peak_tflops": tf_sus / 2.0,
-                                "peak_source": f"bf16 sustained {tf_sus} TF/s ({how}) / 2 = TF32 dense, derived"}}
-        if l1 is not None:
-            # one specific launch, so that `traffic` (ncu --set full, profiles/prof_r1_convtc_v2.md) and the live time refer to
-            # the same work: forward 41x41 -> 39x39 at B = 128
+        roof = roofline_of(fam, nst, B)
+        roof["timing"] = ("CUDA events around every launch of the kernel in an eager (graph-free, single-stream) pass over 4 updates, the "
+                          "stream parked behind a spin kernel while the host queues each update so the events bracket device time only")
+        l1 = fam.get("_conv_tc_fwd_l1")
+        tr = ncu_traffic()
+        if l1 is not None and tr is not None:
+            # one specific launch, so that `traffic` (ncu --set full of this build, profiles/) and the live time refer to the
+            # same work: forward 41x41 -> 39x39 at B = 128 (2B = 256 samples in the [next_obs ; obs] pass)
             us = l1[0] / l1[1] * 1e3
-            roof.update({"traffic": NCU_TRAFFIC["conv_tc_fwd_l1"],
-                         "traffic_launch": {"what": "forward layer 41x41->39x39, B=128", "algorithmic_bytes": l1[3], "live_us": us,
-                                            "achieved_gbs": l1[3] / (us * 1e-6) / 1e9, "ncu_us_cold_cache": 19.2}})
+            roof.update({"traffic": tr.get("dram_bytes_per_launch"),
+                         "traffic_launch": {"what": tr.get("what"), "source": tr.get("source"), "algorithmic_bytes": tr.get("algorithmic_bytes"),
+                                            "live_us_same_shape": us, "ncu_us_cold_cache": tr.get("duration_us")}})
     if world > 1:
         barrier()
+    del rb
+
+    # ---- BASELINE config 4 proper: global batch 1024 sharded over the ranks (strong scaling; N=1: all 1024 on one GPU)
+    strong = None
+    if not a.quick and 1024 % world == 0:
+        Bs = 1024 // world
+        ag4, rb4 = make(B=Bs, Bg=1024, data=data84)
+        st4 = max(20, a.steps // 4)
+        ms4, _ = timed(ag4, rb4, NullLog(), st4, max(3, a.warmup // 2))
+        strong = {"global_batch": 1024, "per_gpu_batch": Bs, "ms_per_step": ms4 / st4, "updates_per_s": st4 / (ms4 / 1e3),
+                  "batch128_equiv_updates_per_s": st4 / (ms4 / 1e3) * 8.0, "steps": st4, "scaling": "strong",
+                  "what": "BASELINE config 4: SGSAC, global batch 1024 split evenly over the ranks, gradients all-reduced over NCCL"}
+        del ag4, rb4
 
     # ---- end-to-end run: host-resident replay ring (pinned), loss read-back every step
-    del rb
-    agent2, rb2 = make("pinned")
+    agent2, rb2 = make(storage="pinned", Bg=Bg, data=data84)
     agent2.defer_logs = True
     L2 = NullLog()
     ms2, _ = timed(agent2, rb2, L2, a.steps, a.warmup)
@@ -350,7 +434,7 @@ def run_b200(a):
     # ---- acting latency: host uint8 stack -> action on the host, one CUDA graph launch per call
     act = None
     if rank == 0:
-        ob = frames[:3].reshape(9, 84, 84)
+        ob = data84[0][:3].reshape(9, 84, 84)
         for fn_name in ("select_action", "sample_action"):
             fn = getattr(agent2, fn_name)
             for _ in range(5):
@@ -360,14 +444,42 @@ def run_b200(a):
                 t0 = time.perf_counter(); fn(ob); ts.append(time.perf_counter() - t0)
             act = dict(act or {}, **{fn_name + "_us": float(np.median(ts) * 1e6)})
         act["how"] = "median host wall time of 200 calls, uint8 (9,84,84) host array in -> float32 (A,) host array out"
+    del agent2, rb2
+    if world > 1:
+        barrier()
 
     if rank != 0:
         _finish(world)
         return
-    cpu = None
+
+    # ---- the other single-GPU configurations of BASELINE.json (rank 0, no collectives): config 3 and config 5
+    others = None
+    if world == 1 and not a.quick:
+        others = {}
+        st = max(40, a.steps // 2)
+        specs = [("config3_sgsac_b256", "sgsac", 256, 2, 84, "BASELINE config 3: SGSAC on CARLA-shaped observations (9x84x84 uint8, A=2), batch 256, overlay pool 2048"),
+                 ("config5_svea_b128", "svea", 128, 6, 84, "BASELINE config 5: SVEA (random_shift pad 4, critic on [obs ; overlay(obs)] = 256 rows), A=6, batch 128"),
+                 ("config5_rad_b128", "rad", 128, 6, 100, "BASELINE config 5: RAD (100x100 frames, random_crop to 84 fused into the gather), A=6, batch 128")]
+        for key, algo, Bc, Ac, size, what in specs:
+            d = data84 if (Ac == 2 and size == 84) else synthetic_sized(8000, Ac, size, seed=3)
+            agc, rbc = make(algorithm=algo, B=Bc, A=Ac, size=size, data=d, capacity=len(d[1]))
+            msc, lc = timed(agc, rbc, NullLog(), st, max(3, a.warmup), collective=False)
+            famc, nc = profile_kernels(agc, rbc, 4)
+            r = roofline_of(famc, nc, Bc)
+            others[key] = {"what": what, "updates_per_s": st / (msc / 1e3), "ms_per_step": msc / st, "steps": st, "gpu_launches": lc,
+                           "batch128_equiv_updates_per_s": st / (msc / 1e3) * Bc / 128.0,
+                           "roofline": {k: r[k] for k in ("bound", "kernel", "achieved", "peak", "unit", "frac", "share_of_step",
+                                                          "launches_per_step", "ms_per_step_in_kernel", "avg_launch_us")}}
+            del agc, rbc
+    cpu, eager = None, None
     if world == 1 and not a.no_cpu_baseline:
         v, cores, sample = time_oracle(4, 1, 40.0)
         cpu = {"value": v, "unit": "updates/s", "cores": cores, "kind": "port", "sample": sample}
+        if not a.quick:
+            try:
+                eager = {"b128": time_torch_eager_gpu(128), "b256": time_torch_eager_gpu(256, steps=4, warmup=2)}
+            except Exception as e:          # a baseline leg must never take the measurement down
+                eager = {"error": repr(e)[:300]}
     gflop = 0.5 * (GFLOP_ODD + GFLOP_EVEN) * Bg
     line = {
         "metric": "SGSAC updates/sec (batch 128, 9x84x84)", "value": value, "unit": "updates/s", "n_gpus": world,
@@ -384,6 +496,7 @@ def run_b200(a):
                        "the current update), are converted / cropped on the device at the start of their step, and the step's loss "
                        "vector is copied device->host"},
         "act_latency": act, "gpu_launches": launches, "clocks": sampler.summary(), "roofline": roof, "cpu_baseline": cpu,
+        "torch_eager_b200": eager, "config4_strong": strong, "other_configs": others,
         "algorithmic_gflop_per_update": gflop, "achieved_tflops_whole_step": gflop * ups / 1e3,
         "kernel_families_ms_per_step": [[r[0], round(r[1], 4), r[2]] for r in (fam_rows or [])[:12]],
         "losses_last_step": last,
@@ -441,6 +554,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--quick", action="store_true", help="headline numbers only (skip config 3 / 4-strong / 5 and the torch-eager baseline)")
     a = ap.parse_args()
     a.warmup = max(a.warmup, 3)
     if a.impl == "reference":

@@ -184,10 +184,12 @@ int sgqn_bce_phase(const float* logits, const uint8_t* mask, float* loss, float*
                    int oy, int ox, int Bg, int round_out, void* stream);
 
 /* ---- optimiser: torch.optim.Adam (sac.py:60-68, sgsac.py:35-39) over a flat range, soft target update
- *      (utils.py:31-33, sac.py:153-158) fused when target != NULL */
+ *      (utils.py:31-33, sac.py:153-158) fused when target != NULL; weight_decay = torch's L2 form (grad += wd * p;
+ *      critic_weight_decay, sac.py:63-65) */
 int sgqn_adam_prep(int* step, float* bc, double b1, double b2, void* stream);
 int sgqn_adam(float* p, const float* g, float* m, float* v, long long n, const float* bc, float lr, float one_minus_b1, float b2,
-              float one_minus_b2, float eps, float* target, long long n_tau0, float tau0, float tau1, void* stream);
+              float one_minus_b2, float eps, float* target, long long n_tau0, float tau0, float tau1, float weight_decay,
+              void* stream);
 int sgqn_ema(const float* p, float* target, long long n, long long n_tau0, float tau0, float tau1, void* stream);
 int sgqn_alpha_adam(double* log_alpha, const double* grad, double* st, int* step, double lr, double b1, double b2, double eps,
                     void* stream);

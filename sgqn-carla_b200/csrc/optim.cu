@@ -22,7 +22,7 @@ extern "C" int sgqn_adam_prep(int* step, float* bc, double b1, double b2, void* 
 __global__ void __launch_bounds__(256)
 adam_kernel(float4* __restrict__ p, const float4* __restrict__ g, float4* __restrict__ m, float4* __restrict__ v, long long n4,
             const float* __restrict__ bc, float lr, float omb1, float b2, float omb2, float eps, float4* __restrict__ target,
-            long long n4_tau0, float tau0, float tau1) {
+            long long n4_tau0, float tau0, float tau1, float wd) {
     const float bc1 = bc[0], bc2s = bc[1];
     const float step_size = lr / bc1;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
@@ -31,6 +31,7 @@ adam_kernel(float4* __restrict__ p, const float4* __restrict__ g, float4* __rest
         float mm[4] = {mv.x, mv.y, mv.z, mv.w}, vq[4] = {vv.x, vv.y, vv.z, vv.w};
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
+            if (wd != 0.f) gg[k] = gg[k] + wd * pp[k];                    // weight_decay: grad.add(param, alpha=wd)  (sac.py:63-65)
             mm[k] = mm[k] + omb1 * (gg[k] - mm[k]);                       // exp_avg.lerp_(grad, 1-beta1)
             vq[k] = vq[k] * b2 + omb2 * gg[k] * gg[k];                    // mul_(beta2).addcmul_(g, g, 1-beta2)
             float denom = sqrtf(vq[k]) / bc2s + eps;
@@ -50,13 +51,14 @@ adam_kernel(float4* __restrict__ p, const float4* __restrict__ g, float4* __rest
 }
 
 extern "C" int sgqn_adam(float* p, const float* g, float* m, float* v, long long n, const float* bc, float lr, float omb1,
-                         float b2, float omb2, float eps, float* target, long long n_tau0, float tau0, float tau1, void* stream) {
+                         float b2, float omb2, float eps, float* target, long long n_tau0, float tau0, float tau1, float weight_decay,
+                         void* stream) {
     if (n <= 0) return 0;
     if ((n & 3) || (n_tau0 & 3)) return (int)cudaErrorInvalidValue;
     long long n4 = n / 4;
     int grid = (int)(cdivll(n4, 256) < 148 * 8 ? cdivll(n4, 256) : 148 * 8);
     adam_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((float4*)p, (const float4*)g, (float4*)m, (float4*)v, n4, bc, lr, omb1, b2, omb2,
-                                                        eps, (float4*)target, n_tau0 / 4, tau0, tau1);
+                                                        eps, (float4*)target, n_tau0 / 4, tau0, tau1, weight_decay);
     return SGQN_CHECK_LAUNCH();
 }
 

@@ -24,12 +24,12 @@ def _ptr(t, off=0):
 
 
 class _Opt:
-    def __init__(self, dev, n, lr, b1, b2=0.999, eps=1e-8):
+    def __init__(self, dev, n, lr, b1, b2=0.999, eps=1e-8, wd=0.0):
         self.m = torch.zeros(n, device=dev)
         self.v = torch.zeros(n, device=dev)
         self.step = torch.zeros(1, dtype=torch.int32, device=dev)
         self.bc = torch.zeros(2, device=dev)
-        self.lr, self.b1, self.b2, self.eps = float(lr), float(b1), float(b2), float(eps)
+        self.lr, self.b1, self.b2, self.eps, self.wd = float(lr), float(b1), float(b2), float(eps), float(wd)
 
 
 class UpdateEngine:
@@ -74,7 +74,7 @@ class UpdateEngine:
         self.alpha_step = torch.zeros(1, dtype=torch.int32, device=dev)
         self.alpha_grad = torch.zeros(1, dtype=torch.float64, device=dev)
         self.target_entropy = -float(np.prod((A,)))
-        self.opt_critic = _Opt(dev, c1 - c0, args.critic_lr, args.critic_beta)
+        self.opt_critic = _Opt(dev, c1 - c0, args.critic_lr, args.critic_beta, wd=getattr(args, "critic_weight_decay", 0.0))
         a0, a1 = L.ranges["actor"]
         self.opt_actor = _Opt(dev, a1 - a0, args.actor_lr, args.actor_beta)
         x0, x1 = L.ranges["aux"]
@@ -376,7 +376,7 @@ class UpdateEngine:
         K.adam_prep(_ptr(opt.step), _ptr(opt.bc), opt.b1, opt.b2, st)
         K.adam(self._p + 4 * o0, self._g + 4 * o0, _ptr(opt.m), _ptr(opt.v), o1 - o0, _ptr(opt.bc), opt.lr,
                float(np.float32(1 - opt.b1)), opt.b2, float(np.float32(1 - opt.b2)), opt.eps,
-               target if target else 0, n_tau0, tau0, tau1, st)
+               target if target else 0, n_tau0, tau0, tau1, opt.wd, st)
 
     def allreduce_grads(self, rng, group="main"):
         if self.dist is not None:

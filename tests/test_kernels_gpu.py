@@ -487,12 +487,30 @@ def test_adam_and_ema_vs_oracle():
         gd = gr.to(DEV)
         K.adam_prep(P(step), P(bc), 0.9, 0.999, ST())
         K.adam(P(pd), P(gd), P(m), P(v), n, P(bc), 1e-3, float(np.float32(0.1)), 0.999, float(np.float32(0.001)), 1e-8,
-               P(tgt), 1024, 0.01, 0.05, ST())
+               P(tgt), 1024, 0.01, 0.05, 0.0, ST())
     assert int(step) == 5
     np.testing.assert_allclose(pd.cpu().numpy(), p["w"].numpy(), rtol=0, atol=2e-6)
     np.testing.assert_allclose(m.cpu().numpy(), opt.m["w"].numpy(), rtol=1e-5, atol=1e-9)
     np.testing.assert_allclose(v.cpu().numpy(), opt.v["w"].numpy(), rtol=1e-5, atol=1e-12)
     np.testing.assert_allclose(tgt.cpu().numpy(), tref.numpy(), rtol=0, atol=2e-6)
+
+
+def test_adam_weight_decay_matches_torch():
+    """critic_weight_decay (sac.py:63-65): torch.optim.Adam's L2 form."""
+    n = 1024
+    g = torch.Generator().manual_seed(1)
+    p0 = torch.randn(n, generator=g)
+    ref = torch.nn.Parameter(p0.clone())
+    opt = torch.optim.Adam([ref], lr=1e-3, betas=(0.9, 0.999), weight_decay=0.01)
+    pd, m, v = p0.clone().to(DEV), torch.zeros(n, device=DEV), torch.zeros(n, device=DEV)
+    step = torch.zeros(1, dtype=torch.int32, device=DEV); bc = torch.zeros(2, device=DEV)
+    for it in range(4):
+        gr = torch.randn(n, generator=g)
+        ref.grad = gr.clone(); opt.step()
+        K.adam_prep(P(step), P(bc), 0.9, 0.999, ST())
+        K.adam(P(pd), P(gr.to(DEV)), P(m), P(v), n, P(bc), 1e-3, float(np.float32(0.1)), 0.999, float(np.float32(0.001)), 1e-8,
+               0, 0, 0.0, 0.0, 0.01, ST())
+    np.testing.assert_allclose(pd.cpu().numpy(), ref.detach().numpy(), rtol=0, atol=2e-6)
 
 
 def test_alpha_adam_fp64():
