@@ -101,6 +101,18 @@ int sgqn_conv1_dgrad_col(const float* dy, const float* w, float* dcol, float* do
 int sgqn_conv_tc(const float* x, const float* w, const float* bias, const float* mask, float* out,
                  float* dbias /* optional: dbias[32] += per-channel sum of the outputs written (atomic) */, int B, int Hr, int Wp,
                  int Hv, int Wv, int shift, int Hq, int Wq, int oy, int ox, int Hm, int Wm, int flags, void* stream);
+/*      A CHAIN of such convs -- the ten SharedCNN layers 2..11 of one encoder pass (modules.py:144-146), or their data
+ *      gradients in reverse order -- as ONE persistent launch (conv_chain.cu): the tiles of all layers form one ticketed
+ *      list and a tile of layer i+1 waits, per tile, for the tiles of layer i that produce its input rows, so there is no
+ *      pipeline fill / drain between layers and a layer's input is still in L2.  layers[i] has the fields of one
+ *      sgqn_conv_tc call; layers[i+1].x must be layers[i].out with layers[i]'s output geometry (Hq, Wq) as its input
+ *      geometry (Hr, Wp).  Results are bit-identical to n_layers sgqn_conv_tc calls (dbias: up to summation order).
+ *      ws: >= 4 + (number of tiles) ints, zero-filled once by the caller, owned by the launches of ONE stream. */
+typedef struct sgqn_conv_layer {
+    const float* x; const float* w; const float* bias; const float* mask; float* out; float* dbias;
+    int B, Hr, Wp, Hv, Wv, shift, Hq, Wq, oy, ox, Hm, Wm, flags;
+} sgqn_conv_layer;
+int sgqn_conv_chain(const sgqn_conv_layer* layers, int n_layers, int* ws, long long ws_ints, void* stream);
 /*      weight gradient of the same convs on tcgen05 (MN-major TF32 operands, reduction over pixels, one
  *      red.global.add per CTA and element): x, dy [B][Hr][Wp][32] share one geometry, dy zero outside its valid region */
 int sgqn_conv_wgrad_tc(const float* x, const float* dy, float* dw, int B, int Hr, int Wp, void* stream);

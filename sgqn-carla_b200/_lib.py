@@ -4,7 +4,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libsgqn_b200.so")
+LIB_PATH = os.environ.get("SGQN_LIB") or os.path.join(_HERE, "libsgqn_b200.so")      # SGQN_LIB: an instrumented debug build
 ABI_VERSION = 2
 
 _p, _i, _ll, _f, _d, _ull = C.c_void_p, C.c_int, C.c_longlong, C.c_float, C.c_double, C.c_ulonglong
@@ -28,6 +28,7 @@ SIGNATURES = {
     "sgqn_conv_wgrad": [_p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p],
     "sgqn_conv1_fwd": [_p, _p, _p, _p, _i, _i, _i, _i, _i, _p],
     "sgqn_conv_tc": [_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p],
+    "sgqn_conv_chain": [_p, _i, _p, _ll, _p],
     "sgqn_conv_wgrad_tc": [_p, _p, _p, _i, _i, _i, _p],
     "sgqn_conv_weights_prep": [_p, _ll, _p, _p, _i, _p],
     "sgqn_pad_copy": [_p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p],
@@ -71,6 +72,21 @@ SIGNATURES = {
     "sgqn_alpha_adam": [_p, _p, _p, _p, _d, _d, _d, _d, _p],
     "sgqn_rng_step": [_ull, _p, _p, _p, _p, _i, _p, _i, _p, _p, _p, _i, _i, _ull, _p],
 }
+
+
+
+class ConvLayer(C.Structure):
+    """sgqn_conv_layer (include/sgqn_b200.h): one layer of a sgqn_conv_chain call = the arguments of one sgqn_conv_tc call."""
+    _fields_ = [(n, _p) for n in ("x", "w", "bias", "mask", "out", "dbias")] + \
+               [(n, _i) for n in ("B", "Hr", "Wp", "Hv", "Wv", "shift", "Hq", "Wq", "oy", "ox", "Hm", "Wm", "flags")]
+
+
+def conv_layers(rows):
+    """rows: tuples in sgqn_conv_tc argument order (x, w, bias, mask, out, dbias, B, Hr, Wp, Hv, Wv, shift, Hq, Wq, oy, ox, Hm, Wm,
+    flags) -> (ctypes array, its address, n)."""
+    arr = (ConvLayer * len(rows))(*[ConvLayer(*r) for r in rows])
+    return arr, C.addressof(arr), len(rows)
+
 
 _lib = None
 launch_count = 0          # kernels-launching ABI calls made (bench.py's `gpu_launches` bookkeeping)

@@ -8,6 +8,8 @@
 Everything underneath runs on the hand-written sm_100a kernels of libsgqn_b200.so (engine.py); there is no
 PyTorch-op fallback for the update path.
 """
+import contextlib
+import gc
 import os
 from collections import OrderedDict
 
@@ -21,6 +23,23 @@ from .engine import UpdateEngine, _ptr
 from .layout import reference_key_map
 from .lazylog import LazyScalar, _Ring
 from .replay import ReplayBuffer
+
+
+@contextlib.contextmanager
+def _capture(graph):
+    """torch.cuda.graph(graph) with the cyclic garbage collector parked for the duration of the capture.  A collection that
+    happens to run in the middle of a capture can finalise objects of EARLIER agents / buffers (reference cycles keep them
+    alive until a collection): releasing a pinned host tensor records a CUDA event and destroying a CUDAGraph resets it --
+    both are illegal while a stream is capturing, invalidate the capture and abort the process from a destructor."""
+    gc.collect()
+    was_enabled = gc.isenabled()
+    gc.disable()
+    try:
+        with torch.cuda.graph(graph):
+            yield
+    finally:
+        if was_enabled:
+            gc.enable()
 
 
 class _ModuleView(object):
@@ -273,7 +292,7 @@ class SAC(object):
         if slot["graph"] is None and slot["runs"] >= 1 and self.use_cuda_graphs:
             g = torch.cuda.CUDAGraph()
             c0 = _lib.launch_count
-            with torch.cuda.graph(g):
+            with _capture(g):
                 body()
             slot["graph"], slot["nodes"] = g, _lib.launch_count - c0
             _lib.launch_count = c0
@@ -463,7 +482,7 @@ class SAC(object):
                 return
             g = torch.cuda.CUDAGraph()
             c0 = _lib.launch_count
-            with torch.cuda.graph(g):
+            with _capture(g):
                 self._run_update(replay_buffer, step)
             self._graphs[kind] = g
             self._graph_nodes[kind] = _lib.launch_count - c0

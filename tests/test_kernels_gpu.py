@@ -952,3 +952,49 @@ def test_conv1_dgrad_fused_matches_materialised_path(B):
     ref = F.conv_transpose2d(d.permute(0, 3, 1, 2).double(), tf32_round(w).double(), stride=2, output_padding=1) / 255.0
     close(d1, ref.float(), rtol=2e-3, atol=2e-3 * float(ref.abs().max()), what="conv1 dgrad fused vs torch")
     assert float(d1[:, :, 83].abs().max()) == 0.0 and float(d1[:, :, :, 83].abs().max()) == 0.0
+
+
+# ------------------------------------------------------------------ the ten 32->32 convs as one persistent launch
+@pytest.mark.parametrize("B", [3, 16, 40])
+def test_conv_chain_equals_per_layer_launches(B):
+    """conv_chain.cu (ticketed tile list over all layers, per-tile producer / consumer flags) against ten sgqn_conv_tc launches:
+    forward activations and data gradients (plain and guided) are BIT-identical, bias gradients equal up to the order of the
+    per-CTA partial sums; repeated launches on one workspace (epoch / ticket re-arming) stay correct."""
+    import sgqn_carla_b200 as S
+    from sgqn_carla_b200.engine import _ptr
+    from sgqn_carla_b200.layout import ENC_H, FEAT
+    args = S.default_args(algorithm="sac", batch_size=B)
+    agent = S.make_agent((9, 84, 84), (2,), args)
+    eng = agent.engine
+    g = torch.Generator().manual_seed(B)
+    from oracle import sgsac_oracle as O
+    agent.set_parameters(O.init_params((9, 84, 84), 2, O.Args(**vars(args)), g, dense_std=0.05))
+    obs = torch.randint(0, 256, (2 * B, 9, 84, 84), generator=g).float().to(DEV)
+    dfeat = (torch.randn(2 * B, FEAT, generator=g) * 1e-2).to(DEV)
+    outs = {}
+    for chain in (False, True, True):                       # the third pass re-uses the workspace of the second
+        eng.chain = chain
+        for t in eng.actS + [x for x in eng.gpad if x is not None] + [eng.dbuf[0], eng.grads, eng.obs_grad]:
+            t.zero_()
+        eng.enc_fwd(_ptr(obs), 2 * B, eng.actS, B, col_from=0)
+        acts = [a.clone() for a in eng.actS]
+        eng.enc_bwd(_ptr(dfeat), 2 * B, eng.actS, B, _ptr(obs), 1, True)
+        torch.cuda.synchronize()
+        gp = [x.clone() for x in eng.gpad if x is not None] + [eng.dbuf[0].clone()]
+        grads = eng.lay.unpack(eng.grads)
+        eng.enc_bwd(_ptr(dfeat), B, eng.actS, B, 0, 2, False, dobs=_ptr(eng.obs_grad))
+        torch.cuda.synchronize()
+        outs[len(outs)] = (acts, gp, grads, eng.obs_grad.clone())
+    ref = outs[0]
+    assert float(ref[0][10].abs().max()) > 0 and float(ref[3].abs().max()) > 0
+    for k in (1, 2):
+        acts, gp, grads, og = outs[k]
+        for l, (a, b) in enumerate(zip(acts, ref[0])):
+            assert torch.equal(a, b), ("act", l, k)
+        for l, (a, b) in enumerate(zip(gp, ref[1])):
+            assert torch.equal(a, b), ("d act", l, k)
+        assert torch.equal(og, ref[3]), ("guided attribution", k)
+        for l in range(11):
+            for wb in ("weight", "bias"):
+                a, b = grads[f"cnn.{l}.{wb}"], ref[2][f"cnn.{l}.{wb}"]
+                assert float((a - b).abs().max()) <= 1e-5 * float(b.abs().max()) + 1e-12, (l, wb, k)
