@@ -199,6 +199,32 @@ def profile_kernels(agent, rb, nsteps=4):
         agent.engine.overlap = overlap
         for n, fn in saved.items():
             setattr(api, n, fn)
+    # the dominant kernel as the product runs it: the conv_tc launches of ONE update, in program order, re-issued back to back
+    # on one stream inside a CUDA graph (programmatic dependent launch overlaps each launch's prologue with its predecessor's
+    # last tiles, layer l+1 reads layer l's output from L2) and timed with CUDA events around replays of that graph
+    ingraph = None
+    conv_calls = [(n, args) for n, args, _, _ in recs if n in ("conv_tc", "conv_chain")]
+    conv_calls = conv_calls[-(len(conv_calls) // nsteps) * 2:]          # the last two updates = one odd + one even step
+    if conv_calls and conv_calls[0][0] == "conv_tc":
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            st = torch.cuda.current_stream().cuda_stream
+            for n, args in conv_calls:
+                saved[n](*args[:-1], st)
+        for _ in range(3):
+            g.replay()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 20
+        e0.record()
+        for _ in range(reps):
+            g.replay()
+        e1.record()
+        torch.cuda.synchronize()
+        by = sum(128.0 * a[6] * ((a[9] + 2) * (a[9] + 2) + a[9] * a[9] * (2 if (a[-2] >> 2) & 3 else 1)) for _, a in conv_calls)
+        fl = sum(2.0 * a[6] * a[9] * a[9] * 9 * 32 * 32 for _, a in conv_calls)
+        ingraph = {"launches": len(conv_calls), "us_per_launch": e0.elapsed_time(e1) * 1e3 / (reps * len(conv_calls)),
+                   "bytes_per_launch": by / len(conv_calls), "flops_per_launch": fl / len(conv_calls)}
     dump = os.environ.get("SGQN_PROFILE_CALLS")
     if dump:
         rows = [[n, [a for a in args if isinstance(a, int) and abs(a) < (1 << 31)][:14], round(e0.elapsed_time(e1), 4)] for n, args, e0, e1 in recs]
@@ -269,6 +295,7 @@ def profile_kernels(agent, rb, nsteps=4):
             if args[11] == 0 and args[7] == 43 and args[6] == 2 * PER_GPU_BATCH:   # forward, 41x41 -> 39x39, 256 samples: see ncu_traffic()
                 t0, c0 = fam.get("_conv_tc_fwd_l1", (0.0, 0, 0.0, 0.0))[:2]
                 fam["_conv_tc_fwd_l1"] = (t0 + t, c0 + 1, fl, by)
+    fam["_ingraph"] = ingraph
     return fam, nsteps
 
 
@@ -379,14 +406,28 @@ def run_b200(a):
         tot = sum(v[0] for k, v in fam.items() if not k.startswith("_"))
         hbm, tf_burst, tf_sus, how = peaks()
         kt = fam["_conv3x3_tc_kernel"]                       # (ms, launches, flops, algorithmic bytes) over nst updates
-        achieved = kt[3] / (kt[0] * 1e-3) / 1e9
-        return {"bound": "hbm", "kernel": "conv3x3_chain_kernel (the ten 32->32 SharedCNN layers of a pass, forward or data gradient, per launch)", "achieved": achieved, "peak": hbm,
-                "unit": "GB/s", "frac": achieved / hbm, "traffic": None, "share_of_step": kt[0] / tot,
-                "peak_source": f"HBM copy bandwidth {hbm} GB/s ({how})",
-                "launches_per_step": kt[1] / nst, "ms_per_step_in_kernel": kt[0] / nst,
-                "algorithmic_bytes_per_launch": kt[3] / kt[1], "avg_launch_us": kt[0] / kt[1] * 1e3,
-                "tensor_view": {"achieved_tflops": kt[2] / (kt[0] * 1e-3) / 1e12, "peak_tflops": tf_sus / 2.0,
-                                "peak_source": f"bf16 sustained {tf_sus} TF/s ({how}) / 2 = TF32 dense, derived"}}
+        iso = kt[3] / (kt[0] * 1e-3) / 1e9
+        ig = fam.get("_ingraph")
+        name = "conv3x3_tc_kernel (32->32 SharedCNN layers, forward + data-gradient launches)"
+        r = {"bound": "hbm", "kernel": name, "achieved": iso, "peak": hbm, "unit": "GB/s", "frac": iso / hbm, "traffic": None,
+             "share_of_step": kt[0] / tot, "peak_source": f"HBM copy bandwidth {hbm} GB/s ({how})",
+             "launches_per_step": kt[1] / nst, "ms_per_step_in_kernel": kt[0] / nst,
+             "algorithmic_bytes_per_launch": kt[3] / kt[1], "avg_launch_us": kt[0] / kt[1] * 1e3,
+             "tensor_view": {"achieved_tflops": kt[2] / (kt[0] * 1e-3) / 1e12, "peak_tflops": tf_sus / 2.0,
+                             "peak_source": f"bf16 sustained {tf_sus} TF/s ({how}) / 2 = TF32 dense, derived"}}
+        if ig is not None:
+            # headline = the launches as the product issues them (inside the update's CUDA graph, back to back with programmatic
+            # dependent launch); the isolated-launch figure (launch latency + cold pipeline + idle GPU before every launch) beside it
+            a = ig["bytes_per_launch"] / (ig["us_per_launch"] * 1e-6) / 1e9
+            r.update({"achieved": a, "frac": a / hbm, "avg_launch_us": ig["us_per_launch"],
+                      "algorithmic_bytes_per_launch": ig["bytes_per_launch"], "ms_per_step_in_kernel": ig["us_per_launch"] * kt[1] / nst * 1e-3,
+                      "tensor_view": dict(r["tensor_view"], achieved_tflops=ig["flops_per_launch"] / (ig["us_per_launch"] * 1e-6) / 1e12),
+                      "timing": f"CUDA events around 20 replays of a CUDA graph that holds the {ig['launches']} conv3x3_tc_kernel launches of one odd + one even "
+                                "update in program order on one stream (how the update's own graph runs them: programmatic dependent launch, "
+                                "each layer's input still in L2); average per launch",
+                      "isolated_launch": {"achieved": iso, "frac": iso / hbm, "avg_launch_us": kt[0] / kt[1] * 1e3,
+                                          "timing": "CUDA events around every launch in an eager single-stream pass over 4 updates (idle GPU before each launch)"}})
+        return r
 
     data84 = synthetic(CAPACITY, 2, seed=rank)
     B = PER_GPU_BATCH
@@ -413,8 +454,8 @@ def run_b200(a):
         # conv3x3_tc_kernel (SharedCNN 32->32 layers, forward + data gradient) is the step's dominant kernel.  72 (fwd) /
         # 48 (dgrad) FLOP per algorithmic byte is below the B200 ridge (TF32 692 TF/s / 6.5 TB/s = 106 FLOP/B): HBM-bound.
         roof = roofline_of(fam, nst, B)
-        roof["timing"] = ("CUDA events around every launch of the kernel in an eager (graph-free, single-stream) pass over 4 updates, the "
-                          "stream parked behind a spin kernel while the host queues each update so the events bracket device time only")
+        roof.setdefault("timing", "CUDA events around every launch of the kernel in an eager (graph-free, single-stream) pass over 4 updates, the "
+                        "stream parked behind a spin kernel while the host queues each update so the events bracket device time only")
         l1 = fam.get("_conv_tc_fwd_l1")
         tr = ncu_traffic()
         if l1 is not None and tr is not None:
