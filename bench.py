@@ -28,7 +28,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 # NCCL's own log (communicator sizes, NVLS / ring choice) goes to stderr with everything else a library prints: stdout is
 # redirected to stderr while the benchmark runs (_StdoutToStderr) and carries exactly the one JSON line
-os.environ.setdefault("NCCL_DEBUG", os.environ.get("SGQN_NCCL_DEBUG", "INFO" if int(os.environ.get("WORLD_SIZE", "1")) > 1 else "WARN"))
+os.environ["NCCL_DEBUG"] = os.environ.get("SGQN_NCCL_DEBUG", "INFO" if int(os.environ.get("WORLD_SIZE", "1")) > 1 else "WARN")
 
 import numpy as np  # noqa: E402
 import torch  # noqa: E402
