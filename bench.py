@@ -337,6 +337,17 @@ def time_torch_eager_gpu(B, steps=6, warmup=3):
                     f"{steps} updates ({steps // 2} even + {steps - steps // 2} odd) after {warmup} warm-up"}
 
 
+def build_info():
+    """sgqn-carla_b200/BUILD_INFO.json (written by __graft_entry__.build()): which build of libsgqn_b200.so this process loaded."""
+    p = os.path.join(ROOT, "sgqn-carla_b200", "BUILD_INFO.json")
+    try:
+        d = json.load(open(p))
+        d["so_mtime"] = time.strftime("%Y-%m-%dT%H:%M:%SZ", time.gmtime(os.path.getmtime(os.path.join(ROOT, "sgqn-carla_b200", "libsgqn_b200.so"))))
+        return d
+    except Exception:
+        return None
+
+
 def ncu_traffic():
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed summary of the
     `ncu --set full` capture of THIS build (profiles/traffic_r2.json, written by profiles/summarize.py); None if absent."""
@@ -559,7 +570,7 @@ def run_b200(a):
         "torch_eager_b200": eager, "config4_strong": strong, "other_configs": others,
         "algorithmic_gflop_per_update": gflop, "achieved_tflops_whole_step": gflop * ups / 1e3,
         "kernel_families_ms_per_step": [[r[0], round(r[1], 4), r[2]] for r in (fam_rows or [])[:12]],
-        "losses_last_step": last,
+        "losses_last_step": last, "build_info": build_info(),
     }
     emit(line)
     _finish(world)

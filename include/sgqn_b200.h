@@ -97,7 +97,11 @@ int sgqn_conv1_dgrad_col(const float* dy, const float* w, float* dcol, float* do
  *      sgqn_conv_weights_prep (wf: forward, wd: flipped+transposed for the data gradient).  Output (b,y,x), y < Hv,
  *      x < Wv = sum over taps of x-row q + ky*Wp + kx + shift, q = (b*Hr + y)*Wp + x; it goes to
  *      out[((b*Hq + y+oy)*Wq + x+ox)*32].  flags: bit0 ReLU, bit1 round output to TF32, bits 2-3 mask mode (1 plain ReLU
- *      backward, 2 guided) with the mask value of (b,y,x) at mask[((b*Hm + y)*Wm + x)*32]. */
+ *      backward, 2 guided) with the mask value of (b,y,x) at mask[((b*Hm + y)*Wm + x)*32].
+ *      flags bit 4 ("old weights"): the kernel is a programmatic dependent launch; with this bit it fetches `w` BEFORE
+ *      waiting for the previous kernel of the stream (under that kernel's last tiles).  The caller thereby guarantees that
+ *      `w` was written at least two launches earlier on the stream, or on another stream joined by an event -- true for the
+ *      operand copies of sgqn_conv_weights_prep, refreshed once per optimiser step, never by the producer of `x`. */
 int sgqn_conv_tc(const float* x, const float* w, const float* bias, const float* mask, float* out,
                  float* dbias /* optional: dbias[32] += per-channel sum of the outputs written (atomic) */, int B, int Hr, int Wp,
                  int Hv, int Wv, int shift, int Hq, int Wq, int oy, int ox, int Hm, int Wm, int flags, void* stream);

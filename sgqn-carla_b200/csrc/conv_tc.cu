@@ -50,7 +50,7 @@ struct TcParams {
     const float* mask;
     float* out;
     float* dbias;            // optional: += per-channel sum of the written outputs (bias gradient of the layer below)
-    int relu_out, round_out, mask_mode;
+    int relu_out, round_out, mask_mode, early_w;
 };
 
 // kind::tf32, D fp32, A/B TF32 K-major, M = 128, N = 96 (cute::UMMA::InstrDescriptor)
@@ -92,14 +92,24 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     tc_fence_after();
     uint32_t tmem_base;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
-    // everything above overlapped the previous kernel's last tiles (PDL, common.cuh); global memory from here on
+    // The 36 KB of weights are fetched BEFORE the grid-dependency wait, under the previous kernel's last tiles: the operand copy
+    // was written by sgqn_conv_weights_prep at least two launches earlier on this stream (or on another stream, joined by an
+    // event), so it is complete and visible by the time the previous kernel let this one start (contract, sgqn_b200.h).
+    // Callers that cannot promise this leave flags bit 4 clear: the weights are then fetched after the wait.
+    if (warp == 0 && lane == 0 && p.early_w) {
+        mbar_expect_tx(wbar, kWBytes);
+        for (int t = 0; t < 9; ++t) tma_load_2d(&tmW, wbar, w_sm + t * 4096, t * 32, 0);
+    }
+    // everything above overlapped the previous kernel's last tiles (PDL, common.cuh); activations / gradients from here on
     pdl_wait();
     pdl_launch();
 
     if (warp == 0) {
         if (lane == 0) {
-            mbar_expect_tx(wbar, kWBytes);
-            for (int t = 0; t < 9; ++t) tma_load_2d(&tmW, wbar, w_sm + t * 4096, t * 32, 0);
+            if (!p.early_w) {
+                mbar_expect_tx(wbar, kWBytes);
+                for (int t = 0; t < 9; ++t) tma_load_2d(&tmW, wbar, w_sm + t * 4096, t * 32, 0);
+            }
             int stage = 0; uint32_t phase = 0;
             for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
                 // one halo tile per output tile: the 9 tap operands are row-shifted views of it (9x less L2->SM traffic)
@@ -303,7 +313,7 @@ extern "C" int sgqn_conv_tc(const float* x, const float* w, const float* bias, c
     p.Hq = Hq; p.Wq = Wq; p.oy = oy; p.ox = ox; p.Hm = Hm; p.Wm = Wm;
     p.num_tiles = (p.total_q + kTileOut - 1) / kTileOut;
     p.bias = bias; p.mask = mask; p.out = out; p.dbias = dbias;
-    p.relu_out = flags & 1; p.round_out = (flags >> 1) & 1; p.mask_mode = (flags >> 2) & 3;
+    p.relu_out = flags & 1; p.round_out = (flags >> 1) & 1; p.mask_mode = (flags >> 2) & 3; p.early_w = (flags >> 4) & 1;
     if (p.mask_mode && !mask) return (int)cudaErrorInvalidValue;
     p.halo_rows = (kTileM + 2 * Wp + 7) / 8 * 8;                   // whole 1024-byte swizzle atoms
     if (p.halo_rows > 256) return (int)cudaErrorInvalidValue;      // TMA box limit

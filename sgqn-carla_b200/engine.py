@@ -230,7 +230,7 @@ class UpdateEngine:
                 last = l == 10                                  # the feature map that feeds the projection is compact
                 rows.append((_ptr(acts[l - 1], row0 * (hi + 2) * hi * 32), _ptr(wf, (l - 1) * 9216), W(f"cnn.{l}.bias"), 0,
                              _ptr(acts[l], row0 * (ho * ho if last else (ho + 2) * ho) * 32), 0, n, hi + 2, hi, ho, ho, 0,
-                             ho if last else ho + 2, ho, 0, 0, 0, 0, 0 if last else 3))
+                             ho if last else ho + 2, ho, 0, 0, 0, 0, (0 if last else 3) | 16))     # bit 4: weights are old (prep_conv_weights)
             self._convs(rows, self.wsS if acts is self.actS else self.wsT, st)
             return
         K.conv1_im2col(x_ptr, col, n, hin, st)
@@ -351,10 +351,10 @@ class UpdateEngine:
                 db = self.G(f"cnn.{l - 1}.bias") if wgrad else 0
                 if l > 1:
                     rows.append((_ptr(self.gpad[l]), _ptr(self.wd, (l - 1) * 9216), 0, a_in, _ptr(self.gpad[l - 1]), db, n, ho + 4, ho + 2,
-                                 hi, hi, -2, hi + 4, hi + 2, 2, 0, hi + 2, hi, 2 | (mode << 2)))
+                                 hi, hi, -2, hi + 4, hi + 2, 2, 0, hi + 2, hi, 2 | (mode << 2) | 16))
                 else:
                     rows.append((_ptr(self.gpad[1]), _ptr(self.wd), 0, a_in, _ptr(self.dbuf[0]), db, n, ho + 4, ho + 2, hi, hi, -2,
-                                 hi, hi, 0, 0, hi + 2, hi, 2 | (mode << 2)))
+                                 hi, hi, 0, 0, hi + 2, hi, 2 | (mode << 2) | 16))
             self._convs(rows, self.wsS, st)                  # (backward passes run on the update's main stream only)
             if wgrad:
                 ws = st
@@ -384,10 +384,10 @@ class UpdateEngine:
             db = self.G(f"cnn.{l - 1}.bias") if wgrad else 0    # sum of d(act_{l-1}) = bias gradient of layer l-1
             if l > 1:
                 K.conv_tc(d, _ptr(self.wd, (l - 1) * 9216), 0, a_in, _ptr(self.gpad[l - 1]), db, n, ho + 4, ho + 2, hi, hi, -2,
-                          hi + 4, hi + 2, 2, 0, hi + 2, hi, 2 | (mode << 2), st)
+                          hi + 4, hi + 2, 2, 0, hi + 2, hi, 2 | (mode << 2) | 16, st)
             else:                                       # d(act_0) compact: consumed by the first-conv kernels
                 K.conv_tc(d, _ptr(self.wd), 0, a_in, _ptr(self.dbuf[0]), db, n, ho + 4, ho + 2, hi, hi, -2,
-                          hi, hi, 0, 0, hi + 2, hi, 2 | (mode << 2), st)
+                          hi, hi, 0, 0, hi + 2, hi, 2 | (mode << 2) | 16, st)
         self._conv1_bwd(_ptr(self.dbuf[0]), n, acts, row0, wgrad, dobs)
         if side is not None:                            # join: the gradient buffers are reused by the next backward
             ev = torch.cuda.Event(); ev.record(side); main.wait_event(ev)
