@@ -199,6 +199,10 @@ int sgqn_bce(const float* logits, const uint8_t* mask, float* loss, float* dlogi
 int sgqn_bce_phase(const float* logits, const uint8_t* mask, float* loss, float* dlogits, int B, int H, int W, int Hq, int Wq,
                    int oy, int ox, int Bg, int round_out, void* stream);
 
+/* CURL (curl.py:35-37, modules.py:270-281): cross entropy of the (B,B) logits z_a W z_pos^T against the diagonal;
+ * *loss += mean (caller zero-fills), dlogits = (softmax - I) / Bg */
+int sgqn_ce_diag(const float* logits, int ld, float* loss, float* dlogits, int lddl, int B, int Bg, void* stream);
+
 /* ---- optimiser: torch.optim.Adam (sac.py:60-68, sgsac.py:35-39) over a flat range, soft target update
  *      (utils.py:31-33, sac.py:153-158) fused when target != NULL; weight_decay = torch's L2 form (grad += wd * p;
  *      critic_weight_decay, sac.py:63-65) */

@@ -87,5 +87,7 @@ def ref_params(agent):
             out[n] = sds[mod][key]
         if O._in_group(n, O.CRITIC_GROUP):
             out["t_" + n] = sds["critic_target"][key]
+    if hasattr(agent, "curl_head"):
+        out["curl.W"] = agent.curl_head.W.detach()
     out["log_alpha"] = agent.log_alpha.detach()
     return out

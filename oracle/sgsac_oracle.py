@@ -113,12 +113,14 @@ def _ref_key_map(num_layers=11):
     for j in (0, 2):
         for wb in ("weight", "bias"):
             m[f"fdec.{j}.{wb}"] = [("attribution_predictor", f"features_decoder.{j}.{wb}")]
+    m["curl.W"] = [("curl_head", "W")]                              # modules.py:264-268
     return m
 
 
 CRITIC_GROUP = ("cnn.", "critic_proj.", "Q1.", "Q2.")           # sac.py:63-65 critic.parameters()
 ACTOR_GROUP = ("cnn.", "actor_proj.", "actor_mlp.")             # sac.py:60-62 actor.parameters()
 AUX_GROUP = ("cnn.", "critic_proj.", "dec.", "fdec.")           # sgsac.py:35-39 attribution_predictor.parameters()
+CURL_GROUP = ("cnn.", "critic_proj.", "curl.")                  # curl.py:16-20 curl_head.parameters() = critic encoder + W
 TARGET_Q = ("Q1.", "Q2.")                                        # sac.py:154-155 (critic_tau)
 TARGET_ENC = ("cnn.", "critic_proj.")                            # sac.py:156-158 (encoder_tau)
 
@@ -163,6 +165,8 @@ def init_params(obs_shape, action_dim, args, gen=None, dense_std=None):
     shapes["dec.conv3.weight"] = (9, 64, 3, 3); shapes["dec.conv3.bias"] = (9,)
     shapes["fdec.0.weight"] = (256, 100); shapes["fdec.0.bias"] = (256,)
     shapes["fdec.2.weight"] = (100, 256); shapes["fdec.2.bias"] = (100,)
+    if getattr(args, "algorithm", "") == "curl":
+        shapes["curl.W"] = (P, P)                                   # CURLHead.W = torch.rand(out_dim, out_dim), modules.py:268
 
     p = OrderedDict()
     for name, shp in shapes.items():
@@ -170,6 +174,8 @@ def init_params(obs_shape, action_dim, args, gen=None, dense_std=None):
             t = torch.randn(*shp, generator=g) * dense_std
             if name.endswith("proj.1.weight"):
                 t = t + 1.0
+        elif name == "curl.W":
+            t = torch.rand(*shp, generator=g)
         elif name.startswith(("dec.", "fdec.")):
             # torch default Conv2d / Linear init: kaiming_uniform(a=sqrt(5)) == U(+-1/sqrt(fan_in))
             wshape = shapes[name.rsplit(".", 1)[0] + ".weight"]
@@ -519,6 +525,12 @@ class ReplayOracle:
             obs = random_crop(obs, crop[0], crop[1]); nxt = random_crop(nxt, crop[2], crop[3])
         return obs, a, r, nxt, nd
 
+    def sample_curl(self, idxs, crop):
+        """utils.py:142-156; crop = (w1p, h1p, w1, h1, w1n, h1n): pos, obs, next_obs crops (the reference draws them in this order)."""
+        obs, a, r, nxt, nd = self.sample(idxs)
+        pos = random_crop(obs, crop[0], crop[1])
+        return random_crop(obs, crop[2], crop[3]), a, r, random_crop(nxt, crop[4], crop[5]), nd, pos
+
     def sample_drq(self, idxs, shift, pad=4):
         """utils.py:158-171; shift=(dy,dx,dyn,dxn)."""
         obs, a, r, nxt, nd = self.sample(idxs)
@@ -673,6 +685,8 @@ class OracleSAC:
         sds = {"actor": agent.actor.state_dict(), "critic": agent.critic.state_dict()}
         if hasattr(agent, "attribution_predictor"):
             sds["attribution_predictor"] = agent.attribution_predictor.state_dict()
+        if hasattr(agent, "curl_head"):
+            sds["curl_head"] = agent.curl_head.state_dict()
         for n, refs in _ref_key_map().items():
             mod, key = refs[0]
             if mod in sds:
@@ -780,7 +794,49 @@ class OracleSVEA(OracleSAC):
         return loss + b * (F.mse_loss(q1a, target_q) + F.mse_loss(q2a, target_q))
 
 
-ALGOS = {"sac": OracleSAC, "rad": OracleSAC, "drq": OracleSAC, "svea": OracleSVEA, "sgsac": OracleSGSAC}
+class OracleCURL(OracleSAC):
+    """curl.py:11-57 (+ CURLHead, modules.py:264-281): SAC on random crops plus the contrastive auxiliary update."""
+
+    def __init__(self, obs_shape, action_shape, args, params=None, dense_std=None, seed=0, tf32=False):
+        super().__init__(obs_shape, action_shape, args, params, dense_std, seed, tf32=tf32)
+        self.aux_names = [n for n in self.p.keys() if _in_group(n, CURL_GROUP)]
+        self.aux_opt = Adam(self.aux_names, args.aux_lr, args.aux_beta)
+
+    def update_curl(self, x, x_pos, L=None, step=None):
+        """curl.py:27-43: z_a = critic encoder(x), z_pos = target encoder(x_pos) (no grad); logits = z_a W z_pos^T minus the
+        row maximum; cross entropy against the diagonal."""
+        gp = self._grad_params(self.aux_names)
+        z_a = projection(gp, cnn_forward(gp, x, tf32=self.tf32), "critic_proj")
+        with torch.no_grad():
+            z_pos = projection(self.p, cnn_forward(self.p, x_pos, pre="t_cnn", tf32=self.tf32), "t_critic_proj")
+        Wz = torch.matmul(gp["curl.W"], z_pos.T)
+        logits = torch.matmul(z_a, Wz)
+        logits = logits - torch.max(logits, 1)[0][:, None]
+        labels = torch.arange(logits.shape[0]).long()
+        curl_loss = F.cross_entropy(logits, labels)
+        grads = torch.autograd.grad(curl_loss, [gp[n] for n in self.aux_names])
+        g = dict(zip(self.aux_names, grads))
+        self.trace.update(curl_logits=logits.detach(), aux_loss=curl_loss.detach(), aux_grads=g, z_a=z_a.detach(), z_pos=z_pos)
+        with torch.no_grad():
+            self.aux_opt.step(self.p, g)
+        if L is not None:
+            L.log("train/aux_loss", curl_loss, step)
+
+    def update_from_batch(self, batch, rnd, L, step):
+        """curl.py:45-57 after sample_curl (utils.py:142-156): batch = (obs, action, reward, next_obs, not_done, pos)."""
+        obs, action, reward, next_obs, not_done, pos = batch
+        self.trace = dict(obs=obs, next_obs=next_obs, pos=pos)
+        self.update_critic(obs, action, reward, next_obs, not_done, rnd, L, step)
+        if step % self.args.actor_update_freq == 0:
+            self.update_actor_and_alpha(obs, rnd, L, step)
+        if step % self.args.critic_target_update_freq == 0:
+            self.soft_update_critic_target()
+        if step % self.args.aux_update_freq == 0:
+            self.update_curl(obs, pos, L, step)
+        return self.trace
+
+
+ALGOS = {"sac": OracleSAC, "rad": OracleSAC, "drq": OracleSAC, "svea": OracleSVEA, "sgsac": OracleSGSAC, "curl": OracleCURL}
 
 
 def make_oracle(obs_shape, action_shape, args, **kw):

@@ -510,6 +510,51 @@ class DrQ(SAC):
     sample_mode = "shift"
 
 
+class CURL(SAC):
+    """curl.py:11-57: SAC on random crops (100 -> 84) plus the contrastive auxiliary update on a second crop of obs
+    (`replay_buffer.sample_curl()`, utils.py:142-156)."""
+    algorithm = "curl"
+
+    def __init__(self, obs_shape, action_shape, args, **kw):
+        super().__init__(obs_shape, action_shape, args, **kw)
+        self.aux_update_freq = args.aux_update_freq
+        self.curl_head = _ModuleView(self, "curl_head")
+
+    def _modules(self):
+        return dict(super()._modules(), curl_head=self.curl_head)
+
+    def _log_cols(self, step):
+        cols = super()._log_cols(step)
+        if step % self.aux_update_freq == 0:
+            cols.append(("train/aux_loss", 4))
+        return cols
+
+    def _step_kind(self, step):
+        return super()._step_kind(step) + (step % self.aux_update_freq == 0,)
+
+    def supply(self, offs_pos=None, **kw):
+        """+ offs_pos: (B,2) crop offsets of the second crop of obs."""
+        super().supply(**kw)
+        self._supplied["offs_pos"] = offs_pos
+
+    def _run_update(self, replay_buffer, step):
+        eng, B = self.engine, self.batch_size
+        if not isinstance(replay_buffer, ReplayBuffer):
+            raise TypeError("CURL samples obs / next_obs / pos from the same indices: use sgqn_carla_b200.ReplayBuffer")
+        s = self._supplied
+        off_n = max(1, replay_buffer.Hs - 84)
+        self._draw(replay_buffer)                         # idxs, obs / next_obs crop offsets, noise (consumes self._supplied)
+        # the third crop (`pos`): own Philox stream; only the offsets are used
+        K.rng_step(eng.seed ^ 0x2545F491, _ptr(eng.rng_counter), 0, 0, 0, 1, _ptr(eng.offs_pos), off_n, 0, 0, 0, B, eng.A, 0, eng.st)
+        if s and s.get("offs_pos") is not None:
+            eng.offs_pos[0].copy_(torch.as_tensor(np.asarray(s["offs_pos"]), dtype=torch.int32).reshape(B, 2))
+        self._sample_into_engine(replay_buffer)
+        hs = replay_buffer.Hs
+        K.replay_gather(_ptr(replay_buffer.frames), _ptr(replay_buffer.fidx), _ptr(eng.idxs), _ptr(eng.offs_pos) if hs > 84 else 0,
+                        _ptr(eng.pos), _ptr(eng.pos_scratch), B, hs, 84, 0, 4, eng.st)
+        self._engine_update(step)
+
+
 class SVEA(SAC):
     """svea.py:12-63: critic on cat(obs, random_overlay(obs)); places365 images are host-supplied / pooled."""
     algorithm = "svea"
@@ -676,7 +721,7 @@ class SGSAC(SAC):
         return mask.reshape(B, 3, 1, 84, 84).expand(B, 3, 3, 84, 84).reshape(B, 9, 84, 84).bool()
 
 
-algorithm = {"sac": SAC, "rad": RAD, "drq": DrQ, "svea": SVEA, "sgsac": SGSAC}
+algorithm = {"sac": SAC, "rad": RAD, "drq": DrQ, "svea": SVEA, "sgsac": SGSAC, "curl": CURL}
 
 
 def make_agent(obs_shape, action_shape, args, **kw):

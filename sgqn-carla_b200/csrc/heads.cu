@@ -355,3 +355,30 @@ extern "C" int sgqn_bce(const float* logits, const uint8_t* mask, float* loss, f
     bce_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(logits, mask, loss, dlogits, H, W, Hq, Wq, oy, ox, Cs, npix, inv_n, round_out);
     return SGQN_CHECK_LAUNCH();
 }
+
+
+// ---------------------------------------------------------------- CURL contrastive loss (curl.py:35-37, modules.py:270-281)
+// logits [B][ld] = z_a W z_pos^T; label of row i = i.  loss += sum_i (logsumexp_j l_ij - l_ii) / Bg;  dlogits = (softmax - I) / Bg.
+// (The reference subtracts the row maximum first; the cross entropy does not change under a per-row shift, nor does its gradient.)
+// One warp per row.
+__global__ void __launch_bounds__(128) ce_diag_kernel(const float* __restrict__ logits, int ld, float* __restrict__ loss,
+                                                      float* __restrict__ dlogits, int lddl, int B, float inv_n) {
+    const int row = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (row >= B) return;
+    const float* l = logits + (size_t)row * ld;
+    float m = -INFINITY;
+    for (int j = lane; j < B; j += 32) m = fmaxf(m, l[j]);
+    m = warp_max(m);
+    float s = 0.f;
+    for (int j = lane; j < B; j += 32) s += expf(l[j] - m);
+    s = warp_sum(s);
+    const float lse = m + logf(s);
+    float* d = dlogits + (size_t)row * lddl;
+    for (int j = lane; j < B; j += 32) d[j] = (expf(l[j] - lse) - (j == row ? 1.f : 0.f)) * inv_n;
+    if (lane == 0) atomicAdd(loss, (lse - l[row]) * inv_n);
+}
+extern "C" int sgqn_ce_diag(const float* logits, int ld, float* loss, float* dlogits, int lddl, int B, int Bg, void* stream) {
+    if (B <= 0) return 0;
+    ce_diag_kernel<<<cdiv(B, 4), 128, 0, (cudaStream_t)stream>>>(logits, ld, loss, dlogits, lddl, B, 1.0f / (float)Bg);
+    return SGQN_CHECK_LAUNCH();
+}

@@ -64,7 +64,8 @@ class UpdateEngine:
         self.dist = dist
         self.algorithm = algorithm
         self.H = int(args.hidden_dim)
-        self.lay = ParamLayout(self.A, self.H, int(args.projection_dim), int(args.num_shared_layers), int(args.num_filters))
+        self.lay = ParamLayout(self.A, self.H, int(args.projection_dim), int(args.num_shared_layers), int(args.num_filters),
+                               algorithm=algorithm)
         L, dev, B, A, H = self.lay, self.dev, self.B, self.A, self.H
         self.params = torch.zeros(L.total, device=dev)
         self.grads = torch.zeros(L.total, device=dev)
@@ -156,6 +157,13 @@ class UpdateEngine:
                 self.w3f, self.w3d, self.b3p = f32(64 * 9 * 64), f32(64 * 9 * 64), f32(64)
                 self.dw2p, self.db2p = f32(256 * 9 * 128), f32(256)
                 self.dw3p, self.db3p = f32(64 * 9 * 64), f32(64)
+        if algorithm == "curl":
+            self.pos = f32(B, 9, 84, 84)                # the second random crop of obs (utils.py:152)
+            self.pos_scratch = f32(B, 9, 84, 84)
+            self.offs_pos = torch.zeros(2, B, 2, dtype=torch.int32, device=dev)
+            self.cu = f32(B, L.P); self.dcu = f32(B, L.P)              # u = z_pos W^T and its gradient
+            self.clog = f32(B, B); self.dclog = f32(B, B)              # logits z_a u^T and their gradient
+            self.dh_c = f32(B, L.P)
         if algorithm == "svea":
             self.places = f32(B, 3, 84 * 84)            # host-supplied overlay images of one step
             self.places_pool, self.places_from_pool = None, False      # float (N,3,84*84) in [0,1] on the device
@@ -711,6 +719,49 @@ class UpdateEngine:
         K.conv_fwd(_ptr(self.d2), Wp("dec.conv3.weight"), Wp("dec.conv3.bias"), _ptr(self.lg), B, 42, 42, 64, DEC_C3, 1, 2, 1, 0, st)
         return self.lg[:B * 84 * 84 * DEC_C3].reshape(B, 84, 84, DEC_C3)[..., :9].permute(0, 3, 1, 2).contiguous()
 
+    def update_curl(self):
+        """curl.py:27-43 (CURLHead.compute_logits, modules.py:270-281): z_a = critic encoder(obs) with gradient, z_pos = target
+        encoder(pos) without; logits = z_a W z_pos^T, cross entropy against the diagonal; Adam over (SharedCNN, critic
+        projection, W).  The contrastive loss couples every sample of the batch with every other: single-GPU only."""
+        B, A, L, st, a = self.B, self.A, self.lay, self.st, self.args
+        P, P1 = L.P, L.P + A
+        if self.dist is not None:
+            raise RuntimeError("CURL's (B,B) contrastive logits are not shardable over the batch")
+        # z_pos: target encoder + target projection of the second crop (no gradient)
+        ev_t = None
+        if self.overlap:
+            main = torch.cuda.current_stream()
+            ev = torch.cuda.Event(); ev.record(main); self.side.wait_event(ev)
+            with torch.cuda.stream(self.side):
+                self.enc_fwd(_ptr(self.pos), B, self.actT, target=True)
+                self.proj_fwd(_ptr(self.actT[10]), B, "critic_proj", _ptr(self.zT), _ptr(self.haT), P1, target=True)
+                ev_t = torch.cuda.Event(); ev_t.record(self.side)
+        # z_a: the critic's encoder (updated weights) on obs, activations kept for the backward pass
+        self.enc_fwd(_ptr(self.obs2), B, self.actS, B, col_from=0)
+        self.proj_fwd(_ptr(self.actS[10], B * FEAT), B, "critic_proj", _ptr(self.zS), _ptr(self.haS), P1)
+        if ev_t is not None:
+            torch.cuda.current_stream().wait_event(ev_t)
+        else:
+            self.enc_fwd(_ptr(self.pos), B, self.actT, target=True)
+            self.proj_fwd(_ptr(self.actT[10]), B, "critic_proj", _ptr(self.zT), _ptr(self.haT), P1, target=True)
+        W, dW = self.P("curl.W"), self.G("curl.W")
+        K.linear_fwd(_ptr(self.haT), P1, 0, W, 0, 0, 0, _ptr(self.cu), P, 0, B, P, P, 0, 1, 0, st)             # u = z_pos W^T  (B,P)
+        K.linear_fwd(_ptr(self.haS), P1, 0, _ptr(self.cu), 0, 0, 0, _ptr(self.clog), B, 0, B, B, P, 0, 1, 0, st)  # logits = z_a u^T  (B,B)
+        K.zero(_ptr(self.logs, 4), 4, st)
+        K.ce_diag(_ptr(self.clog), B, _ptr(self.logs, 4), _ptr(self.dclog), B, B, self.Bg, st)
+        x0, x1 = L.ranges["aux"]
+        K.zero(self._g + 4 * x0, 4 * (x1 - x0), st)
+        K.zero(_ptr(self.dcu), 4 * B * P, st)
+        K.linear_dgrad(_ptr(self.dclog), B, 0, _ptr(self.cu), 0, 0, 0, 0, _ptr(self.dh_c), P, 0, B, B, P, 0, 0, 1, st)    # d z_a = dlogits u
+        K.linear_wgrad(_ptr(self.haS), P1, 0, _ptr(self.dclog), B, 0, _ptr(self.dcu), 0, 0, 0, B, B, P, 0, 1, st)         # d u = dlogits^T z_a
+        K.linear_wgrad(_ptr(self.haT), P1, 0, _ptr(self.dcu), P, 0, dW, 0, 0, 0, B, P, P, 0, 1, st)                       # d W = d u^T z_pos
+        dfeat = _ptr(self.dbuf[1])
+        self.proj_bwd(_ptr(self.dh_c), P, B, _ptr(self.zS), _ptr(self.haS), P1, "critic_proj", _ptr(self.dzS),
+                      feat_ptr=_ptr(self.actS[10], B * FEAT), dfeat=dfeat)
+        self.enc_bwd(dfeat, B, self.actS, B, _ptr(self.obs2), 1, True)
+        self.adam(self.opt_aux, (x0, x1))
+        self.prep_conv_weights()
+
     def _decoder_simt(self, B, st, Wp, G, x0, x1):
         """AttributionDecoder convs + BCE + their backward on the fp32 CUDA-core kernels (compact NHWC buffers)."""
         K.conv_fwd(_ptr(self.dl), Wp("dec.conv1.weight"), Wp("dec.conv1.bias"), _ptr(self.d1), B, 21, 21, 32, 128, 1, 1, 1, 0, st)
@@ -817,6 +868,8 @@ class UpdateEngine:
         if do_actor:
             self.shared_obs_fwd()
             self.update_actor_and_alpha()
+        if self.algorithm == "curl" and step % a.aux_update_freq == 0:
+            self.update_curl()
         self._finish_logs()
 
     def _finish_logs(self):

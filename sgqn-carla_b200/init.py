@@ -45,4 +45,6 @@ def init_params(action_dim, args, seed=None):
     p["dec.conv3.weight"], p["dec.conv3.bias"] = default((9, 64, 3, 3), 576), default((9,), 576)
     p["fdec.0.weight"], p["fdec.0.bias"] = default((256, 100), 100), default((256,), 100)
     p["fdec.2.weight"], p["fdec.2.bias"] = default((100, 256), 256), default((100,), 256)
+    if getattr(args, "algorithm", "") == "curl":
+        p["curl.W"] = torch.rand(P, P, generator=g)           # modules.py:268
     return p

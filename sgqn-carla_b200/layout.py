@@ -30,7 +30,7 @@ def _al4(n):
 
 
 class ParamLayout:
-    def __init__(self, action_dim, hidden_dim=1024, proj_dim=100, num_layers=11, num_filters=32, in_ch=9):
+    def __init__(self, action_dim, hidden_dim=1024, proj_dim=100, num_layers=11, num_filters=32, in_ch=9, algorithm="sgsac"):
         assert num_filters == 32 and num_layers == 11 and proj_dim == 100, \
             "the attribution decoder hard-codes 32x21x21 features and a 100-d embedding (modules.py:315-318)"
         self.A, self.H, self.P, self.L, self.nf, self.in_ch = action_dim, hidden_dim, proj_dim, num_layers, num_filters, in_ch
@@ -72,6 +72,8 @@ class ParamLayout:
         self.ranges["dec"] = (dec0, off)
         add("fdec.0.weight", (256, 100)); add("fdec.0.bias", (256,))
         add("fdec.2.weight", (100, 256)); add("fdec.2.bias", (100,))
+        if algorithm == "curl":                               # CURLHead.W (modules.py:264-268): optimised with the critic encoder (curl.py:16-20)
+            add("curl.W", (P, P))
         self.ranges["aux"] = (enc0, off)
         act0 = off
         self._add_proj(add, "actor_proj")
@@ -172,4 +174,8 @@ def reference_key_map(num_layers=11):
     for j in (0, 2):
         for wb in ("weight", "bias"):
             m[f"fdec.{j}.{wb}"] = [("attribution_predictor", f"features_decoder.{j}.{wb}")]
+    m["curl.W"] = [("curl_head", "W")]
+    for n in list(m):                                         # curl_head.encoder IS the critic's encoder (curl.py:16)
+        if n.startswith(("cnn.", "critic_proj.")):
+            m[n] = m[n] + [("curl_head", "encoder." + m[n][0][1][len("encoder."):])]
     return m

@@ -93,7 +93,11 @@ def test_layout_roundtrip_and_ranges():
     stored = flat[o:o + 100 * FEAT].reshape(100, 441, 32)
     assert torch.equal(stored[7, 5, 3], w[7, 3 * 441 + 5])
     keys = reference_key_map()
-    assert set(keys) == set(lay.entries)
+    assert set(keys) == set(lay.entries) | {"curl.W"}            # CURLHead.W only exists in the CURL layout ...
+    curl = ParamLayout(2, algorithm="curl")
+    assert set(keys) == set(curl.entries)
+    x0, x1 = curl.ranges["aux"]                                  # ... inside the range its optimiser owns (curl.py:16-20)
+    assert x0 <= curl.off("curl.W") < x1 and x0 == curl.off("cnn.0.weight")
 
 
 def test_lazy_scalar_arithmetic_without_device():

@@ -640,3 +640,47 @@ def test_svea_draws_fresh_overlay_images_and_is_graph_captured():
 def O_overlay(obs, imgs):
     from oracle import sgsac_oracle as O
     return O.random_overlay_places(obs.clone(), imgs)
+
+
+@pytest.mark.parametrize("precision,dense", [("fp32", 0.05), ("tf32", None), ("tf32", 0.05)])
+def test_curl_updates_match_oracle(precision, dense):
+    """CURL (curl.py:11-57): SAC on 100 -> 84 random crops + the contrastive update (critic encoder on obs,
+    target encoder on a second crop, bilinear logits, cross entropy against the diagonal, Adam over encoder + W), every update
+    started from the oracle's state (teacher forcing), with the oracle pinned bit-exactly to the reference's CURL
+    (tests/test_oracle_pin.py::test_oracle_equals_reference_live[curl-*])."""
+    B, A = 8, 2
+    tf = precision == "tf32"
+    agent, rb, orc, rep, args = _mk(algorithm="curl", B=B, A=A, size=100, dense=dense, precision=precision)
+    assert "curl.W" in orc.p and list(agent.curl_head.state_dict())[-1] == "W"
+    rs = np.random.RandomState(6)
+    L, Lo = _L(), _L()
+    for step in (2, 3, 4, 5):
+        idxs = rs.randint(0, 48, size=B); rnd = _rnd(rs, B, A, "curl")
+        offs = rs.randint(0, 16, size=(2, B, 2)); offs_pos = rs.randint(0, 16, size=(B, 2))
+        batch = rep.sample_curl(idxs, (offs_pos[:, 0], offs_pos[:, 1], offs[0, :, 0], offs[0, :, 1], offs[1, :, 0], offs[1, :, 1]))
+        _force_state(agent, orc)
+        orc.update_from_batch(batch, rnd, Lo, step)
+        agent.supply(idxs=idxs, noise_next=rnd["noise_next"], noise_pi=rnd["noise_pi"], offs=offs, offs_pos=offs_pos)
+        agent.update(rb, L, step)
+        torch.cuda.synchronize()
+        assert torch.equal(agent.engine.pos.cpu(), batch[5]) and torch.equal(agent.engine.obs2[:B].cpu(), batch[0])
+        keys = [k for (s, k) in Lo.rows if s == step]
+        assert sorted(keys) == sorted(k for (s, k) in L.rows if s == step)
+        assert ("train/aux_loss" in keys) == (step % 2 == 0)
+        for k in keys:
+            loose = tf and dense and k != "train_critic/loss"
+            np.testing.assert_allclose(float(L.rows[(step, k)]), float(Lo.rows[(step, k)]), rtol=3e-2 if loose else 1e-3,
+                                       atol=1e-5 if k == "train_critic/loss" else (2e-2 if loose else 2e-3), err_msg=f"{step} {k}")
+        mine = agent.get_parameters()
+        for n, ref in orc.p.items():
+            if n not in mine:
+                continue
+            d = (mine[n].cpu().double() - ref.double()).abs()
+            lr = 1e-3 + (3e-4 if n.startswith(("cnn.", "critic_proj.")) else 0.0)
+            assert float(d.max()) <= 2.1 * lr + 1e-6 * float(ref.abs().max()), (step, n, float(d.max()))
+            assert float(d.mean()) <= ((0.1 if dense else 0.05) if tf else 0.01) * lr + 4.2 * lr / d.numel(), (step, n, float(d.mean()))
+    # device-RNG, graph-captured CURL updates stay finite
+    for step in range(6, 12):
+        agent.update(rb, L, step)
+    torch.cuda.synchronize()
+    assert len(agent._graphs) == 2 and all(np.isfinite(float(v)) for v in L.rows.values())
