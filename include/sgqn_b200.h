@@ -203,6 +203,10 @@ int sgqn_bce_phase(const float* logits, const uint8_t* mask, float* loss, float*
  * *loss += mean (caller zero-fills), dlogits = (softmax - I) / Bg */
 int sgqn_ce_diag(const float* logits, int ld, float* loss, float* dlogits, int lddl, int B, int Bg, void* stream);
 
+/* PAD (pad.py:42-43): F.mse_loss(pred, target) over (rows_global x width) elements; *loss += (caller zero-fills), dpred */
+int sgqn_mse_loss(const float* pred, const float* target, float* loss, float* dpred, int rows, int width, int rows_global,
+                  void* stream);
+
 /* ---- optimiser: torch.optim.Adam (sac.py:60-68, sgsac.py:35-39) over a flat range, soft target update
  *      (utils.py:31-33, sac.py:153-158) fused when target != NULL; weight_decay = torch's L2 form (grad += wd * p;
  *      critic_weight_decay, sac.py:63-65) */

@@ -78,8 +78,9 @@ def ref_params(agent):
     """canonical name -> tensor view of the live reference parameters (+ target, log_alpha)."""
     sds = {"actor": agent.actor.state_dict(), "critic": agent.critic.state_dict(),
            "critic_target": agent.critic_target.state_dict()}
-    if hasattr(agent, "attribution_predictor"):
-        sds["attribution_predictor"] = agent.attribution_predictor.state_dict()
+    for extra in ("attribution_predictor", "curl_head", "pad_head"):
+        if hasattr(agent, extra):
+            sds[extra] = getattr(agent, extra).state_dict()
     out = {}
     for n, refs in O._ref_key_map().items():
         mod, key = refs[0]
@@ -87,7 +88,5 @@ def ref_params(agent):
             out[n] = sds[mod][key]
         if O._in_group(n, O.CRITIC_GROUP):
             out["t_" + n] = sds["critic_target"][key]
-    if hasattr(agent, "curl_head"):
-        out["curl.W"] = agent.curl_head.W.detach()
     out["log_alpha"] = agent.log_alpha.detach()
     return out

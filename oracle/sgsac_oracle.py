@@ -114,12 +114,19 @@ def _ref_key_map(num_layers=11):
         for wb in ("weight", "bias"):
             m[f"fdec.{j}.{wb}"] = [("attribution_predictor", f"features_decoder.{j}.{wb}")]
     m["curl.W"] = [("curl_head", "W")]                              # modules.py:264-268
+    for j in (0, 1):                                                # PAD's own projection + inverse-dynamics MLP (pad.py:18-25)
+        for wb in ("weight", "bias"):
+            m[f"pad_proj.{j}.{wb}"] = [("pad_head", f"encoder.projection.projection.{j}.{wb}")]
+    for j in (0, 2, 4):
+        for wb in ("weight", "bias"):
+            m[f"pad_mlp.{j}.{wb}"] = [("pad_head", f"mlp.{j}.{wb}")]
     return m
 
 
 CRITIC_GROUP = ("cnn.", "critic_proj.", "Q1.", "Q2.")           # sac.py:63-65 critic.parameters()
 ACTOR_GROUP = ("cnn.", "actor_proj.", "actor_mlp.")             # sac.py:60-62 actor.parameters()
 AUX_GROUP = ("cnn.", "critic_proj.", "dec.", "fdec.")           # sgsac.py:35-39 attribution_predictor.parameters()
+PAD_GROUP = ("cnn.", "pad_proj.", "pad_mlp.")                    # pad.py:34-37 pad_head.parameters()
 CURL_GROUP = ("cnn.", "critic_proj.", "curl.")                  # curl.py:16-20 curl_head.parameters() = critic encoder + W
 TARGET_Q = ("Q1.", "Q2.")                                        # sac.py:154-155 (critic_tau)
 TARGET_ENC = ("cnn.", "critic_proj.")                            # sac.py:156-158 (encoder_tau)
@@ -165,6 +172,12 @@ def init_params(obs_shape, action_dim, args, gen=None, dense_std=None):
     shapes["dec.conv3.weight"] = (9, 64, 3, 3); shapes["dec.conv3.bias"] = (9,)
     shapes["fdec.0.weight"] = (256, 100); shapes["fdec.0.bias"] = (256,)
     shapes["fdec.2.weight"] = (100, 256); shapes["fdec.2.bias"] = (100,)
+    if getattr(args, "algorithm", "") == "pad":
+        shapes["pad_proj.0.weight"] = (P, FEAT); shapes["pad_proj.0.bias"] = (P,)
+        shapes["pad_proj.1.weight"] = (P,); shapes["pad_proj.1.bias"] = (P,)
+        shapes["pad_mlp.0.weight"] = (H, 2 * P); shapes["pad_mlp.0.bias"] = (H,)
+        shapes["pad_mlp.2.weight"] = (H, H); shapes["pad_mlp.2.bias"] = (H,)
+        shapes["pad_mlp.4.weight"] = (A, H); shapes["pad_mlp.4.bias"] = (A,)
     if getattr(args, "algorithm", "") == "curl":
         shapes["curl.W"] = (P, P)                                   # CURLHead.W = torch.rand(out_dim, out_dim), modules.py:268
 
@@ -685,8 +698,9 @@ class OracleSAC:
         sds = {"actor": agent.actor.state_dict(), "critic": agent.critic.state_dict()}
         if hasattr(agent, "attribution_predictor"):
             sds["attribution_predictor"] = agent.attribution_predictor.state_dict()
-        if hasattr(agent, "curl_head"):
-            sds["curl_head"] = agent.curl_head.state_dict()
+        for extra in ("curl_head", "pad_head"):
+            if hasattr(agent, extra):
+                sds[extra] = getattr(agent, extra).state_dict()
         for n, refs in _ref_key_map().items():
             mod, key = refs[0]
             if mod in sds:
@@ -836,7 +850,41 @@ class OracleCURL(OracleSAC):
         return self.trace
 
 
-ALGOS = {"sac": OracleSAC, "rad": OracleSAC, "drq": OracleSAC, "svea": OracleSVEA, "sgsac": OracleSGSAC, "curl": OracleCURL}
+class OraclePAD(OracleSAC):
+    """pad.py:11-63 (+ InverseDynamics, modules.py:284-303): SAC on random crops plus the inverse-dynamics auxiliary update
+    through the shared CNN, PAD's own projection and a 3-layer MLP."""
+
+    def __init__(self, obs_shape, action_shape, args, params=None, dense_std=None, seed=0, tf32=False):
+        super().__init__(obs_shape, action_shape, args, params, dense_std, seed, tf32=tf32)
+        self.aux_names = [n for n in self.p.keys() if _in_group(n, PAD_GROUP)]
+        self.aux_opt = Adam(self.aux_names, args.aux_lr, args.aux_beta)
+
+    def update_inverse_dynamics(self, obs, obs_next, action, L=None, step=None):
+        """pad.py:39-49"""
+        gp = self._grad_params(self.aux_names)
+        h = projection(gp, cnn_forward(gp, obs, tf32=self.tf32), "pad_proj")
+        h_next = projection(gp, cnn_forward(gp, obs_next, tf32=self.tf32), "pad_proj")
+        pred_action = mlp3(gp, torch.cat([h, h_next], dim=1), "pad_mlp")
+        pad_loss = F.mse_loss(pred_action, action)
+        grads = torch.autograd.grad(pad_loss, [gp[n] for n in self.aux_names])
+        g = dict(zip(self.aux_names, grads))
+        self.trace.update(pad_pred=pred_action.detach(), aux_loss=pad_loss.detach(), aux_grads=g)
+        with torch.no_grad():
+            self.aux_opt.step(self.p, g)
+        if L is not None:
+            L.log("train/aux_loss", pad_loss, step)
+
+    def update_from_batch(self, batch, rnd, L, step):
+        """pad.py:51-63"""
+        obs, action, reward, next_obs, not_done = batch
+        super().update_from_batch(batch, rnd, L, step)
+        if step % self.args.aux_update_freq == 0:
+            self.update_inverse_dynamics(obs, next_obs, action, L, step)
+        return self.trace
+
+
+ALGOS = {"sac": OracleSAC, "rad": OracleSAC, "drq": OracleSAC, "svea": OracleSVEA, "sgsac": OracleSGSAC, "curl": OracleCURL,
+         "pad": OraclePAD}
 
 
 def make_oracle(obs_shape, action_shape, args, **kw):

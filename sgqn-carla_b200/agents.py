@@ -510,6 +510,28 @@ class DrQ(SAC):
     sample_mode = "shift"
 
 
+class PAD(SAC):
+    """pad.py:11-63: SAC on random crops (100 -> 84) plus the inverse-dynamics auxiliary update (obs, next_obs -> action)."""
+    algorithm = "pad"
+
+    def __init__(self, obs_shape, action_shape, args, **kw):
+        super().__init__(obs_shape, action_shape, args, **kw)
+        self.aux_update_freq = args.aux_update_freq
+        self.pad_head = _ModuleView(self, "pad_head")
+
+    def _modules(self):
+        return dict(super()._modules(), pad_head=self.pad_head)
+
+    def _log_cols(self, step):
+        cols = super()._log_cols(step)
+        if step % self.aux_update_freq == 0:
+            cols.append(("train/aux_loss", 4))
+        return cols
+
+    def _step_kind(self, step):
+        return super()._step_kind(step) + (step % self.aux_update_freq == 0,)
+
+
 class CURL(SAC):
     """curl.py:11-57: SAC on random crops (100 -> 84) plus the contrastive auxiliary update on a second crop of obs
     (`replay_buffer.sample_curl()`, utils.py:142-156)."""
@@ -721,7 +743,7 @@ class SGSAC(SAC):
         return mask.reshape(B, 3, 1, 84, 84).expand(B, 3, 3, 84, 84).reshape(B, 9, 84, 84).bool()
 
 
-algorithm = {"sac": SAC, "rad": RAD, "drq": DrQ, "svea": SVEA, "sgsac": SGSAC, "curl": CURL}
+algorithm = {"sac": SAC, "rad": RAD, "drq": DrQ, "svea": SVEA, "sgsac": SGSAC, "curl": CURL, "pad": PAD}
 
 
 def make_agent(obs_shape, action_shape, args, **kw):

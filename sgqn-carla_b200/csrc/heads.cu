@@ -382,3 +382,27 @@ extern "C" int sgqn_ce_diag(const float* logits, int ld, float* loss, float* dlo
     ce_diag_kernel<<<cdiv(B, 4), 128, 0, (cudaStream_t)stream>>>(logits, ld, loss, dlogits, lddl, B, 1.0f / (float)Bg);
     return SGQN_CHECK_LAUNCH();
 }
+
+
+// ---------------------------------------------------------------- mean-squared error (PAD inverse dynamics, pad.py:42-43)
+// *loss += sum (pred - target)^2 * inv_n ; dpred = 2 (pred - target) * inv_n ; inv_n = 1 / (global rows * width)
+__global__ void __launch_bounds__(256) mse_loss_kernel(const float* __restrict__ pred, const float* __restrict__ target,
+                                                       float* __restrict__ loss, float* __restrict__ dpred, int n, float inv_n) {
+    __shared__ float sh[33];
+    float acc = 0.f;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const float d = pred[i] - target[i];
+        acc += d * d;
+        dpred[i] = 2.f * d * inv_n;
+    }
+    const float tot = block_sum(acc, sh);
+    if (threadIdx.x == 0) atomicAdd(loss, tot * inv_n);
+}
+extern "C" int sgqn_mse_loss(const float* pred, const float* target, float* loss, float* dpred, int rows, int width, int rows_global,
+                             void* stream) {
+    const int n = rows * width;
+    if (n <= 0) return 0;
+    const int grid = cdiv(n, 256) < 64 ? cdiv(n, 256) : 64;
+    mse_loss_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(pred, target, loss, dpred, n, 1.0f / ((float)rows_global * (float)width));
+    return SGQN_CHECK_LAUNCH();
+}

@@ -157,6 +157,10 @@ class UpdateEngine:
                 self.w3f, self.w3d, self.b3p = f32(64 * 9 * 64), f32(64 * 9 * 64), f32(64)
                 self.dw2p, self.db2p = f32(256 * 9 * 128), f32(256)
                 self.dw3p, self.db3p = f32(64 * 9 * 64), f32(64)
+        if algorithm == "pad":
+            self.z_p = f32(2 * B, L.P); self.dz_p = f32(2 * B, L.P)     # PAD projection pre-activations of [next_obs ; obs]
+            self.joint = f32(B, 2 * L.P); self.djoint = f32(B, 2 * L.P)  # cat[h(obs), h(next_obs)]
+            self.pad_pred = f32(B, A); self.dpad_pred = f32(B, A)
         if algorithm == "curl":
             self.pos = f32(B, 9, 84, 84)                # the second random crop of obs (utils.py:152)
             self.pos_scratch = f32(B, 9, 84, 84)
@@ -719,6 +723,43 @@ class UpdateEngine:
         K.conv_fwd(_ptr(self.d2), Wp("dec.conv3.weight"), Wp("dec.conv3.bias"), _ptr(self.lg), B, 42, 42, 64, DEC_C3, 1, 2, 1, 0, st)
         return self.lg[:B * 84 * 84 * DEC_C3].reshape(B, 84, 84, DEC_C3)[..., :9].permute(0, 3, 1, 2).contiguous()
 
+    def update_pad(self):
+        """pad.py:39-49 (InverseDynamics.forward, modules.py:298-303): h = encoder(obs), h' = encoder(next_obs) through the shared
+        CNN and PAD's own projection, MLP(cat[h, h']) -> predicted action, MSE against the taken action; Adam over (SharedCNN,
+        PAD projection, MLP).  The shared CNN runs once over [next_obs ; obs] (one 2B batch)."""
+        B, A, L, H, st, a = self.B, self.A, self.lay, self.H, self.st, self.args
+        P = L.P
+        Wp, G = self.P, self.G
+        feat = self.actS[10]
+        self.enc_fwd(_ptr(self.obs3), 2 * B, self.actS, 0, col_from=0)
+        # encoder rows [0,B) = next_obs -> joint[:, P:2P], rows [B,2B) = obs -> joint[:, :P]
+        self.proj_fwd(_ptr(feat), B, "pad_proj", _ptr(self.z_p), _ptr(self.joint, P), 2 * P)
+        self.proj_fwd(_ptr(feat, B * FEAT), B, "pad_proj", _ptr(self.z_p, B * P), _ptr(self.joint), 2 * P)
+        K.linear_fwd(_ptr(self.joint), 2 * P, 0, Wp("pad_mlp.0.weight"), 0, Wp("pad_mlp.0.bias"), 0, _ptr(self.az1), H, 0, B, H, 2 * P, 0, 1, 0, st)
+        (self.lin_fwd if B >= 32 else K.linear_fwd)(_ptr(self.az1), H, 0, Wp("pad_mlp.2.weight"), 0, Wp("pad_mlp.2.bias"), 0,
+                                                    _ptr(self.az2), H, 0, B, H, H, 1, 1, 2, st)
+        K.linear_fwd(_ptr(self.az2), H, 0, Wp("pad_mlp.4.weight"), 0, Wp("pad_mlp.4.bias"), 0, _ptr(self.pad_pred), A, 0, B, A, H, 1, 1, 2, st)
+        K.zero(_ptr(self.logs, 4), 4, st)
+        K.mse_loss(_ptr(self.pad_pred), _ptr(self.action), _ptr(self.logs, 4), _ptr(self.dpad_pred), B, A, self.Bg, st)
+        x0, x1 = L.ranges["aux"]
+        K.zero(self._g + 4 * x0, 4 * (x1 - x0), st)
+        K.linear_dgrad(_ptr(self.dpad_pred), A, 0, Wp("pad_mlp.4.weight"), 0, _ptr(self.az2), H, 0, _ptr(self.daz2), H, 0, B, A, H, 1, 0, 1, st)
+        self.lin_dgrad(_ptr(self.daz2), H, 0, Wp("pad_mlp.2.weight"), 0, _ptr(self.az1), H, 0, _ptr(self.daz1), H, 0, B, H, H, 1, 2, 1, st)
+        K.linear_dgrad(_ptr(self.daz1), H, 0, Wp("pad_mlp.0.weight"), 0, 0, 0, 0, _ptr(self.djoint), 2 * P, 0, B, H, 2 * P, 0, 2, 1, st)
+        K.linear_wgrad(_ptr(self.az2), H, 0, _ptr(self.dpad_pred), A, 0, G("pad_mlp.4.weight"), 0, G("pad_mlp.4.bias"), 0, B, A, H, 1, 1, st)
+        self.lin_wgrad(_ptr(self.az1), H, 0, _ptr(self.daz2), H, 0, G("pad_mlp.2.weight"), 0, G("pad_mlp.2.bias"), 0, B, H, H, 1, 1, st)
+        K.linear_wgrad(_ptr(self.joint), 2 * P, 0, _ptr(self.daz1), H, 0, G("pad_mlp.0.weight"), 0, G("pad_mlp.0.bias"), 0, B, H, 2 * P, 0, 1, st)
+        dfeat = self.dbuf[1]
+        self.proj_bwd(_ptr(self.djoint, P), 2 * P, B, _ptr(self.z_p), _ptr(self.joint, P), 2 * P, "pad_proj", _ptr(self.dz_p),
+                      feat_ptr=_ptr(feat), dfeat=_ptr(dfeat))
+        self.proj_bwd(_ptr(self.djoint), 2 * P, B, _ptr(self.z_p, B * P), _ptr(self.joint), 2 * P, "pad_proj", _ptr(self.dz_p, B * P),
+                      feat_ptr=_ptr(feat, B * FEAT), dfeat=_ptr(dfeat, B * FEAT))
+        self.enc_bwd(_ptr(dfeat), 2 * B, self.actS, 0, _ptr(self.obs3), 1, True)
+        if self.dist is not None:
+            self.allreduce_grads((x0, x1))
+        self.adam(self.opt_aux, (x0, x1))
+        self.prep_conv_weights()
+
     def update_curl(self):
         """curl.py:27-43 (CURLHead.compute_logits, modules.py:270-281): z_a = critic encoder(obs) with gradient, z_pos = target
         encoder(pos) without; logits = z_a W z_pos^T, cross entropy against the diagonal; Adam over (SharedCNN, critic
@@ -870,6 +911,8 @@ class UpdateEngine:
             self.update_actor_and_alpha()
         if self.algorithm == "curl" and step % a.aux_update_freq == 0:
             self.update_curl()
+        if self.algorithm == "pad" and step % a.aux_update_freq == 0:
+            self.update_pad()
         self._finish_logs()
 
     def _finish_logs(self):

@@ -45,6 +45,12 @@ def init_params(action_dim, args, seed=None):
     p["dec.conv3.weight"], p["dec.conv3.bias"] = default((9, 64, 3, 3), 576), default((9,), 576)
     p["fdec.0.weight"], p["fdec.0.bias"] = default((256, 100), 100), default((256,), 100)
     p["fdec.2.weight"], p["fdec.2.bias"] = default((100, 256), 256), default((100,), 256)
+    if getattr(args, "algorithm", "") == "pad":               # InverseDynamics.apply(weight_init), modules.py:296
+        p["pad_proj.0.weight"], p["pad_proj.0.bias"] = ortho(P, FEAT), torch.zeros(P)
+        p["pad_proj.1.weight"], p["pad_proj.1.bias"] = torch.ones(P), torch.zeros(P)
+        p["pad_mlp.0.weight"], p["pad_mlp.0.bias"] = ortho(H, 2 * P), torch.zeros(H)
+        p["pad_mlp.2.weight"], p["pad_mlp.2.bias"] = ortho(H, H), torch.zeros(H)
+        p["pad_mlp.4.weight"], p["pad_mlp.4.bias"] = ortho(A, H), torch.zeros(A)
     if getattr(args, "algorithm", "") == "curl":
         p["curl.W"] = torch.rand(P, P, generator=g)           # modules.py:268
     return p

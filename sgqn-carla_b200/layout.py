@@ -72,6 +72,11 @@ class ParamLayout:
         self.ranges["dec"] = (dec0, off)
         add("fdec.0.weight", (256, 100)); add("fdec.0.bias", (256,))
         add("fdec.2.weight", (100, 256)); add("fdec.2.bias", (100,))
+        if algorithm == "pad":                                # InverseDynamics (modules.py:284-303) on PAD's own projection (pad.py:18-25)
+            self._add_proj(add, "pad_proj")
+            add("pad_mlp.0.weight", (H, 2 * P)); add("pad_mlp.0.bias", (H,))
+            add("pad_mlp.2.weight", (H, H)); add("pad_mlp.2.bias", (H,))
+            add("pad_mlp.4.weight", (A, H)); add("pad_mlp.4.bias", (A,))
         if algorithm == "curl":                               # CURLHead.W (modules.py:264-268): optimised with the critic encoder (curl.py:16-20)
             add("curl.W", (P, P))
         self.ranges["aux"] = (enc0, off)
@@ -178,4 +183,13 @@ def reference_key_map(num_layers=11):
     for n in list(m):                                         # curl_head.encoder IS the critic's encoder (curl.py:16)
         if n.startswith(("cnn.", "critic_proj.")):
             m[n] = m[n] + [("curl_head", "encoder." + m[n][0][1][len("encoder."):])]
+    for n in list(m):                                         # pad_head.encoder = shared CNN + PAD's own projection (pad.py:18-25)
+        if n.startswith("cnn."):
+            m[n] = m[n] + [("pad_head", m[n][0][1])]
+    for j in (0, 1):
+        for wb in ("weight", "bias"):
+            m[f"pad_proj.{j}.{wb}"] = [("pad_head", f"encoder.projection.projection.{j}.{wb}")]
+    for j in (0, 2, 4):
+        for wb in ("weight", "bias"):
+            m[f"pad_mlp.{j}.{wb}"] = [("pad_head", f"mlp.{j}.{wb}")]
     return m

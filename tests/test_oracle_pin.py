@@ -33,11 +33,11 @@ def _digest(params, n_samples=16, seed=123):
 # ---------------------------------------------------------------- live vs reference
 @pytest.mark.ref
 @pytest.mark.parametrize("algorithm,dense", [("sgsac", None), ("sgsac", 0.05), ("svea", 0.05), ("sac", None), ("drq", 0.05),
-                                             ("rad", 0.05), ("curl", None), ("curl", 0.05)])
+                                             ("rad", 0.05), ("curl", None), ("curl", 0.05), ("pad", None), ("pad", 0.05)])
 def test_oracle_equals_reference_live(algorithm, dense):
     from oracle import pin, ref_shim as R
     B, A = 3, 2
-    agent, rb, orc, rep, args = pin.build_pair(algorithm, B=B, A=A, dense_std=dense, size=100 if algorithm in ("rad", "curl") else 84)
+    agent, rb, orc, rep, args = pin.build_pair(algorithm, B=B, A=A, dense_std=dense, size=100 if algorithm in ("rad", "curl", "pad") else 84)
     rs = np.random.RandomState(1)
     for step in (2, 3, 4):
         idxs = rs.randint(0, 32, size=B)
@@ -45,7 +45,7 @@ def test_oracle_equals_reference_live(algorithm, dense):
         crop = None
         if algorithm in ("svea", "drq"):                     # sample_drq: random_shift offsets in [0, 8] (utils.py:158-171)
             crop = [(rs.randint(0, 9, size=B), rs.randint(0, 9, size=B)) for _ in range(2)]
-        if algorithm == "rad":                               # sample(): random_crop 100 -> 84, offsets in [0, 15] (augmentations.py:255)
+        if algorithm in ("rad", "pad"):                      # sample(): random_crop 100 -> 84, offsets in [0, 15] (augmentations.py:255)
             crop = [(torch.as_tensor(rs.randint(0, 16, size=B)), torch.as_tensor(rs.randint(0, 16, size=B))) for _ in range(2)]
         if algorithm == "curl":                              # sample_curl: pos, obs, next_obs crops in this order (utils.py:152-154)
             crop = [(torch.as_tensor(rs.randint(0, 16, size=B)), torch.as_tensor(rs.randint(0, 16, size=B))) for _ in range(3)]
@@ -53,7 +53,7 @@ def test_oracle_equals_reference_live(algorithm, dense):
         L = R.NullLogger()
         if algorithm in ("svea", "drq"):
             batch = rep.sample_drq(idxs, (crop[0][0], crop[0][1], crop[1][0], crop[1][1]))
-        elif algorithm == "rad":
+        elif algorithm in ("rad", "pad"):
             batch = rep.sample(idxs, (crop[0][0], crop[0][1], crop[1][0], crop[1][1]))
         elif algorithm == "curl":
             batch = rep.sample_curl(idxs, (crop[0][0], crop[0][1], crop[1][0], crop[1][1], crop[2][0], crop[2][1]))

@@ -684,3 +684,44 @@ def test_curl_updates_match_oracle(precision, dense):
         agent.update(rb, L, step)
     torch.cuda.synchronize()
     assert len(agent._graphs) == 2 and all(np.isfinite(float(v)) for v in L.rows.values())
+
+
+@pytest.mark.parametrize("precision,dense", [("fp32", 0.05), ("tf32", None), ("tf32", 0.05)])
+def test_pad_updates_match_oracle(precision, dense):
+    """PAD (pad.py:11-63): SAC on 100 -> 84 random crops + the inverse-dynamics update (shared CNN over
+    [next_obs ; obs] as one batch, PAD's own projection, 3-layer MLP, MSE against the action, Adam over CNN + projection + MLP),
+    teacher-forced against the oracle, which is pinned bit-exactly to the reference's PAD."""
+    B, A = 8, 2
+    tf = precision == "tf32"
+    agent, rb, orc, rep, args = _mk(algorithm="pad", B=B, A=A, size=100, dense=dense, precision=precision)
+    assert list(agent.pad_head.state_dict())[-1] == "mlp.4.bias"
+    rs = np.random.RandomState(8)
+    L, Lo = _L(), _L()
+    for step in (2, 3, 4, 5):
+        idxs = rs.randint(0, 48, size=B); rnd = _rnd(rs, B, A, "pad")
+        offs = rs.randint(0, 16, size=(2, B, 2))
+        batch = rep.sample(idxs, (offs[0, :, 0], offs[0, :, 1], offs[1, :, 0], offs[1, :, 1]))
+        _force_state(agent, orc)
+        orc.update_from_batch(batch, rnd, Lo, step)
+        _supply(agent, idxs, rnd, offs)
+        agent.update(rb, L, step)
+        torch.cuda.synchronize()
+        keys = [k for (s, k) in Lo.rows if s == step]
+        assert sorted(keys) == sorted(k for (s, k) in L.rows if s == step)
+        assert ("train/aux_loss" in keys) == (step % 2 == 0)
+        for k in keys:
+            loose = tf and dense and k != "train_critic/loss"
+            np.testing.assert_allclose(float(L.rows[(step, k)]), float(Lo.rows[(step, k)]), rtol=3e-2 if loose else 1e-3,
+                                       atol=1e-5 if k == "train_critic/loss" else (2e-2 if loose else 2e-3), err_msg=f"{step} {k}")
+        mine = agent.get_parameters()
+        for n, ref in orc.p.items():
+            if n not in mine:
+                continue
+            d = (mine[n].cpu().double() - ref.double()).abs()
+            lr = 1e-3 + (3e-4 if n.startswith("cnn.") else 0.0)
+            assert float(d.max()) <= 2.1 * lr + 1e-6 * float(ref.abs().max()), (step, n, float(d.max()))
+            assert float(d.mean()) <= ((0.1 if dense else 0.05) if tf else 0.01) * lr + 4.2 * lr / d.numel(), (step, n, float(d.mean()))
+    for step in range(6, 12):
+        agent.update(rb, L, step)
+    torch.cuda.synchronize()
+    assert len(agent._graphs) == 2 and all(np.isfinite(float(v)) for v in L.rows.values())
