@@ -19,18 +19,15 @@ def test_sgsac_full_batch_first_update(B):
     rs = np.random.RandomState(3)
     idxs = rs.randint(0, 2 * B, size=B); rnd = _rnd(rs, B, A, "sgsac")
     L, Lo = _L(), _L()
-    if B == 128:
-        orc.update_from_batch(rep.sample(idxs), rnd, Lo, 2)
+    orc.update_from_batch(rep.sample(idxs), rnd, Lo, 2)       # the TF32-rounding oracle (_mk): ~1 s (B=128) / ~2 s (B=256) of CPU
     _supply(agent, idxs, rnd)
     agent.update(rb, L, 2)
     torch.cuda.synchronize()
     vals = {k: float(v) for (s, k), v in L.rows.items()}
     assert set(vals) == {"train_critic/loss", "train_actor/loss", "train_alpha/loss", "train_alpha/value", "train/aux_loss"}
     assert all(np.isfinite(v) for v in vals.values()), vals
-    if B == 128:
-        for (s, k), v in Lo.rows.items():
-            rt = 3e-3 if k in ("train_critic/loss", "train_alpha/value", "train/aux_loss") else 2e-2
-            np.testing.assert_allclose(vals[k], float(v), rtol=rt, atol=3e-3, err_msg=k)
+    for (s, k), v in Lo.rows.items():                         # rel 1e-3 (+ 2e-3 abs for the losses computed after the critic's Adam step)
+        np.testing.assert_allclose(vals[k], float(v), rtol=1e-3, atol=1e-5 if k == "train_critic/loss" else 2e-3, err_msg=k)
     # structure of the saliency products (rl_utils.py:76-82, sgsac.py:67-70), any size.  Checked after an ODD step: on
     # even steps the overlay-augmented s_tilde re-uses the masked rows once the critic gradients are out.
     _supply(agent, idxs, rnd)
@@ -61,7 +58,7 @@ def test_svea_config5_first_update():
     _supply(agent, idxs, rnd, offs)
     agent.update(rb, L, 2)
     for (s, k), v in Lo.rows.items():
-        np.testing.assert_allclose(float(L.rows[(s, k)]), float(v), rtol=3e-3 if k == "train_critic/loss" else 2e-2, atol=3e-3, err_msg=k)
+        np.testing.assert_allclose(float(L.rows[(s, k)]), float(v), rtol=1e-3, atol=1e-5 if k == "train_critic/loss" else 2e-3, err_msg=k)
 
 
 def test_rad_config5_first_update():
@@ -75,7 +72,7 @@ def test_rad_config5_first_update():
     _supply(agent, idxs, rnd, offs)
     agent.update(rb, L, 2)
     for (s, k), v in Lo.rows.items():
-        np.testing.assert_allclose(float(L.rows[(s, k)]), float(v), rtol=3e-3 if k == "train_critic/loss" else 2e-2, atol=3e-3, err_msg=k)
+        np.testing.assert_allclose(float(L.rows[(s, k)]), float(v), rtol=1e-3, atol=1e-5 if k == "train_critic/loss" else 2e-3, err_msg=k)
 
 
 def test_gather_roundtrip_large():
