@@ -207,6 +207,14 @@ int sgqn_ce_diag(const float* logits, int ld, float* loss, float* dlogits, int l
 int sgqn_mse_loss(const float* pred, const float* target, float* loss, float* dpred, int rows, int width, int rows_global,
                   void* stream);
 
+/* SODA (soda.py:41-49; SODAMLP, modules.py:116-129): BatchNorm1d in training mode (batch mean / biased variance, eps 1e-5)
+ * fused with the ReLU that follows it, forward (stats = {mean[P], rstd[P]}) and backward (dgamma / dbeta +=, caller zero-fills);
+ * mse(normalize(h0), normalize(h1)) with its gradient w.r.t. h0 */
+int sgqn_bn_relu_fwd(const float* x, const float* gamma, const float* beta, float* y, float* stats, int M, int P, void* stream);
+int sgqn_bn_relu_bwd(const float* dy, const float* x, const float* y, const float* gamma, const float* stats, float* dx,
+                     float* dgamma, float* dbeta, int M, int P, void* stream);
+int sgqn_soda_loss(const float* h0, const float* h1, float* loss, float* dh0, int M, int P, int M_global, void* stream);
+
 /* ---- optimiser: torch.optim.Adam (sac.py:60-68, sgsac.py:35-39) over a flat range, soft target update
  *      (utils.py:31-33, sac.py:153-158) fused when target != NULL; weight_decay = torch's L2 form (grad += wd * p;
  *      critic_weight_decay, sac.py:63-65) */

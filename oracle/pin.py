@@ -78,7 +78,7 @@ def ref_params(agent):
     """canonical name -> tensor view of the live reference parameters (+ target, log_alpha)."""
     sds = {"actor": agent.actor.state_dict(), "critic": agent.critic.state_dict(),
            "critic_target": agent.critic_target.state_dict()}
-    for extra in ("attribution_predictor", "curl_head", "pad_head"):
+    for extra in ("attribution_predictor", "curl_head", "pad_head", "predictor", "predictor_target"):
         if hasattr(agent, extra):
             sds[extra] = getattr(agent, extra).state_dict()
     out = {}
@@ -88,5 +88,7 @@ def ref_params(agent):
             out[n] = sds[mod][key]
         if O._in_group(n, O.CRITIC_GROUP):
             out["t_" + n] = sds["critic_target"][key]
+        if "predictor_target" in sds and O._in_group(n, O.SODA_GROUP):
+            out["st_" + n] = sds["predictor_target"][key if mod == "predictor" else refs[0][1]]
     out["log_alpha"] = agent.log_alpha.detach()
     return out

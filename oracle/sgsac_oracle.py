@@ -70,6 +70,8 @@ class Args:
         self.aux_lr = 3e-4
         self.aux_beta = 0.9
         self.aux_update_freq = 2
+        self.soda_batch_size = 256
+        self.soda_tau = 0.005
         self.svea_alpha = 0.5
         self.svea_beta = 0.5
         self.sgqn_quantile = 0.5
@@ -120,12 +122,17 @@ def _ref_key_map(num_layers=11):
     for j in (0, 2, 4):
         for wb in ("weight", "bias"):
             m[f"pad_mlp.{j}.{wb}"] = [("pad_head", f"mlp.{j}.{wb}")]
+    for j in (0, 1, 3):                                             # SODA: encoder projection SODAMLP + predictor SODAMLP (soda.py:19-27)
+        for wb in ("weight", "bias"):
+            m[f"soda_proj.{j}.{wb}"] = [("predictor", f"encoder.projection.mlp.{j}.{wb}")]
+            m[f"soda_pred.{j}.{wb}"] = [("predictor", f"mlp.mlp.{j}.{wb}")]
     return m
 
 
 CRITIC_GROUP = ("cnn.", "critic_proj.", "Q1.", "Q2.")           # sac.py:63-65 critic.parameters()
 ACTOR_GROUP = ("cnn.", "actor_proj.", "actor_mlp.")             # sac.py:60-62 actor.parameters()
 AUX_GROUP = ("cnn.", "critic_proj.", "dec.", "fdec.")           # sgsac.py:35-39 attribution_predictor.parameters()
+SODA_GROUP = ("cnn.", "soda_proj.", "soda_pred.")               # soda.py:32-34 predictor.parameters()
 PAD_GROUP = ("cnn.", "pad_proj.", "pad_mlp.")                    # pad.py:34-37 pad_head.parameters()
 CURL_GROUP = ("cnn.", "critic_proj.", "curl.")                  # curl.py:16-20 curl_head.parameters() = critic encoder + W
 TARGET_Q = ("Q1.", "Q2.")                                        # sac.py:154-155 (critic_tau)
@@ -178,6 +185,11 @@ def init_params(obs_shape, action_dim, args, gen=None, dense_std=None):
         shapes["pad_mlp.0.weight"] = (H, 2 * P); shapes["pad_mlp.0.bias"] = (H,)
         shapes["pad_mlp.2.weight"] = (H, H); shapes["pad_mlp.2.bias"] = (H,)
         shapes["pad_mlp.4.weight"] = (A, H); shapes["pad_mlp.4.bias"] = (A,)
+    if getattr(args, "algorithm", "") == "soda":                    # SODAMLP: Linear -> BatchNorm1d -> ReLU -> Linear (modules.py:116-129)
+        for pre, fan in (("soda_proj", FEAT), ("soda_pred", P)):
+            shapes[f"{pre}.0.weight"] = (P, fan); shapes[f"{pre}.0.bias"] = (P,)
+            shapes[f"{pre}.1.weight"] = (P,); shapes[f"{pre}.1.bias"] = (P,)
+            shapes[f"{pre}.3.weight"] = (P, P); shapes[f"{pre}.3.bias"] = (P,)
     if getattr(args, "algorithm", "") == "curl":
         shapes["curl.W"] = (P, P)                                   # CURLHead.W = torch.rand(out_dim, out_dim), modules.py:268
 
@@ -195,7 +207,7 @@ def init_params(obs_shape, action_dim, args, gen=None, dense_std=None):
             fan_in = int(np.prod(wshape[1:]))
             bound = 1.0 / math.sqrt(fan_in)
             t = (torch.rand(*shp, generator=g) * 2 - 1) * bound
-        elif name.endswith("proj.1.weight"):
+        elif name.endswith("proj.1.weight") or name == "soda_pred.1.weight":
             t = torch.ones(*shp)
         elif name.endswith("bias"):
             t = torch.zeros(*shp)
@@ -698,7 +710,7 @@ class OracleSAC:
         sds = {"actor": agent.actor.state_dict(), "critic": agent.critic.state_dict()}
         if hasattr(agent, "attribution_predictor"):
             sds["attribution_predictor"] = agent.attribution_predictor.state_dict()
-        for extra in ("curl_head", "pad_head"):
+        for extra in ("curl_head", "pad_head", "predictor"):
             if hasattr(agent, extra):
                 sds[extra] = getattr(agent, extra).state_dict()
         for n, refs in _ref_key_map().items():
@@ -713,6 +725,12 @@ class OracleSAC:
             if _in_group(n, CRITIC_GROUP):
                 self.p["t_" + n] = tsd[refs[0][1]].detach().clone().float().contiguous()
         self.log_alpha = agent.log_alpha.detach().clone()
+        if hasattr(agent, "predictor_target"):                     # SODA: own EMA copy of the shared CNN + both SODAMLPs
+            psd = agent.predictor_target.state_dict()
+            for n, refs in _ref_key_map().items():
+                if _in_group(n, SODA_GROUP):
+                    key = refs[0][1] if refs[0][0] == "predictor" else refs[0][1]
+                    self.p["st_" + n] = psd[key].detach().clone().float().contiguous()
 
     def state_dicts(self):
         out = {"actor": OrderedDict(), "critic": OrderedDict(), "attribution_predictor": OrderedDict()}
@@ -883,8 +901,53 @@ class OraclePAD(OracleSAC):
         return self.trace
 
 
+def soda_mlp(p, x, pre):
+    """SODAMLP (modules.py:116-129), BatchNorm1d in training mode: batch mean / biased batch variance, eps 1e-5."""
+    x = F.linear(x, p[f"{pre}.0.weight"], p[f"{pre}.0.bias"])
+    x = F.batch_norm(x, None, None, p[f"{pre}.1.weight"], p[f"{pre}.1.bias"], training=True, eps=1e-5)
+    return F.linear(F.relu(x), p[f"{pre}.3.weight"], p[f"{pre}.3.bias"])
+
+
+class OracleSODA(OracleSAC):
+    """soda.py:12-84: SAC on random crops plus the SODA consistency update -- predictor(overlay-augmented crop) against the EMA
+    target encoder of another crop of the same frames, on a separately sampled batch (soda_batch_size)."""
+
+    def __init__(self, obs_shape, action_shape, args, params=None, dense_std=None, seed=0, tf32=False):
+        super().__init__(obs_shape, action_shape, args, params, dense_std, seed, tf32=tf32)
+        self.aux_names = [n for n in self.p.keys() if _in_group(n, SODA_GROUP)]
+        self.aux_opt = Adam(self.aux_names, args.aux_lr, args.aux_beta)
+        for n in self.aux_names:                                    # predictor_target = deepcopy(predictor), soda.py:30
+            self.p.setdefault("st_" + n, self.p[n].clone())
+
+    def update_soda(self, x, aug_x, L=None, step=None):
+        """soda.py:41-69 after the two crops and the overlay: x, aug_x (n,9,84,84)."""
+        gp = self._grad_params(self.aux_names)
+        h0 = soda_mlp(gp, soda_mlp(gp, cnn_forward(gp, aug_x, tf32=self.tf32), "soda_proj"), "soda_pred")
+        with torch.no_grad():
+            h1 = soda_mlp(self.p, cnn_forward(self.p, x, pre="st_cnn", tf32=self.tf32), "st_soda_proj")
+        soda_loss = F.mse_loss(F.normalize(h0, p=2, dim=1), F.normalize(h1, p=2, dim=1))
+        grads = torch.autograd.grad(soda_loss, [gp[n] for n in self.aux_names])
+        g = dict(zip(self.aux_names, grads))
+        self.trace.update(soda_h0=h0.detach(), soda_h1=h1, aux_loss=soda_loss.detach(), aux_grads=g)
+        with torch.no_grad():
+            self.aux_opt.step(self.p, g)
+            tau = self.args.soda_tau                                # utils.soft_update_params(predictor, predictor_target, soda_tau)
+            for n in self.aux_names:
+                t = self.p["st_" + n]
+                t.copy_(tau * self.p[n] + (1 - tau) * t)
+        if L is not None:
+            L.log("train/aux_loss", soda_loss, step)
+
+    def update_from_batch(self, batch, rnd, L, step):
+        """soda.py:71-84; rnd["soda_x"], rnd["soda_aug_x"]: the two crops of the separately sampled SODA batch (overlay applied)."""
+        super().update_from_batch(batch, rnd, L, step)
+        if step % self.args.aux_update_freq == 0:
+            self.update_soda(rnd["soda_x"], rnd["soda_aug_x"], L, step)
+        return self.trace
+
+
 ALGOS = {"sac": OracleSAC, "rad": OracleSAC, "drq": OracleSAC, "svea": OracleSVEA, "sgsac": OracleSGSAC, "curl": OracleCURL,
-         "pad": OraclePAD}
+         "pad": OraclePAD, "soda": OracleSODA}
 
 
 def make_oracle(obs_shape, action_shape, args, **kw):

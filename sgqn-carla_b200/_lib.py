@@ -68,6 +68,9 @@ SIGNATURES = {
     "sgqn_bce": [_p, _p, _p, _p] + [_i] * 10 + [_p],
     "sgqn_ce_diag": [_p, _i, _p, _p, _i, _i, _i, _p],
     "sgqn_mse_loss": [_p, _p, _p, _p, _i, _i, _i, _p],
+    "sgqn_bn_relu_fwd": [_p, _p, _p, _p, _p, _i, _i, _p],
+    "sgqn_bn_relu_bwd": [_p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _p],
+    "sgqn_soda_loss": [_p, _p, _p, _p, _i, _i, _i, _p],
     "sgqn_adam_prep": [_p, _p, _d, _d, _p],
     "sgqn_adam": [_p, _p, _p, _p, _ll, _p, _f, _f, _f, _f, _f, _p, _ll, _f, _f, _f, _p],
     "sgqn_ema": [_p, _p, _ll, _ll, _f, _f, _p],

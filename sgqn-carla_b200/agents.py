@@ -51,35 +51,44 @@ class _ModuleView(object):
         self.training = True
 
     def _names(self):
-        m = "critic" if self._target else self._module
+        m = "critic" if self._target is True else self._module
         return [(n, key) for n, refs in reference_key_map().items() for mod, key in refs if mod == m]
 
-    def state_dict(self):
+    def _slice(self, n):
+        """Stored (flat) segment of parameter n: the online arena, the critic target, or SODA's predictor target."""
         eng = self._agent.engine
-        lay = eng.lay
-        c0 = lay.ranges["critic"][0]
+        if self._target == "soda":
+            return eng.soda_target_slice(n)
+        o, st, _ = eng.lay.entries[n]
+        if self._target:
+            c0 = eng.lay.ranges["critic"][0]
+            return eng.target[o - c0:o - c0 + st]
+        return eng.params[o:o + st]
+
+    def state_dict(self):
+        lay = self._agent.engine.lay
         out = OrderedDict()
         for n, key in self._names():
-            flat = eng.target if self._target else eng.params
-            base = c0 if self._target else 0
-            o, st, _ = lay.entries[n]
-            out[key] = lay.from_stored(n, flat[o - base:o - base + st])
+            if n in lay.entries:
+                out[key] = lay.from_stored(n, self._slice(n))
         return out
 
     def load_state_dict(self, sd, strict=True):
         eng = self._agent.engine
         lay = eng.lay
-        c0 = lay.ranges["critic"][0]
         for n, key in self._names():
+            if n not in lay.entries:
+                continue
             if key not in sd:
                 if strict:
                     raise KeyError(key)
                 continue
-            flat = eng.target if self._target else eng.params
-            base = c0 if self._target else 0
-            o, st, _ = lay.entries[n]
-            flat[o - base:o - base + st].copy_(lay.to_stored(n, sd[key]).to(flat.device))
-        eng.prep_conv_weights(target=self._target)
+            seg = self._slice(n)
+            seg.copy_(lay.to_stored(n, sd[key]).to(seg.device))
+        if self._target == "soda":
+            eng.prep_soda_target_weights()
+        else:
+            eng.prep_conv_weights(target=bool(self._target))
         eng.prep_dec_weights()
 
     def parameters(self):
@@ -153,6 +162,11 @@ class SAC(object):
         crit = [n for n in lay.entries if c0 <= lay.off(n) < c1]
         lay.pack({n: canonical["t_" + n] for n in crit if "t_" + n in canonical}, eng.target, names=crit, base=c0)
         eng.prep_conv_weights(target=True)
+        if eng.algorithm == "soda":                                # SODA's predictor target: st_<name>
+            for n in lay.entries:
+                if "st_" + n in canonical:
+                    eng.soda_target_slice(n).copy_(lay.to_stored(n, canonical["st_" + n]).to(eng.dev))
+            eng.prep_soda_target_weights()
         for which, st in (optim or {}).items():
             opt = self._optims()[which]
             r0, r1 = lay.ranges[which]
@@ -185,6 +199,11 @@ class SAC(object):
         crit = [n for n in eng.lay.entries if c0 <= eng.lay.off(n) < c1]
         for n, t in eng.lay.unpack(eng.target, crit, base=c0).items():
             out["t_" + n] = t
+        if eng.algorithm == "soda":
+            c0s, c1s = eng.lay.ranges["cnn"]; s0, s1 = eng.lay.ranges["soda"]
+            for n in eng.lay.entries:
+                if c0s <= eng.lay.off(n) < c1s or s0 <= eng.lay.off(n) < s1:
+                    out["st_" + n] = eng.lay.from_stored(n, eng.soda_target_slice(n))
         out["log_alpha"] = eng.log_alpha.clone().reshape(())
         return out
 
@@ -510,6 +529,83 @@ class DrQ(SAC):
     sample_mode = "shift"
 
 
+class SODA(SAC):
+    """soda.py:12-84: SAC on random crops (100 -> 84) plus the SODA consistency update on a separately sampled batch of
+    `soda_batch_size` observations (two crops, one of them overlaid with a places image; SODAMLPs with BatchNorm1d; EMA target)."""
+    algorithm = "soda"
+
+    def __init__(self, obs_shape, action_shape, args, **kw):
+        super().__init__(obs_shape, action_shape, args, **kw)
+        self.aux_update_freq = args.aux_update_freq
+        self.soda_batch_size, self.soda_tau = args.soda_batch_size, args.soda_tau
+        self.predictor = _ModuleView(self, "predictor")
+        self.predictor_target = _ModuleView(self, "predictor", target="soda")
+        self.places_pool = None
+        p = _init.init_params(action_shape[0], args)
+        p.update({"st_" + n: p[n].clone() for n in p if n.startswith(("cnn.", "soda_"))})     # deepcopy(predictor), soda.py:30
+        self.set_training_state(p)
+
+    def _modules(self):
+        return dict(super()._modules(), predictor=self.predictor, predictor_target=self.predictor_target)
+
+    def set_parameters(self, canonical, sync_target=True):
+        super().set_parameters(canonical, sync_target)
+        if sync_target and hasattr(self.engine, "soda_target"):   # a fresh parameter set: the predictor target is its copy
+            eng = self.engine
+            for n in eng.lay.entries:
+                if n in canonical and n.startswith(("cnn.", "soda_")):
+                    eng.soda_target_slice(n).copy_(eng.lay.to_stored(n, canonical[n]).to(eng.dev))
+            eng.prep_soda_target_weights()
+
+    def set_places_pool(self, imgs):
+        t = torch.as_tensor(imgs, dtype=torch.float32)
+        assert t.dim() == 4 and tuple(t.shape[1:]) == (3, 84, 84), "places pool: float images (N,3,84,84) in [0,1]"
+        self.places_pool = t.to(self.engine.dev).contiguous()
+        self.engine.places_pool = self.places_pool.reshape(t.shape[0], 3, -1)
+        self._graphs.clear(); self._eager_runs.clear()
+
+    def load_places_dir(self, data_dirs, n=4096, use_val=False, seed=0):
+        from .datasets import load_places_pool
+        self.set_places_pool(load_places_pool(data_dirs, n, 84, use_val, seed))
+
+    def _log_cols(self, step):
+        cols = super()._log_cols(step)
+        if step % self.aux_update_freq == 0:
+            cols.append(("train/aux_loss", 4))
+        return cols
+
+    def _step_kind(self, step):
+        return super()._step_kind(step) + (step % self.aux_update_freq == 0,)
+
+    def supply(self, soda_idxs=None, soda_offs=None, soda_places=None, **kw):
+        """+ the SODA batch of the next update: indices (n,), crop offsets (2,n,2) for x / aug_x, overlay images (n,3,84,84)."""
+        super().supply(**kw)
+        self._supplied.update(soda_idxs=soda_idxs, soda_offs=soda_offs, soda_places=soda_places)
+
+    def update(self, replay_buffer, L, step, count=0):
+        eng = self.engine
+        if not isinstance(replay_buffer, ReplayBuffer):
+            raise TypeError("SODA samples its own second batch from the buffer: use sgqn_carla_b200.ReplayBuffer")
+        s = self._supplied
+        if step % self.aux_update_freq == 0:
+            if s is not None and s.get("soda_idxs") is not None:
+                n = eng.ns
+                eng.soda_idxs.copy_(torch.as_tensor(np.asarray(s["soda_idxs"]), dtype=torch.int64))
+                eng.soda_offs[:2].copy_(torch.as_tensor(np.asarray(s["soda_offs"]), dtype=torch.int32).reshape(2, n, 2))
+                eng.soda_places.copy_(torch.as_tensor(s["soda_places"], dtype=torch.float32).reshape(n, 3, -1))
+                eng.soda_supplied = dict(places=True)
+            elif self.places_pool is None:
+                raise RuntimeError("SODA needs an overlay image pool: agent.set_places_pool(float images (N,3,84,84) in [0,1])")
+        eng.soda_src = dict(frames=_ptr(replay_buffer.frames), fidx=_ptr(replay_buffer.fidx), n_valid=_ptr(replay_buffer.n_valid),
+                            Hs=replay_buffer.Hs)
+        super().update(replay_buffer, L, step, count)
+
+    def _run_update(self, replay_buffer, step):           # (the SODA batch is gathered straight from the ring: no staged prefetch)
+        self._draw(replay_buffer)
+        self._sample_into_engine(replay_buffer)
+        self._engine_update(step)
+
+
 class PAD(SAC):
     """pad.py:11-63: SAC on random crops (100 -> 84) plus the inverse-dynamics auxiliary update (obs, next_obs -> action)."""
     algorithm = "pad"
@@ -743,7 +839,7 @@ class SGSAC(SAC):
         return mask.reshape(B, 3, 1, 84, 84).expand(B, 3, 3, 84, 84).reshape(B, 9, 84, 84).bool()
 
 
-algorithm = {"sac": SAC, "rad": RAD, "drq": DrQ, "svea": SVEA, "sgsac": SGSAC, "curl": CURL, "pad": PAD}
+algorithm = {"sac": SAC, "rad": RAD, "drq": DrQ, "svea": SVEA, "sgsac": SGSAC, "curl": CURL, "pad": PAD, "soda": SODA}
 
 
 def make_agent(obs_shape, action_shape, args, **kw):

@@ -11,7 +11,7 @@ def default_args(**overrides):
         num_shared_layers=11, num_head_layers=0, num_filters=32, projection_dim=100, encoder_tau=0.05,
         init_temperature=0.1, alpha_lr=1e-4, alpha_beta=0.5,
         aux_lr=3e-4, aux_beta=0.9, aux_update_freq=2,
-        svea_alpha=0.5, svea_beta=0.5, sgqn_quantile=0.5, consistency=1, alpha_blending=0.2,
+        soda_batch_size=256, soda_tau=0.005, svea_alpha=0.5, svea_beta=0.5, sgqn_quantile=0.5, consistency=1, alpha_blending=0.2,
         seed=10081, log_dir="logs", image_size=84, image_crop_size=84,
     )
     a.update(overrides)

@@ -406,3 +406,86 @@ extern "C" int sgqn_mse_loss(const float* pred, const float* target, float* loss
     mse_loss_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(pred, target, loss, dpred, n, 1.0f / ((float)rows_global * (float)width));
     return SGQN_CHECK_LAUNCH();
 }
+
+
+// ---------------------------------------------------------------- SODA (soda.py:41-49, modules.py:116-129)
+// BatchNorm1d in training mode over x[M][P] (+ ReLU): y = relu(gamma * (x - mean) * rstd + beta), biased batch variance, eps 1e-5;
+// stats[0..P) = mean, stats[P..2P) = rstd for the backward pass.  One warp per feature (M <= a few thousand rows: tiny).
+__global__ void __launch_bounds__(128) bn_relu_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
+                                                          const float* __restrict__ beta, float* __restrict__ y,
+                                                          float* __restrict__ stats, int M, int P) {
+    const int f = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (f >= P) return;
+    float s = 0.f;
+    for (int r = lane; r < M; r += 32) s += x[(size_t)r * P + f];
+    const float mean = warp_sum(s) / (float)M;
+    float v = 0.f;
+    for (int r = lane; r < M; r += 32) { const float d = x[(size_t)r * P + f] - mean; v += d * d; }
+    const float rstd = rsqrtf(warp_sum(v) / (float)M + 1e-5f);
+    const float g = gamma[f], b = beta[f];
+    for (int r = lane; r < M; r += 32) y[(size_t)r * P + f] = fmaxf((x[(size_t)r * P + f] - mean) * rstd * g + b, 0.f);
+    if (lane == 0) { stats[f] = mean; stats[P + f] = rstd; }
+}
+// backward of the above: dy arrives for the ReLU output; dx, dgamma += , dbeta += (caller zero-fills the two)
+__global__ void __launch_bounds__(128) bn_relu_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x,
+                                                          const float* __restrict__ y, const float* __restrict__ gamma,
+                                                          const float* __restrict__ stats, float* __restrict__ dx,
+                                                          float* __restrict__ dgamma, float* __restrict__ dbeta, int M, int P) {
+    const int f = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (f >= P) return;
+    const float mean = stats[f], rstd = stats[P + f], g = gamma[f];
+    float s1 = 0.f, s2 = 0.f;
+    for (int r = lane; r < M; r += 32) {
+        const size_t i = (size_t)r * P + f;
+        const float d = y[i] > 0.f ? dy[i] : 0.f;
+        const float xh = (x[i] - mean) * rstd;
+        s1 += d; s2 += d * xh;
+    }
+    s1 = warp_sum(s1); s2 = warp_sum(s2);
+    for (int r = lane; r < M; r += 32) {
+        const size_t i = (size_t)r * P + f;
+        const float d = y[i] > 0.f ? dy[i] : 0.f;
+        const float xh = (x[i] - mean) * rstd;
+        dx[i] = g * rstd * (d - s1 / (float)M - xh * s2 / (float)M);
+    }
+    if (lane == 0) { atomicAdd(dgamma + f, s2); atomicAdd(dbeta + f, s1); }
+}
+extern "C" int sgqn_bn_relu_fwd(const float* x, const float* gamma, const float* beta, float* y, float* stats, int M, int P, void* stream) {
+    if (M <= 0 || P <= 0) return 0;
+    bn_relu_fwd_kernel<<<cdiv(P, 4), 128, 0, (cudaStream_t)stream>>>(x, gamma, beta, y, stats, M, P);
+    return SGQN_CHECK_LAUNCH();
+}
+extern "C" int sgqn_bn_relu_bwd(const float* dy, const float* x, const float* y, const float* gamma, const float* stats, float* dx,
+                                float* dgamma, float* dbeta, int M, int P, void* stream) {
+    if (M <= 0 || P <= 0) return 0;
+    bn_relu_bwd_kernel<<<cdiv(P, 4), 128, 0, (cudaStream_t)stream>>>(dy, x, y, gamma, stats, dx, dgamma, dbeta, M, P);
+    return SGQN_CHECK_LAUNCH();
+}
+
+// loss = mse(normalize(h0), normalize(h1)) (F.normalize p=2, eps 1e-12; mean over M*P), dh0 = d loss / d h0.  One warp per row.
+__global__ void __launch_bounds__(128) soda_loss_kernel(const float* __restrict__ h0, const float* __restrict__ h1,
+                                                        float* __restrict__ loss, float* __restrict__ dh0, int M, int P, float inv_n) {
+    const int row = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (row >= M) return;
+    const float* a = h0 + (size_t)row * P;
+    const float* b = h1 + (size_t)row * P;
+    float na = 0.f, nb = 0.f;
+    for (int i = lane; i < P; i += 32) { na += a[i] * a[i]; nb += b[i] * b[i]; }
+    na = fmaxf(sqrtf(warp_sum(na)), 1e-12f); nb = fmaxf(sqrtf(warp_sum(nb)), 1e-12f);
+    float l = 0.f, dot = 0.f;                          // dot = <a_hat, dL/da_hat>
+    for (int i = lane; i < P; i += 32) {
+        const float ah = a[i] / na, d = ah - b[i] / nb;
+        l += d * d; dot += ah * (2.f * d * inv_n);
+    }
+    l = warp_sum(l); dot = warp_sum(dot);
+    for (int i = lane; i < P; i += 32) {
+        const float ah = a[i] / na, d = ah - b[i] / nb;
+        dh0[(size_t)row * P + i] = (2.f * d * inv_n - ah * dot) / na;
+    }
+    if (lane == 0) atomicAdd(loss, l * inv_n);
+}
+extern "C" int sgqn_soda_loss(const float* h0, const float* h1, float* loss, float* dh0, int M, int P, int M_global, void* stream) {
+    if (M <= 0) return 0;
+    soda_loss_kernel<<<cdiv(M, 4), 128, 0, (cudaStream_t)stream>>>(h0, h1, loss, dh0, M, P, 1.0f / ((float)M_global * (float)P));
+    return SGQN_CHECK_LAUNCH();
+}

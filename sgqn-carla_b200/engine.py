@@ -85,6 +85,8 @@ class UpdateEngine:
 
         R = 2 * B                                       # rows of the critic heads: [clean | masked] or [obs | aug]
         E = 3 * B                                       # encoder rows of the critic slot: [next_obs | obs | masked / aug]
+        self.ns = int(getattr(args, "soda_batch_size", 256)) if algorithm == "soda" else 0     # SODA's own batch (soda.py:16)
+        Ec, Rc, Bt = max(E, self.ns), max(R, self.ns), max(B, self.ns)                       # conv workspaces must hold it too
         f32 = lambda *s: torch.zeros(*s, device=dev)
         # One observation buffer so that encoder passes which share weights run as ONE batch: [next_obs ; obs] before
         # the critic update (actor(next_obs) and critic(obs), sac.py:109,114) and [obs ; s_tilde] after it (attribution
@@ -94,12 +96,12 @@ class UpdateEngine:
         self.obs2 = self.obs3[B:]                       # [obs ; masked_obs / overlay-augmented obs]
         self.action = f32(B, A); self.reward = f32(B, 1); self.not_done = f32(B, 1)
         # activations: NHWC, post-ReLU; layers 0..9 carry 2 spare zero rows per sample ([n][h+2][h][32], tcgen05 path)
-        self.actS = [f32(E * (h + 2) * h * 32) for h in ENC_H]  # critic slot (encoder rows = obs3 rows)
-        self.actT = [f32(B * (h + 2) * h * 32) for h in ENC_H]  # target-network / acting slot
-        self.dbuf = [f32(R * 41 * 41 * 32), f32(R * 41 * 41 * 32)]
+        self.actS = [f32(Ec * (h + 2) * h * 32) for h in ENC_H]  # critic slot (encoder rows = obs3 rows)
+        self.actT = [f32(Bt * (h + 2) * h * 32) for h in ENC_H]  # target-network / acting slot
+        self.dbuf = [f32(Rc * 41 * 41 * 32), f32(Rc * 41 * 41 * 32)]
         # im2col matrices of the first conv (col[n*1681][84]) per slot: built once per observation batch by enc_fwd and
         # re-used by that slot's weight gradient; dcol is the attribution's data-gradient workspace
-        self.colS, self.colT = f32(E * 1681 * 96), f32(B * 1681 * 96)
+        self.colS, self.colT = f32(Ec * 1681 * 96), f32(B * 1681 * 96)
         self.dcol = f32(B * 1681 * 96) if precision != "tf32" else None
         self.w1p, self.w1p_t = f32(32 * 96), f32(32 * 96)          # TF32 operand copies of cnn.0 ([32][96]) / target
         self.w1d = f32(96 * 32)                                    # ... transposed ([96][32]): data-gradient operand
@@ -107,7 +109,7 @@ class UpdateEngine:
         # transposed for the data gradient; forward copy of the target net) and one zero-bordered (pad 2) gradient
         # buffer per layer -- borders are written once here (zeros) and never again.
         self.wf, self.wd, self.wf_t, self.wd_t = f32(10 * 9216), f32(10 * 9216), f32(10 * 9216), f32(10 * 9216)
-        self.gpad = [None] + [f32(R * (h + 4) * (h + 2) * 32) for h in ENC_H[1:]]    # d(act_l): [n][h+4][h+2][32]
+        self.gpad = [None] + [f32(Rc * (h + 4) * (h + 2) * 32) for h in ENC_H[1:]]    # d(act_l): [n][h+4][h+2][32]
         P1 = L.P + A
         self.zS, self.haS, self.dzS, self.dhaS = f32(R, L.P), f32(R, P1), f32(R, L.P), f32(R, P1)
         self.zT, self.haT, self.dzT, self.dhaT = f32(B, L.P), f32(B, P1), f32(B, L.P), f32(B, P1)
@@ -157,6 +159,22 @@ class UpdateEngine:
                 self.w3f, self.w3d, self.b3p = f32(64 * 9 * 64), f32(64 * 9 * 64), f32(64)
                 self.dw2p, self.db2p = f32(256 * 9 * 128), f32(256)
                 self.dw3p, self.db3p = f32(64 * 9 * 64), f32(64)
+        if algorithm == "soda":
+            ns, P = self.ns, L.P
+            c0s, c1s = L.ranges["cnn"]; s0, s1 = L.ranges["soda"]
+            self.soda_target = f32((c1s - c0s) + (s1 - s0))            # EMA copy of [SharedCNN | soda_proj | soda_pred] (soda.py:30)
+            self.wf_st, self.wd_st, self.w1p_st = f32(10 * 9216), f32(10 * 9216), f32(32 * 96)
+            self.soda_x, self.soda_aug, self.soda_scratch = f32(ns, 9, 84, 84), f32(ns, 9, 84, 84), f32(ns, 9, 84, 84)
+            self.soda_idxs = torch.zeros(ns, dtype=torch.int64, device=dev)
+            self.soda_ovl = torch.zeros(ns, dtype=torch.int64, device=dev)
+            self.soda_offs = torch.zeros(3, ns, 2, dtype=torch.int32, device=dev)      # [x crop | aug_x crop | zeros]
+            self.soda_places = f32(ns, 3, 84 * 84)                                       # host-supplied overlay images (parity runs)
+            self.soda_counter = torch.zeros(1, dtype=torch.int64, device=dev)
+            self.sy1, self.sa1, self.ss, self.sy2, self.sa2, self.sh0 = (f32(ns, P) for _ in range(6))
+            self.sy1t, self.sa1t, self.sh1 = (f32(ns, P) for _ in range(3))
+            self.dsh0, self.dsa2, self.dsy2, self.dss, self.dsa1, self.dsy1 = (f32(ns, P) for _ in range(6))
+            self.sstat1, self.sstat2, self.sstat_t = f32(2 * P), f32(2 * P), f32(2 * P)
+            self.places_pool, self.soda_src, self.soda_supplied = None, None, None
         if algorithm == "pad":
             self.z_p = f32(2 * B, L.P); self.dz_p = f32(2 * B, L.P)     # PAD projection pre-activations of [next_obs ; obs]
             self.joint = f32(B, 2 * L.P); self.djoint = f32(B, 2 * L.P)  # cat[h(obs), h(next_obs)]
@@ -176,7 +194,7 @@ class UpdateEngine:
         # Measured: bit-identical, but at 128-256 samples still 5-10 % slower per pass than ten PDL-chained
         # launches inside a CUDA graph, and the weight gradients lose their overlap with the data-gradient launches -> opt-in.
         self.chain = precision == "tf32" and os.environ.get("SGQN_CHAIN", "0") == "1"
-        ws_ints = 4 + 2 * B * 104 + 64
+        ws_ints = 4 + max(2 * B, self.ns) * 104 + 64
         self.wsS = torch.zeros(ws_ints, dtype=torch.int32, device=dev)
         self.wsT = torch.zeros(ws_ints, dtype=torch.int32, device=dev)
         self.debug_masked_obs = None
@@ -193,6 +211,24 @@ class UpdateEngine:
 
     def T(self, name):                                  # target copy of a critic-range parameter
         return self._t + 4 * (self.lay.off(name) - self._c0)
+
+    def ST(self, name):                                 # SODA target copy: [cnn range | soda range] of the parameter arena
+        c0s, c1s = self.lay.ranges["cnn"]
+        o = self.lay.off(name)
+        if c0s <= o < c1s:
+            return self.soda_target.data_ptr() + 4 * (o - c0s)
+        return self.soda_target.data_ptr() + 4 * ((c1s - c0s) + o - self.lay.ranges["soda"][0])
+
+    def soda_target_slice(self, name):
+        c0s, c1s = self.lay.ranges["cnn"]
+        o, stn, _ = self.lay.entries[name]
+        base = (o - c0s) if c0s <= o < c1s else (c1s - c0s) + o - self.lay.ranges["soda"][0]
+        return self.soda_target[base:base + stn]
+
+    def prep_soda_target_weights(self):
+        ls = self.lay.off("cnn.2.weight") - self.lay.off("cnn.1.weight")
+        K.conv_weights_prep(self.ST("cnn.1.weight"), ls, _ptr(self.wf_st), _ptr(self.wd_st), 10, self.st)
+        K.conv1_weights_prep(self.ST("cnn.0.weight"), _ptr(self.w1p_st), 0, self.st)
 
     @property
     def st(self):
@@ -224,8 +260,10 @@ class UpdateEngine:
         """SharedCNN forward (modules.py:132-152): x (n,9,hin,hin) fp32 NCHW -> acts[0..10] rows [row0, row0+n).
         col_from (tf32 path): the first conv also leaves the im2col matrix of the samples >= col_from in the slot's col
         buffer for the weight gradient of a backward pass over these rows (None: no backward follows)."""
-        W = self.T if target else self.P
-        wf = self.wf_t if target else self.wf
+        # target: False = online weights, True = the critic target, "soda" = SODA's own EMA copy of the SharedCNN
+        W = self.ST if target == "soda" else (self.T if target else self.P)
+        wf = self.wf_st if target == "soda" else (self.wf_t if target else self.wf)
+        w1p = self.w1p_st if target == "soda" else (self.w1p_t if target else self.w1p)
         st = self.st
         # activations are stored AFTER the ReLU that follows each conv (the last conv has none) and rounded to TF32,
         # the operand format of the next layer's tcgen05 MMA; 1[x>0] for the backward is 1[relu(x)>0].
@@ -234,7 +272,7 @@ class UpdateEngine:
         if tc:
             # pitch-linear layout [n][h+2][h][32]: the 2 spare rows per sample stay zero (never written) so that the
             # weight-gradient kernel can pair activations and the zero-bordered output gradient row by row
-            K.conv1_fused_tc(x_ptr, _ptr(self.w1p_t if target else self.w1p), W("cnn.0.bias"), _ptr(acts[0], row0 * 43 * 41 * 32),
+            K.conv1_fused_tc(x_ptr, _ptr(w1p), W("cnn.0.bias"), _ptr(acts[0], row0 * 43 * 41 * 32),
                              col if col_from is not None else 0, n, hin, col_from if col_from is not None else n, st)
             rows = []
             for l in range(1, 11):
@@ -723,6 +761,84 @@ class UpdateEngine:
         K.conv_fwd(_ptr(self.d2), Wp("dec.conv3.weight"), Wp("dec.conv3.bias"), _ptr(self.lg), B, 42, 42, 64, DEC_C3, 1, 2, 1, 0, st)
         return self.lg[:B * 84 * 84 * DEC_C3].reshape(B, 84, 84, DEC_C3)[..., :9].permute(0, 3, 1, 2).contiguous()
 
+    def _soda_mlp_fwd(self, x, ldx, n, pre, y, a, stats, out, W, big):
+        """SODAMLP (modules.py:116-129): Linear -> BatchNorm1d (training statistics) -> ReLU -> Linear."""
+        P, st = self.lay.P, self.st
+        Kdim = FEAT if big else P
+        (self.lin_fwd if big else K.linear_fwd)(x, ldx, 0, W(f"{pre}.0.weight"), 0, W(f"{pre}.0.bias"), 0, y, P, 0, n, P, Kdim, 0, 1,
+                                                2 if big else 0, st)
+        K.bn_relu_fwd(y, W(f"{pre}.1.weight"), W(f"{pre}.1.bias"), a, stats, n, P, st)
+        K.linear_fwd(a, P, 0, W(f"{pre}.3.weight"), 0, W(f"{pre}.3.bias"), 0, out, P, 0, n, P, P, 0, 1, 0, st)
+
+    def _soda_mlp_bwd(self, dout, x, ldx, n, pre, y, a, stats, da, dy, dx, big):
+        """Backward of _soda_mlp_fwd: parameter gradients into the arena; dx (n, K) is written (zero-filled here for the split-K path)."""
+        P, st, G, Wp = self.lay.P, self.st, self.G, self.P
+        Kdim = FEAT if big else P
+        K.linear_wgrad(a, P, 0, dout, P, 0, G(f"{pre}.3.weight"), 0, G(f"{pre}.3.bias"), 0, n, P, P, 0, 1, st)
+        K.linear_dgrad(dout, P, 0, Wp(f"{pre}.3.weight"), 0, 0, 0, 0, da, P, 0, n, P, P, 0, 0, 1, st)
+        K.bn_relu_bwd(da, y, a, Wp(f"{pre}.1.weight"), stats, dy, G(f"{pre}.1.weight"), G(f"{pre}.1.bias"), n, P, st)
+        (self.lin_wgrad if big else K.linear_wgrad)(x, ldx, 0, dy, P, 0, G(f"{pre}.0.weight"), 0, G(f"{pre}.0.bias"), 0, n, P, Kdim, 0, 1, st)
+        (self.lin_dgrad if big else K.linear_dgrad)(dy, P, 0, Wp(f"{pre}.0.weight"), 0, 0, 0, 0, dx, Kdim, 0, n, P, Kdim, 0, 0, 1, st)
+
+    def update_soda(self):
+        """soda.py:41-69: a separately sampled batch of soda_batch_size observations, two random crops, places overlay on one of
+        them; predictor(aug_x) against the EMA target encoder of x (BatchNorm1d batch statistics on both), normalised MSE; Adam
+        over (SharedCNN, both SODAMLPs); EMA of the target copy.  BatchNorm couples the batch: single-GPU only."""
+        L, st, a, ns, P = self.lay, self.st, self.args, self.ns, self.lay.P
+        if self.dist is not None:
+            raise RuntimeError("SODA's BatchNorm1d statistics are not shardable over the batch")
+        src, sup = self.soda_src, self.soda_supplied
+        self.soda_supplied = None
+        hs = src["Hs"]
+        if sup is None:
+            K.rng_step(self.seed ^ 0x534F4441, _ptr(self.soda_counter), src["n_valid"], _ptr(self.soda_idxs), _ptr(self.soda_ovl),
+                       int(self.places_pool.shape[0]), _ptr(self.soda_offs), max(1, hs - 84), 0, 0, 0, ns, self.A, 0, st)
+        offs = lambda k: (_ptr(self.soda_offs, k * ns * 2) if hs > 84 else 0)
+        K.replay_gather(src["frames"], src["fidx"], _ptr(self.soda_idxs), offs(0), _ptr(self.soda_x), _ptr(self.soda_scratch), ns, hs, 84, 0, 4, st)
+        K.replay_gather(src["frames"], src["fidx"], _ptr(self.soda_idxs), offs(1), _ptr(self.soda_aug), _ptr(self.soda_scratch), ns, hs, 84, 0, 4, st)
+        al = 0.2                                                   # random_overlay(aug_x): default alpha_blending (augmentations.py:79)
+        if sup is not None and sup.get("places") is not None:
+            K.overlay_f32(_ptr(self.soda_aug), _ptr(self.soda_places), 0, float(np.float32(1 - al)), float(np.float32(al)), _ptr(self.soda_aug), ns, 84 * 84, st)
+        else:
+            K.overlay_f32(_ptr(self.soda_aug), _ptr(self.places_pool), _ptr(self.soda_ovl), float(np.float32(1 - al)), float(np.float32(al)),
+                          _ptr(self.soda_aug), ns, 84 * 84, st)
+        # target branch (no gradient) beside the online one
+        ev_t = None
+        def target_branch():
+            self.enc_fwd(_ptr(self.soda_x), ns, self.actT, target="soda")
+            self._soda_mlp_fwd(_ptr(self.actT[10]), FEAT, ns, "soda_proj", _ptr(self.sy1t), _ptr(self.sa1t), _ptr(self.sstat_t), _ptr(self.sh1), self.ST, True)
+        if self.overlap:
+            main = torch.cuda.current_stream()
+            ev = torch.cuda.Event(); ev.record(main); self.side.wait_event(ev)
+            with torch.cuda.stream(self.side):
+                target_branch()
+                ev_t = torch.cuda.Event(); ev_t.record(self.side)
+        self.enc_fwd(_ptr(self.soda_aug), ns, self.actS, 0, col_from=0)
+        feat = _ptr(self.actS[10])
+        self._soda_mlp_fwd(feat, FEAT, ns, "soda_proj", _ptr(self.sy1), _ptr(self.sa1), _ptr(self.sstat1), _ptr(self.ss), self.P, True)
+        self._soda_mlp_fwd(_ptr(self.ss), P, ns, "soda_pred", _ptr(self.sy2), _ptr(self.sa2), _ptr(self.sstat2), _ptr(self.sh0), self.P, False)
+        if ev_t is not None:
+            torch.cuda.current_stream().wait_event(ev_t)
+        else:
+            target_branch()
+        K.zero(_ptr(self.logs, 4), 4, st)
+        K.soda_loss(_ptr(self.sh0), _ptr(self.sh1), _ptr(self.logs, 4), _ptr(self.dsh0), ns, P, ns, st)
+        x0, x1 = L.ranges["aux"]
+        K.zero(self._g + 4 * x0, 4 * (x1 - x0), st)
+        self._soda_mlp_bwd(_ptr(self.dsh0), _ptr(self.ss), P, ns, "soda_pred", _ptr(self.sy2), _ptr(self.sa2), _ptr(self.sstat2),
+                           _ptr(self.dsa2), _ptr(self.dsy2), _ptr(self.dss), False)
+        dfeat = _ptr(self.dbuf[1])
+        self._soda_mlp_bwd(_ptr(self.dss), feat, FEAT, ns, "soda_proj", _ptr(self.sy1), _ptr(self.sa1), _ptr(self.sstat1),
+                           _ptr(self.dsa1), _ptr(self.dsy1), dfeat, True)
+        self.enc_bwd(dfeat, ns, self.actS, 0, _ptr(self.soda_aug), 1, True)
+        self.adam(self.opt_aux, (x0, x1))
+        tau = float(a.soda_tau)
+        c0s, c1s = L.ranges["cnn"]; s0, s1 = L.ranges["soda"]
+        K.ema(self._p + 4 * c0s, _ptr(self.soda_target), c1s - c0s, 0, tau, tau, st)       # soft_update_params(predictor, predictor_target, soda_tau)
+        K.ema(self._p + 4 * s0, _ptr(self.soda_target, c1s - c0s), s1 - s0, 0, tau, tau, st)
+        self.prep_conv_weights()
+        self.prep_soda_target_weights()
+
     def update_pad(self):
         """pad.py:39-49 (InverseDynamics.forward, modules.py:298-303): h = encoder(obs), h' = encoder(next_obs) through the shared
         CNN and PAD's own projection, MLP(cat[h, h']) -> predicted action, MSE against the taken action; Adam over (SharedCNN,
@@ -913,6 +1029,8 @@ class UpdateEngine:
             self.update_curl()
         if self.algorithm == "pad" and step % a.aux_update_freq == 0:
             self.update_pad()
+        if self.algorithm == "soda" and step % a.aux_update_freq == 0:
+            self.update_soda()
         self._finish_logs()
 
     def _finish_logs(self):

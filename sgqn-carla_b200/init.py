@@ -45,6 +45,21 @@ def init_params(action_dim, args, seed=None):
     p["dec.conv3.weight"], p["dec.conv3.bias"] = default((9, 64, 3, 3), 576), default((9,), 576)
     p["fdec.0.weight"], p["fdec.0.bias"] = default((256, 100), 100), default((256,), 100)
     p["fdec.2.weight"], p["fdec.2.bias"] = default((100, 256), 256), default((100,), 256)
+    if getattr(args, "algorithm", "") == "soda":
+        # SODAMLP / SODAPredictor .apply(weight_init) (modules.py:126,309): orthogonal Linear, default BatchNorm (1, 0).  The
+        # predictor's apply() also re-initialises the SHARED CNN it wraps -- after critic_target was deep-copied from the critic
+        # (sac.py:54) -- so the critic target keeps the first draw and the SODA target (deepcopy of the predictor) gets the second.
+        for pre, fan in (("soda_proj", FEAT), ("soda_pred", P)):
+            p[f"{pre}.0.weight"], p[f"{pre}.0.bias"] = ortho(P, fan), torch.zeros(P)
+            p[f"{pre}.1.weight"], p[f"{pre}.1.bias"] = torch.ones(P), torch.zeros(P)
+            p[f"{pre}.3.weight"], p[f"{pre}.3.bias"] = ortho(P, P), torch.zeros(P)
+        for n in [k for k in p if k.startswith(("cnn.", "critic_proj.", "Q1.", "Q2."))]:
+            p["t_" + n] = p[n].clone()
+        for k in range(int(args.num_shared_layers)):
+            cin = 9 if k == 0 else nf
+            w = torch.zeros(nf, cin, 3, 3)
+            w[:, :, 1, 1] = ortho(nf, cin, math.sqrt(2.0))
+            p[f"cnn.{k}.weight"] = w
     if getattr(args, "algorithm", "") == "pad":               # InverseDynamics.apply(weight_init), modules.py:296
         p["pad_proj.0.weight"], p["pad_proj.0.bias"] = ortho(P, FEAT), torch.zeros(P)
         p["pad_proj.1.weight"], p["pad_proj.1.bias"] = torch.ones(P), torch.zeros(P)

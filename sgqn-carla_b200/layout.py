@@ -72,6 +72,13 @@ class ParamLayout:
         self.ranges["dec"] = (dec0, off)
         add("fdec.0.weight", (256, 100)); add("fdec.0.bias", (256,))
         add("fdec.2.weight", (100, 256)); add("fdec.2.bias", (100,))
+        if algorithm == "soda":                               # SODAMLP of the SODA encoder + SODAPredictor's SODAMLP (soda.py:19-27)
+            soda0 = off
+            for pre, fan in (("soda_proj", FEAT), ("soda_pred", P)):
+                add(f"{pre}.0.weight", (P, fan)); add(f"{pre}.0.bias", (P,))
+                add(f"{pre}.1.weight", (P,)); add(f"{pre}.1.bias", (P,))
+                add(f"{pre}.3.weight", (P, P)); add(f"{pre}.3.bias", (P,))
+            self.ranges["soda"] = (soda0, off)
         if algorithm == "pad":                                # InverseDynamics (modules.py:284-303) on PAD's own projection (pad.py:18-25)
             self._add_proj(add, "pad_proj")
             add("pad_mlp.0.weight", (H, 2 * P)); add("pad_mlp.0.bias", (H,))
@@ -192,4 +199,11 @@ def reference_key_map(num_layers=11):
     for j in (0, 2, 4):
         for wb in ("weight", "bias"):
             m[f"pad_mlp.{j}.{wb}"] = [("pad_head", f"mlp.{j}.{wb}")]
+    for n in list(m):                                         # predictor.encoder = shared CNN + SODAMLP projection (soda.py:19-27)
+        if n.startswith("cnn."):
+            m[n] = m[n] + [("predictor", m[n][0][1])]
+    for j in (0, 1, 3):
+        for wb in ("weight", "bias"):
+            m[f"soda_proj.{j}.{wb}"] = [("predictor", f"encoder.projection.mlp.{j}.{wb}")]
+            m[f"soda_pred.{j}.{wb}"] = [("predictor", f"mlp.mlp.{j}.{wb}")]
     return m

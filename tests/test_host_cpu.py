@@ -93,13 +93,16 @@ def test_layout_roundtrip_and_ranges():
     stored = flat[o:o + 100 * FEAT].reshape(100, 441, 32)
     assert torch.equal(stored[7, 5, 3], w[7, 3 * 441 + 5])
     keys = reference_key_map()
-    extra = {n for n in keys if n.startswith(("curl.", "pad_"))}
+    extra = {n for n in keys if n.startswith(("curl.", "pad_", "soda_"))}
     assert set(keys) - extra == set(lay.entries)                 # CURLHead.W / the PAD head only exist in their algorithm's layout ...
     curl = ParamLayout(2, algorithm="curl")
     assert set(curl.entries) - set(lay.entries) == {"curl.W"}
     pad = ParamLayout(2, algorithm="pad")
     assert set(pad.entries) - set(lay.entries) == {n for n in extra if n.startswith("pad_")}
     assert pad.ranges["aux"][0] <= pad.off("pad_mlp.4.bias") < pad.ranges["aux"][1]
+    soda = ParamLayout(2, algorithm="soda")
+    assert set(soda.entries) - set(lay.entries) == {n for n in extra if n.startswith("soda_")}
+    assert soda.ranges["soda"][1] == soda.ranges["aux"][1] and (soda.ranges["soda"][1] - soda.ranges["soda"][0]) % 4 == 0
     x0, x1 = curl.ranges["aux"]                                  # ... inside the range its optimiser owns (curl.py:16-20)
     assert x0 <= curl.off("curl.W") < x1 and x0 == curl.off("cnn.0.weight")
 

@@ -202,3 +202,43 @@ def test_quantile_threshold_matches_torch():
     a[7] = torch.round(a[7] * 4) / 4
     for q in (0.5, 0.9, 0.95, 0.98, 0.999, 0.0, 1.0):
         assert torch.equal(O.quantile_threshold(a, q), torch.quantile(a, q, 1)), q
+
+
+@pytest.mark.ref
+@pytest.mark.parametrize("dense", [None, 0.05])
+def test_oracle_soda_equals_reference_live(dense):
+    """SODA (soda.py:12-84): SAC on 100 -> 84 crops + the consistency update on a separately sampled batch (two crops, places
+    overlay, SODAMLPs with BatchNorm1d in training mode, EMA target copy of CNN + MLPs).  Oracle against the UNMODIFIED
+    reference: bit-identical losses and parameters (incl. the predictor target) over three updates."""
+    from oracle import pin, ref_shim as R
+    B, A, n = 3, 2, 5
+    agent, rb, orc, rep, args = pin.build_pair("soda", B=B, A=A, dense_std=dense, size=100, extra_args=("--soda_batch_size", str(n)))
+    rs = np.random.RandomState(2)
+    T = R.TAPE
+    for step in (2, 3, 4):
+        idxs = rs.randint(0, 32, size=B); idxs2 = rs.randint(0, 32, size=n)
+        rnd = pin.make_rnd(rs, B, A, 16)
+        crop = [(torch.as_tensor(rs.randint(0, 16, size=B)), torch.as_tensor(rs.randint(0, 16, size=B))) for _ in range(2)]
+        crop2 = [(torch.as_tensor(rs.randint(0, 16, size=n)), torch.as_tensor(rs.randint(0, 16, size=n))) for _ in range(2)]
+        places = torch.as_tensor(rs.rand(n, 3, 84, 84).astype(np.float32))
+        T.idxs[:] = [idxs, idxs2]
+        T.noise[:] = [rnd["noise_next"], rnd["noise_pi"]]
+        T.crop[:] = crop + crop2                              # sample(): obs, next_obs; update_soda: x, aug_x (soda.py:56-57)
+        T.places[:] = [places]
+        L = R.NullLogger()
+        agent.update(rb, L, step)
+        ref_logs = {k: v for k, v, _ in L.rows}
+        batch = rep.sample(idxs, (crop[0][0], crop[0][1], crop[1][0], crop[1][1]))
+        x100 = torch.as_tensor(rep.stacks(idxs2)[0]).float()
+        rnd["soda_x"] = O.random_crop(x100, crop2[0][0], crop2[0][1])
+        rnd["soda_aug_x"] = O.random_overlay_places(O.random_crop(x100, crop2[1][0], crop2[1][1]), places)
+        Lo = R.NullLogger()
+        orc.update_from_batch(batch, rnd, Lo, step)
+        ol = {k: v for k, v, _ in Lo.rows}
+        assert set(ol) == set(ref_logs) and ("train/aux_loss" in ol) == (step % 2 == 0)
+        for k in ref_logs:
+            assert ol[k] == ref_logs[k], (step, k)
+        for name, t in pin.ref_params(agent).items():
+            o = orc.log_alpha if name == "log_alpha" else orc.p[name]
+            assert torch.equal(t, o), (step, name)
+        assert any(k.startswith("st_soda_proj") for k in pin.ref_params(agent))
