@@ -116,6 +116,7 @@ class UpdateEngine:
         self.z_a, self.h_a, self.dz_a, self.dh_a = f32(B, L.P), f32(B, L.P), f32(B, L.P), f32(B, L.P)   # actor projection
         self.q = f32(2, R); self.dq = f32(2, R)
         self.z1 = f32(2, R, H); self.z2 = f32(2, R, H); self.dz1 = f32(2, R, H); self.dz2 = f32(2, R, H)
+        self.z1t = f32(2, B, H); self.z2t = f32(2, B, H)          # target trunks: own scratch (they run beside the online ones)
         self.az1 = f32(B, H); self.az2 = f32(B, H); self.daz1 = f32(B, H); self.daz2 = f32(B, H)
         self.raw = f32(B, 2 * A); self.draw = f32(B, 2 * A)
         self.mu = f32(B, A); self.pi = f32(B, A); self.log_pi = f32(B); self.log_std = f32(B, A)
@@ -336,9 +337,12 @@ class UpdateEngine:
         z1, z2 = _ptr(self.z1, row0 * H), _ptr(self.z2, row0 * H)
         out = _ptr(self.tq) if target else _ptr(self.q, row0)
         obs_ = self.B if target else R
-        K.linear_fwd(ha, P1, 0, W("Q1.0.weight"), qs, W("Q1.0.bias"), qs, z1, H, R * H, n, H, P1, 0, nheads, 0, st)
-        self.lin_fwd(z1, H, R * H, W("Q1.2.weight"), qs, W("Q1.2.bias"), qs, z2, H, R * H, n, H, H, 1, nheads, 2, st)
-        K.linear_fwd(z2, H, R * H, W("Q1.4.weight"), qs, W("Q1.4.bias"), qs, out, 1, obs_, n, 1, H, 1, nheads, 2, st)
+        zs = R * H                                      # head stride of the hidden activations
+        if target:
+            z1, z2, zs = _ptr(self.z1t), _ptr(self.z2t), self.B * H
+        K.linear_fwd(ha, P1, 0, W("Q1.0.weight"), qs, W("Q1.0.bias"), qs, z1, H, zs, n, H, P1, 0, nheads, 0, st)
+        self.lin_fwd(z1, H, zs, W("Q1.2.weight"), qs, W("Q1.2.bias"), qs, z2, H, zs, n, H, H, 1, nheads, 2, st)
+        K.linear_fwd(z2, H, zs, W("Q1.4.weight"), qs, W("Q1.4.bias"), qs, out, 1, obs_, n, 1, H, 1, nheads, 2, st)
 
     def q_dgrad(self, dq, dq_bs, n, row0, nheads, mode, dha):
         """Backward of the Q trunks to their input (n, P+A), heads summed.  mode 1 plain, 2 guided."""
@@ -503,20 +507,30 @@ class UpdateEngine:
             self._early_ev = None
 
     # ------------------------------------------------------------------ the update
-    def target_q_pass(self):
-        """sac.py:108-112 / sgsac.py:53-57 (no grad): actor(next_obs), critic_target(next_obs, a')."""
+    def target_q_pass(self, critic_rows=False):
+        """sac.py:108-112 / sgsac.py:53-57 (no grad): actor(next_obs), critic_target(next_obs, a'); with critic_rows also
+        critic(obs, action) (sac.py:114 / sgsac.py:59) on the obs half of the shared encoder pass.
+        After the online encoder three chains of small launches are independent -- actor(next_obs) (5), the target
+        projection (2) and the online critic heads on obs (6) -- and each fills a fraction of the SMs: with overlap they run on
+        three streams and meet at the target Q trunks / at the end."""
         B, A, L, st = self.B, self.A, self.lay, self.st
         a = self.args
         nx = _ptr(self.next_obs)
-        ev_t = None
+        ev_t = ev_c = None
         if self.overlap:                                # target encoder (B rows) beside the online one (2B rows)
             main = torch.cuda.current_stream()
             ev = torch.cuda.Event(); ev.record(main); self.side.wait_event(ev)
             with torch.cuda.stream(self.side):
                 self.enc_fwd(nx, B, self.actT, target=True)
+                self.proj_fwd(_ptr(self.actT[10]), B, "critic_proj", _ptr(self.zT), _ptr(self.haT), L.P + A, target=True)
                 ev_t = torch.cuda.Event(); ev_t.record(self.side)
         self.enc_fwd(_ptr(self.obs3), 2 * B, self.actS, 0, col_from=B)   # online encoder over [next_obs ; obs] in one batch (the obs half is
                                                                          # differentiated by the critic backward)
+        if critic_rows and self.overlap:
+            ev = torch.cuda.Event(); ev.record(main); self.side2.wait_event(ev)
+            with torch.cuda.stream(self.side2):
+                self.critic_fwd_rows(0, B, encode=False)
+                ev_c = torch.cuda.Event(); ev_c.record(self.side2)
         self.proj_fwd(_ptr(self.actS[10]), B, "actor_proj", _ptr(self.z_a), _ptr(self.h_a), L.P)
         self.actor_mlp_fwd(B)
         K.actor_head_fwd(_ptr(self.raw), _ptr(self.noise_next), float(a.actor_log_std_min), float(a.actor_log_std_max),
@@ -525,8 +539,12 @@ class UpdateEngine:
             torch.cuda.current_stream().wait_event(ev_t)
         else:
             self.enc_fwd(nx, B, self.actT, target=True)
-        self.proj_fwd(_ptr(self.actT[10]), B, "critic_proj", _ptr(self.zT), _ptr(self.haT), L.P + A, target=True)
+            self.proj_fwd(_ptr(self.actT[10]), B, "critic_proj", _ptr(self.zT), _ptr(self.haT), L.P + A, target=True)
         self.q_fwd(_ptr(self.haT), B, 0, 2, target=True)
+        if ev_c is not None:
+            torch.cuda.current_stream().wait_event(ev_c)
+        elif critic_rows:
+            self.critic_fwd_rows(0, B, encode=False)
 
     def actor_mlp_fwd(self, n):
         L, H, A, st = self.lay, self.H, self.A, self.st
@@ -578,8 +596,7 @@ class UpdateEngine:
         P1 = L.P + A
         if mode == 1:
             self._obs_minmax_fork()
-        self.target_q_pass()
-        self.critic_fwd_rows(0, B, encode=False)        # obs went through the encoder with next_obs
+        self.target_q_pass(critic_rows=True)            # + critic(obs, action): obs went through the encoder with next_obs
         R = B
         if mode == 1:
             self.attribution(B, _ptr(self.haS), _ptr(self.zS), _ptr(self.obs_grad))
