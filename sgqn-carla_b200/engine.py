@@ -495,8 +495,9 @@ class UpdateEngine:
         if self.cstream is None:
             self.dist.all_reduce_sum(self.grads[rng[0]:rng[1]], "early")
             return
-        ev = torch.cuda.Event(); ev.record(after if after is not None else torch.cuda.current_stream())
-        self.cstream.wait_event(ev)
+        ev = torch.cuda.Event(); ev.record(torch.cuda.current_stream()); self.cstream.wait_event(ev)
+        if after is not None:                           # pieces of the range were produced on a forked stream
+            ev = torch.cuda.Event(); ev.record(after); self.cstream.wait_event(ev)
         with torch.cuda.stream(self.cstream):
             self.dist.all_reduce_sum(self.grads[rng[0]:rng[1]], "early")
             self._early_ev = torch.cuda.Event(); self._early_ev.record(self.cstream)
@@ -677,8 +678,9 @@ class UpdateEngine:
         if want_mask:
             K.attribution_mask(_ptr(self.obs_grad), 0, 0, 0, self.quantile, _ptr(self.mask), 0, B, 84 * 84, 0, st)
 
-    def update_actor_and_alpha(self, finish=True):
-        """sac.py:125-151; expects shared_obs_fwd() state (critic slot, head rows [0,B))."""
+    def update_actor_and_alpha(self, finish=True, fork_wgrad=True):
+        """sac.py:125-151; expects shared_obs_fwd() state (critic slot, head rows [0,B)).  fork_wgrad: the MLP's weight
+        gradients on the side stream beside its data gradients (off when the whole update already runs beside the aux update)."""
         B, A, L, H, st, a = self.B, self.A, self.lay, self.H, self.st, self.args
         P1 = L.P + A
         lmin, lmax = float(a.actor_log_std_min), float(a.actor_log_std_max)
@@ -695,20 +697,25 @@ class UpdateEngine:
         a0, a1 = L.ranges["actor"]
         K.zero(self._g + 4 * a0, 4 * (a1 - a0), st)
         # actor MLP backward
+        fork = fork_wgrad and self.overlap
         K.linear_dgrad(_ptr(self.draw), 2 * A, 0, self.P("actor_mlp.4.weight"), 0, _ptr(self.az2), H, 0, _ptr(self.daz2), H, 0,
                        B, 2 * A, H, 1, 0, 1, st)
+        ws = self._fork() if fork else st
+        K.linear_wgrad(_ptr(self.az2), H, 0, _ptr(self.draw), 2 * A, 0, self.G("actor_mlp.4.weight"), 0,
+                       self.G("actor_mlp.4.bias"), 0, B, 2 * A, H, 1, 1, ws)
+        self.lin_wgrad(_ptr(self.az1), H, 0, _ptr(self.daz2), H, 0, self.G("actor_mlp.2.weight"), 0,
+                       self.G("actor_mlp.2.bias"), 0, B, H, H, 1, 1, ws)
         self.lin_dgrad(_ptr(self.daz2), H, 0, self.P("actor_mlp.2.weight"), 0, _ptr(self.az1), H, 0, _ptr(self.daz1), H, 0,
                        B, H, H, 1, 2, 1, st)
+        ws = self._fork() if fork else st
+        K.linear_wgrad(_ptr(self.h_a), L.P, 0, _ptr(self.daz1), H, 0, self.G("actor_mlp.0.weight"), 0,
+                       self.G("actor_mlp.0.bias"), 0, B, H, L.P, 0, 1, ws)
         K.linear_dgrad(_ptr(self.daz1), H, 0, self.P("actor_mlp.0.weight"), 0, 0, 0, 0, _ptr(self.dh_a), L.P, 0,
                        B, H, L.P, 0, 2, 1, st)
-        K.linear_wgrad(_ptr(self.az2), H, 0, _ptr(self.draw), 2 * A, 0, self.G("actor_mlp.4.weight"), 0,
-                       self.G("actor_mlp.4.bias"), 0, B, 2 * A, H, 1, 1, st)
-        self.lin_wgrad(_ptr(self.az1), H, 0, _ptr(self.daz2), H, 0, self.G("actor_mlp.2.weight"), 0,
-                       self.G("actor_mlp.2.bias"), 0, B, H, H, 1, 1, st)
-        K.linear_wgrad(_ptr(self.h_a), L.P, 0, _ptr(self.daz1), H, 0, self.G("actor_mlp.0.weight"), 0,
-                       self.G("actor_mlp.0.bias"), 0, B, H, L.P, 0, 1, st)
         self.proj_bwd(_ptr(self.dh_a), L.P, B, _ptr(self.z_a), _ptr(self.h_a), L.P, "actor_proj", _ptr(self.dz_a),
                       feat_ptr=_ptr(self.actS[10], B * FEAT), dfeat=0)
+        if fork:
+            self._join()
         if finish:
             self.actor_finish()
 
@@ -739,13 +746,14 @@ class UpdateEngine:
             self._decoder_tc(B, st, Wp, G, x0, x1)
         else:
             self._decoder_simt(B, st, Wp, G, x0, x1)
+        wside = self.side if self.overlap else None     # (the decoder's weight gradients were issued there, _decoder_tc)
         K.linear_wgrad(ha, P1, 0, _ptr(self.ddl), FEAT, 0, G("dec.proj.weight"), 0, G("dec.proj.bias"), 0,
-                       B, FEAT, P1, 0, 1, st)
-        self._early_reduce(L.ranges["dec"])             # decoder gradients are complete: exchange them under the encoder backward
+                       B, FEAT, P1, 0, 1, self._fork())
+        self._early_reduce(L.ranges["dec"], after=wside)     # decoder gradients are complete: exchange them under the encoder backward
         K.linear_dgrad(_ptr(self.ddl), FEAT, 0, Wp("dec.proj.weight"), 0, 0, 0, 0, _ptr(self.dhaT), P1, 0, B, FEAT, P1, 0, 2, 1, st)
         dfeat = _ptr(self.dbuf[1])
         self.proj_bwd(_ptr(self.dhaT), P1, B, z, ha, P1, "critic_proj", _ptr(self.dzT), feat_ptr=feat, dfeat=dfeat)
-        self._early_reduce(L.ranges["critic_proj"], after=self.side if self.overlap else None)
+        self._early_reduce(L.ranges["critic_proj"], after=wside)
         self.enc_bwd(dfeat, B, self.actS, 2 * B, _ptr(self.s_tilde), 1, True)
         self.allreduce_grads(L.ranges["cnn"])           # (fdec.* never receives a gradient: not exchanged)
         self._early_join()
@@ -1021,7 +1029,7 @@ class UpdateEngine:
             main = torch.cuda.current_stream()
             ev = torch.cuda.Event(); ev.record(main); self.side2.wait_event(ev)
             with torch.cuda.stream(self.side2):         # incl. its gradient exchange ("actor" communicator) and optimiser steps
-                self.update_actor_and_alpha(finish=True)
+                self.update_actor_and_alpha(finish=True, fork_wgrad=False)
                 ev2 = torch.cuda.Event(); ev2.record(self.side2)
             self.update_aux()
             main.wait_event(ev2)
