@@ -36,6 +36,34 @@ static inline int launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, si
 }
 
 static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+
+// Zero-fill of `batch` strided [rows][cols] blocks as ONE kernel node with a programmatic edge on both sides (a memset node per
+// block in front of every split-K GEMM cost the update's graph a node hop each, and cannot be a PDL predecessor).
+static __global__ void zero2d_kernel(float* __restrict__ p, int ld, long long bs, int rows, int cols, int vec) {
+    pdl_wait();
+    pdl_launch();
+    float* base = p + (long long)blockIdx.y * bs;
+    if (vec) {
+        const int c4 = cols >> 2;
+        for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < (long long)rows * c4; i += (long long)gridDim.x * blockDim.x) {
+            const int r = (int)(i / c4), c = (int)(i - (long long)r * c4);
+            reinterpret_cast<float4*>(base + (long long)r * ld)[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    } else {
+        for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < (long long)rows * cols; i += (long long)gridDim.x * blockDim.x) {
+            const int r = (int)(i / cols), c = (int)(i - (long long)r * cols);
+            base[(long long)r * ld + c] = 0.f;
+        }
+    }
+}
+static inline int zero2d(float* p, int ld, long long bs, int rows, int cols, int batch, void* stream) {
+    if (rows <= 0 || cols <= 0 || batch <= 0) return 0;
+    const int vec = !((size_t)p & 15) && !(ld & 3) && !(bs & 3) && !(cols & 3);
+    long long n = (long long)rows * (vec ? cols >> 2 : cols);
+    int gx = (int)((n + 255) / 256);
+    if (gx > 592) gx = 592;
+    return launch_pdl(zero2d_kernel, dim3(gx, batch), dim3(256), 0, stream, p, ld, bs, rows, cols, vec);
+}
 static inline long long cdivll(long long a, long long b) { return (a + b - 1) / b; }
 
 __device__ __forceinline__ float warp_sum(float v) {

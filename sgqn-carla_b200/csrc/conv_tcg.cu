@@ -32,6 +32,7 @@ struct GParams {
     const float* mask;
     float* out;
     int relu_out, round_out, mask_mode, upsample;
+    int w_resident;         // every (chunk, tap) weight tile stays in shared memory for the whole launch (<= ~150 KB of weights)
     int shuffle;            // 0 none, 1 depth-to-space (phase channels -> 2x2 pixels), 2 space-to-depth (pixel -> phase channels)
 };
 
@@ -78,6 +79,12 @@ conv3x3_tcg_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     if (warp == 0) {
         if (lane == 0) {
             int as = 0, ws = 0; uint32_t aph = 0, wph = 0;
+            if (p.w_resident) {                              // the whole weight block once (re-streaming it per tile made the small
+                mbar_expect_tx(wfull0, p.kc * p.ntaps * kWBytes);   // decoder convs L2-bound: 147 KB of weights per 28 KB halo tile)
+                for (int c = 0; c < p.kc; ++c)
+                    for (int t = 0; t < p.ntaps; ++t)
+                        tma_load_2d(&tmW, wfull0, w_sm + (c * p.ntaps + t) * kWBytes, t * p.cin + c * 32, 0);
+            }
             for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
                 const int r0 = tile * kTileM + p.shift;
                 for (int c = 0; c < p.kc; ++c) {
@@ -86,6 +93,7 @@ conv3x3_tcg_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                     for (int pc = 0; pc < p.pieces; ++pc)
                         tma_load_2d(&tmA, afull0 + 8 * as, a_sm + as * p.a_bytes + pc * p.piece_rows * 128, c * 32, r0 + pc * p.piece_rows);
                     if (++as == p.a_stages) { as = 0; aph ^= 1u; }
+                    if (p.w_resident) continue;
                     for (int t = 0; t < p.ntaps; ++t) {
                         mbar_wait(wempty0 + 8 * ws, wph ^ 1u);
                         mbar_expect_tx(wfull0 + 8 * ws, kWBytes);
@@ -98,6 +106,7 @@ conv3x3_tcg_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     } else if (warp == 1) {
         if (lane == 0) {
             int as = 0, ws = 0; uint32_t aph = 0, wph = 0; int acc = 0; uint32_t acc_phase = 0;
+            if (p.w_resident) { mbar_wait(wfull0, 0); tc_fence_after(); }
             for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
                 mbar_wait(tempty0 + 8 * acc, acc_phase ^ 1u);
                 tc_fence_after();
@@ -108,14 +117,17 @@ conv3x3_tcg_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                     const uint64_t a0 = make_desc_sw128(a_sm + as * p.a_bytes);
                     const uint32_t rowq = (uint32_t)p.Wp * 8u;
                     for (int t = 0; t < p.ntaps; ++t) {
-                        mbar_wait(wfull0 + 8 * ws, wph);
-                        tc_fence_after();
+                        if (!p.w_resident) {
+                            mbar_wait(wfull0 + 8 * ws, wph);
+                            tc_fence_after();
+                        }
                         const uint64_t ad = a0 + (uint64_t)(p.ntaps == 9 ? (t / 3) * rowq + (t % 3) * 8u : 0u);
-                        const uint64_t bd = make_desc_sw128(w_sm + ws * kWBytes);
+                        const uint64_t bd = make_desc_sw128(w_sm + (p.w_resident ? c * p.ntaps + t : ws) * kWBytes);
                         if ((c | t) == 0) tc_mma_tf32_zero(d_tmem, ad, bd, kIdescN);
                         else tc_mma_tf32_acc(d_tmem, ad, bd, kIdescN);
 #pragma unroll
                         for (int k = 1; k < 4; ++k) tc_mma_tf32_acc(d_tmem, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), kIdescN);
+                        if (p.w_resident) continue;
                         tc_commit(wempty0 + 8 * ws);
                         if (++ws == p.w_stages) { ws = 0; wph ^= 1u; }
                     }
@@ -321,7 +333,8 @@ extern "C" int sgqn_conv_tcg_taps(const float* x, const float* wop, const float*
     if (p.piece_rows > 256) return (int)cudaErrorInvalidValue;
     p.a_bytes = p.pieces * p.piece_rows * 128;
     const int wb = Cout * 128;
-    p.w_stages = kMaxW;
+    p.w_resident = kSmemBudget - 4096 - p.kc * ntaps * wb >= 2 * p.a_bytes;
+    p.w_stages = p.w_resident ? p.kc * ntaps : kMaxW;
     while (p.w_stages > 2 && kSmemBudget - 4096 - p.w_stages * wb < 2 * p.a_bytes) --p.w_stages;
     p.a_stages = (kSmemBudget - 4096 - p.w_stages * wb) / p.a_bytes;
     if (p.a_stages > kMaxA) p.a_stages = kMaxA;

@@ -51,11 +51,10 @@ extern "C" int sgqn_linear_fwd(const float* x, int ldx, long long xbs, const flo
     RowMajorC a{x, ldx, xbs, relu_in, aligned16(x) && (ldx % 4 == 0) && (xbs % 4 == 0)};
     RowMajorC b{w, K, wbs, 0, aligned16(w) && (K % 4 == 0) && (wbs % 4 == 0)};
     EpStore ep{y, ldy, ybs, bias, bbs, nullptr, 0, 0, 0, splitk ? 1 : 0, 1.0f, 0, 0, 0};
-    if (splitk == 2)                 // zero-fill here (strided rows, per batch), then split-K with atomics
-        for (int bi = 0; bi < batch; ++bi) {
-            cudaError_t e = cudaMemset2DAsync(y + bi * ybs, (size_t)ldy * 4, 0, (size_t)N * 4, (size_t)M, (cudaStream_t)stream);
-            if (e != cudaSuccess) return (int)e;
-        }
+    if (splitk == 2) {               // zero-fill here (strided rows, per batch), then split-K with atomics
+        int rc = zero2d(y, ldy, ybs, M, N, batch, stream);
+        if (rc) return rc;
+    }
     return launch_gemm<64, 64, 16, 4, 4>(a, b, ep, M, N, K, batch, splitk ? 64 : 1, (cudaStream_t)stream);
 }
 
@@ -68,10 +67,8 @@ extern "C" int sgqn_linear_dgrad(const float* dy, int lddy, long long dybs, cons
     EpStore ep{dx, lddx, dxbs, nullptr, 0, zmask, ldm, mbs, mode, accumulate ? 1 : 0, 1.0f, 0, 0, 0};
     if (accumulate == 2) {           // zero-fill here, then split-K with atomics (the plain ReLU mask distributes over the sum)
         if (mode == 2) return (int)cudaErrorInvalidValue;
-        for (int bi = 0; bi < batch; ++bi) {
-            cudaError_t e = cudaMemset2DAsync(dx + bi * dxbs, (size_t)lddx * 4, 0, (size_t)K * 4, (size_t)M, (cudaStream_t)stream);
-            if (e != cudaSuccess) return (int)e;
-        }
+        int rc = zero2d(dx, lddx, dxbs, M, K, batch, stream);
+        if (rc) return rc;
     }
     return launch_gemm<64, 64, 16, 4, 4>(a, b, ep, M, K, N, batch, accumulate ? 64 : 1, (cudaStream_t)stream);
 }

@@ -318,6 +318,8 @@ gemm_simt_kernel(AL al, BL bl, EP ep, int M, int N, int K, int nsplit, int klen)
     static_assert(TM % 4 == 0 && TN % 4 == 0 && BK % 4 == 0, "tile shape");
     __shared__ __align__(16) float As[BK][BM + 4];
     __shared__ __align__(16) float Bs[BK][BN + 4];
+    pdl_wait();
+    pdl_launch();
     const int tid = threadIdx.x;
     const int i0 = blockIdx.x * BM, j0 = blockIdx.y * BN;
     const int batch = blockIdx.z / nsplit, split = blockIdx.z - batch * nsplit;
@@ -385,8 +387,8 @@ static int launch_gemm(const AL& al, const BL& bl, const EP& ep, int M, int N, i
     int klen = cdiv(cdiv(K, nsplit), BK) * BK;
     nsplit = cdiv(K, klen);
     dim3 grid(tm, tn, batch * nsplit);
-    gemm_simt_kernel<BM, BN, BK, TM, TN, AL, BL, EP><<<grid, (BM / TM) * (BN / TN), 0, st>>>(al, bl, ep, M, N, K, nsplit, klen);
-    return SGQN_CHECK_LAUNCH();
+    return launch_pdl(gemm_simt_kernel<BM, BN, BK, TM, TN, AL, BL, EP>, grid, dim3((BM / TM) * (BN / TN)), 0, st, al, bl, ep, M, N, K,
+                      nsplit, klen);
 }
 
 }  // namespace sgqn

@@ -96,6 +96,8 @@ gemm3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     tc_fence_after();
     uint32_t tmem_base;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+    pdl_wait();                                        // operands / C come from the kernels before (common.cuh: PDL rules)
+    pdl_launch();
 
     if (warp == 0) {
         if (lane == 0) {
@@ -282,13 +284,6 @@ int make_operand_map(CUtensorMap* tm, const float* ptr, int rows, int kdim, int 
 
 struct Operand { const float* ptr; int ld; long long bs; int mn; int relu; };
 
-int zero_rows(float* p, int ld, long long bs, int rows, int cols, int batch, cudaStream_t st) {
-    for (int bi = 0; bi < batch; ++bi) {
-        cudaError_t e = cudaMemset2DAsync(p + bi * bs, (size_t)ld * 4, 0, (size_t)cols * 4, (size_t)rows, st);
-        if (e != cudaSuccess) return (int)e;
-    }
-    return 0;
-}
 
 // C[batch][M][N] (+)= sum_k A[m][k] B[n][k].  accumulate 1: add onto what C holds (red.add); 0: overwrite -- with split-K
 // (max_split > 1 and enough k-blocks to fill the SMs) C is zero-filled here and the splits meet through red.add,
@@ -327,15 +322,14 @@ int launch_gemm3(const Operand& A, const Operand& B, int M, int N, int K, int ba
     p.idesc = idesc_tf32(bn, A.mn != 0, B.mn != 0);
     p.c = c; p.ldc = ldc; p.cbs = cbs; p.bias = bias; p.bbs = bbs; p.mask = mask; p.ldm = ldm; p.mbs = mbs; p.mode = mode;
     p.atomic = (accumulate || nsplit > 1) ? 1 : 0;
-    if (!accumulate && nsplit > 1) { int rc = zero_rows(c, ldc, cbs, M, N, batch, st); if (rc) return rc; }
+    if (!accumulate && nsplit > 1) { int rc = zero2d(c, ldc, cbs, M, N, batch, st); if (rc) return rc; }
     CUtensorMap tmA, tmB;
     int rc = make_operand_map(&tmA, A.ptr, M, K, A.ld, A.bs, batch, A.mn, 128);
     if (rc) return rc;
     rc = make_operand_map(&tmB, B.ptr, N, K, B.ld, B.bs, batch, B.mn, bn);
     if (rc) return rc;
     dim3 grid(tiles_m * p.tiles_n, nsplit, batch);
-    gemm3_tc_kernel<<<grid, kGtThreads, kGtSmem, st>>>(tmA, tmB, p);
-    return SGQN_CHECK_LAUNCH();
+    return launch_pdl(gemm3_tc_kernel, grid, dim3(kGtThreads), kGtSmem, st, tmA, tmB, p);
 }
 
 __global__ void guided_mask_kernel(float* __restrict__ dx, int lddx, long long dxbs, const float* __restrict__ z, int ldm, long long mbs,

@@ -120,5 +120,7 @@ extern "C" int sgqn_crop_shift(const float* x, const int32_t* offs, float* y, in
 
 extern "C" int sgqn_zero(void* p, long long bytes, void* stream) {
     if (bytes <= 0) return 0;
+    if (!(bytes & 3) && !((size_t)p & 3) && bytes < (1ll << 32))      // a kernel node with programmatic edges (common.cuh) instead of a memset node
+        return zero2d((float*)p, 0, 0, 1, (int)(bytes >> 2), 1, stream);
     return (int)cudaMemsetAsync(p, 0, (size_t)bytes, (cudaStream_t)stream);
 }

@@ -475,7 +475,10 @@ def test_rad_crop_and_actions_at_100():
         agent.update(rb, L, step)
         for (s, k), v in Lo.rows.items():
             if s == step:            # tf32 product path vs the TF32-rounding oracle, reference initialisation; free-running
-                np.testing.assert_allclose(float(L.rows[(s, k)]), float(v), rtol=1e-3 if step == 2 else 2e-2, atol=2e-3)
+                # step 3 follows one sign-sensitive Adam step at B = 4: the split-K atomics reorder sums run to run, near-zero
+                # gradient elements flip sign and the critic loss lands on one of a few discrete values -- 30 fresh runs
+                # (tools/flaky_rad.py) gave 0.7929 .. 0.8179 around the oracle's 0.8156 (mode 0.8071), with or without PDL
+                np.testing.assert_allclose(float(L.rows[(s, k)]), float(v), rtol=1e-3 if step == 2 else 4e-2, atol=2e-3)
     x = rep.stacks(np.array([5]))[0][0]
     # after 2 free-running updates (two sign-sensitive Adam steps of 1e-3 on weights of scale ~3e-2; the same check from
     # identical parameters is part of test_teacher_forced_updates_match_oracle: 1e-3)
