@@ -337,6 +337,8 @@ extern "C" int sgqn_conv_tc(const float* x, const float* w, const float* bias, c
 // flipped taps, transposed channels).  `lstride` = distance between consecutive layers' weights in `w` (floats).
 __global__ void conv_weights_prep_kernel(const float* __restrict__ w, long long lstride, float* __restrict__ wf,
                                          float* __restrict__ wd, int n_layers) {
+    pdl_wait();
+    pdl_launch();
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_layers * 9216) return;
     int l = i / 9216, r = i - l * 9216;
@@ -348,13 +350,15 @@ __global__ void conv_weights_prep_kernel(const float* __restrict__ w, long long 
 extern "C" int sgqn_conv_weights_prep(const float* w, long long lstride, float* wf, float* wd, int n_layers, void* stream) {
     int n = n_layers * 9216;
     if (n <= 0) return 0;
-    conv_weights_prep_kernel<<<cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>(w, lstride, wf, wd, n_layers);
+    { int rc_ = launch_pdl(conv_weights_prep_kernel, dim3(cdiv(n, 256)), dim3(256), 0, (cudaStream_t)stream, w, lstride, wf, wd, n_layers); if (rc_) return rc_; }
     return SGQN_CHECK_LAUNCH();
 }
 
 // compact [B][H][W][C] -> rows [oy, oy+H), cols [ox, ox+W) of a zero-initialised [B][Hq][Wq][C] buffer
 __global__ void pad_copy_kernel(const float4* __restrict__ src, float4* __restrict__ dst, int H, int W, int C4, int Hq, int Wq,
                                 int oy, int ox, int round_out, long long total) {
+    pdl_wait();
+    pdl_launch();
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= total) return;
     int c = (int)(i % C4); long long t = i / C4;
@@ -369,8 +373,8 @@ extern "C" int sgqn_pad_copy(const float* src, float* dst, int B, int H, int W, 
     if (C & 3) return (int)cudaErrorInvalidValue;
     long long total = (long long)B * H * W * (C / 4);
     if (total <= 0) return 0;
-    pad_copy_kernel<<<(unsigned)cdivll(total, 256), 256, 0, (cudaStream_t)stream>>>((const float4*)src, (float4*)dst, H, W,
-                                                                                   C / 4, Hq, Wq, oy, ox, round_out, total);
+    { int rc_ = launch_pdl(pad_copy_kernel, dim3((unsigned)cdivll(total, 256)), dim3(256), 0, (cudaStream_t)stream, (const float4*)src, (float4*)dst, H, W,
+                                                                                   C / 4, Hq, Wq, oy, ox, round_out, total); if (rc_) return rc_; }
     return SGQN_CHECK_LAUNCH();
 }
 

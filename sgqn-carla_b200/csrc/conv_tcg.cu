@@ -389,6 +389,8 @@ __device__ __forceinline__ int phase_tap(int a, int k) { return a == 0 ? (k == 0
 // (data-gradient operand), bphi: [4*Cg] = bias replicated per phase (0 in the padding channels).
 __global__ void conv_weights_prep_phase_kernel(const float* __restrict__ w, const float* __restrict__ bias, float* __restrict__ wf,
                                                float* __restrict__ wd, float* __restrict__ bphi, int Cin, int Cout_real, int Cg) {
+    pdl_wait();
+    pdl_launch();
     const int Np = 4 * Cg;
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= Np * 9 * Cin) return;
@@ -408,7 +410,7 @@ extern "C" int sgqn_conv_weights_prep_phase(const float* w, const float* bias, f
                                             int Cout_real, int Cg, void* stream) {
     int n = 4 * Cg * 9 * Cin;
     if (n <= 0 || Cout_real > Cg) return (int)cudaErrorInvalidValue;
-    conv_weights_prep_phase_kernel<<<cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>(w, bias, wf, wd, bphi, Cin, Cout_real, Cg);
+    { int rc_ = launch_pdl(conv_weights_prep_phase_kernel, dim3(cdiv(n, 256)), dim3(256), 0, (cudaStream_t)stream, w, bias, wf, wd, bphi, Cin, Cout_real, Cg); if (rc_) return rc_; }
     return SGQN_CHECK_LAUNCH();
 }
 
@@ -416,6 +418,8 @@ extern "C" int sgqn_conv_weights_prep_phase(const float* w, const float* bias, f
 // db[co] += sum_p dbphi[p*Cg + co].  Single writer per element (plain +=).
 __global__ void conv_phase_fold_kernel(const float* __restrict__ dwphi, const float* __restrict__ dbphi, float* __restrict__ dw,
                                        float* __restrict__ db, int Cin, int Cout_real, int Cg) {
+    pdl_wait();
+    pdl_launch();
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= Cout_real * 9 * Cin) return;
     int co = i / (9 * Cin), r = i - co * 9 * Cin, t = r / Cin, ci = r - t * Cin, ky = t / 3, kx = t % 3;
@@ -431,7 +435,7 @@ extern "C" int sgqn_conv_phase_fold(const float* dwphi, const float* dbphi, floa
                                     void* stream) {
     int n = Cout_real * 9 * Cin;
     if (n <= 0 || Cout_real > Cg) return (int)cudaErrorInvalidValue;
-    conv_phase_fold_kernel<<<cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>(dwphi, dbphi, dw, db, Cin, Cout_real, Cg);
+    { int rc_ = launch_pdl(conv_phase_fold_kernel, dim3(cdiv(n, 256)), dim3(256), 0, (cudaStream_t)stream, dwphi, dbphi, dw, db, Cin, Cout_real, Cg); if (rc_) return rc_; }
     return SGQN_CHECK_LAUNCH();
 }
 

@@ -11,6 +11,8 @@ static inline int aligned16(const void* p) { return (((uintptr_t)p) & 15) == 0; 
 
 // ---------------------------------------------------------------- column sums (bias gradients)
 __global__ void colsum_kernel(const float* __restrict__ x, int ld, int M, int N, float* __restrict__ out, int rows_per_block) {
+    pdl_wait();
+    pdl_launch();
     // block: 256 threads = 8 row-lanes x 32 columns
     __shared__ float sh[8][33];
     int col = blockIdx.y * 32 + (threadIdx.x & 31);
@@ -36,7 +38,7 @@ static int launch_colsum(const float* x, int ld, int M, int N, float* out, cudaS
     int rpb = cdiv(M, want);
     if (rpb < 64) rpb = 64;
     dim3 grid(cdiv(M, rpb), ctas_y);
-    colsum_kernel<<<grid, 256, 0, st>>>(x, ld, M, N, out, rpb);
+    { int rc_ = launch_pdl(colsum_kernel, dim3(grid), dim3(256), 0, st, x, ld, M, N, out, rpb); if (rc_) return rc_; }
     return SGQN_CHECK_LAUNCH();
 }
 
@@ -273,6 +275,8 @@ extern "C" int sgqn_conv1_im2col96(const float* obs, float* col, int B, int Hin,
 // TF32 operand copy of the first conv's weights for the per-position GEMM: wp[32][96] = rna(w[32][81]), zero padded
 // ... and, optionally, its transpose wd[96][32] = the operand of the data gradient dcol[pix][96] = d(act_0)[pix][32] * W
 __global__ void conv1_weights_prep_kernel(const float* __restrict__ w, float* __restrict__ wp, float* __restrict__ wd) {
+    pdl_wait();
+    pdl_launch();
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= 32 * 96) return;
     int co = i / 96, c = i - co * 96;
@@ -282,7 +286,7 @@ __global__ void conv1_weights_prep_kernel(const float* __restrict__ w, float* __
     if (wd) wd[c * 32 + co] = __uint_as_float(r);
 }
 extern "C" int sgqn_conv1_weights_prep(const float* w, float* wp, float* wd, void* stream) {
-    conv1_weights_prep_kernel<<<12, 256, 0, (cudaStream_t)stream>>>(w, wp, wd);
+    { int rc_ = launch_pdl(conv1_weights_prep_kernel, dim3(12), dim3(256), 0, (cudaStream_t)stream, w, wp, wd); if (rc_) return rc_; }
     return SGQN_CHECK_LAUNCH();
 }
 

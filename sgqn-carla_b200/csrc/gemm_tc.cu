@@ -334,6 +334,8 @@ int launch_gemm3(const Operand& A, const Operand& B, int M, int N, int K, int ba
 
 __global__ void guided_mask_kernel(float* __restrict__ dx, int lddx, long long dxbs, const float* __restrict__ z, int ldm, long long mbs,
                                    int M, int K) {
+    pdl_wait();
+    pdl_launch();
     const int b = blockIdx.z;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < (long long)M * K; i += (long long)gridDim.x * blockDim.x) {
         int m = (int)(i / K), k = (int)(i - (long long)m * K);
@@ -365,7 +367,7 @@ extern "C" int sgqn_linear_dgrad_tc(const float* dy, int lddy, long long dybs, c
                           64, st);
     if (rc || mode != 2) return rc;
     long long n = (long long)M * K;
-    guided_mask_kernel<<<dim3((unsigned)((n + 255) / 256), 1, batch), 256, 0, st>>>(dx, lddx, dxbs, zmask, ldm, mbs, M, K);
+    { int rc_ = launch_pdl(guided_mask_kernel, dim3(dim3((unsigned)((n + 255) / 256), 1, batch)), dim3(256), 0, st, dx, lddx, dxbs, zmask, ldm, mbs, M, K); if (rc_) return rc_; }
     return SGQN_CHECK_LAUNCH();
 }
 

@@ -8,6 +8,8 @@
 __global__ void __launch_bounds__(256)
 ln_tanh_fwd_kernel(const float* __restrict__ z, const float* __restrict__ gamma, const float* __restrict__ beta,
                    float* __restrict__ h, int ldh, int M, int P) {
+    pdl_wait();
+    pdl_launch();
     int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (row >= M) return;
     const float* zr = z + (size_t)row * P;
@@ -24,7 +26,7 @@ ln_tanh_fwd_kernel(const float* __restrict__ z, const float* __restrict__ gamma,
 extern "C" int sgqn_ln_tanh_fwd(const float* z, const float* gamma, const float* beta, float* h, int ldh, int M, int P,
                                 void* stream) {
     if (M <= 0) return 0;
-    ln_tanh_fwd_kernel<<<cdiv(M, 8), 256, 0, (cudaStream_t)stream>>>(z, gamma, beta, h, ldh, M, P);
+    { int rc_ = launch_pdl(ln_tanh_fwd_kernel, dim3(cdiv(M, 8)), dim3(256), 0, (cudaStream_t)stream, z, gamma, beta, h, ldh, M, P); if (rc_) return rc_; }
     return SGQN_CHECK_LAUNCH();
 }
 
@@ -33,6 +35,8 @@ __global__ void __launch_bounds__(256)
 ln_tanh_bwd_kernel(const float* __restrict__ dh, int lddh, const float* __restrict__ z, const float* __restrict__ h, int ldh,
                    const float* __restrict__ gamma, float* __restrict__ dz, float* __restrict__ dgamma,
                    float* __restrict__ dbeta, int M, int P) {
+    pdl_wait();
+    pdl_launch();
     int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (row >= M) return;
     const float* zr = z + (size_t)row * P;
@@ -63,12 +67,14 @@ ln_tanh_bwd_kernel(const float* __restrict__ dh, int lddh, const float* __restri
 extern "C" int sgqn_ln_tanh_bwd(const float* dh, int lddh, const float* z, const float* h, int ldh, const float* gamma,
                                 float* dz, float* dgamma, float* dbeta, int M, int P, void* stream) {
     if (M <= 0) return 0;
-    ln_tanh_bwd_kernel<<<cdiv(M, 8), 256, 0, (cudaStream_t)stream>>>(dh, lddh, z, h, ldh, gamma, dz, dgamma, dbeta, M, P);
+    { int rc_ = launch_pdl(ln_tanh_bwd_kernel, dim3(cdiv(M, 8)), dim3(256), 0, (cudaStream_t)stream, dh, lddh, z, h, ldh, gamma, dz, dgamma, dbeta, M, P); if (rc_) return rc_; }
     return SGQN_CHECK_LAUNCH();
 }
 
 // dst[:, col0:col0+n] = src[:, :n]
 __global__ void set_cols_kernel(float* __restrict__ dst, int ld, int col0, const float* __restrict__ src, int lds, int M, int n) {
+    pdl_wait();
+    pdl_launch();
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= M * n) return;
     int r = i / n, c = i - r * n;
@@ -76,7 +82,7 @@ __global__ void set_cols_kernel(float* __restrict__ dst, int ld, int col0, const
 }
 extern "C" int sgqn_set_cols(float* dst, int ld, int col0, const float* src, int lds, int M, int n, void* stream) {
     if (M * n <= 0) return 0;
-    set_cols_kernel<<<cdiv(M * n, 256), 256, 0, (cudaStream_t)stream>>>(dst, ld, col0, src, lds, M, n);
+    { int rc_ = launch_pdl(set_cols_kernel, dim3(cdiv(M * n, 256)), dim3(256), 0, (cudaStream_t)stream, dst, ld, col0, src, lds, M, n); if (rc_) return rc_; }
     return SGQN_CHECK_LAUNCH();
 }
 
@@ -85,6 +91,8 @@ extern "C" int sgqn_set_cols(float* dst, int ld, int col0, const float* src, int
 __global__ void actor_head_fwd_kernel(const float* __restrict__ raw, const float* __restrict__ noise, float lmin, float lmax,
                                       float* __restrict__ mu_t, float* __restrict__ pi_t, int ldpi, float* __restrict__ log_pi,
                                       float* __restrict__ log_std, int M, int A) {
+    pdl_wait();
+    pdl_launch();
     int r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= M) return;
     float resid = 0.f, corr = 0.f;
@@ -108,7 +116,7 @@ __global__ void actor_head_fwd_kernel(const float* __restrict__ raw, const float
 extern "C" int sgqn_actor_head_fwd(const float* raw, const float* noise, float lmin, float lmax, float* mu_t, float* pi_t,
                                    int ldpi, float* log_pi, float* log_std, int M, int A, void* stream) {
     if (M <= 0) return 0;
-    actor_head_fwd_kernel<<<cdiv(M, 128), 128, 0, (cudaStream_t)stream>>>(raw, noise, lmin, lmax, mu_t, pi_t, ldpi, log_pi, log_std, M, A);
+    { int rc_ = launch_pdl(actor_head_fwd_kernel, dim3(cdiv(M, 128)), dim3(128), 0, (cudaStream_t)stream, raw, noise, lmin, lmax, mu_t, pi_t, ldpi, log_pi, log_std, M, A); if (rc_) return rc_; }
     return SGQN_CHECK_LAUNCH();
 }
 
@@ -117,6 +125,8 @@ extern "C" int sgqn_actor_head_fwd(const float* raw, const float* noise, float l
 __global__ void actor_head_bwd_kernel(const float* __restrict__ raw, const float* __restrict__ noise,
                                       const float* __restrict__ dpi, int lddpi, const double* __restrict__ log_alpha, float lmin,
                                       float lmax, float* __restrict__ draw, int M, int A, int Bg) {
+    pdl_wait();
+    pdl_launch();
     int r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= M) return;
     float glp = (float)exp(*log_alpha) / (float)Bg;
@@ -139,8 +149,8 @@ __global__ void actor_head_bwd_kernel(const float* __restrict__ raw, const float
 extern "C" int sgqn_actor_head_bwd(const float* raw, const float* noise, const float* dpi, int lddpi, const double* log_alpha,
                                    float lmin, float lmax, float* draw, int M, int A, int Bg, void* stream) {
     if (M <= 0) return 0;
-    actor_head_bwd_kernel<<<cdiv(M, 128), 128, 0, (cudaStream_t)stream>>>(raw, noise, dpi, lddpi, log_alpha, lmin, lmax, draw, M, A,
-                                                                          Bg > 0 ? Bg : M);
+    { int rc_ = launch_pdl(actor_head_bwd_kernel, dim3(cdiv(M, 128)), dim3(128), 0, (cudaStream_t)stream, raw, noise, dpi, lddpi, log_alpha, lmin, lmax, draw, M, A,
+                                                                          Bg > 0 ? Bg : M); if (rc_) return rc_; }
     return SGQN_CHECK_LAUNCH();
 }
 
@@ -155,6 +165,8 @@ critic_loss_kernel(const float* __restrict__ q, long long qs, const float* __res
                    const float* __restrict__ next_log_pi, const float* __restrict__ reward, const float* __restrict__ not_done,
                    const double* __restrict__ log_alpha, float discount, int mode, float wa, float wb, float* __restrict__ target_q,
                    float* __restrict__ dq, float* __restrict__ loss, int B, int Bg) {
+    pdl_wait();
+    pdl_launch();
     __shared__ float sh[33];
     float alpha = (float)exp(*log_alpha);
     float acc = 0.f;
@@ -186,8 +198,8 @@ critic_loss_kernel(const float* __restrict__ q, long long qs, const float* __res
 extern "C" int sgqn_critic_loss(const float* q, long long qs, const float* tq1, const float* tq2, const float* next_log_pi,
                                 const float* reward, const float* not_done, const double* log_alpha, float discount, int mode,
                                 float wa, float wb, float* target_q, float* dq, float* loss, int B, int Bg, void* stream) {
-    critic_loss_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(q, qs, tq1, tq2, next_log_pi, reward, not_done, log_alpha, discount,
-                                                            mode, wa, wb, target_q, dq, loss, B, Bg);
+    { int rc_ = launch_pdl(critic_loss_kernel, dim3(1), dim3(256), 0, (cudaStream_t)stream, q, qs, tq1, tq2, next_log_pi, reward, not_done, log_alpha, discount,
+                                                            mode, wa, wb, target_q, dq, loss, B, Bg); if (rc_) return rc_; }
     return SGQN_CHECK_LAUNCH();
 }
 
@@ -197,6 +209,8 @@ __global__ void __launch_bounds__(256)
 actor_loss_kernel(const float* __restrict__ q, long long qs, const float* __restrict__ log_pi, const double* __restrict__ log_alpha,
                   float target_entropy, float* __restrict__ dq, float* __restrict__ out, double* __restrict__ alpha_grad, int B,
                   int Bg) {
+    pdl_wait();
+    pdl_launch();
     __shared__ float sh[33];
     double alpha_d = exp(*log_alpha);
     float alpha = (float)alpha_d;
@@ -221,7 +235,7 @@ actor_loss_kernel(const float* __restrict__ q, long long qs, const float* __rest
 
 extern "C" int sgqn_actor_loss(const float* q, long long qs, const float* log_pi, const double* log_alpha, float target_entropy,
                                float* dq, float* out, double* alpha_grad, int B, int Bg, void* stream) {
-    actor_loss_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(q, qs, log_pi, log_alpha, target_entropy, dq, out, alpha_grad, B, Bg);
+    { int rc_ = launch_pdl(actor_loss_kernel, dim3(1), dim3(256), 0, (cudaStream_t)stream, q, qs, log_pi, log_alpha, target_entropy, dq, out, alpha_grad, B, Bg); if (rc_) return rc_; }
     return SGQN_CHECK_LAUNCH();
 }
 
@@ -299,6 +313,8 @@ bce_vec_kernel(const float* __restrict__ logits, const uint8_t* __restrict__ mas
 __global__ void __launch_bounds__(256)
 bce_phase_kernel(const float* __restrict__ logits, const uint8_t* __restrict__ mask, float* __restrict__ loss,
                  float* __restrict__ dlogits, int H, int W, int Hq, int Wq, int oy, int ox, long long nitems, float inv_n, int round_out) {
+    pdl_wait();
+    pdl_launch();
     __shared__ float sh[33];
     float acc = 0.f;
     const int Hl = H >> 1, Wl = W >> 1, HW = H * W;
@@ -336,7 +352,7 @@ extern "C" int sgqn_bce_phase(const float* logits, const uint8_t* mask, float* l
     if (nitems <= 0) return 0;
     float inv_n = 1.0f / ((float)Bg * 9.0f * (float)(H * W));
     int grid = (int)(cdivll(nitems, 256) < 4736 ? cdivll(nitems, 256) : 4736);
-    bce_phase_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(logits, mask, loss, dlogits, H, W, Hq, Wq, oy, ox, nitems, inv_n, round_out);
+    { int rc_ = launch_pdl(bce_phase_kernel, dim3(grid), dim3(256), 0, (cudaStream_t)stream, logits, mask, loss, dlogits, H, W, Hq, Wq, oy, ox, nitems, inv_n, round_out); if (rc_) return rc_; }
     return SGQN_CHECK_LAUNCH();
 }
 

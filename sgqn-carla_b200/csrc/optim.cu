@@ -6,6 +6,8 @@
 
 // state[0] = step count (as float bits of int), bc[0] = 1 - b1^t, bc[1] = sqrt(1 - b2^t)
 __global__ void adam_prep_kernel(int* __restrict__ step, float* __restrict__ bc, double b1, double b2) {
+    pdl_wait();
+    pdl_launch();
     int t = *step + 1;
     *step = t;
     bc[0] = (float)(1.0 - pow(b1, (double)t));
@@ -13,7 +15,7 @@ __global__ void adam_prep_kernel(int* __restrict__ step, float* __restrict__ bc,
 }
 
 extern "C" int sgqn_adam_prep(int* step, float* bc, double b1, double b2, void* stream) {
-    adam_prep_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(step, bc, b1, b2);
+    { int rc_ = launch_pdl(adam_prep_kernel, dim3(1), dim3(1), 0, (cudaStream_t)stream, step, bc, b1, b2); if (rc_) return rc_; }
     return SGQN_CHECK_LAUNCH();
 }
 
@@ -23,6 +25,8 @@ __global__ void __launch_bounds__(256)
 adam_kernel(float4* __restrict__ p, const float4* __restrict__ g, float4* __restrict__ m, float4* __restrict__ v, long long n4,
             const float* __restrict__ bc, float lr, float omb1, float b2, float omb2, float eps, float4* __restrict__ target,
             long long n4_tau0, float tau0, float tau1, float wd) {
+    pdl_wait();
+    pdl_launch();
     const float bc1 = bc[0], bc2s = bc[1];
     const float step_size = lr / bc1;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
@@ -57,14 +61,16 @@ extern "C" int sgqn_adam(float* p, const float* g, float* m, float* v, long long
     if ((n & 3) || (n_tau0 & 3)) return (int)cudaErrorInvalidValue;
     long long n4 = n / 4;
     int grid = (int)(cdivll(n4, 256) < 148 * 8 ? cdivll(n4, 256) : 148 * 8);
-    adam_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((float4*)p, (const float4*)g, (float4*)m, (float4*)v, n4, bc, lr, omb1, b2, omb2,
-                                                        eps, (float4*)target, n_tau0 / 4, tau0, tau1, weight_decay);
+    { int rc_ = launch_pdl(adam_kernel, dim3(grid), dim3(256), 0, (cudaStream_t)stream, (float4*)p, (const float4*)g, (float4*)m, (float4*)v, n4, bc, lr, omb1, b2, omb2,
+                                                        eps, (float4*)target, n_tau0 / 4, tau0, tau1, weight_decay); if (rc_) return rc_; }
     return SGQN_CHECK_LAUNCH();
 }
 
 // EMA only (soft_update_params when it cannot ride on an Adam launch)
 __global__ void __launch_bounds__(256)
 ema_kernel(const float4* __restrict__ p, float4* __restrict__ target, long long n4, long long n4_tau0, float tau0, float tau1) {
+    pdl_wait();
+    pdl_launch();
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
         float tau = i < n4_tau0 ? tau0 : tau1;
         float4 pv = __ldg(p + i), tv = target[i];
@@ -78,13 +84,15 @@ extern "C" int sgqn_ema(const float* p, float* target, long long n, long long n_
     if ((n & 3) || (n_tau0 & 3)) return (int)cudaErrorInvalidValue;
     long long n4 = n / 4;
     int grid = (int)(cdivll(n4, 256) < 148 * 8 ? cdivll(n4, 256) : 148 * 8);
-    ema_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const float4*)p, (float4*)target, n4, n_tau0 / 4, tau0, tau1);
+    { int rc_ = launch_pdl(ema_kernel, dim3(grid), dim3(256), 0, (cudaStream_t)stream, (const float4*)p, (float4*)target, n4, n_tau0 / 4, tau0, tau1); if (rc_) return rc_; }
     return SGQN_CHECK_LAUNCH();
 }
 
 // fp64 scalar Adam for log_alpha; st = {m, v}, step = device int
 __global__ void alpha_adam_kernel(double* __restrict__ log_alpha, const double* __restrict__ grad, double* __restrict__ st,
                                   int* __restrict__ step, double lr, double b1, double b2, double eps) {
+    pdl_wait();
+    pdl_launch();
     int t = *step + 1; *step = t;
     double g = *grad;
     double m = st[0] + (1.0 - b1) * (g - st[0]);
@@ -96,7 +104,7 @@ __global__ void alpha_adam_kernel(double* __restrict__ log_alpha, const double* 
 }
 extern "C" int sgqn_alpha_adam(double* log_alpha, const double* grad, double* st, int* step, double lr, double b1, double b2,
                                double eps, void* stream) {
-    alpha_adam_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(log_alpha, grad, st, step, lr, b1, b2, eps);
+    { int rc_ = launch_pdl(alpha_adam_kernel, dim3(1), dim3(1), 0, (cudaStream_t)stream, log_alpha, grad, st, step, lr, b1, b2, eps); if (rc_) return rc_; }
     return SGQN_CHECK_LAUNCH();
 }
 
@@ -122,6 +130,8 @@ __global__ void rng_step_kernel(unsigned long long seed, unsigned long long* __r
                                 int64_t* __restrict__ idxs, int64_t* __restrict__ overlay_ids, int pool_n, int32_t* __restrict__ offs,
                                 int off_n, float* __restrict__ noise_next, float* __restrict__ noise_pi, float* __restrict__ u,
                                 int B, int A, unsigned long long seed_u) {
+    pdl_wait();
+    pdl_launch();
     const int nA = B * A;
     const int total = 3 * B + nA + 1;
     int id = blockIdx.x * blockDim.x + threadIdx.x;
@@ -154,14 +164,18 @@ __global__ void rng_step_kernel(unsigned long long seed, unsigned long long* __r
         *u = (float)(r[0] >> 8) * (1.0f / 16777216.0f);   // [0,1)
     }
 }
-__global__ void rng_advance_kernel(unsigned long long* counter) { *counter += 1ull; }
+__global__ void rng_advance_kernel(unsigned long long* counter) {
+    pdl_wait();
+    pdl_launch();
+    *counter += 1ull;
+}
 
 extern "C" int sgqn_rng_step(unsigned long long seed, unsigned long long* counter, const int* n_valid, int64_t* idxs,
                              int64_t* overlay_ids, int pool_n, int32_t* offs, int off_n, float* noise_next, float* noise_pi,
                              float* u, int B, int A, unsigned long long seed_u, void* stream) {
     int total = 3 * B + B * A + 1;
-    rng_step_kernel<<<cdiv(total, 128), 128, 0, (cudaStream_t)stream>>>(seed, counter, n_valid, idxs, overlay_ids, pool_n, offs, off_n,
-                                                                     noise_next, noise_pi, u, B, A, seed_u);
-    rng_advance_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(counter);
+    { int rc_ = launch_pdl(rng_step_kernel, dim3(cdiv(total, 128)), dim3(128), 0, (cudaStream_t)stream, seed, counter, n_valid, idxs, overlay_ids, pool_n, offs, off_n,
+                                                                     noise_next, noise_pi, u, B, A, seed_u); if (rc_) return rc_; }
+    { int rc_ = launch_pdl(rng_advance_kernel, dim3(1), dim3(1), 0, (cudaStream_t)stream, counter); if (rc_) return rc_; }
     return SGQN_CHECK_LAUNCH();
 }

@@ -9,6 +9,8 @@ __global__ void __launch_bounds__(256)
 replay_gather_kernel(const uint8_t* __restrict__ frames, const int32_t* __restrict__ fidx, const int64_t* __restrict__ idxs,
                      const int32_t* __restrict__ offs, float* __restrict__ obs, float* __restrict__ next_obs, int B, int Hs,
                      int Ho, int mode, int pad) {
+    pdl_wait();
+    pdl_launch();
     int blk = blockIdx.x;
     int j = blk % 3; int t = blk / 3; int which = t & 1; int b = t >> 1;
     long long tr = idxs[b];
@@ -48,7 +50,7 @@ extern "C" int sgqn_replay_gather(const uint8_t* frames, const int32_t* fidx, co
     if (B <= 0) return 0;
     if (Ho & 3) return (int)cudaErrorInvalidValue;
     if (mode == 0 && Ho > Hs) return (int)cudaErrorInvalidValue;
-    replay_gather_kernel<<<6 * B, 256, 0, (cudaStream_t)stream>>>(frames, fidx, idxs, offs, obs, next_obs, B, Hs, Ho, mode, pad);
+    { int rc_ = launch_pdl(replay_gather_kernel, dim3(6 * B), dim3(256), 0, (cudaStream_t)stream, frames, fidx, idxs, offs, obs, next_obs, B, Hs, Ho, mode, pad); if (rc_) return rc_; }
     return SGQN_CHECK_LAUNCH();
 }
 
@@ -87,6 +89,8 @@ extern "C" int sgqn_frames_copy(const uint8_t* frames, const int32_t* fidx, cons
 // actions / rewards / not_dones rows of the sampled transitions
 __global__ void take_rows_kernel(const float* __restrict__ src, const int64_t* __restrict__ idxs, float* __restrict__ dst,
                                  int B, int width) {
+    pdl_wait();
+    pdl_launch();
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= B * width) return;
     int b = i / width, c = i - b * width;
@@ -95,7 +99,7 @@ __global__ void take_rows_kernel(const float* __restrict__ src, const int64_t* _
 
 extern "C" int sgqn_take_rows(const float* src, const int64_t* idxs, float* dst, int B, int width, void* stream) {
     if (B * width <= 0) return 0;
-    take_rows_kernel<<<cdiv(B * width, 256), 256, 0, (cudaStream_t)stream>>>(src, idxs, dst, B, width);
+    { int rc_ = launch_pdl(take_rows_kernel, dim3(cdiv(B * width, 256)), dim3(256), 0, (cudaStream_t)stream, src, idxs, dst, B, width); if (rc_) return rc_; }
     return SGQN_CHECK_LAUNCH();
 }
 

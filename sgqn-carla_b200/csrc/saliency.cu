@@ -7,6 +7,8 @@
 
 // ---------------------------------------------------------------- global min / max of the obs batch (sgsac.py:68-69)
 __global__ void __launch_bounds__(256) minmax_partial_kernel(const float4* __restrict__ x, long long n4, float* __restrict__ part) {
+    pdl_wait();
+    pdl_launch();
     float lo = INFINITY, hi = -INFINITY;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
         float4 v = __ldg(x + i);
@@ -23,6 +25,8 @@ __global__ void __launch_bounds__(256) minmax_partial_kernel(const float4* __res
     }
 }
 __global__ void minmax_final_kernel(const float* __restrict__ part, int nblk, float* __restrict__ out) {
+    pdl_wait();
+    pdl_launch();
     float lo = INFINITY, hi = -INFINITY;
     for (int i = threadIdx.x; i < nblk; i += 32) { lo = fminf(lo, part[2 * i]); hi = fmaxf(hi, part[2 * i + 1]); }
     lo = warp_min(lo); hi = warp_max(hi);
@@ -33,8 +37,8 @@ __global__ void minmax_final_kernel(const float* __restrict__ part, int nblk, fl
 extern "C" int sgqn_minmax(const float* x, long long n, float* scratch, float* out4, void* stream) {
     if (n <= 0 || (n & 3)) return (int)cudaErrorInvalidValue;
     int nblk = 296;
-    minmax_partial_kernel<<<nblk, 256, 0, (cudaStream_t)stream>>>((const float4*)x, n / 4, scratch);
-    minmax_final_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(scratch, nblk, out4);
+    { int rc_ = launch_pdl(minmax_partial_kernel, dim3(nblk), dim3(256), 0, (cudaStream_t)stream, (const float4*)x, n / 4, scratch); if (rc_) return rc_; }
+    { int rc_ = launch_pdl(minmax_final_kernel, dim3(1), dim3(32), 0, (cudaStream_t)stream, scratch, nblk, out4); if (rc_) return rc_; }
     return SGQN_CHECK_LAUNCH();
 }
 
@@ -52,6 +56,8 @@ __global__ void __launch_bounds__(256)
 attribution_mask_kernel(const float* __restrict__ grad, const float* __restrict__ obs, const float* __restrict__ mm,
                         const float* __restrict__ u, float quantile, uint8_t* __restrict__ mask, float* __restrict__ masked,
                         int HW, int mm_neg) {
+    pdl_wait();
+    pdl_launch();
     extern __shared__ uint32_t keys[];
     __shared__ uint32_t hist[256];
     __shared__ uint32_t s_prefix, s_krem;
@@ -158,13 +164,15 @@ extern "C" int sgqn_attribution_mask(const float* grad, const float* obs, const 
         cudaError_t e = cudaFuncSetAttribute(attribution_mask_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return (int)e;
     }
-    attribution_mask_kernel<<<3 * B, 256, smem, (cudaStream_t)stream>>>(grad, obs, minmax, u, quantile, mask, masked_obs, HW, minmax_neg);
+    { int rc_ = launch_pdl(attribution_mask_kernel, dim3(3 * B), dim3(256), smem, (cudaStream_t)stream, grad, obs, minmax, u, quantile, mask, masked_obs, HW, minmax_neg); if (rc_) return rc_; }
     return SGQN_CHECK_LAUNCH();
 }
 
 // ---------------------------------------------------------------- overlay: ((1-a)*(x/255) + a*(img/255))*255
 __global__ void overlay_u8_kernel(const float* __restrict__ obs, const uint8_t* __restrict__ pool, const int64_t* __restrict__ ids,
                                   float one_minus_alpha, float alpha, float* __restrict__ out, int HW, long long total) {
+    pdl_wait();
+    pdl_launch();
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= total) return;
     int p = (int)(i % HW); long long t = i / HW; int c = (int)(t % 9); int b = (int)(t / 9);
@@ -188,7 +196,7 @@ extern "C" int sgqn_overlay_u8(const float* obs, const uint8_t* pool, const int6
                                float* out, int B, int HW, void* stream) {
     long long total = (long long)B * 9 * HW;
     if (total <= 0) return 0;
-    overlay_u8_kernel<<<(unsigned)cdivll(total, 256), 256, 0, (cudaStream_t)stream>>>(obs, pool, ids, one_minus_alpha, alpha, out, HW, total);
+    { int rc_ = launch_pdl(overlay_u8_kernel, dim3((unsigned)cdivll(total, 256)), dim3(256), 0, (cudaStream_t)stream, obs, pool, ids, one_minus_alpha, alpha, out, HW, total); if (rc_) return rc_; }
     return SGQN_CHECK_LAUNCH();
 }
 extern "C" int sgqn_overlay_f32(const float* obs, const float* imgs, const int64_t* ids, float one_minus_alpha, float alpha,
