@@ -64,6 +64,7 @@ conv3x3_tcg_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(kTmemCols) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
+    pdl_wait();                                        // (the bias below is the first read of memory an earlier kernel wrote)
     if (warp >= 2) {
         for (int i = threadIdx.x - 64; i < N; i += 256) {
             float bv = p.bias ? __ldg(p.bias + i) : 0.f;
@@ -75,6 +76,7 @@ conv3x3_tcg_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     tc_fence_after();
     uint32_t tmem_base;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+    pdl_launch();
 
     if (warp == 0) {
         if (lane == 0) {
@@ -289,8 +291,7 @@ int launch_tcg(const CUtensorMap& tmA, const CUtensorMap& tmW, const GParams& p,
         inited = 1;
     }
     int grid = p.num_tiles < num_sms ? p.num_tiles : num_sms;
-    conv3x3_tcg_kernel<N><<<grid, 320, smem, st>>>(tmA, tmW, p);
-    return SGQN_CHECK_LAUNCH();
+    return launch_pdl(conv3x3_tcg_kernel<N>, dim3(grid), dim3(320), smem, st, tmA, tmW, p);
 }
 
 }  // namespace
@@ -498,6 +499,8 @@ conv3x3_wgrad_tcg_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_c
     tc_fence_after();
     uint32_t tmem_base;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+    pdl_wait();
+    pdl_launch();
 
     if (warp == 0) {
         if (lane == 0) {
@@ -608,8 +611,7 @@ int launch_wgrad_tcg(const CUtensorMap& tmX, const CUtensorMap& tmD, GwParams& p
     p.kb_per_cta = (p.kb_total + gx - 1) / gx;
     gx = (p.kb_total + p.kb_per_cta - 1) / p.kb_per_cta;
     int smem = p.stages * p.stage_bytes + 1024 + 1024 + 256;
-    conv3x3_wgrad_tcg_kernel<N><<<dim3(gx, gy), 192, smem, st>>>(tmX, tmD, p);
-    return SGQN_CHECK_LAUNCH();
+    return launch_pdl(conv3x3_wgrad_tcg_kernel<N>, dim3(gx, gy), dim3(192), smem, st, tmX, tmD, p);
 }
 
 }  // namespace
