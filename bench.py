@@ -364,7 +364,7 @@ def run_b200(a):
     import torch.distributed as dist
     import sgqn_carla_b200 as S
     from sgqn_carla_b200 import _lib
-    from sgqn_carla_b200.dist import GradSync
+    from sgqn_carla_b200.dist import GradSync, P2PGradSync
 
     world, rank, local = env_int("WORLD_SIZE", 1), env_int("RANK", 0), env_int("LOCAL_RANK", 0)
     torch.cuda.set_device(local)
@@ -372,7 +372,8 @@ def run_b200(a):
     if world > 1:
         import datetime
         dist.init_process_group("nccl", device_id=torch.device("cuda", local), timeout=datetime.timedelta(seconds=180))
-        sync = GradSync()
+        # gradient exchange: our peer-memory kernels (csrc/p2p.cu) unless SGQN_P2P=0 asks for the NCCL communicators
+        sync = P2PGradSync() if os.environ.get("SGQN_P2P", "1") == "1" else GradSync()
 
     def barrier():
         if world > 1:
@@ -560,7 +561,9 @@ def run_b200(a):
                    "per_gpu_batch": B, "global_batch": Bg, "parallelism": f"dp{world}" if world > 1 else "single",
                    "replay_capacity": CAPACITY, "l2_policy": "inputs larger than L2 (423 MB frame ring, random gather; ~390 MB activations per encoder pass)",
                    "value_definition": "global updates/s x (global_batch/128)",
-                   "cuda_graphs": bool(agent.use_cuda_graphs), "conv_precision": agent.engine.precision},
+                   "cuda_graphs": bool(agent.use_cuda_graphs), "conv_precision": agent.engine.precision,
+                   "collectives": "none" if sync is None else ("own kernels over NVLink peer memory (csrc/p2p.cu)"
+                                                               if getattr(sync, "arena", None) is not None else "NCCL")},
         "e2e": {"value": e2e_v, "unit": "updates/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "how": "agent.update(replay_buffer, L, step) with the replay frame ring in pinned HOST memory: every step the sampled "
                        "uint8 frames of the NEXT batch cross PCIe into a device staging ring (zero-copy kernel on a side stream, under "

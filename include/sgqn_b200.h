@@ -232,6 +232,20 @@ int sgqn_rng_step(unsigned long long seed, unsigned long long* counter, const in
                   int pool_n, int32_t* offs, int off_n, float* noise_next, float* noise_pi, float* u, int B, int A,
                   unsigned long long seed_u, void* stream);
 
+/* ---- gradient exchange of the batch-sharded update over NVLink peer memory (new functionality; the reference is
+ *      single-GPU and has no counterpart).  bases: HOST array of `world` device pointers = the base of every rank's symmetric arena
+ *      (same layout everywhere, peer-mapped); the arena starts with a header of flags | control words | small slots whose sizes the
+ *      sgqn_p2p_layout() reports (zero-filled once by the host); offsets are bytes from the arena base.  A slot (0..7) is used
+ *      from one stream per rank and every rank issues a slot's calls in the same order.
+ *      allreduce_sum: in place over arena[data_off : data_off + 4n], two-shot (rank r reduces slice r in rank order and writes it to
+ *      every rank), `ctas` (<= 32) CTAs of 256 threads, no shared memory.  small: dst[0:n] = reduction over ranks of src[0:n]
+ *      (op 0 fp32 sum, 1 fp32 max, 2 fp64 sum; n <= 32 / 16), one 64-thread CTA. */
+int sgqn_p2p_layout(long long* out3);     /* HOST pointer: {flag block, control block, small slots} sizes in bytes */
+int sgqn_p2p_allreduce_sum(const void* const* bases, int rank, int world, long long flags_off, long long ctl_off, int slot,
+                           long long data_off, long long n, int ctas, void* stream);
+int sgqn_p2p_small(const void* const* bases, int rank, int world, long long flags_off, long long ctl_off, long long small_off, int slot,
+                   const void* src, void* dst, int n, int op, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -44,3 +44,86 @@ class GradSync(object):
 
     def log_scale(self, col):
         return 1.0 / self.world if col == 3 else 1.0
+
+
+class P2PGradSync(GradSync):
+    """The same exchanges through our own kernels over NVLink peer memory (csrc/p2p.cu) instead of NCCL kernels.
+
+    The update's kernels are persistent, one CTA per SM with ~all of its shared memory; an NCCL CTA cannot share an SM with
+    them, so a collective that overlaps the backward pass costs whole SMs.  `sgqn_p2p_allreduce_sum` (two-shot, in place,
+    rank r reduces slice r in rank order -> every replica holds bit-identical sums) and `sgqn_p2p_small` (min / max, loss
+    vector, alpha gradient) use no shared memory and few registers, so their CTAs run BESIDE the resident compute CTAs.
+
+    The gradient arena is carved out of one symmetric allocation (torch.distributed._symmetric_memory: same layout on every
+    rank, every peer's copy mapped into this process); `attach()` is collective.  One slot (flags + call counter) per
+    issuing stream, like the NCCL communicators above.  Tensors outside the arena fall back to NCCL."""
+    SLOTS = {"main": 0, "early": 1, "actor": 2, "minmax": 3, "logs": 4, "alpha": 5}
+
+    def __init__(self, group=None, extra_groups=True, ctas=16):
+        super().__init__(group, extra_groups)
+        self.rank = dist.get_rank(group)
+        self.ctas = ctas
+        self.arena = None
+
+    def attach(self, n_floats, device):
+        """Collective.  Returns a zero-filled flat fp32 tensor of n_floats inside the symmetric arena."""
+        import ctypes as C
+        import torch.distributed._symmetric_memory as symm
+        from ._lib import K
+        lay = (C.c_longlong * 3)()
+        K.p2p_layout(lay)
+        header = (sum(lay) + 255) // 256 * 256
+        need = header // 4 + (n_floats + 3) // 4 * 4
+        if self.arena is None or self.arena.numel() < need:
+            self.arena = symm.empty(need, dtype=torch.float32, device=device)
+            self.hdl = symm.rendezvous(self.arena, self.group if self.group is not None else dist.group.WORLD)
+            self.arena.zero_()
+            torch.cuda.synchronize(device)
+            dist.barrier(self.group)                   # nobody signals into a header that is still being cleared
+            ptrs = [int(p) for p in self.hdl.buffer_ptrs]
+            assert len(ptrs) == self.world and ptrs[self.rank] == self.arena.data_ptr()
+            self.bases = (C.c_void_p * 8)(*(ptrs + [0] * (8 - self.world)))
+            self.flags_off, self.ctl_off, self.small_off, self.data_off = 0, lay[0], lay[0] + lay[1], header
+        g = self.arena[self.data_off // 4: self.data_off // 4 + n_floats]
+        g.zero_()
+        return g
+
+    def _offset(self, t):
+        if self.arena is None or t.dtype != torch.float32 or not t.is_contiguous():
+            return None
+        off = t.data_ptr() - self.arena.data_ptr()
+        if off < self.data_off or off + 4 * t.numel() > 4 * self.arena.numel() or (off & 15) or (t.numel() & 3):
+            return None
+        return off
+
+    def _small(self, t, slot, op):
+        from ._lib import K
+        K.p2p_small(self.bases, self.rank, self.world, self.flags_off, self.ctl_off, self.small_off, self.SLOTS[slot],
+                    t.data_ptr(), t.data_ptr(), t.numel(), op, torch.cuda.current_stream().cuda_stream)
+
+    def all_reduce_sum(self, flat, group="main"):
+        off = self._offset(flat)
+        if off is not None:
+            from ._lib import K
+            K.p2p_allreduce_sum(self.bases, self.rank, self.world, self.flags_off, self.ctl_off, self.SLOTS[group], off,
+                                flat.numel(), self.ctas, torch.cuda.current_stream().cuda_stream)
+        elif self.arena is not None and flat.dtype == torch.float64 and flat.numel() <= 16 and flat.is_contiguous():
+            self._small(flat, "alpha", 2)              # the fp64 alpha gradient (issued from the actor update's stream)
+        else:
+            super().all_reduce_sum(flat, group)
+
+    def all_reduce_minmax(self, mm, group="minmax"):
+        if self.arena is None:
+            return super().all_reduce_minmax(mm, group)
+        self._small(mm[2:4], "minmax", 1)
+
+    def all_reduce_logs(self, logs, group="main"):
+        if self.arena is None or logs.numel() > 32:
+            return super().all_reduce_logs(logs, group)
+        self._small(logs, "logs", 0)
+
+    def timeouts(self):
+        """Barrier time-outs recorded by the kernels (a peer that never arrived); 0 in a healthy run."""
+        lay = (self.small_off - self.ctl_off) // 4
+        ctl = self.arena[self.ctl_off // 4: self.ctl_off // 4 + lay].view(torch.int32).reshape(-1, 4)
+        return int(ctl[:, 2].sum())

@@ -68,7 +68,8 @@ class UpdateEngine:
                                algorithm=algorithm)
         L, dev, B, A, H = self.lay, self.dev, self.B, self.A, self.H
         self.params = torch.zeros(L.total, device=dev)
-        self.grads = torch.zeros(L.total, device=dev)
+        # gradient arena: inside the ranks' symmetric (peer-mapped) allocation when the exchange runs over NVLink peer memory
+        self.grads = dist.attach(L.total, dev) if hasattr(dist, "attach") else torch.zeros(L.total, device=dev)
         c0, c1 = L.ranges["critic"]
         self.target = torch.zeros(c1 - c0, device=dev)
         self.log_alpha = torch.tensor([math.log(args.init_temperature)], dtype=torch.float64, device=dev)
