@@ -238,11 +238,13 @@ int sgqn_rng_step(unsigned long long seed, unsigned long long* counter, const in
  *      sgqn_p2p_layout() reports (zero-filled once by the host); offsets are bytes from the arena base.  A slot (0..7) is used
  *      from one stream per rank and every rank issues a slot's calls in the same order.
  *      allreduce_sum: in place over arena[data_off : data_off + 4n], two-shot (rank r reduces slice r in rank order and writes it to
- *      every rank), `ctas` (<= 32) CTAs of 256 threads, no shared memory.  small: dst[0:n] = reduction over ranks of src[0:n]
+ *      every rank), `ctas` (<= 160) CTAs of 128 threads, no shared memory; with a staging area (stage_off >= 0: 2 x 8 x stage_stride
+ *      bytes inside the arena) ranges of <= stage_stride bytes are pushed to every peer and summed locally behind ONE barrier.
+ *      small: dst[0:n] = reduction over ranks of src[0:n]
  *      (op 0 fp32 sum, 1 fp32 max, 2 fp64 sum; n <= 32 / 16), one 64-thread CTA. */
 int sgqn_p2p_layout(long long* out3);     /* HOST pointer: {flag block, control block, small slots} sizes in bytes */
 int sgqn_p2p_allreduce_sum(const void* const* bases, int rank, int world, long long flags_off, long long ctl_off, int slot,
-                           long long data_off, long long n, int ctas, void* stream);
+                           long long data_off, long long n, int ctas, long long stage_off, long long stage_stride, void* stream);
 int sgqn_p2p_small(const void* const* bases, int rank, int world, long long flags_off, long long ctl_off, long long small_off, int slot,
                    const void* src, void* dst, int n, int op, void* stream);
 

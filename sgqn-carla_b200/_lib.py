@@ -55,7 +55,7 @@ SIGNATURES = {
     "sgqn_pool2_bwd": [_p, _p, _p, _i, _i, _i, _i, _p],
     "sgqn_upsample2_bwd": [_p, _p, _p, _i, _i, _i, _i, _p],
     "sgqn_p2p_layout": [_p],
-    "sgqn_p2p_allreduce_sum": [_p, _i, _i, _ll, _ll, _i, _ll, _ll, _i, _p],
+    "sgqn_p2p_allreduce_sum": [_p, _i, _i, _ll, _ll, _i, _ll, _ll, _i, _ll, _ll, _p],
     "sgqn_p2p_small": [_p, _i, _i, _ll, _ll, _ll, _i, _p, _p, _i, _i, _p],
     "sgqn_minmax": [_p, _ll, _p, _p, _p],
     "sgqn_attribution_mask": [_p, _p, _p, _p, _f, _p, _p, _i, _i, _i, _p],

@@ -4,8 +4,9 @@
 // passes the `world` base pointers):   [ flags | control | small slots | ... gradient arena ... ].
 // Why not NCCL: the update's kernels are persistent, one CTA per SM with ~all of its shared memory.  An NCCL CTA cannot
 // share an SM with them, so every collective that overlaps the backward pass takes SMs away and the persistent kernels
-// finish in two waves.  These kernels use no shared memory, 256 threads and <= 32 registers per thread: their CTAs fit
-// BESIDE a resident conv / GEMM CTA, and the tiny exchanges (min/max, loss vector, alpha gradient) are one 64-thread CTA.
+// finish in two waves.  These kernels use no shared memory, 128 threads and <= 64 registers per thread: their CTAs fit
+// BESIDE a resident conv / GEMM CTA (one per SM: 148 x 128 threads keep ~1 MB of peer loads in flight), and the tiny
+// exchanges (min/max, loss vector, alpha gradient) are one 64-thread CTA.
 //
 // sgqn_p2p_allreduce_sum: in place, two-shot.  Rank r owns slice r of the range: after a cross-GPU barrier (every peer's
 // gradients are complete) it reads slice r from every rank in rank order (so every replica ends up with bit-identical
@@ -22,9 +23,9 @@
 namespace {
 
 constexpr int kMaxWorld = 8;
-constexpr int kMaxCtas = 32;
+constexpr int kMaxCtas = 160;
 constexpr int kSlots = 8;
-constexpr int kUnroll = 2;                         // 16-byte loads in flight per thread and peer
+constexpr int kUnroll = 4;                         // 16-byte loads in flight per thread and peer
 
 struct Peers { char* base[kMaxWorld]; };
 
@@ -61,7 +62,7 @@ __device__ __forceinline__ void xbarrier(const Peers& P, int rank, int world, lo
     __syncthreads();
 }
 
-__global__ void __launch_bounds__(256, 6)            // <= 40 registers: a CTA fits beside a resident 576-thread conv CTA
+__global__ void __launch_bounds__(128, 8)            // <= 64 registers x 128 threads: a CTA fits beside a resident 576-thread conv CTA
 p2p_allreduce_kernel(Peers P, int rank, int world, long long flags_off, long long ctl_off, int slot, long long data_off, long long n4) {
     pdl_wait();                                        // (no early launch_dependents: the next kernel reads what the last barrier publishes)
     uint32_t* ctl = reinterpret_cast<uint32_t*>(P.base[rank] + ctl_off) + slot * 4;     // {calls so far, CTAs done, barrier time-outs}
@@ -95,6 +96,44 @@ p2p_allreduce_kernel(Peers P, int rank, int world, long long flags_off, long lon
     if (threadIdx.x == 0) {
         const uint32_t prev = atomicAdd(ctl + 1, 1u);
         if (prev == gridDim.x - 1) {                    // every CTA of this call has read the counter: advance it
+            ctl[1] = 0u;
+            __threadfence();
+            *reinterpret_cast<volatile uint32_t*>(ctl) = e;
+        }
+    }
+}
+
+// Small ranges (the 0.38 MB SharedCNN gradients that the optimiser step waits for): ONE barrier instead of two.  Every rank
+// pushes its whole range into slot [parity][rank] of every peer's staging area, one barrier, then every rank adds the `world`
+// copies in rank order (bit-identical replicas again).  Staging is double-buffered by call parity: a rank can only be one call
+// ahead of a peer (its next barrier needs that peer's ticket), so the copy a slow peer is still reading is never overwritten.
+__global__ void __launch_bounds__(128, 8)
+p2p_allreduce_push_kernel(Peers P, int rank, int world, long long flags_off, long long ctl_off, int slot, long long data_off, long long n4,
+                          long long stage_off, long long stage_stride) {
+    pdl_wait();
+    uint32_t* ctl = reinterpret_cast<uint32_t*>(P.base[rank] + ctl_off) + slot * 4;
+    const uint32_t e = *reinterpret_cast<volatile uint32_t*>(ctl) + 1u;
+    const long long par_off = stage_off + (long long)(e & 1u) * kMaxWorld * stage_stride;
+    float4* mine = reinterpret_cast<float4*>(P.base[rank] + data_off);
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+        const float4 v = mine[i];
+        for (int p = 0; p < world; ++p)
+            if (p != rank) reinterpret_cast<float4*>(P.base[p] + par_off + rank * stage_stride)[i] = v;
+    }
+    xbarrier(P, rank, world, flags_off, slot, e, ctl + 2);
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int p = 0; p < world; ++p) {
+            const float4 v = p == rank ? mine[i] : ld_volatile4(reinterpret_cast<const float4*>(P.base[rank] + par_off + p * stage_stride) + i);
+            acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+        }
+        mine[i] = acc;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const uint32_t prev = atomicAdd(ctl + 1, 1u);
+        if (prev == gridDim.x - 1) {
             ctl[1] = 0u;
             __threadfence();
             *reinterpret_cast<volatile uint32_t*>(ctl) = e;
@@ -155,15 +194,23 @@ extern "C" int sgqn_p2p_layout(long long* out3) {
     return 0;
 }
 
-// In-place sum over the ranks of arena[data_off : data_off + 4 n] (bytes; data_off and n*4 multiples of 16).
+// In-place sum over the ranks of arena[data_off : data_off + 4 n] (bytes; data_off and n*4 multiples of 16).  stage_off >= 0
+// names a staging area of 2 * 8 * stage_stride bytes inside the arena: ranges of at most stage_stride bytes then take the
+// one-barrier push form, larger ones the two-shot form.
 extern "C" int sgqn_p2p_allreduce_sum(const void* const* bases, int rank, int world, long long flags_off, long long ctl_off, int slot,
-                                      long long data_off, long long n, int ctas, void* stream) {
+                                      long long data_off, long long n, int ctas, long long stage_off, long long stage_stride,
+                                      void* stream) {
     if (n <= 0) return 0;
     Peers P;
     int rc = fill_peers(&P, bases, rank, world);
     if (rc) return rc;
     if ((n & 3) || (data_off & 15) || slot < 0 || slot >= kSlots || ctas < 1 || ctas > kMaxCtas) return (int)cudaErrorInvalidValue;
-    return launch_pdl(p2p_allreduce_kernel, dim3(ctas), dim3(256), 0, stream, P, rank, world, flags_off, ctl_off, slot, data_off, n / 4);
+    if (stage_off >= 0 && 4 * n <= stage_stride) {
+        if ((stage_off & 15) || (stage_stride & 15)) return (int)cudaErrorInvalidValue;
+        return launch_pdl(p2p_allreduce_push_kernel, dim3(ctas), dim3(128), 0, stream, P, rank, world, flags_off, ctl_off, slot, data_off,
+                          n / 4, stage_off, stage_stride);
+    }
+    return launch_pdl(p2p_allreduce_kernel, dim3(ctas), dim3(128), 0, stream, P, rank, world, flags_off, ctl_off, slot, data_off, n / 4);
 }
 
 // dst[0:n] = reduce over the ranks of src[0:n] (device pointers local to this rank, may alias); op 0 fp32 sum, 1 fp32 max, 2 fp64 sum.

@@ -58,8 +58,9 @@ class P2PGradSync(GradSync):
     rank, every peer's copy mapped into this process); `attach()` is collective.  One slot (flags + call counter) per
     issuing stream, like the NCCL communicators above.  Tensors outside the arena fall back to NCCL."""
     SLOTS = {"main": 0, "early": 1, "actor": 2, "minmax": 3, "logs": 4, "alpha": 5}
+    STAGE_STRIDE = 512 << 10          # bytes per rank of the one-barrier ("push") form: the "main" slot's small ranges
 
-    def __init__(self, group=None, extra_groups=True, ctas=16):
+    def __init__(self, group=None, extra_groups=True, ctas=148):
         super().__init__(group, extra_groups)
         self.rank = dist.get_rank(group)
         self.ctas = ctas
@@ -72,7 +73,8 @@ class P2PGradSync(GradSync):
         from ._lib import K
         lay = (C.c_longlong * 3)()
         K.p2p_layout(lay)
-        header = (sum(lay) + 255) // 256 * 256
+        stage_off = (sum(lay) + 255) // 256 * 256
+        header = stage_off + 2 * 8 * self.STAGE_STRIDE
         need = header // 4 + (n_floats + 3) // 4 * 4
         if self.arena is None or self.arena.numel() < need:
             self.arena = symm.empty(need, dtype=torch.float32, device=device)
@@ -84,6 +86,7 @@ class P2PGradSync(GradSync):
             assert len(ptrs) == self.world and ptrs[self.rank] == self.arena.data_ptr()
             self.bases = (C.c_void_p * 8)(*(ptrs + [0] * (8 - self.world)))
             self.flags_off, self.ctl_off, self.small_off, self.data_off = 0, lay[0], lay[0] + lay[1], header
+            self.stage_off = stage_off
         g = self.arena[self.data_off // 4: self.data_off // 4 + n_floats]
         g.zero_()
         return g
@@ -106,7 +109,8 @@ class P2PGradSync(GradSync):
         if off is not None:
             from ._lib import K
             K.p2p_allreduce_sum(self.bases, self.rank, self.world, self.flags_off, self.ctl_off, self.SLOTS[group], off,
-                                flat.numel(), self.ctas, torch.cuda.current_stream().cuda_stream)
+                                flat.numel(), self.ctas, self.stage_off if group == "main" else -1, self.STAGE_STRIDE,
+                                torch.cuda.current_stream().cuda_stream)
         elif self.arena is not None and flat.dtype == torch.float64 and flat.numel() <= 16 and flat.is_contiguous():
             self._small(flat, "alpha", 2)              # the fp64 alpha gradient (issued from the actor update's stream)
         else:

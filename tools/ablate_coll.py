@@ -7,7 +7,7 @@ import torch.distributed as dist
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import sgqn_carla_b200 as S
-from sgqn_carla_b200.dist import GradSync
+from sgqn_carla_b200.dist import GradSync, P2PGradSync
 import bench
 
 world, rank, local = int(os.environ["WORLD_SIZE"]), int(os.environ["RANK"]), int(os.environ["LOCAL_RANK"])
@@ -16,10 +16,17 @@ dist.init_process_group("nccl", device_id=torch.device("cuda", local), timeout=d
 B = 128
 
 
-class SkipSync(GradSync):
+Base = P2PGradSync if os.environ.get("SGQN_P2P", "1") == "1" else GradSync
+
+
+class SkipSync(Base):
     skip = frozenset()
 
     def all_reduce_sum(self, flat, group="main"):
+        if flat.dtype == torch.float64 and "alpha" in self.skip:
+            return
+        if group + "_tiny" in self.skip:            # keep the launch and the barriers, move (almost) no data
+            return super().all_reduce_sum(flat[:4], group)
         if group not in self.skip:
             super().all_reduce_sum(flat, group)
 
@@ -39,7 +46,9 @@ class NullLog:
 
 sync = SkipSync()
 data = bench.synthetic_sized(20000, 2, 84)
-for skip in ((), ("early",), ("actor",), ("main",), ("minmax",), ("logs",), ("early", "actor", "main", "minmax", "logs")):
+if len(sys.argv) > 1:
+    sync.ctas = int(sys.argv[1])
+for skip in ((), ("early_tiny",), ("early",), ("actor",), ("alpha",), ("main",), ("minmax",), ("logs",), ("early", "actor", "alpha", "main", "minmax", "logs")):
     SkipSync.skip = frozenset(skip)
     args = S.default_args(algorithm="sgsac", batch_size=B, sgqn_quantile=0.95, seed=1 + rank)
     ag = S.make_agent((9, 84, 84), (2,), args, dist=sync, global_batch=B * world)
@@ -61,6 +70,6 @@ for skip in ((), ("early",), ("actor",), ("main",), ("minmax",), ("logs",), ("ea
     dist.barrier(); torch.cuda.synchronize()
     t = torch.tensor([e0.elapsed_time(e1) / 40], device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MAX)
     if rank == 0:
-        print(f"world {world}  without {','.join(skip) or '-':32s} {float(t):.3f} ms/step", flush=True)
+        print(f"world {world} {Base.__name__} without {','.join(skip) or '-':32s} {float(t):.3f} ms/step", flush=True)
     del ag, rb
 dist.destroy_process_group()
