@@ -490,7 +490,9 @@ def run_b200(a):
         ms4, _ = timed(ag4, rb4, NullLog(), st4, max(3, a.warmup // 2))
         strong = {"global_batch": 1024, "per_gpu_batch": Bs, "ms_per_step": ms4 / st4, "updates_per_s": st4 / (ms4 / 1e3),
                   "batch128_equiv_updates_per_s": st4 / (ms4 / 1e3) * 8.0, "steps": st4, "scaling": "strong",
-                  "what": "BASELINE config 4: SGSAC, global batch 1024 split evenly over the ranks, gradients all-reduced over NCCL"}
+                  "what": "BASELINE config 4: SGSAC, global batch 1024 split evenly over the ranks, gradients summed across the ranks ("
+                          + ("own kernels over NVLink peer memory" if getattr(sync, "arena", None) is not None else
+                             ("NCCL" if sync is not None else "single rank: no exchange")) + ")"}
         del ag4, rb4
 
     # ---- end-to-end run: host-resident replay ring (pinned), loss read-back every step

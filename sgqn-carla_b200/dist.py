@@ -77,13 +77,23 @@ class P2PGradSync(GradSync):
         header = stage_off + 2 * 8 * self.STAGE_STRIDE
         need = header // 4 + (n_floats + 3) // 4 * 4
         if self.arena is None or self.arena.numel() < need:
-            self.arena = symm.empty(need, dtype=torch.float32, device=device)
-            self.hdl = symm.rendezvous(self.arena, self.group if self.group is not None else dist.group.WORLD)
+            ok, self.fallback_reason = 1, None
+            try:
+                arena = symm.empty(need, dtype=torch.float32, device=device)
+                hdl = symm.rendezvous(arena, self.group if self.group is not None else dist.group.WORLD)
+                ptrs = [int(p) for p in hdl.buffer_ptrs]
+                assert len(ptrs) == self.world and ptrs[self.rank] == arena.data_ptr()
+            except Exception as e:                     # no peer mapping on this box: every rank falls back to the NCCL communicators
+                ok, self.fallback_reason = 0, repr(e)
+            flag = torch.tensor([ok], device=device)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)
+            if int(flag) == 0:
+                self.arena = None
+                return torch.zeros(n_floats, device=device)
+            self.arena, self.hdl = arena, hdl
             self.arena.zero_()
             torch.cuda.synchronize(device)
             dist.barrier(self.group)                   # nobody signals into a header that is still being cleared
-            ptrs = [int(p) for p in self.hdl.buffer_ptrs]
-            assert len(ptrs) == self.world and ptrs[self.rank] == self.arena.data_ptr()
             self.bases = (C.c_void_p * 8)(*(ptrs + [0] * (8 - self.world)))
             self.flags_off, self.ctl_off, self.small_off, self.data_off = 0, lay[0], lay[0] + lay[1], header
             self.stage_off = stage_off
