@@ -456,6 +456,18 @@ def run_b200(a):
     assert all(np.isfinite(v) for v in last.values()), last
     ups = a.steps / (ms / 1000.0)
     value = ups * (Bg / PER_GPU_BATCH)
+    sharded = None
+    if world > 1:
+        # the replicas must still hold bit-identical parameters after the timed updates (every rank applied the same summed
+        # gradients): element-wise max == min over the ranks, outside the timed region
+        torch.cuda.synchronize()
+        mx, mn = agent.engine.params.clone(), agent.engine.params.clone()
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX); dist.all_reduce(mn, op=dist.ReduceOp.MIN)
+        sharded = {"replicas_bit_identical": bool(torch.equal(mx, mn)), "parameters_compared": int(mx.numel()),
+                   "updates_before_check": a.steps + a.warmup}
+        if getattr(sync, "arena", None) is not None:
+            sharded["p2p_barrier_timeouts"] = sync.timeouts()
+        del mx, mn
 
     # ---- kernel-family profile + roofline of the dominant family (rank 0)
     roof, fam_rows = None, None
@@ -572,7 +584,7 @@ def run_b200(a):
                        "the current update), are converted / cropped on the device at the start of their step, and the step's loss "
                        "vector is copied device->host"},
         "act_latency": act, "gpu_launches": launches, "clocks": sampler.summary(), "roofline": roof, "cpu_baseline": cpu,
-        "torch_eager_b200": eager, "config4_strong": strong, "other_configs": others,
+        "torch_eager_b200": eager, "config4_strong": strong, "sharded_check": sharded, "other_configs": others,
         "algorithmic_gflop_per_update": gflop, "achieved_tflops_whole_step": gflop * ups / 1e3,
         "kernel_families_ms_per_step": [[r[0], round(r[1], 4), r[2]] for r in (fam_rows or [])[:12]],
         "losses_last_step": last, "build_info": build_info(),
