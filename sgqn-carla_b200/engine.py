@@ -732,22 +732,29 @@ class UpdateEngine:
         K.alpha_adam(_ptr(self.log_alpha), _ptr(self.alpha_grad), _ptr(self.alpha_st), _ptr(self.alpha_step),
                      float(a.alpha_lr), float(a.alpha_beta), 0.999, 1e-8, st)
 
-    def update_aux(self):
+    def update_aux(self, phase="all"):
         """sgsac.py:82-102,163-167: overlay -> attribution predictor -> BCE vs mask of attribution #2.  The overlay, the
-        encoder and the projection of s_tilde ran in shared_obs_fwd(with_aux=True): head rows [B, 2B)."""
+        encoder and the projection of s_tilde ran in shared_obs_fwd(with_aux=True): head rows [B, 2B).
+        phase "fwd": the predictor's forward up to the logits (needs neither the mask nor anything attribution #2 touches, so
+        update_sgsac runs it beside attribution #2's chain of small head kernels); "bwd": BCE against the mask onwards."""
         B, A, L, st, a = self.B, self.A, self.lay, self.st, self.args
         P1 = L.P + A
         ha, z = _ptr(self.haS, B * P1), _ptr(self.zS, B * L.P)
         feat = _ptr(self.actS[10], 2 * B * FEAT)
         Wp, G = self.P, self.G
-        K.linear_fwd(ha, P1, 0, Wp("dec.proj.weight"), 0, Wp("dec.proj.bias"), 0, _ptr(self.dl), FEAT, 0,
-                     B, FEAT, P1, 0, 1, 0, st)
         x0, x1 = L.ranges["aux"]
+        if phase in ("all", "fwd"):
+            K.linear_fwd(ha, P1, 0, Wp("dec.proj.weight"), 0, Wp("dec.proj.bias"), 0, _ptr(self.dl), FEAT, 0,
+                         B, FEAT, P1, 0, 1, 0, st)
+            if self.precision == "tf32":
+                self._decoder_tc_fwd(B, st, Wp)
+            if phase == "fwd":
+                return
         if self.precision == "tf32":
-            self._decoder_tc(B, st, Wp, G, x0, x1)
+            self._decoder_tc_bwd(B, st, Wp, G, x0, x1)
         else:
             self._decoder_simt(B, st, Wp, G, x0, x1)
-        wside = self.side if self.overlap else None     # (the decoder's weight gradients were issued there, _decoder_tc)
+        wside = self.side if self.overlap else None     # (the decoder's weight gradients were issued there, _decoder_tc_bwd)
         K.linear_wgrad(ha, P1, 0, _ptr(self.ddl), FEAT, 0, G("dec.proj.weight"), 0, G("dec.proj.bias"), 0,
                        B, FEAT, P1, 0, 1, self._fork())
         self._early_reduce(L.ranges["dec"], after=wside)     # decoder gradients are complete: exchange them under the encoder backward
@@ -962,7 +969,7 @@ class UpdateEngine:
         K.conv_wgrad(_ptr(self.dl), _ptr(self.dd1), G("dec.conv1.weight"), G("dec.conv1.bias"), B, 21, 21, 32, 128, 1, 1, 1, 0, st)
         K.conv_dgrad(_ptr(self.dd1), Wp("dec.conv1.weight"), _ptr(self.dl), _ptr(self.ddl), B, 21, 21, 32, 128, 1, 1, st)
 
-    def _decoder_tc(self, B, st, Wp, G, x0, x1):
+    def _decoder_tc_fwd(self, B, st, Wp):
         """The same on the generalised tcgen05 kernels (conv_tcg.cu).  Every conv reads a zero-bordered pitch-linear
         buffer [B][H+2][W+2][C] (image at rows [1,H+1), cols [0,W)).  conv2 / conv3 -- the convs that follow F.upsample
         (modules.py:327-337) -- run in sub-pixel form at the resolution of their PRE-upsample input: 4x the output
@@ -976,6 +983,9 @@ class UpdateEngine:
                    44, 44, 1, 0, 0, 0, R | (1 << 5), st)      # relu(conv2(up2(.))) at 42x42 (depth-to-space epilogue)
         K.conv_tcg(_ptr(self.xin3), _ptr(self.w3f), _ptr(self.b3p), 0, _ptr(self.lgp), B, 44, 44, 64, 64, 42, 42, -1,
                    44, 44, 1, 0, 0, 0, 0, st)                 # conv3(up2(.)) logits, kept in phase layout
+
+    def _decoder_tc_bwd(self, B, st, Wp, G, x0, x1):
+        """BCE of the phase-layout logits against the attribution mask and the decoder's backward (weight gradients forked)."""
         K.zero(_ptr(self.logs, 4), 4, st)
         K.bce_phase(_ptr(self.lgp), _ptr(self.mask), _ptr(self.logs, 4), _ptr(self.dlgp), B, 84, 84, 44, 44, 1, 0, self.Bg, 1, st)
         K.zero(self._g + 4 * x0, 4 * (x1 - x0), st)
@@ -1020,7 +1030,15 @@ class UpdateEngine:
         self.critic_step(with_ema=do_target)
         if do_actor or do_aux:
             self.shared_obs_fwd(with_aux=do_aux)
+        ev_f = None
         if do_aux:
+            if self.overlap and self.precision == "tf32":
+                # the predictor's forward (big kernels) beside attribution #2's head chain (a dozen small dependent launches)
+                main = torch.cuda.current_stream()
+                ev = torch.cuda.Event(); ev.record(main); self.side3.wait_event(ev)
+                with torch.cuda.stream(self.side3):
+                    self.update_aux("fwd")
+                    ev_f = torch.cuda.Event(); ev_f.record(self.side3)
             # attribution #2 with the updated critic feeds only update_aux's mask (sgsac.py:175-176,83); on steps
             # without an aux update the reference computes it and discards it (no side effects).
             self.attribution2(want_mask=True)
@@ -1032,13 +1050,17 @@ class UpdateEngine:
             with torch.cuda.stream(self.side2):         # incl. its gradient exchange ("actor" communicator) and optimiser steps
                 self.update_actor_and_alpha(finish=True, fork_wgrad=False)
                 ev2 = torch.cuda.Event(); ev2.record(self.side2)
-            self.update_aux()
+            if ev_f is not None:
+                main.wait_event(ev_f)
+            self.update_aux("bwd" if ev_f is not None else "all")
             main.wait_event(ev2)
         else:
             if do_actor:
                 self.update_actor_and_alpha()
             if do_aux:
-                self.update_aux()
+                if ev_f is not None:
+                    torch.cuda.current_stream().wait_event(ev_f)
+                self.update_aux("bwd" if ev_f is not None else "all")
         self._finish_logs()
 
     def update_sac(self, step, mode=0):
