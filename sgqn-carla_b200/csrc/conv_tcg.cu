@@ -32,16 +32,20 @@ struct GParams {
     const float* mask;
     float* out;
     int relu_out, round_out, mask_mode, upsample;
+    int pair, num_iters;    // pair: TWO position tiles (M = 256, two accumulators) per pass over the weight tiles; iterations = tiles / (1 + pair)
     int w_resident;         // every (chunk, tap) weight tile stays in shared memory for the whole launch (<= ~150 KB of weights)
     int shuffle;            // 0 none, 1 depth-to-space (phase channels -> 2x2 pixels), 2 space-to-depth (pixel -> phase channels)
 };
 
-template <int N>
+template <int N, int T>
 __global__ void __launch_bounds__(320, 1)
 conv3x3_tcg_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, GParams p) {
     constexpr int kWBytes = N * 128;
     constexpr uint32_t kIdescN = idesc_tf32(N, false, false);
-    constexpr int kTmemCols = 2 * N <= 64 ? 64 : (2 * N <= 128 ? 128 : (2 * N <= 256 ? 256 : 512));   // power of two >= two accumulators
+    // accumulators: T position tiles per iteration (T = 2: "pair" mode), double-buffered while 2 T N columns fit the 512 of TMEM
+    constexpr int nbuf = 2 * T * N <= 512 ? 2 : 1;
+    constexpr int acc_cols = nbuf * T * N;
+    constexpr uint32_t kTmemCols = acc_cols <= 64 ? 64 : (acc_cols <= 128 ? 128 : (acc_cols <= 256 ? 256 : 512));
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t a_sm = base;
@@ -87,8 +91,8 @@ conv3x3_tcg_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                     for (int t = 0; t < p.ntaps; ++t)
                         tma_load_2d(&tmW, wfull0, w_sm + (c * p.ntaps + t) * kWBytes, t * p.cin + c * 32, 0);
             }
-            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-                const int r0 = tile * kTileM + p.shift;
+            for (int it = blockIdx.x; it < p.num_iters; it += gridDim.x) {
+                const int r0 = it * T * kTileM + p.shift;
                 for (int c = 0; c < p.kc; ++c) {
                     mbar_wait(aempty0 + 8 * as, aph ^ 1u);
                     mbar_expect_tx(afull0 + 8 * as, p.a_bytes);
@@ -109,10 +113,10 @@ conv3x3_tcg_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         if (lane == 0) {
             int as = 0, ws = 0; uint32_t aph = 0, wph = 0; int acc = 0; uint32_t acc_phase = 0;
             if (p.w_resident) { mbar_wait(wfull0, 0); tc_fence_after(); }
-            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+            for (int it = blockIdx.x; it < p.num_iters; it += gridDim.x) {
                 mbar_wait(tempty0 + 8 * acc, acc_phase ^ 1u);
                 tc_fence_after();
-                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * N);
+                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * T * N);
                 for (int c = 0; c < p.kc; ++c) {
                     mbar_wait(afull0 + 8 * as, aph);
                     tc_fence_after();
@@ -125,10 +129,15 @@ conv3x3_tcg_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                         }
                         const uint64_t ad = a0 + (uint64_t)(p.ntaps == 9 ? (t / 3) * rowq + (t % 3) * 8u : 0u);
                         const uint64_t bd = make_desc_sw128(w_sm + (p.w_resident ? c * p.ntaps + t : ws) * kWBytes);
-                        if ((c | t) == 0) tc_mma_tf32_zero(d_tmem, ad, bd, kIdescN);
-                        else tc_mma_tf32_acc(d_tmem, ad, bd, kIdescN);
 #pragma unroll
-                        for (int k = 1; k < 4; ++k) tc_mma_tf32_acc(d_tmem, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), kIdescN);
+                        for (int h = 0; h < T; ++h) {            // the weight tile serves every position tile of the iteration
+                            const uint64_t adh = ad + (uint64_t)(h * (kTileM * 128 >> 4));
+                            const uint32_t dh = d_tmem + (uint32_t)(h * N);
+                            if ((c | t) == 0) tc_mma_tf32_zero(dh, adh, bd, kIdescN);
+                            else tc_mma_tf32_acc(dh, adh, bd, kIdescN);
+#pragma unroll
+                            for (int k = 1; k < 4; ++k) tc_mma_tf32_acc(dh, adh + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), kIdescN);
+                        }
                         if (p.w_resident) continue;
                         tc_commit(wempty0 + 8 * ws);
                         if (++ws == p.w_stages) { ws = 0; wph ^= 1u; }
@@ -137,7 +146,7 @@ conv3x3_tcg_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                     if (++as == p.a_stages) { as = 0; aph ^= 1u; }
                 }
                 tc_commit(tfull0 + 8 * acc);
-                if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+                if (++acc == nbuf) { acc = 0; acc_phase ^= 1u; }
             }
         }
     } else {
@@ -150,17 +159,19 @@ conv3x3_tcg_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             int acc = 0; uint32_t acc_phase = 0;
             const int HW = p.Hr * p.Wp;
             constexpr int NG = N / 4;                    // channels per phase
-            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-                const int q = tile * kTileM + row;
-                const int b = q / HW; const int r2 = q - b * HW; const int y = r2 / p.Wp; const int x = r2 - y * p.Wp;
-                const bool valid = q < p.total_q && y < p.Hv && x < p.Wv;
+            for (int it = blockIdx.x; it < p.num_iters; it += gridDim.x) {
                 mbar_wait(tfull0 + 8 * acc, acc_phase);
                 tc_fence_after();
+#pragma unroll 1
+              for (int h = 0; h < T; ++h) {
+                const int q = (it * T + h) * kTileM + row;
+                const int b = q / HW; const int r2 = q - b * HW; const int y = r2 / p.Wp; const int x = r2 - y * p.Wp;
+                const bool valid = q < p.total_q && y < p.Hv && x < p.Wv;
 #pragma unroll 1
                 for (int g = 0; g < N / 2 / 32; ++g) {
                     const int c0 = half * (N / 2) + g * 32;
                     uint32_t v[32];
-                    const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * N + c0);
+                    const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)((acc * T + h) * N + c0);
                     asm volatile(
                         "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
                         "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
@@ -194,9 +205,10 @@ conv3x3_tcg_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                         reinterpret_cast<float4*>(dst)[c4] = make_float4(o[0], o[1], o[2], o[3]);
                     }
                 }
+              }
                 tc_fence_before();
                 mbar_arrive(tempty0 + 8 * acc);
-                if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+                if (++acc == nbuf) { acc = 0; acc_phase ^= 1u; }
             }
         } else {
         constexpr int CPW = N / 2;                       // accumulator columns per epilogue warp
@@ -205,16 +217,18 @@ conv3x3_tcg_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         const int row = quarter * 32 + lane;
         int acc = 0; uint32_t acc_phase = 0;
         const int HW = p.Hr * p.Wp;
-        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-            const int q = tile * kTileM + row;
-            const int b = q / HW; const int r2 = q - b * HW; const int y = r2 / p.Wp; const int x = r2 - y * p.Wp;
-            const bool valid = q < p.total_q && y < p.Hv && x < p.Wv;
+        for (int it = blockIdx.x; it < p.num_iters; it += gridDim.x) {
             mbar_wait(tfull0 + 8 * acc, acc_phase);
             tc_fence_after();
+#pragma unroll
+          for (int h = 0; h < T; ++h) {
+            const int q = (it * T + h) * kTileM + row;
+            const int b = q / HW; const int r2 = q - b * HW; const int y = r2 / p.Wp; const int x = r2 - y * p.Wp;
+            const bool valid = q < p.total_q && y < p.Hv && x < p.Wv;
             uint32_t v[CPW];
 #pragma unroll
             for (int g = 0; g < CPW / 16; ++g) {
-                const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * N + half * CPW + g * 16);
+                const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)((acc * T + h) * N + half * CPW + g * 16);
                 asm volatile(
                     "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
                     "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
@@ -225,9 +239,10 @@ conv3x3_tcg_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                     : "r"(taddr) : "memory");
             }
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            tc_fence_before();
-            mbar_arrive(tempty0 + 8 * acc);
-            if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+            if (h == T - 1) {                              // every accumulator of the iteration is in registers: release the set
+                tc_fence_before();
+                mbar_arrive(tempty0 + 8 * acc);
+            }
             if (!valid) continue;
             const int c0 = half * CPW;
             const float* mk = p.mask_mode ? p.mask + ((size_t)(b * p.Hm + y) * p.Wm + x) * N + c0 : nullptr;
@@ -268,6 +283,8 @@ conv3x3_tcg_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                     reinterpret_cast<float4*>(dst0 + (size_t)p.Wq * N + N)[c4] = ov;
                 }
             }
+          }
+            if (++acc == nbuf) { acc = 0; acc_phase ^= 1u; }
         }
             }
     }
@@ -279,19 +296,19 @@ conv3x3_tcg_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     }
 }
 
-template <int N>
+template <int N, int T>
 int launch_tcg(const CUtensorMap& tmA, const CUtensorMap& tmW, const GParams& p, int smem, cudaStream_t st) {
     static int inited = 0, num_sms = 0;
     if (!inited) {
-        cudaError_t e = cudaFuncSetAttribute(conv3x3_tcg_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget);
+        cudaError_t e = cudaFuncSetAttribute(conv3x3_tcg_kernel<N, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget);
         if (e != cudaSuccess) return (int)e;
         int dev = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
         inited = 1;
     }
-    int grid = p.num_tiles < num_sms ? p.num_tiles : num_sms;
-    return launch_pdl(conv3x3_tcg_kernel<N>, dim3(grid), dim3(320), smem, st, tmA, tmW, p);
+    int grid = p.num_iters < num_sms ? p.num_iters : num_sms;
+    return launch_pdl(conv3x3_tcg_kernel<N, T>, dim3(grid), dim3(320), smem, st, tmA, tmW, p);
 }
 
 }  // namespace
@@ -328,8 +345,16 @@ extern "C" int sgqn_conv_tcg_taps(const float* x, const float* wop, const float*
     if ((p.shuffle == 1) != (Cout == 256) || (Cout == 256 && (p.mask_mode || p.upsample)) || (p.shuffle == 2 && p.upsample) || p.shuffle == 3)
         return (int)cudaErrorInvalidValue;      // N = 256 exists for the depth-to-space phase conv only
     if (p.mask_mode && !mask) return (int)cudaErrorInvalidValue;
-    int halo = ntaps == 9 ? kTileM + 2 * Wp + 2 : kTileM;
-    p.pieces = halo > 256 ? 2 : 1;
+    static int num_sms_h = 0;
+    if (!num_sms_h) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&num_sms_h, cudaDevAttrMultiProcessorCount, dev); }
+    const int wbytes_all = (Cin / 32) * ntaps * Cout * 128;
+    // Weights too large to stay resident are re-streamed per iteration (L2 -> SM bound at 16 KB per 4 MMAs): two position tiles
+    // per weight tile halve that traffic.  N = 128 keeps two accumulator SETS (4 x 128 columns): conv2's data gradient 122 -> 94 us.
+    // At N = 256 the pair fills TMEM, the epilogue is exposed and the launch gets slower (68 -> 77 us, measured): not used there.
+    p.pair = (ntaps == 9 && Cout == 128 && wbytes_all > 160 * 1024 && p.num_tiles > num_sms_h) ? 1 : 0;
+    p.num_iters = (p.num_tiles + p.pair) / (1 + p.pair);
+    int halo = ntaps == 9 ? (1 + p.pair) * kTileM + 2 * Wp + 2 : kTileM;
+    p.pieces = (halo + 255) / 256;
     p.piece_rows = ((halo + p.pieces - 1) / p.pieces + 7) / 8 * 8;
     if (p.piece_rows > 256) return (int)cudaErrorInvalidValue;
     p.a_bytes = p.pieces * p.piece_rows * 128;
@@ -347,11 +372,11 @@ extern "C" int sgqn_conv_tcg_taps(const float* x, const float* wop, const float*
     rc = make_map_2d(&tmW, wop, (uint64_t)ntaps * Cin, (uint64_t)Cout, 32, (uint32_t)Cout);
     if (rc) return rc;
     cudaStream_t st = (cudaStream_t)stream;
-    if (Cout == 32) return launch_tcg<32>(tmA, tmW, p, smem, st);
-    if (Cout == 64) return launch_tcg<64>(tmA, tmW, p, smem, st);
-    if (Cout == 96) return launch_tcg<96>(tmA, tmW, p, smem, st);
-    if (Cout == 256) return launch_tcg<256>(tmA, tmW, p, smem, st);
-    return launch_tcg<128>(tmA, tmW, p, smem, st);
+    if (Cout == 32) return launch_tcg<32, 1>(tmA, tmW, p, smem, st);
+    if (Cout == 64) return launch_tcg<64, 1>(tmA, tmW, p, smem, st);
+    if (Cout == 96) return launch_tcg<96, 1>(tmA, tmW, p, smem, st);
+    if (Cout == 256) return launch_tcg<256, 1>(tmA, tmW, p, smem, st);
+    return p.pair ? launch_tcg<128, 2>(tmA, tmW, p, smem, st) : launch_tcg<128, 1>(tmA, tmW, p, smem, st);
 }
 
 // TF32 operand copies of a [Cout][9][Cin] conv weight (Cout_real <= Cout rows are real, the rest of wf/wd is zero-filled):

@@ -758,7 +758,8 @@ def test_conv_tcg_forward_dgrad_wgrad(B, H, Cin, Co, Cs):
     close(dw.reshape(Cs, 3, 3, Cin).permute(0, 3, 1, 2)[:Co], wr.grad.float(), rtol=3e-5, what="conv_wgrad_tcg")
 
 
-@pytest.mark.parametrize("B,Hl,Cin,Co,Cg", [(2, 42, 64, 9, 16), (3, 10, 64, 9, 16), (1, 21, 32, 5, 8), (2, 21, 128, 64, 64), (1, 7, 128, 64, 64)])
+@pytest.mark.parametrize("B,Hl,Cin,Co,Cg", [(2, 42, 64, 9, 16), (3, 10, 64, 9, 16), (1, 21, 32, 5, 8), (2, 21, 128, 64, 64), (1, 7, 128, 64, 64),
+                                          (46, 21, 128, 64, 64)])    # 191 position tiles > #SMs: two tiles per weight pass (pair mode), odd tail
 def test_phase_conv_equals_conv_after_upsample(B, Hl, Cin, Co, Cg):
     """conv3x3(pad 1) o F.upsample(x, 2) in its sub-pixel form (sgqn_conv_weights_prep_phase + sgqn_conv_tcg at low
     resolution + sgqn_conv_phase_fold) against torch on the materialised upsampled tensor: forward (phase layout, or
