@@ -8,6 +8,8 @@
 // tile per chunk, ring "A"), and the weights do not fit in shared memory, so the [N][32] weight tile of every
 // (chunk, tap) streams through its own TMA ring "W".  The epilogue can scatter every output pixel to the 2x2 block of
 // the next layer's zero-bordered input (ReLU + nearest upsample + TF32 rounding fused into the producer).
+#include <type_traits>
+
 #include "tc_common.cuh"
 #include "../../include/sgqn_b200.h"
 
@@ -122,6 +124,45 @@ conv3x3_tcg_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                     tc_fence_after();
                     const uint64_t a0 = make_desc_sw128(a_sm + as * p.a_bytes);
                     const uint32_t rowq = (uint32_t)p.Wp * 8u;
+                    if (p.ntaps == 9) {
+                        // the nine taps as straight-line code, one copy per weight mode: the issuing thread, not the tensor pipe, paces
+                        // 36-cycle MMAs when every tap costs a loop trip with two divisions and a mode test (conv3 forward 70 -> 44 us,
+                        // conv1 data gradient 40 -> 26 us, conv2 data gradient 94 -> 86 us)
+                        const uint64_t b0 = make_desc_sw128(w_sm + c * 9 * kWBytes);
+                        auto taps = [&](auto resident_tag) {
+                            constexpr bool kResident = decltype(resident_tag)::value;
+#pragma unroll
+                            for (int t = 0; t < 9; ++t) {
+                                uint64_t bd;
+                                if constexpr (kResident) {
+                                    bd = b0 + (uint64_t)(t * (kWBytes >> 4));
+                                } else {
+                                    mbar_wait(wfull0 + 8 * ws, wph);
+                                    tc_fence_after();
+                                    bd = make_desc_sw128(w_sm + ws * kWBytes);
+                                }
+                                const uint64_t ad = a0 + (uint64_t)((uint32_t)(t / 3) * rowq + (uint32_t)(t % 3) * 8u);
+#pragma unroll
+                                for (int h = 0; h < T; ++h) {    // the weight tile serves every position tile of the iteration
+                                    const uint64_t adh = ad + (uint64_t)(h * (kTileM * 128 >> 4));
+                                    const uint32_t dh = d_tmem + (uint32_t)(h * N);
+                                    if (t == 0 && c == 0) tc_mma_tf32_zero(dh, adh, bd, kIdescN);
+                                    else tc_mma_tf32_acc(dh, adh, bd, kIdescN);
+#pragma unroll
+                                    for (int k = 1; k < 4; ++k) tc_mma_tf32_acc(dh, adh + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), kIdescN);
+                                }
+                                if constexpr (!kResident) {
+                                    tc_commit(wempty0 + 8 * ws);
+                                    if (++ws == p.w_stages) { ws = 0; wph ^= 1u; }
+                                }
+                            }
+                        };
+                        if (p.w_resident) taps(std::true_type{});
+                        else taps(std::false_type{});
+                        tc_commit(aempty0 + 8 * as);
+                        if (++as == p.a_stages) { as = 0; aph ^= 1u; }
+                        continue;
+                    }
                     for (int t = 0; t < p.ntaps; ++t) {
                         if (!p.w_resident) {
                             mbar_wait(wfull0 + 8 * ws, wph);
