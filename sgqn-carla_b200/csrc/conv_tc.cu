@@ -467,12 +467,12 @@ conv3x3_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
                 const uint32_t sb = base + stage * p.stage_bytes;
                 mbar_wait(full0 + 8 * stage, phase);
                 tc_fence_after();
-#pragma unroll 4
-                for (int j = 0; j < kWgRows / 8; ++j) {
-                    const uint64_t ad = make_desc_mn_sw128(sb + j * 1024, 128);                 // atoms: kx = 0..3 row shifts
-                    const uint64_t bd = make_desc_mn_sw128(sb + kWgXBytes + j * 1024, lbo_d);   // atoms: 0, Wp, 2 Wp row shifts
-                    tc_mma_tf32(tmem_base, ad, bd, kIdescMN, (kb != kb0 || j != 0) ? 1u : 0u);
-                }
+                const uint64_t ad0 = make_desc_mn_sw128(sb, 128);                               // atoms: kx = 0..3 row shifts
+                const uint64_t bd0 = make_desc_mn_sw128(sb + kWgXBytes, lbo_d);                 // atoms: 0, Wp, 2 Wp row shifts
+                const uint32_t first = kb != kb0 ? 1u : 0u;
+#pragma unroll
+                for (int j = 0; j < kWgRows / 8; ++j)            // k-step j: +1024 bytes = +64 in the descriptors' address field
+                    tc_mma_tf32(tmem_base, ad0 + (uint64_t)(j * 64), bd0 + (uint64_t)(j * 64), kIdescMN, j ? 1u : first);
                 tc_commit(empty0 + 8 * stage);
                 if (++stage == p.stages) { stage = 0; phase ^= 1u; }
             }

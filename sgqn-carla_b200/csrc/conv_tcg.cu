@@ -590,28 +590,35 @@ conv3x3_wgrad_tcg_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_c
                 const uint32_t sb = base + stage * p.stage_bytes;
                 mbar_wait(full0 + 8 * stage, phase);
                 tc_fence_after();
-#pragma unroll 1
-                for (int j = 0; j < kGwRows / 8; ++j) {
-                    const uint64_t bd = make_desc_mn32(sb + p.kc * xtile + j * 1024, dtile);
-                    if (p.fuse) {
-                        for (int f = 0; f < 3; ++f)
-                            for (int c = 0; c < p.kc; ++c) {
-                                const uint64_t ad = make_desc_mn32(sb + c * xtile + (uint32_t)(f * p.Wp) * 128u + j * 1024, 128);
-                                tc_mma_tf32(tmem_base + (uint32_t)((f * p.kc + c) * N), ad, bd, kIdescMN, (kb != kb0 || j != 0) ? 1u : 0u);
-                            }
-                        continue;
-                    }
-                    if (p.ntaps == 1) {
-                        // per-position GEMM: no row shifts, so the four 32-row M atoms are the channel chunks themselves (their
-                        // tiles are xtile bytes apart; a 4th atom past kc = 3 reads the dY tile: finite garbage in accumulator
-                        // rows nobody reads) -- one MMA per k-step instead of one per chunk with three quarters of M wasted
-                        const uint64_t ad = make_desc_mn32(sb + j * 1024, xtile);
-                        tc_mma_tf32(tmem_base, ad, bd, kIdescMN, (kb != kb0 || j != 0) ? 1u : 0u);
-                        continue;
-                    }
+                // One descriptor pair per accumulator, then the kGwRows / 8 k-steps as straight-line code (+1024 bytes = +64 in the
+                // descriptors' address field): the issuing thread paces these short MMAs, so nothing is recomputed per MMA.  Every
+                // accumulator still receives its k-steps in the same order as before.
+                const uint64_t bd0 = make_desc_mn32(sb + p.kc * xtile, dtile);
+                const uint32_t first = kb != kb0 ? 1u : 0u;
+                if (p.fuse) {
+                    for (int f = 0; f < 3; ++f)
+                        for (int c = 0; c < p.kc; ++c) {
+                            const uint64_t ad0 = make_desc_mn32(sb + c * xtile + (uint32_t)(f * p.Wp) * 128u, 128);
+                            const uint32_t d = tmem_base + (uint32_t)((f * p.kc + c) * N);
+#pragma unroll
+                            for (int j = 0; j < kGwRows / 8; ++j)
+                                tc_mma_tf32(d, ad0 + (uint64_t)(j * 64), bd0 + (uint64_t)(j * 64), kIdescMN, j ? 1u : first);
+                        }
+                } else if (p.ntaps == 1) {
+                    // per-position GEMM: no row shifts, so the four 32-row M atoms are the channel chunks themselves (their
+                    // tiles are xtile bytes apart; a 4th atom past kc = 3 reads the dY tile: finite garbage in accumulator
+                    // rows nobody reads) -- one MMA per k-step instead of one per chunk with three quarters of M wasted
+                    const uint64_t ad0 = make_desc_mn32(sb, xtile);
+#pragma unroll
+                    for (int j = 0; j < kGwRows / 8; ++j)
+                        tc_mma_tf32(tmem_base, ad0 + (uint64_t)(j * 64), bd0 + (uint64_t)(j * 64), kIdescMN, j ? 1u : first);
+                } else {
                     for (int c = 0; c < p.kc; ++c) {
-                        const uint64_t ad = make_desc_mn32(sb + c * xtile + j * 1024, 128);    // atoms = row shifts kx = 0..3
-                        tc_mma_tf32(tmem_base + (uint32_t)(c * N), ad, bd, kIdescMN, (kb != kb0 || j != 0) ? 1u : 0u);
+                        const uint64_t ad0 = make_desc_mn32(sb + c * xtile, 128);    // atoms = row shifts kx = 0..3
+                        const uint32_t d = tmem_base + (uint32_t)(c * N);
+#pragma unroll
+                        for (int j = 0; j < kGwRows / 8; ++j)
+                            tc_mma_tf32(d, ad0 + (uint64_t)(j * 64), bd0 + (uint64_t)(j * 64), kIdescMN, j ? 1u : first);
                     }
                 }
                 tc_commit(empty0 + 8 * stage);

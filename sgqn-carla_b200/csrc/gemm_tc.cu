@@ -123,18 +123,20 @@ gemm3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     } else if (warp == 1) {
         if (lane == 0) {
             int stage = 0; uint32_t phase = 0;
+            // descriptors of stage 0 and what one k-step / one stage adds to their address field (>> 4): nothing is rebuilt per MMA --
+            // the issuing thread is on the critical path of these 4..8 k-block launches
+            const uint64_t ab0 = p.a_mn ? make_desc_mn32(base, 4096) : make_desc_sw128(base);
+            const uint64_t bb0 = p.b_mn ? make_desc_mn32(base + kGtTile, 4096) : make_desc_sw128(base + kGtTile);
+            const uint64_t ka = p.a_mn ? 64u : 2u, kbi = p.b_mn ? 64u : 2u;
+            constexpr uint64_t kSmall = (2 * kGtTile) >> 4, kStageInc = kGtStage >> 4;
             for (int kb = kb0; kb < kb1; ++kb) {
-                const uint32_t sa = base + stage * kGtStage, sb = sa + kGtTile;
+                const uint64_t ab_s = ab0 + (uint64_t)stage * kStageInc, bb_s = bb0 + (uint64_t)stage * kStageInc;
                 mbar_wait(conv0 + 8 * stage, phase);
                 tc_fence_after();
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
-                    const uint64_t ab = p.a_mn ? make_desc_mn32(sa + k * 1024, 4096) : make_desc_sw128(sa) + (uint64_t)(2 * k);
-                    const uint64_t as = p.a_mn ? make_desc_mn32(sa + 2 * kGtTile + k * 1024, 4096)
-                                               : make_desc_sw128(sa + 2 * kGtTile) + (uint64_t)(2 * k);
-                    const uint64_t bb = p.b_mn ? make_desc_mn32(sb + k * 1024, 4096) : make_desc_sw128(sb) + (uint64_t)(2 * k);
-                    const uint64_t bs = p.b_mn ? make_desc_mn32(sb + 2 * kGtTile + k * 1024, 4096)
-                                               : make_desc_sw128(sb + 2 * kGtTile) + (uint64_t)(2 * k);
+                    const uint64_t ab = ab_s + (uint64_t)k * ka, as = ab + kSmall;
+                    const uint64_t bb = bb_s + (uint64_t)k * kbi, bs = bb + kSmall;
                     tc_mma_tf32(tmem_base, as, bb, p.idesc, (kb != kb0 || k != 0) ? 1u : 0u);     // small terms first
                     tc_mma_tf32_acc(tmem_base, ab, bs, p.idesc);
                     tc_mma_tf32_acc(tmem_base, ab, bb, p.idesc);
