@@ -58,6 +58,18 @@ def test_ctypes_signatures_match_header():
             assert ct is want, (name, a)
 
 
+def test_p2p_arena_header_layout():
+    """The header the peer-memory collectives expect in front of the gradient arena (csrc/p2p.cu): a host-side query, no GPU."""
+    import ctypes as C
+    lay = (C.c_longlong * 3)()
+    _lib.K.p2p_layout(lay)
+    flags, ctl, small = list(lay)
+    assert flags == 8 * 160 * 8 * 4 and ctl == 8 * 16 and small == 8 * 2 * 8 * 128      # slots x CTAs x ranks, slots x 4 words, slots x parity x ranks x 128 B
+    assert all(v % 16 == 0 for v in (flags, ctl, small))
+    with pytest.raises(_lib.KernelError):
+        _lib.K.p2p_layout(None)
+
+
 def test_missing_library_fails_loudly(monkeypatch):
     monkeypatch.setattr(_lib, "_lib", None)
     monkeypatch.setattr(_lib, "LIB_PATH", "/nonexistent/libsgqn_b200.so")
