@@ -57,7 +57,7 @@ class P2PGradSync(GradSync):
     The gradient arena is carved out of one symmetric allocation (torch.distributed._symmetric_memory: same layout on every
     rank, every peer's copy mapped into this process); `attach()` is collective.  One slot (flags + call counter) per
     issuing stream, like the NCCL communicators above.  Tensors outside the arena fall back to NCCL."""
-    SLOTS = {"main": 0, "early": 1, "actor": 2, "minmax": 3, "logs": 4, "alpha": 5}
+    SLOTS = {"main": 0, "early": 1, "actor": 2, "minmax": 3, "logs": 4, "alpha": 5, "main_big": 6}
     STAGE_STRIDE = 512 << 10          # bytes per rank of the one-barrier ("push") form: the "main" slot's small ranges
 
     def __init__(self, group=None, extra_groups=True, ctas=148):
@@ -118,8 +118,13 @@ class P2PGradSync(GradSync):
         off = self._offset(flat)
         if off is not None:
             from ._lib import K
-            K.p2p_allreduce_sum(self.bases, self.rank, self.world, self.flags_off, self.ctl_off, self.SLOTS[group], off,
-                                flat.numel(), self.ctas, self.stage_off if group == "main" else -1, self.STAGE_STRIDE,
+            # the one-barrier push form and the two-shot form count their barrier tickets differently (e vs 2e-1, 2e), so they never
+            # share a slot: "main" ranges that fit the staging area push on slot "main", larger ones (PAD's whole aux range) go
+            # two-shot on their own slot -- same stream, same order on every rank
+            push = group == "main" and 4 * flat.numel() <= self.STAGE_STRIDE
+            slot = self.SLOTS["main_big" if (group == "main" and not push) else group]
+            K.p2p_allreduce_sum(self.bases, self.rank, self.world, self.flags_off, self.ctl_off, slot, off,
+                                flat.numel(), self.ctas, self.stage_off if push else -1, self.STAGE_STRIDE,
                                 torch.cuda.current_stream().cuda_stream)
         elif self.arena is not None and flat.dtype == torch.float64 and flat.numel() <= 16 and flat.is_contiguous():
             self._small(flat, "alpha", 2)              # the fp64 alpha gradient (issued from the actor update's stream)
