@@ -70,9 +70,8 @@ class P2PGradSync(GradSync):
         """Collective.  Returns a zero-filled flat fp32 tensor of n_floats inside the symmetric arena."""
         import ctypes as C
         import torch.distributed._symmetric_memory as symm
-        from ._lib import K
         lay = (C.c_longlong * 3)()
-        K.p2p_layout(lay)
+        self._k().p2p_layout(lay)
         stage_off = (sum(lay) + 255) // 256 * 256
         header = stage_off + 2 * 8 * self.STAGE_STRIDE
         need = header // 4 + (n_floats + 3) // 4 * 4
@@ -101,6 +100,15 @@ class P2PGradSync(GradSync):
         g.zero_()
         return g
 
+    @staticmethod
+    def _k():
+        from ._lib import K                            # (late: dist.py itself stays importable without the extension)
+        return K
+
+    @staticmethod
+    def _stream():
+        return torch.cuda.current_stream().cuda_stream
+
     def _offset(self, t):
         if self.arena is None or t.dtype != torch.float32 or not t.is_contiguous():
             return None
@@ -110,22 +118,20 @@ class P2PGradSync(GradSync):
         return off
 
     def _small(self, t, slot, op):
-        from ._lib import K
-        K.p2p_small(self.bases, self.rank, self.world, self.flags_off, self.ctl_off, self.small_off, self.SLOTS[slot],
-                    t.data_ptr(), t.data_ptr(), t.numel(), op, torch.cuda.current_stream().cuda_stream)
+        self._k().p2p_small(self.bases, self.rank, self.world, self.flags_off, self.ctl_off, self.small_off, self.SLOTS[slot],
+                    t.data_ptr(), t.data_ptr(), t.numel(), op, self._stream())
 
     def all_reduce_sum(self, flat, group="main"):
         off = self._offset(flat)
         if off is not None:
-            from ._lib import K
             # the one-barrier push form and the two-shot form count their barrier tickets differently (e vs 2e-1, 2e), so they never
             # share a slot: "main" ranges that fit the staging area push on slot "main", larger ones (PAD's whole aux range) go
             # two-shot on their own slot -- same stream, same order on every rank
             push = group == "main" and 4 * flat.numel() <= self.STAGE_STRIDE
             slot = self.SLOTS["main_big" if (group == "main" and not push) else group]
-            K.p2p_allreduce_sum(self.bases, self.rank, self.world, self.flags_off, self.ctl_off, slot, off,
+            self._k().p2p_allreduce_sum(self.bases, self.rank, self.world, self.flags_off, self.ctl_off, slot, off,
                                 flat.numel(), self.ctas, self.stage_off if push else -1, self.STAGE_STRIDE,
-                                torch.cuda.current_stream().cuda_stream)
+                                self._stream())
         elif self.arena is not None and flat.dtype == torch.float64 and flat.numel() <= 16 and flat.is_contiguous():
             self._small(flat, "alpha", 2)              # the fp64 alpha gradient (issued from the actor update's stream)
         else:

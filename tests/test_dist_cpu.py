@@ -33,6 +33,34 @@ WORKER = textwrap.dedent("""
         s.all_reduce_sum(t, name)
         assert float(t) == 3.0, (name, t)
     assert len({id(g) for g in s.groups.values()}) == len(s.GROUPS)
+    # P2PGradSync host logic (the kernels need GPUs: tests/test_dist_gpu.py): which slot / form a call takes, and what falls back
+    # to the communicators.  A CPU tensor stands in for the symmetric arena, a recorder for the C ABI.
+    calls = []
+    class Rec:
+        def p2p_allreduce_sum(self, *a): calls.append(("sum",) + a)
+        def p2p_small(self, *a): calls.append(("small",) + a)
+    p = m.P2PGradSync()
+    p._k = lambda: Rec()
+    p._stream = lambda: 0
+    head = 8192
+    p.arena = torch.zeros(head + (1 << 20)); p.bases = None
+    p.flags_off, p.ctl_off, p.small_off, p.stage_off, p.data_off = 0, 64, 128, 4096, 4 * head
+    g = p.arena[head:]
+    S = p.SLOTS
+    p.all_reduce_sum(g[1000:1000 + 96000], "main")                 # 0.38 MB on main: push form, staging area given
+    p.all_reduce_sum(g[0:400000], "main")                          # 1.6 MB on main: two-shot on its own slot, no staging
+    p.all_reduce_sum(g[4000:4000 + 96000], "early")                # other slots: always two-shot
+    assert [c[6] for c in calls] == [S["main"], S["main_big"], S["early"]], calls
+    assert [c[10] for c in calls] == [p.stage_off, -1, -1] and calls[0][7] == 4 * (head + 1000) and calls[0][8] == 96000
+    t = g[2:2 + 96000].clone(); t.fill_(1.0 + r)                   # not inside the arena -> the communicator (gloo here)
+    p.all_reduce_sum(t, "main")
+    assert float(t[0]) == 3.0 and len(calls) == 3
+    u = g[2:2 + 96000]; u.fill_(1.0 + r)                           # inside, but not 16-byte aligned -> the communicator
+    p.all_reduce_sum(u, "main")
+    assert float(u[0]) == 3.0 and len(calls) == 3
+    p.all_reduce_sum(torch.zeros(1, dtype=torch.float64), "actor")
+    p.all_reduce_minmax(torch.zeros(4)); p.all_reduce_logs(torch.zeros(8))
+    assert [(c[0], c[7], c[10], c[11]) for c in calls[3:]] == [("small", S["alpha"], 1, 2), ("small", S["minmax"], 2, 1), ("small", S["logs"], 8, 0)]
     dist.destroy_process_group()
     print("rank", r, "ok")
 """)
